@@ -1,0 +1,99 @@
+// dn_params.h -- kernel-side parameter block of libdronenav (host + device).
+//
+// Everything a control step needs that is not per-env state travels in ONE by-value
+// kernel argument (`__grid_constant__`, i.e. the constant bank): CF2X constants
+// (Sol/resources/safegym/cf2x.urdf:5,11-12,34; Sol/PyBullet/BaseAviary.py:76,163-176),
+// the PBDroneEnv constructor arguments (Sol/Model/Environments/PBDroneEnv.py:41-169) and
+// pointers to the handle's HBM-resident state.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace dn {
+
+// One reward family covers PBDroneEnv._computeReward (PBDroneEnv.py:475-571) and its
+// variants dummy_env.py:446-550 / ThrustEnv.py:368-513: same state machine, different
+// constants.
+struct RewardParams {
+    float crash;             // returned as is (NOT divided), PBDroneEnv.py:489-490
+    float final_bonus;       // all targets reached, :544
+    float capture_bonus;     // one target reached, :550
+    float capture_orient_w;  // :551
+    float exp_w, exp_k;      // exp_w * exp(-exp_k * d), :555
+    float progress_w;        // (prev_d - d) * progress_w unless just_found, :556
+    float orient_w;          // :557
+    float smooth_lin_thr, smooth_ang_thr;  // :599
+    float smooth_w;          // 1 = smoothness term on, 0 = off (ThrustEnv)
+    float divisor;           // :571
+};
+
+struct Stats {               // device mirror of dn_stats
+    double             return_sum;
+    unsigned long long length_sum, episodes, successes, found_targets, crashes, truncations;
+};
+
+// Per-env persistent state in HBM: seven float4 planes ("structure of float4 arrays"),
+// plane p of env i at s[p][i].  One LDG.128 / STG.128 per plane per env, consecutive
+// lanes touch consecutive 16-byte words -> every warp request is 512 contiguous bytes.
+//   s0 = pos.xyz        | dist               (BaseAviary.pos ; PBDroneEnv._distance_to_target)
+//   s1 = quat.xyzw                           (BaseAviary.quat)
+//   s2 = vel.xyz        | prev_dist          (BaseAviary.vel ; _prev_distance_to_target)
+//   s3 = rpy_rates.xyz  | ep_return          (BaseAviary.rpy_rates ; Monitor)
+//   s4 = ang_v.xyz      | bits{steps:20, just_found:1, target_idx:11}
+//   s5 = prev_vel.xyz   | ep_length (int bits)
+//   s6 = prev_ang_v.xyz | episode_count (uint bits, Philox counter)
+// current_vel / current_ang_v of the reference are vel / ang_v at step entry and are
+// not stored.  112 B read + 112 B written per env-step.
+constexpr int kPlanes = 7;
+
+struct Params {
+    int   n;
+    int   substeps;
+    int   act_type;
+    int   normalize_actions;
+    int   physics;
+    int   obs_dim;
+    int   cylinder;
+    int   circle;
+    int   max_steps;
+    int   num_targets;
+    int   spawn_mode;
+    int   reward_id;
+    float dt;
+    float threshold;
+    float x_low, y_low, z_low, x_high, y_high, z_high;
+    float max_target_dist;
+    float init_pos[3];
+    float init_quat[4];
+    float init_obs[12];      // observation of the spawn pose (entries 0..11)
+    float init_seg_base[3];  // INIT_XYZS[0], base of segment 0 (PBDroneEnv.py:746-748)
+    // action map (PBDroneEnv.py:113-116,872-895,949-971; env_utils.py:8-59)
+    float a_low, a_high, kf, km, pwm_scale, pwm_const, pwm_min, pwm_max, hover_rpm;
+    // rigid body (BaseAviary.py:899-958)
+    float gravity, inv_m, arm_over_sqrt2, ixx, iyy, izz, inv_ixx, inv_iyy, inv_izz;
+    // add-ons (BaseAviary.py:798-865)
+    float drag_xy, drag_z, gnd_coeff, prop_radius, gnd_h_clip, collision_half_h;
+    float prop_x[4], prop_y[4];
+    RewardParams rw;
+    unsigned long long seed;
+    long long env_id_offset;
+    const float4* targets;   // [T] (x,y,z,0)
+    const float4* segs;      // [T][2] {ext_p1.xyz, ext_len} {unit.xyz, seg_len}; non-circle cylinder
+    float4* s[kPlanes];
+    float* last_rpm_sum;     // [N], drag only
+    float* obs_rms;          // [(2*obs_dim+1)][N] mean planes | var planes | count, normalize_obs only
+    Stats* stats;
+};
+
+struct StepIO {
+    const float4* actions;
+    float*    obs;
+    float*    reward;
+    uint8_t*  done;
+    float*    terminal_obs;
+    int32_t*  found_targets;
+    float*    episode_return;
+    int32_t*  episode_length;
+};
+
+}  // namespace dn

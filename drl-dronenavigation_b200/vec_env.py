@@ -1,0 +1,186 @@
+"""SB3 ``VecEnv`` protocol over the fused CUDA step.
+
+``GpuDroneVecEnv`` stands where the reference builds
+``SubprocVecEnv([make_env(...) for i in range(num_envs)])``
+(Sol/Model/PBDroneSimulator.py:653-681): same attributes (``num_envs``,
+``observation_space``, ``action_space``), same numpy ``reset`` / ``step_async`` /
+``step_wait`` contract with the worker's auto-reset semantics
+(``terminal_observation``, ``TimeLimit.truncated``, Monitor's ``episode`` dict,
+``found_targets``), but one kernel launch per vector step instead of N processes.
+Host buffers are pinned; every ``step`` is H2D(actions) -> kernel -> D2H(results) on
+the environment's stream.
+"""
+from __future__ import annotations
+
+import pickle
+import time
+from typing import Any, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .batched_env import BatchedDroneEnv
+from .constants import CF2X
+from .spaces import Box
+
+try:  # pragma: no cover - SB3 is absent in the build image
+    from stable_baselines3.common.vec_env import VecEnv as _SB3VecEnv  # type: ignore
+    from stable_baselines3.common.monitor import Monitor as _SB3Monitor  # type: ignore
+    _HAVE_SB3 = True
+except Exception:  # noqa: BLE001
+    _SB3VecEnv = object
+    _SB3Monitor = None
+    _HAVE_SB3 = False
+
+
+def action_space(normalize_actions: bool) -> Box:
+    """PBDroneEnv._actionSpace (PBDroneEnv.py:225-243)."""
+    if normalize_actions:
+        return Box(low=-1 * np.ones(4, dtype=np.float32), high=np.ones(4, dtype=np.float32), shape=(4,), dtype=np.float32)
+    lo, hi = CF2X.physical_action_bounds()
+    return Box(low=lo, high=hi, dtype=np.float32)
+
+
+def observation_space(include_distance: bool) -> Box:
+    """PBDroneEnv._observationSpace (PBDroneEnv.py:245-286)."""
+    low = np.array([-1, -1, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1], dtype=np.float32)
+    high = np.ones(12, dtype=np.float32)
+    if include_distance:
+        low, high = np.append(low, 0).astype(np.float32), np.append(high, 1).astype(np.float32)
+    return Box(low=low, high=high, dtype=np.float32)
+
+
+class GpuDroneVecEnv(_SB3VecEnv):
+    """Vectorised PBDroneEnv on one GPU.  Keyword arguments are PBDroneEnv's
+    (PBDroneEnv.py:41-65); ``normalize_obs=True`` fuses the ``NormalizeObservation``
+    wrapper that make_env always applies (PBDroneSimulator.py:181)."""
+
+    def __init__(self, num_envs: int, target_points, threshold=0.3, discount=0.999, max_steps=4096,
+                 aviary_dim=(-1, -1, 0, 1, 1, 1), include_distance=True, normalize_actions=True,
+                 normalize_obs=True, device=None, **env_kwargs):
+        self.core = BatchedDroneEnv(num_envs, target_points, threshold=threshold, discount=discount,
+                                    max_steps=max_steps, aviary_dim=aviary_dim,
+                                    include_distance=include_distance, normalize_actions=normalize_actions,
+                                    normalize_obs=normalize_obs, device=device, **env_kwargs)
+        obs_space, act_space = observation_space(include_distance), action_space(normalize_actions)
+        if _HAVE_SB3:  # pragma: no cover
+            super().__init__(num_envs, obs_space, act_space)
+        else:
+            self.num_envs, self.observation_space, self.action_space = num_envs, obs_space, act_space
+        self.render_mode = None
+        N, D = num_envs, self.core.obs_dim
+        pin = lambda *shape, dtype: torch.empty(*shape, dtype=dtype).pin_memory()
+        self._h_actions = pin(N, 4, dtype=torch.float32)
+        self._h_obs = pin(N, D, dtype=torch.float32)
+        self._h_rew = pin(N, dtype=torch.float32)
+        self._h_done = pin(N, dtype=torch.uint8)
+        self._h_term = pin(N, D, dtype=torch.float32)
+        self._h_found = pin(N, dtype=torch.int32)
+        self._h_epr = pin(N, dtype=torch.float32)
+        self._h_epl = pin(N, dtype=torch.int32)
+        self._d_actions = torch.zeros(N, 4, dtype=torch.float32, device=self.core.device)
+        self._stream = torch.cuda.Stream(device=self.core.device)
+        torch.cuda.synchronize(self.core.device)   # allocations above were made on the default stream
+        self._t_start = time.time()
+        self._pending = False
+        self.h2d_bytes_per_step = self._h_actions.numel() * 4
+        self.d2h_bytes_per_step = (self._h_obs.numel() * 4 + N * 4 + N + N * 4)   # obs, reward, done, found
+        self._attrs = {"INIT_XYZS": self.core.INIT_XYZS, "INIT_RPYS": self.core.INIT_RPYS,
+                       "CTRL_FREQ": env_kwargs.get("ctrl_freq", 240), "PYB_FREQ": env_kwargs.get("pyb_freq", 240),
+                       "G": CF2X.G}
+
+    # ------------------------------------------------------------- VecEnv API
+    def reset(self) -> np.ndarray:
+        with torch.cuda.stream(self._stream):
+            obs = self.core.reset()
+            self._h_obs.copy_(obs, non_blocking=True)
+        self._stream.synchronize()
+        return self._h_obs.numpy().copy()
+
+    def step_async(self, actions: np.ndarray) -> None:
+        a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 4)
+        self._h_actions.numpy()[...] = a
+        c = self.core
+        with torch.cuda.stream(self._stream):
+            self._d_actions.copy_(self._h_actions, non_blocking=True)
+            c.step(self._d_actions)
+            self._h_obs.copy_(c.obs, non_blocking=True)
+            self._h_rew.copy_(c.reward, non_blocking=True)
+            self._h_done.copy_(c.done, non_blocking=True)
+            self._h_found.copy_(c.found_targets, non_blocking=True)
+            # rows of these three are only meaningful where done; tiny next to obs for small N
+            self._h_term.copy_(c.terminal_obs, non_blocking=True)
+            self._h_epr.copy_(c.episode_return, non_blocking=True)
+            self._h_epl.copy_(c.episode_length, non_blocking=True)
+        self._pending = True
+
+    def step_wait(self):
+        if not self._pending:
+            raise RuntimeError("step_wait() called without step_async()")
+        self._stream.synchronize()
+        self._pending = False
+        obs = self._h_obs.numpy().copy()
+        rews = self._h_rew.numpy().copy()
+        bits = self._h_done.numpy()
+        dones = bits != 0
+        found = self._h_found.numpy()
+        infos: List[dict] = [{"found_targets": int(found[i]), "TimeLimit.truncated": False} for i in range(self.num_envs)]
+        if dones.any():
+            term = self._h_term.numpy()
+            epr, epl = self._h_epr.numpy(), self._h_epl.numpy()
+            now = round(time.time() - self._t_start, 6)
+            for i in np.nonzero(dones)[0]:
+                info = infos[i]
+                info["TimeLimit.truncated"] = bool(bits[i] & L.DN_DONE_TRUNCATED) and not bool(bits[i] & L.DN_DONE_TERMINATED)
+                info["terminal_observation"] = term[i].copy()
+                info["episode"] = {"r": round(float(epr[i]), 6), "l": int(epl[i]), "t": now}
+        return obs, rews, dones, infos
+
+    def step(self, actions: np.ndarray):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self) -> None:
+        self.core.close()
+
+    def seed(self, seed: Optional[int] = None) -> List[Optional[int]]:
+        # the reference's env ignores seeds ("Seeding not implemented on pybullet side", PBDroneSimulator.py:690)
+        return [None if seed is None else seed + i for i in range(self.num_envs)]
+
+    def _indices(self, indices) -> Sequence[int]:
+        if indices is None:
+            return range(self.num_envs)
+        if isinstance(indices, int):
+            return [indices]
+        return indices
+
+    def get_attr(self, attr_name: str, indices=None) -> List[Any]:
+        if attr_name == "render_mode":
+            return [None for _ in self._indices(indices)]
+        if attr_name in self._attrs:
+            return [self._attrs[attr_name] for _ in self._indices(indices)]
+        raise AttributeError(attr_name)
+
+    def set_attr(self, attr_name: str, value: Any, indices=None) -> None:
+        raise AttributeError(f"{attr_name}: per-env attributes of the GPU environment are read-only")
+
+    def env_method(self, method_name: str, *args, indices=None, **kwargs) -> List[Any]:
+        raise AttributeError(f"{method_name}: not available on the GPU environment")
+
+    def env_is_wrapped(self, wrapper_class, indices=None) -> List[bool]:
+        # Monitor's bookkeeping is fused into the kernel: info["episode"] is emitted on done
+        is_monitor = _SB3Monitor is not None and wrapper_class is _SB3Monitor
+        return [bool(is_monitor or getattr(wrapper_class, "__name__", "") == "Monitor") for _ in self._indices(indices)]
+
+    def get_images(self):
+        return [None] * self.num_envs
+
+    def render(self, mode: Optional[str] = None):
+        return None
+
+    # the reference calls eval_env.save(path) (PBDroneSimulator.py:746): persist the obs-RMS state
+    def save(self, path: str) -> None:
+        state = {k: v.cpu().numpy() for k, v in self.core.get_state().items()}
+        with open(path, "wb") as f:
+            pickle.dump({"obs_rms": state.get("obs_rms"), "obs_dim": self.core.obs_dim}, f)

@@ -1,0 +1,189 @@
+/*
+ * dronenav.h -- C ABI of libdronenav.so, the B200 (sm_100a) batched drone-navigation
+ * environment.
+ *
+ * The reference (eRGiBi/DRL-DroneNavigation) is pure Python and has no FFI of its own;
+ * its boundary for this path is the Python object protocol of
+ *   - PBDroneEnv.reset / PBDroneEnv.step   (Sol/Model/Environments/PBDroneEnv.py:609-665, 171-199)
+ *   - BaseAviary.step                      (Sol/PyBullet/BaseAviary.py:324-453)
+ *   - SB3 SubprocVecEnv + Monitor + NormalizeObservation built by
+ *     PBDroneSimulator.make_env            (Sol/Model/PBDroneSimulator.py:136-204, 653-681)
+ * Each entry point below names the reference interface it replaces.  The Python side
+ * (drl-dronenavigation_b200/vec_env.py, env.py) binds these with ctypes; the binding a
+ * reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - return 0 on success, a negative DN_E* code on failure; dn_last_error() returns a
+ *     thread-local message for the last failure on the calling thread;
+ *   - every I/O buffer is CALLER-OWNED DEVICE memory (plain pointers, no torch types)
+ *     and must stay alive until the work enqueued on `stream` has completed;
+ *   - all work is enqueued on the caller's stream (pass the raw cudaStream_t as void*;
+ *     NULL = legacy default stream); no hidden synchronisation, no host allocation on
+ *     the step path, CUDA-graph capturable;
+ *   - one handle per device shard; a handle is not thread-safe; handles are independent;
+ *   - there is NO CPU fallback: without a CUDA device dn_create fails with DN_ECUDA.
+ */
+#ifndef DRONENAV_H_
+#define DRONENAV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DN_ABI_VERSION 1
+
+/* error codes */
+#define DN_OK        0
+#define DN_EINVAL   -1   /* bad argument / config */
+#define DN_ECUDA    -2   /* CUDA runtime error (message has the cudaError string) */
+#define DN_ENOMEM   -3
+
+/* ActionType (Sol/PyBullet/enums.py:36-43) -- only the RPM-producing types are on the path */
+#define DN_ACT_THRUST     0   /* PBDroneEnv._preprocessAction, PBDroneEnv.py:872-895 */
+#define DN_ACT_RPM        1   /* BaseSingleAgentAviary.py:176-179 */
+#define DN_ACT_ONE_D_RPM  2   /* BaseSingleAgentAviary.py:211-212 (uses action[:,0]) */
+
+/* physics flags.  0 == Physics.DYN (BaseAviary.py:899-973).  The add-ons restate the
+ * PYB_* formulas inside the DYN integrator (documented extension). */
+#define DN_PHYS_DYN            0
+#define DN_PHYS_DRAG           1   /* BaseAviary._drag, BaseAviary.py:838-865 */
+#define DN_PHYS_GROUND_EFFECT  2   /* BaseAviary._groundEffect, BaseAviary.py:798-834 */
+#define DN_PHYS_GROUND_CONTACT 4   /* analytic substitute for p.getContactPoints(), PBDroneEnv.py:699 */
+
+/* reward functions (reward_id) */
+#define DN_REWARD_DEFAULT   0   /* PBDroneEnv._computeReward, PBDroneEnv.py:475-571 */
+#define DN_REWARD_DUMMY     1   /* dummy_env.py:446-550 */
+#define DN_REWARD_THRUSTENV 2   /* ThrustEnv.py:368-513 */
+#define DN_REWARD_HER       3   /* HerPBDroneEnv.py:314-398 */
+#define DN_REWARD_REACHING  4   /* Rewarder.py reaching-progress (arXiv 2310.10943) */
+#define DN_REWARD_PROGRESS  5   /* Rewarder.py projection progress (arXiv 2103.08624) */
+#define DN_REWARD_HOVER     6   /* upstream HoverAviary.py:65-76 */
+#define DN_NUM_REWARDS      7
+
+/* spawn modes for (auto-)reset.  0 is the reference behaviour (PBDroneEnv.py:609-665). */
+#define DN_SPAWN_FIXED      0   /* INIT_XYZS / INIT_RPYS, deterministic */
+#define DN_SPAWN_LINE       1   /* Philox: within 0.1 m of a random target-pair line (PBDroneEnv.py:622-629) */
+#define DN_SPAWN_MIDPOINT   2   /* Philox: segment midpoint with rolled target order (PBDroneEnv.py:641-648) */
+
+/* done byte written by dn_step */
+#define DN_DONE_TERMINATED  1
+#define DN_DONE_TRUNCATED   2
+
+typedef struct dn_env dn_env;
+
+/* Constructor arguments: PBDroneEnv.__init__ kwargs (PBDroneEnv.py:41-65) restricted to the
+ * ones that reach the hot path, plus the shard description.  Geometry is double so the
+ * host-side derived tables are computed in the reference's precision before being
+ * rounded to FP32 for the kernel. */
+typedef struct dn_config {
+    int32_t  abi_version;        /* = DN_ABI_VERSION */
+    int32_t  num_envs;           /* N, environments owned by this handle */
+    int64_t  env_id_offset;      /* global id of local env 0 (Philox subsequence = global env id) */
+    uint64_t seed;
+    int32_t  pyb_freq;           /* PBDroneEnv.py:49 */
+    int32_t  ctrl_freq;          /* PBDroneEnv.py:50 ; substeps S = pyb_freq / ctrl_freq */
+    int32_t  act_type;           /* DN_ACT_* */
+    int32_t  normalize_actions;  /* PBDroneEnv.py:63,173-176 (rescale_action) */
+    int32_t  physics;            /* DN_PHYS_* flags */
+    int32_t  reward_id;          /* DN_REWARD_* */
+    int32_t  include_distance;   /* PBDroneEnv.py:62 -> obs dim 13 (else 12) */
+    int32_t  cylinder;           /* PBDroneEnv.py:59 */
+    int32_t  circle;             /* PBDroneEnv.py:60 */
+    int32_t  max_steps;          /* PBDroneEnv.py:43,79 */
+    int32_t  spawn_mode;         /* DN_SPAWN_* */
+    int32_t  normalize_obs;      /* fuse normalize.NormalizeObservation (normalize.py:50-97), per env */
+    double   threshold;          /* PBDroneEnv.py:43,77 */
+    double   discount;           /* PBDroneEnv.py:43,78 */
+    double   aviary_dim[6];      /* x_low,y_low,z_low,x_high,y_high,z_high (PBDroneEnv.py:83) */
+    double   init_xyz[3];        /* INIT_XYZS[0] (BaseAviary.py:248-257) */
+    double   init_rpy[3];        /* INIT_RPYS[0] (BaseAviary.py:258-263) */
+    int32_t  num_targets;        /* T */
+    int32_t  reserved0;
+    const double* targets;       /* HOST pointer, [T,3] row-major (copied by dn_create) */
+} dn_config;
+
+/* Buffers of one dn_step call.  Device pointers, caller-owned.  Nullable where noted. */
+typedef struct dn_step_io {
+    const float* actions;        /* [N,4] f32 (ONE_D_RPM reads column 0)                       */
+    float*       obs;            /* [N,obs_dim] f32 : obs of the step, or the reset obs if done */
+    float*       reward;         /* [N] f32                                                     */
+    uint8_t*     done;           /* [N] u8 : DN_DONE_TERMINATED | DN_DONE_TRUNCATED             */
+    float*       terminal_obs;   /* [N,obs_dim] f32, rows written only where done; nullable     */
+    int32_t*     found_targets;  /* [N] i32 info["found_targets"] (PBDroneEnv.py:434-442); nullable */
+    float*       episode_return; /* [N] f32 Monitor info["episode"]["r"], written where done; nullable */
+    int32_t*     episode_length; /* [N] i32 Monitor info["episode"]["l"], written where done; nullable */
+} dn_step_io;
+
+/* Row-major per-field view used to upload / download the full per-env state (parity tests
+ * upload the oracle's state; checkpointing downloads it).  Device pointers, any may be NULL. */
+typedef struct dn_state_view {
+    float*    pos;            /* [N,3]  BaseAviary.pos                                   */
+    float*    quat;           /* [N,4]  BaseAviary.quat, (x,y,z,w)                        */
+    float*    vel;            /* [N,3]  BaseAviary.vel                                   */
+    float*    rpy_rates;      /* [N,3]  BaseAviary.rpy_rates (body rates, BaseAviary.py:958) */
+    float*    ang_v;          /* [N,3]  BaseAviary.ang_v (world, BaseAviary.py:952-956)   */
+    float*    prev_vel;       /* [N,3]  PBDroneEnv.prev_vel                              */
+    float*    prev_ang_v;     /* [N,3]  PBDroneEnv.prev_ang_v                            */
+    float*    dist;           /* [N]    PBDroneEnv._distance_to_target                   */
+    float*    prev_dist;      /* [N]    PBDroneEnv._prev_distance_to_target              */
+    int32_t*  target_idx;     /* [N]    PBDroneEnv._current_target_index                 */
+    int32_t*  steps;          /* [N]    PBDroneEnv._steps                                */
+    uint8_t*  just_found;     /* [N]    PBDroneEnv.just_found                            */
+    float*    ep_return;      /* [N]    Monitor running return                           */
+    int32_t*  ep_length;      /* [N]    Monitor running length                           */
+    uint32_t* episode_count;  /* [N]    episodes finished so far (Philox counter)        */
+    float*    last_rpm_sum;   /* [N]    sum(last_clipped_action) (drag only, BaseAviary.py:429,442) */
+    float*    obs_rms;        /* [N,2*obs_dim+1] mean | var | count (normalize.py:10-47); only if normalize_obs */
+} dn_state_view;
+
+/* Aggregated Monitor statistics since the last clear (SB3 Monitor / ep_info_buffer). */
+typedef struct dn_stats {
+    double   return_sum;      /* sum of finished-episode returns   */
+    uint64_t length_sum;      /* sum of finished-episode lengths   */
+    uint64_t episodes;        /* finished episodes                 */
+    uint64_t successes;       /* episodes that ended with _is_done (all targets reached) */
+    uint64_t found_targets;   /* sum of found_targets at episode end */
+    uint64_t crashes;         /* episodes ended by the -10 branch  */
+    uint64_t truncations;     /* episodes ended by max_steps only  */
+} dn_stats;
+
+int         dn_abi_version(void);
+const char* dn_last_error(void);
+
+/* PBDroneEnv.__init__ + BaseAviary.__init__ for N environments on `device`
+ * (PBDroneEnv.py:41-169, BaseAviary.py:27-272).  Allocates the persistent SoA state. */
+int dn_create(const dn_config* cfg, int device, dn_env** out);
+int dn_destroy(dn_env* env);
+
+int dn_num_envs(const dn_env* env);
+int dn_obs_dim(const dn_env* env);
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t dn_launch_count(const dn_env* env);
+
+/* PBDroneEnv.reset (PBDroneEnv.py:609-665 over BaseAviary.py:276-320) for every env, or
+ * for the envs with mask[i] != 0.  Writes the reset observation rows (unmasked rows are
+ * left untouched).  mask and obs_out may be NULL. */
+int dn_reset(dn_env* env, const uint8_t* mask, float* obs_out, void* stream);
+
+/* One control step of every env = PBDroneEnv.step (PBDroneEnv.py:171-199) including the
+ * SubprocVecEnv worker's auto-reset and Monitor bookkeeping.  ONE kernel launch. */
+int dn_step(dn_env* env, const dn_step_io* io, void* stream);
+
+/* `num_steps` consecutive control steps in ONE launch with state held in registers:
+ * step t reads actions[t] ([num_steps,N,4]).  Per-step outputs are [num_steps,...]-shaped
+ * when `per_step_outputs` != 0, otherwise only the last step's outputs are written
+ * ([N,...]).  Used for open-loop rollouts / the step-only throughput benchmark. */
+int dn_step_many(dn_env* env, const dn_step_io* io, int num_steps, int per_step_outputs, void* stream);
+
+int dn_get_state(dn_env* env, const dn_state_view* view, void* stream);
+int dn_set_state(dn_env* env, const dn_state_view* view, void* stream);
+
+/* Copies the aggregated statistics to host (synchronises `stream`); clears them if `clear`. */
+int dn_episode_stats(dn_env* env, dn_stats* host_out, int clear, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRONENAV_H_ */

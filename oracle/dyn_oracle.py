@@ -1,0 +1,735 @@
+"""CPU ORACLE (test infrastructure, NOT product code).
+
+A numpy restatement of the reference's per-environment control step for the
+``Physics.DYN`` path of eRGiBi/DRL-DroneNavigation.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import this file; the product package never does.
+
+PARITY UNPINNED: the reference holds no golden vector, known-answer test or
+fixture for this path, its DYN branch is unreachable as
+shipped (``Sol/PyBullet/BaseAviary.py:418`` forces ``Physics.PYB``) and would
+crash on the undefined ``self.TIMESTEP`` (``BaseAviary.py:944``), and neither
+``pybullet`` nor ``gymnasium`` nor ``stable_baselines3`` is installable here
+(no network).  The oracle is therefore a restatement of the cited lines with
+``TIMESTEP := PYB_TIMESTEP``; the analytic known-answer tests in
+``tests/test_oracle_kat.py`` and the fixtures under ``tests/golden/`` are
+minted by us from this file.
+
+What each piece follows (all paths relative to ``/root/reference``):
+
+* constants                 ``Sol/resources/safegym/cf2x.urdf:5,11-12,34``;
+                            ``Sol/PyBullet/BaseAviary.py:76,84-85,163-176``
+* action map (THRUST)       ``Sol/Model/Environments/PBDroneEnv.py:872-895,949-971``;
+                            ``Sol/Model/env_utils.py:8-59``
+* action map (RPM)          ``Sol/PyBullet/BaseSingleAgentAviary.py:176-179,211-212``
+* substep loop / ordering   ``Sol/PyBullet/BaseAviary.py:407-453``
+* rigid body                ``Sol/PyBullet/BaseAviary.py:899-973``
+* drag / ground effect      ``Sol/PyBullet/BaseAviary.py:838-865,798-834`` (formulas only;
+                            "DYN + drag + ground effect" is our documented extension)
+* observation               ``PBDroneEnv.py:296-398``
+* reward                    ``PBDroneEnv.py:475-607``
+* termination / truncation  ``PBDroneEnv.py:444-473,678-786``
+* post-step / reset         ``PBDroneEnv.py:201-223,609-665``; ``BaseAviary.py:276-320,527-598``
+* wrappers                  ``Sol/Model/Environments/normalize.py:10-147`` and the SB3
+                            ``Monitor`` / ``SubprocVecEnv`` worker auto-reset contract
+* third-party pybullet math restated from the published bullet3 algorithms
+  (``btMatrix3x3::setRotation`` and ``pybullet.c:getEulerFromQuaternion``);
+  pybullet is unpinned by the reference (absent from requirements.txt / uv.lock).
+
+Arithmetic follows the reference dtype-for-dtype: the THRUST action path and
+the per-motor force / z-torque products are float32 (numpy keeps float32 for
+float32-array x python-scalar), everything downstream is float64, the
+observation is cast to float32 at the end.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# constants
+# --------------------------------------------------------------------------
+
+
+@dataclass(frozen=True)
+class CF2XConstants:
+    """CF2X physical constants (safegym/cf2x.urdf:5,11-12,34) and the values
+    BaseAviary derives from them (BaseAviary.py:76,163-176)."""
+
+    M: float = 0.027
+    L: float = 0.0397
+    THRUST2WEIGHT_RATIO: float = 2.25
+    IXX: float = 1.4e-5
+    IYY: float = 1.4e-5
+    IZZ: float = 2.17e-5
+    KF: float = 3.16e-10
+    KM: float = 7.94e-12
+    COLLISION_H: float = 0.025
+    COLLISION_R: float = 0.06
+    COLLISION_Z_OFFSET: float = 0.0
+    MAX_SPEED_KMH: float = 30.0
+    GND_EFF_COEFF: float = 11.36859
+    PROP_RADIUS: float = 2.31348e-2
+    DRAG_COEFF_XY: float = 9.1785e-7
+    DRAG_COEFF_Z: float = 10.311e-7
+    DW_COEFF_1: float = 2267.18
+    DW_COEFF_2: float = 0.16
+    DW_COEFF_3: float = -0.11
+    PWM2RPM_SCALE: float = 0.2685
+    PWM2RPM_CONST: float = 4070.3
+    MIN_PWM: float = 20000.0
+    MAX_PWM: float = 65535.0
+    G: float = 9.8
+    # safegym prop layout (safegym/cf2x.urdf:42,54,66,78), used by the ground-effect extension only.
+    # It is the layout the DYN torque mix (BaseAviary.py:931-932) is consistent with:
+    # tau_x = sum(y_i f_i) = (f0+f1-f2-f3) d, tau_y = -sum(x_i f_i) = (-f0+f1+f2-f3) d.
+    PROP_XY: tuple = ((0.028, 0.028), (-0.028, 0.028), (-0.028, -0.028), (0.028, -0.028))
+
+    @property
+    def GRAVITY(self) -> float:
+        return self.G * self.M
+
+    @property
+    def HOVER_RPM(self) -> float:
+        return float(np.sqrt(self.GRAVITY / (4 * self.KF)))
+
+    @property
+    def MAX_RPM(self) -> float:
+        return float(np.sqrt((self.THRUST2WEIGHT_RATIO * self.GRAVITY) / (4 * self.KF)))
+
+    @property
+    def MAX_THRUST(self) -> float:
+        return 4 * self.KF * self.MAX_RPM ** 2
+
+    @property
+    def GND_EFF_H_CLIP(self) -> float:
+        return float(0.25 * self.PROP_RADIUS * np.sqrt(
+            (15 * self.MAX_RPM ** 2 * self.KF * self.GND_EFF_COEFF) / self.MAX_THRUST))
+
+    @property
+    def J(self) -> np.ndarray:
+        return np.diag([self.IXX, self.IYY, self.IZZ])
+
+    @property
+    def J_INV(self) -> np.ndarray:
+        return np.linalg.inv(self.J)
+
+
+CF2X = CF2XConstants()
+
+
+# --------------------------------------------------------------------------
+# pybullet math helpers restated (bullet3: LinearMath/btMatrix3x3.h setRotation;
+# examples/pybullet/pybullet.c pybullet_getEulerFromQuaternion)
+# --------------------------------------------------------------------------
+
+
+def bullet_matrix_from_quaternion(q) -> np.ndarray:
+    """p.getMatrixFromQuaternion (BaseAviary.py:920): btMatrix3x3::setRotation."""
+    x, y, z, w = (float(q[0]), float(q[1]), float(q[2]), float(q[3]))
+    d = x * x + y * y + z * z + w * w
+    s = 2.0 / d
+    xs, ys, zs = x * s, y * s, z * s
+    wx, wy, wz = w * xs, w * ys, w * zs
+    xx, xy, xz = x * xs, x * ys, x * zs
+    yy, yz, zz = y * ys, y * zs, z * zs
+    return np.array([
+        [1.0 - (yy + zz), xy - wz, xz + wy],
+        [xy + wz, 1.0 - (xx + zz), yz - wx],
+        [xz - wy, yz + wx, 1.0 - (xx + yy)],
+    ])
+
+
+def bullet_euler_from_quaternion(q) -> np.ndarray:
+    """p.getEulerFromQuaternion (BaseAviary.py:597)."""
+    x, y, z, w = (float(q[0]), float(q[1]), float(q[2]), float(q[3]))
+    sqx, sqy, sqz, squ = x * x, y * y, z * z, w * w
+    sarg = -2.0 * (x * z - w * y)
+    if sarg <= -0.99999:
+        return np.array([0.0, -0.5 * math.pi, 2.0 * math.atan2(x, -y)])
+    if sarg >= 0.99999:
+        return np.array([0.0, 0.5 * math.pi, 2.0 * math.atan2(-x, y)])
+    return np.array([
+        math.atan2(2.0 * (y * z + w * x), squ - sqx - sqy + sqz),
+        math.asin(sarg),
+        math.atan2(2.0 * (x * y + w * z), squ + sqx - sqy - sqz),
+    ])
+
+
+def bullet_quaternion_from_euler(rpy) -> np.ndarray:
+    """p.getQuaternionFromEuler (BaseAviary.py:567): btQuaternion::setEulerZYX."""
+    r, p_, y = (float(rpy[0]) * 0.5, float(rpy[1]) * 0.5, float(rpy[2]) * 0.5)
+    cr, sr = math.cos(r), math.sin(r)
+    cp, sp = math.cos(p_), math.sin(p_)
+    cy, sy = math.cos(y), math.sin(y)
+    return np.array([
+        sr * cp * cy - cr * sp * sy,
+        cr * sp * cy + sr * cp * sy,
+        cr * cp * sy - sr * sp * cy,
+        cr * cp * cy + sr * sp * sy,
+    ])
+
+
+def bullet_pose_readback(q) -> np.ndarray:
+    """resetBasePositionAndOrientation -> getBasePositionAndOrientation
+    (BaseAviary.py:946-950 then :596) goes through a btTransform, so the
+    quaternion that comes back is unit length (its sign may flip, which no
+    downstream quantity can observe: R(q), the Euler angles and _integrateQ are
+    all even / linear in q).  Restated as a plain normalisation."""
+    q = np.asarray(q, dtype=np.float64)
+    return q / math.sqrt(float(np.dot(q, q)))
+
+
+# --------------------------------------------------------------------------
+# action maps
+# --------------------------------------------------------------------------
+
+
+def physical_action_bounds(c: CF2XConstants = CF2X):
+    """PBDroneEnv.py:113-116 (float32 arrays)."""
+    a_low = c.KF * (c.PWM2RPM_SCALE * c.MIN_PWM + c.PWM2RPM_CONST) ** 2
+    a_high = c.KF * (c.PWM2RPM_SCALE * c.MAX_PWM + c.PWM2RPM_CONST) ** 2
+    return np.full(4, a_low, np.float32), np.full(4, a_high, np.float32)
+
+
+def rescale_action(action, bounds):
+    """PBDroneEnv.py:949-971.  NB: maps physical -> normalised although it is fed
+    a normalised action; reproduced as is."""
+    min_action = np.zeros(4, dtype=np.float32) + bounds[0]
+    max_action = np.zeros(4, dtype=np.float32) + bounds[1]
+    low = -1 * np.ones(4, dtype=np.float32)
+    high = np.ones(4, dtype=np.float32)
+    out = low + (high - low) * ((action - min_action) / (max_action - min_action))
+    return np.clip(out, low, high)
+
+
+def thrust_to_rpm(action, bounds, c: CF2XConstants = CF2X):
+    """PBDroneEnv.py:872-895 + env_utils.py:8-59 for a 4-vector (n_motor = 1)."""
+    thrust = np.clip(action, bounds[0], bounds[1])
+    n_motor = 4 // int(thrust.size)
+    thrust = np.clip(thrust, np.zeros_like(thrust), None)
+    pwm = (np.sqrt(thrust / n_motor / c.KF) - c.PWM2RPM_CONST) / c.PWM2RPM_SCALE
+    pwm = np.clip(np.array(pwm), c.MIN_PWM, c.MAX_PWM)
+    return c.PWM2RPM_SCALE * pwm + c.PWM2RPM_CONST
+
+
+def rpm_action_to_rpm(action, c: CF2XConstants = CF2X, numpy_legacy_cast: bool = True):
+    """BaseSingleAgentAviary.py:176-179.  Under the reference's pinned numpy 1.26
+    (uv.lock:231-232) ``np.float64 scalar * float32 array`` stays float32
+    (value-based casting); numpy >= 2 would promote to float64.  The pinned
+    behaviour is the default."""
+    a = np.asarray(action)
+    if numpy_legacy_cast and a.dtype == np.float32:
+        one_plus = np.float32(1) + np.float32(0.05) * a
+        return np.float32(c.HOVER_RPM) * one_plus
+    return np.array(c.HOVER_RPM * (1 + 0.05 * a))
+
+
+# --------------------------------------------------------------------------
+# the environment (PBDroneEnv + BaseAviary, Physics.DYN)
+# --------------------------------------------------------------------------
+
+PHYSICS_DYN = "dyn"
+PHYSICS_DYN_DRAG = "dyn_drag"
+PHYSICS_DYN_GND = "dyn_gnd"
+PHYSICS_DYN_GND_DRAG = "dyn_gnd_drag"
+
+ACT_THRUST = "thrust"
+ACT_RPM = "rpm"
+ACT_ONE_D_RPM = "one_d_rpm"
+
+
+class OracleDroneEnv:
+    """Single-environment restatement.  Attribute names follow the reference so
+    the code can be read side by side with PBDroneEnv.py / BaseAviary.py."""
+
+    def __init__(self, target_points, threshold, discount, max_steps, aviary_dim,
+                 initial_xyzs=None, initial_rpys=None, physics=PHYSICS_DYN,
+                 pyb_freq=240, ctrl_freq=240, act=ACT_THRUST, cylinder=True,
+                 circle=False, include_distance=False, normalize_actions=False,
+                 ground_contact=False, consts: CF2XConstants = CF2X):
+        self.C = consts
+        self.ACT_TYPE = act
+        self.PHYSICS = physics
+        self._target_points = np.array(target_points, dtype=np.float64)
+        self._threshold = threshold
+        self._discount = discount
+        self._max_steps = max_steps
+        self._aviary_dim = aviary_dim
+        (self._x_low, self._y_low, self._z_low,
+         self._x_high, self._y_high, self._z_high) = [float(v) for v in aviary_dim]
+        self.circle_radius = 1            # PBDroneEnv.py:84 (hard-coded)
+        self.cylinder = cylinder
+        self.circle = circle
+        self.include_distance = include_distance
+        self._max_target_dist = max(abs(self._x_low) + self._x_high,
+                                    abs(self._y_low) + self._y_high, self._z_high)
+        self.ground_contact = ground_contact  # documented extension; off = DYN (no contacts)
+
+        # BaseAviary.__init__ : frequencies (BaseAviary.py:79-85)
+        if pyb_freq % ctrl_freq != 0:
+            raise ValueError("pyb_freq is not divisible by ctrl_freq")
+        self.PYB_FREQ, self.CTRL_FREQ = pyb_freq, ctrl_freq
+        self.PYB_STEPS_PER_CTRL = int(pyb_freq / ctrl_freq)
+        self.PYB_TIMESTEP = 1.0 / pyb_freq
+        self.CTRL_TIMESTEP = 1.0 / ctrl_freq
+        c = consts
+        self.GRAVITY = c.GRAVITY
+        self.HOVER_RPM = c.HOVER_RPM
+        self.J, self.J_INV = c.J, c.J_INV
+        self.DRAG_COEFF = np.array([c.DRAG_COEFF_XY, c.DRAG_COEFF_XY, c.DRAG_COEFF_Z])
+
+        if initial_xyzs is None:  # BaseAviary.py:248-253
+            initial_xyzs = np.array([[0.0, 0.0, c.COLLISION_H / 2 - c.COLLISION_Z_OFFSET + .1]])
+        self.INIT_XYZS = np.array(initial_xyzs, dtype=np.float64).reshape(1, 3)
+        self.INIT_RPYS = (np.zeros((1, 3)) if initial_rpys is None
+                          else np.array(initial_rpys, dtype=np.float64).reshape(1, 3))
+
+        self.physical_action_bounds = physical_action_bounds(c)
+        self.normalize_actions = normalize_actions
+
+        self._housekeeping()
+
+        # PBDroneEnv.__init__ tail (PBDroneEnv.py:122-144)
+        self._current_position = self.INIT_XYZS[0].copy()
+        self.current_vel, self.current_ang_v = np.zeros(3), np.zeros(3)
+        self.prev_vel, self.prev_ang_v = np.zeros(3), np.zeros(3)
+        self._distance_to_target = np.linalg.norm(self._current_position - self._target_points[0])
+        self._prev_distance_to_target = np.linalg.norm(self._current_position - self._target_points[0])
+        self._current_target_index = 0
+        self.just_found = False
+        self._is_done = False
+        self._steps = 0
+        # test instrumentation: signed distances of this step's threshold comparisons to their
+        # thresholds (so FP32-vs-FP64 near-ties can be recognised); never read by the step itself
+        self.margins = []
+
+    # ---- BaseAviary._housekeeping (BaseAviary.py:527-584), DYN part --------
+    def _housekeeping(self):
+        self.step_counter = 0
+        self.last_clipped_action = np.zeros(4)
+        self.pos = self.INIT_XYZS[0].astype(np.float64).copy()
+        self.quat = bullet_pose_readback(bullet_quaternion_from_euler(self.INIT_RPYS[0]))
+        self.rpy = bullet_euler_from_quaternion(self.quat)
+        self.vel = np.zeros(3)
+        self.ang_v = np.zeros(3)
+        self.rpy_rates = np.zeros(3)
+
+    # ---- spaces -------------------------------------------------------------
+    @property
+    def obs_dim(self):
+        return 13 if self.include_distance else 12
+
+    # ---- reset (BaseAviary.py:276-320 then PBDroneEnv.py:609-665) ----------
+    def reset(self, seed=None, options=None):
+        self._housekeeping()
+        initial_obs = self._computeObs()      # BEFORE the distances are reset
+        initial_info = self._computeInfo()    # found_targets of the previous episode
+        self._is_done = False
+        self._current_target_index = 0
+        self._steps = 0
+        self._distance_to_target = np.linalg.norm(self._current_position - self._target_points[0])
+        self._prev_distance_to_target = np.linalg.norm(self._current_position - self._target_points[0])
+        self.prev_vel, self.prev_ang_v = np.zeros(3), np.zeros(3)
+        self.current_vel, self.current_ang_v = np.zeros(3), np.zeros(3)
+        self.just_found = False
+        return initial_obs, initial_info
+
+    # ---- step (PBDroneEnv.py:171-199 around BaseAviary.py:324-453) ---------
+    def step(self, action):
+        action = np.asarray(action)
+        self.margins = []
+        a = self.rescale_action(action) if self.normalize_actions else action
+        rpm = np.reshape(self._preprocessAction(a), 4)
+        for _ in range(self.PYB_STEPS_PER_CTRL):
+            # kinematics are (re)read from Bullet before every substep when S > 1
+            # (BaseAviary.py:413-415) and after the last one (:444); with the DYN
+            # set/get pair that is the pose read-back applied in _dynamics below.
+            self._dynamics(rpm)
+            self.last_clipped_action = np.array(rpm, dtype=np.float64)
+        self.rpy = bullet_euler_from_quaternion(self.quat)
+        obs = self._computeObs()
+        reward = self._computeReward()
+        terminated = self._computeTerminated()
+        truncated = self._computeTruncated()
+        info = self._computeInfo()
+        self.step_counter += self.PYB_STEPS_PER_CTRL
+        if not terminated:
+            self._update_state_post_step(action)
+        return obs, reward, terminated, truncated, info
+
+    def rescale_action(self, action):
+        return rescale_action(action, self.physical_action_bounds)
+
+    def _preprocessAction(self, action):
+        if self.ACT_TYPE == ACT_THRUST:
+            return thrust_to_rpm(action, self.physical_action_bounds, self.C)
+        if self.ACT_TYPE == ACT_RPM:
+            return rpm_action_to_rpm(action, self.C)
+        if self.ACT_TYPE == ACT_ONE_D_RPM:
+            return np.repeat(rpm_action_to_rpm(np.asarray(action).reshape(-1)[:1], self.C), 4)
+        raise ValueError(self.ACT_TYPE)
+
+    # ---- BaseAviary._dynamics (BaseAviary.py:899-958) ----------------------
+    def _dynamics(self, rpm):
+        c = self.C
+        dt = self.PYB_TIMESTEP
+        pos, quat, vel, rpy_rates = self.pos, self.quat, self.vel, self.rpy_rates
+        rotation = bullet_matrix_from_quaternion(quat)
+        forces = np.array(rpm ** 2) * c.KF                       # float32 on the THRUST path
+        if self.PHYSICS in (PHYSICS_DYN_GND, PHYSICS_DYN_GND_DRAG):
+            forces = forces + self._ground_effect(rpm, rotation)   # extension (a7)
+        thrust = np.array([0, 0, np.sum(forces)])
+        thrust_world_frame = np.dot(rotation, thrust)
+        force_world_frame = thrust_world_frame - np.array([0, 0, self.GRAVITY])
+        if self.PHYSICS in (PHYSICS_DYN_DRAG, PHYSICS_DYN_GND_DRAG):
+            force_world_frame = force_world_frame + self._drag(rotation)  # extension (a7)
+        z_torques = np.array(rpm ** 2) * c.KM
+        z_torque = (-z_torques[0] + z_torques[1] - z_torques[2] + z_torques[3])
+        x_torque = (forces[0] + forces[1] - forces[2] - forces[3]) * (c.L / np.sqrt(2))
+        y_torque = (-forces[0] + forces[1] + forces[2] - forces[3]) * (c.L / np.sqrt(2))
+        torques = np.array([x_torque, y_torque, z_torque], dtype=np.float64)
+        torques = torques - np.cross(rpy_rates, np.dot(self.J, rpy_rates))
+        rpy_rates_deriv = np.dot(self.J_INV, torques)
+        no_pybullet_dyn_accs = force_world_frame / c.M
+        vel = vel + dt * no_pybullet_dyn_accs
+        rpy_rates = rpy_rates + dt * rpy_rates_deriv
+        pos = pos + dt * vel
+        quat = self._integrateQ(quat, rpy_rates, dt)             # TIMESTEP := PYB_TIMESTEP
+        # set pose / velocity in Bullet, then read them back (:946-956, :596-598)
+        self.pos = pos
+        self.quat = bullet_pose_readback(quat)
+        self.vel = vel
+        self.ang_v = np.dot(rotation, rpy_rates)
+        self.rpy_rates = rpy_rates
+
+    @staticmethod
+    def _integrateQ(quat, omega, dt):
+        """BaseAviary.py:960-973."""
+        omega_norm = np.linalg.norm(omega)
+        p, q, r = omega
+        if np.isclose(omega_norm, 0):
+            return quat
+        lambda_ = np.array([
+            [0, r, -q, p],
+            [-r, 0, p, q],
+            [q, -p, 0, r],
+            [-p, -q, -r, 0],
+        ]) * .5
+        theta = omega_norm * dt / 2
+        return np.dot(np.eye(4) * np.cos(theta) + 2 / omega_norm * lambda_ * np.sin(theta), quat)
+
+    # ---- extensions: same formulas as the PYB add-ons, applied inside DYN --
+    def _drag(self, rotation):
+        """BaseAviary.py:838-865: force R.(-DRAG_COEFF * v_world * sum(2 pi rpm_prev/60)),
+        applied to link 4 in LINK_FRAME, i.e. Bullet rotates the vector by R once
+        more -- reproduced literally."""
+        drag_factors = -1 * self.DRAG_COEFF * np.sum(np.array(2 * np.pi * self.last_clipped_action / 60))
+        drag_link = np.dot(rotation, drag_factors * np.array(self.vel))
+        return np.dot(rotation, drag_link)
+
+    def _ground_effect(self, rpm, rotation):
+        """BaseAviary.py:798-834: per-prop extra thrust along body z."""
+        c = self.C
+        rpy = bullet_euler_from_quaternion(self.quat)
+        offs = np.array([[x, y, 0.0] for (x, y) in c.PROP_XY])
+        prop_heights = np.array([self.pos[2] + np.dot(rotation, offs[i])[2] for i in range(4)])
+        prop_heights = np.clip(prop_heights, c.GND_EFF_H_CLIP, np.inf)
+        gnd = (np.array(rpm, dtype=np.float64) ** 2 * c.KF * c.GND_EFF_COEFF
+               * (c.PROP_RADIUS / (4 * prop_heights)) ** 2)
+        if np.abs(rpy[0]) < np.pi / 2 and np.abs(rpy[1]) < np.pi / 2:
+            return gnd
+        return np.zeros(4)
+
+    # ---- observation (PBDroneEnv.py:296-398) -------------------------------
+    def _getDroneStateVector(self):
+        return np.hstack([self.pos, self.quat, self.rpy, self.vel, self.ang_v,
+                          self.last_clipped_action]).reshape(20, )
+
+    def _clipAndNormalizeState(self, state):
+        MAX_LIN_VEL_XY, MAX_LIN_VEL_Z = 3, 1
+        MAX_PITCH_ROLL = np.pi
+        clipped_rp = np.clip(state[7:9], -MAX_PITCH_ROLL, MAX_PITCH_ROLL)
+        clipped_vel_xy = np.clip(state[10:12], -MAX_LIN_VEL_XY, MAX_LIN_VEL_XY)
+        clipped_vel_z = np.clip(state[12], -MAX_LIN_VEL_Z, MAX_LIN_VEL_Z)
+        normalized_pos_xy = state[0:2] / np.array([self._x_high, self._y_high])
+        normalized_pos_z = state[2] / self._z_high
+        normalized_rp = clipped_rp / MAX_PITCH_ROLL
+        normalized_y = state[9] / np.pi
+        normalized_vel_xy = clipped_vel_xy / MAX_LIN_VEL_XY
+        normalized_vel_z = clipped_vel_z / MAX_LIN_VEL_XY       # sic (PBDroneEnv.py:382)
+        n = np.linalg.norm(state[13:16])
+        normalized_ang_vel = state[13:16] / n if n != 0 else state[13:16]
+        return np.hstack([normalized_pos_xy, normalized_pos_z, state[3:7], normalized_rp,
+                          normalized_y, normalized_vel_xy, normalized_vel_z,
+                          normalized_ang_vel, state[16:20]]).reshape(20, )
+
+    def _computeObs(self):
+        obs = self._clipAndNormalizeState(self._getDroneStateVector())
+        ret = np.hstack([obs[0:3], obs[7:10], obs[10:13], obs[13:16]]).reshape(12, )
+        if self.include_distance:
+            ret = np.append(ret, [self._distance_to_target / self._max_target_dist])
+        ret = np.clip(ret, np.finfo(np.float32).min, np.finfo(np.float32).max)
+        return ret.astype(np.float32)
+
+    # ---- info / truncation / termination (PBDroneEnv.py:434-473) -----------
+    def _computeInfo(self):
+        return {"found_targets": self._current_target_index}
+
+    def _computeTruncated(self):
+        return bool(self._max_steps <= self._steps)
+
+    def _computeTerminated(self):
+        return bool(self._is_done or self._has_collision_occurred())
+
+    def current_target(self):
+        if self._current_target_index < len(self._target_points):
+            return self._target_points[self._current_target_index]
+        return None
+
+    def _has_collision_occurred(self):
+        """PBDroneEnv.py:678-707.  DYN never steps Bullet, so getContactPoints() is
+        always empty; ``ground_contact`` is our documented analytic substitute
+        (collision cylinder half-height vs the plane z = 0), off by default."""
+        state = self.pos
+        contact = bool(self.ground_contact and state[2] < self.C.COLLISION_H / 2)
+        self.margins += [state[0] - self._x_high, state[0] - self._x_low, state[1] - self._y_high,
+                         state[1] - self._y_low, state[2] - self._z_high]
+        if self.ground_contact:
+            self.margins.append(state[2] - self.C.COLLISION_H / 2)
+        return bool(state[0] > self._x_high or state[0] < self._x_low or
+                    state[1] > self._y_high or state[1] < self._y_low or
+                    contact or
+                    state[2] > self._z_high or
+                    (self.cylinder and self.is_out_of_cylinder_bounds(state)))
+
+    def is_out_of_cylinder_bounds(self, drone_position, circle_center=(0, 0, 1), extension_length=0.2):
+        """PBDroneEnv.py:718-786 (worker-process numpy error state: 0/0 -> NaN ->
+        comparison False)."""
+        if self.circle:
+            drone_vec = np.array(drone_position, dtype=np.float64)
+            center_vec = np.array(circle_center, dtype=np.float64)
+            center_to_drone_vec = drone_vec - center_vec
+            center_to_drone_vec[2] = 0
+            with np.errstate(all="ignore"):
+                norm_vec = center_to_drone_vec / np.linalg.norm(center_to_drone_vec) * self.circle_radius
+            closest_point = center_vec + norm_vec
+            distance_from_closest_point = np.linalg.norm(drone_position - closest_point)
+            self.margins.append(distance_from_closest_point - self._threshold)
+            return bool(distance_from_closest_point > self._threshold)
+        if self._current_target_index == 0:
+            base1 = np.array(self.INIT_XYZS[0])
+            base2 = np.array(self.current_target())
+        else:
+            base1 = np.array(self._target_points[self._current_target_index - 1])
+            base2 = np.array(self.current_target())
+        line_vec = base2 - base1
+        line_length = np.linalg.norm(line_vec)
+        if line_length == 0:
+            self.margins.append(np.linalg.norm(drone_position - base1) - self._threshold)
+            return bool(np.linalg.norm(drone_position - base1) > self._threshold)
+        line_unit_vec = line_vec / line_length
+        extended_point1 = base1 - extension_length * line_unit_vec
+        extended_point2 = base2 + extension_length * line_unit_vec
+        point1_to_drone_vec = drone_position - extended_point1
+        projection_length = np.dot(point1_to_drone_vec, line_unit_vec)
+        projection_length = np.clip(projection_length, 0, np.linalg.norm(extended_point2 - extended_point1))
+        closest_point_on_line = extended_point1 + projection_length * line_unit_vec
+        distance_from_line = np.linalg.norm(drone_position - closest_point_on_line)
+        self.margins.append(distance_from_line - (self._threshold + extension_length))
+        return bool(distance_from_line > self._threshold + extension_length)
+
+    # ---- reward (PBDroneEnv.py:475-607) -------------------------------------
+    def _computeReward(self):
+        if self._computeTerminated() and not self._is_done:
+            return -10.0
+        reward = np.float32(0.0)
+        self.margins.append(self._distance_to_target - self._threshold)
+        if self._distance_to_target <= self._threshold:
+            self._current_target_index += 1
+            if self._current_target_index == len(self._target_points):
+                reward += 200
+                self._is_done = True
+            else:
+                reward += 75
+                reward += self.orientation_reward(self.current_target()) * 5
+                self.just_found = True
+        else:
+            reward += (np.exp(-2 * self._distance_to_target)) * 3
+            reward += ((self._prev_distance_to_target - self._distance_to_target) * 3000) if not self.just_found else 0
+            reward += self.orientation_reward(self.current_target()) * 3
+            reward += self.smoothness_reward()
+            self.just_found = False
+        self._prev_distance_to_target = self._distance_to_target
+        return reward / 25
+
+    def orientation_reward(self, target_pos):
+        threshold_angle = np.radians(10)
+        forward_vector = self.get_forward_vector()
+        drone_to_target_vector = np.array(target_pos, dtype=np.float64) - np.array(self.pos)
+        with np.errstate(all="ignore"):
+            drone_to_target_vector = drone_to_target_vector / np.linalg.norm(drone_to_target_vector)
+            angle = np.arccos(np.clip(np.dot(forward_vector, drone_to_target_vector), -1.0, 1.0))
+        self.margins.append(angle - threshold_angle)
+        return -1 if angle > threshold_angle else 0
+
+    def get_forward_vector(self):
+        euler = self.rpy
+        return np.array([np.cos(euler[2]) * np.cos(euler[1]),
+                         np.sin(euler[2]) * np.cos(euler[1]),
+                         np.sin(euler[1])])
+
+    def smoothness_reward(self, accel_threshold=0.7, ang_accel_threshold=0.3):
+        lin_acc = np.linalg.norm(self.current_vel - self.prev_vel)
+        ang_acc = np.linalg.norm(self.current_ang_v - self.prev_ang_v)
+        self.margins += [lin_acc - accel_threshold, ang_acc - ang_accel_threshold]
+        linear_penalty = -abs(lin_acc) if lin_acc > accel_threshold else 0
+        angular_penalty = -abs(ang_acc) if ang_acc > ang_accel_threshold else 0
+        return linear_penalty + angular_penalty
+
+    # ---- post-step (PBDroneEnv.py:201-223) ----------------------------------
+    def _update_state_post_step(self, action):
+        self._steps += 1
+        self._current_position = self.pos.copy()
+        self.prev_vel, self.prev_ang_v = self.current_vel.copy(), self.current_ang_v.copy()
+        self.current_vel, self.current_ang_v = self.vel.copy(), self.ang_v.copy()
+        self._distance_to_target = np.linalg.norm(self.current_target() - self._current_position)
+
+    # ---- state exchange with the CUDA path (tests upload identical states) --
+    def set_state(self, st: dict):
+        """Inverse of get_state (test helper): puts the env mid-episode in a given state."""
+        f = lambda k: np.array(st[k], dtype=np.float64).copy()
+        self.pos, self.quat, self.vel = f("pos"), f("quat"), f("vel")
+        self.rpy_rates, self.ang_v = f("rpy_rates"), f("ang_v")
+        self.rpy = bullet_euler_from_quaternion(self.quat)
+        self.prev_vel, self.prev_ang_v = f("prev_vel"), f("prev_ang_v")
+        self.current_vel, self.current_ang_v = self.vel.copy(), self.ang_v.copy()
+        self._current_position = self.pos.copy()
+        self._distance_to_target = float(st["dist"])
+        self._prev_distance_to_target = float(st["prev_dist"])
+        self._current_target_index = int(st["target_idx"])
+        self._steps = int(st["steps"])
+        self.just_found = bool(st["just_found"])
+        self._is_done = False
+        if "last_rpm" in st:
+            self.last_clipped_action = f("last_rpm")
+
+    def get_state(self) -> dict:
+        return dict(pos=self.pos.copy(), quat=self.quat.copy(), vel=self.vel.copy(),
+                    rpy_rates=self.rpy_rates.copy(), ang_v=self.ang_v.copy(),
+                    prev_vel=self.prev_vel.copy(), prev_ang_v=self.prev_ang_v.copy(),
+                    dist=float(self._distance_to_target), prev_dist=float(self._prev_distance_to_target),
+                    target_idx=int(self._current_target_index), steps=int(self._steps),
+                    just_found=bool(self.just_found), last_rpm=self.last_clipped_action.copy())
+
+
+# --------------------------------------------------------------------------
+# wrappers: normalize.py + SB3 Monitor + SubprocVecEnv worker auto-reset
+# --------------------------------------------------------------------------
+
+
+class OracleRunningMeanStd:
+    """normalize.py:10-47."""
+
+    def __init__(self, epsilon=1e-4, shape=()):
+        self.mean = np.zeros(shape, "float64")
+        self.var = np.ones(shape, "float64")
+        self.count = epsilon
+
+    def update(self, x):
+        batch_mean = np.mean(x, axis=0)
+        batch_var = np.var(x, axis=0)
+        batch_count = x.shape[0]
+        delta = batch_mean - self.mean
+        tot_count = self.count + batch_count
+        new_mean = self.mean + delta * batch_count / tot_count
+        m_a = self.var * self.count
+        m_b = batch_var * batch_count
+        M2 = m_a + m_b + np.square(delta) * self.count * batch_count / tot_count
+        self.mean, self.var, self.count = new_mean, M2 / tot_count, tot_count
+
+
+class OracleWorker:
+    """One SubprocVecEnv worker = Monitor(NormalizeObservation(PBDroneEnv)) with
+    the worker loop's auto-reset (PBDroneSimulator.py:153-198; SB3 contract in
+    SURVEY.md a17)."""
+
+    def __init__(self, env: OracleDroneEnv, normalize_obs=True, norm_epsilon=1e-8):
+        self.env = env
+        self.normalize_obs = normalize_obs
+        self.obs_rms = OracleRunningMeanStd(shape=(env.obs_dim,))
+        self.norm_epsilon = norm_epsilon
+        self.ep_return = 0.0
+        self.ep_len = 0
+        self.last_terminated = self.last_truncated = False
+
+    def _normalize(self, obs):
+        if not self.normalize_obs:
+            return obs
+        self.obs_rms.update(np.array([obs]))
+        return ((np.array([obs]) - self.obs_rms.mean) / np.sqrt(self.obs_rms.var + self.norm_epsilon))[0]
+
+    def reset(self):
+        obs, info = self.env.reset()
+        self.ep_return, self.ep_len = 0.0, 0
+        return self._normalize(obs), info
+
+    def step(self, action):
+        obs, reward, terminated, truncated, info = self.env.step(action)
+        self.last_terminated, self.last_truncated = bool(terminated), bool(truncated)
+        obs = self._normalize(obs)
+        self.ep_return += float(reward)
+        self.ep_len += 1
+        done = terminated or truncated
+        info = dict(info)
+        if done:
+            info["episode"] = {"r": round(self.ep_return, 6), "l": self.ep_len}
+        info["TimeLimit.truncated"] = truncated and not terminated
+        if done:
+            info["terminal_observation"] = obs
+            obs, _ = self.reset()
+        return obs, reward, done, info
+
+
+# --------------------------------------------------------------------------
+# tracks (Waypoints.py:108-139,172-197; PBDroneSimulator.py:89-105,129-130)
+# --------------------------------------------------------------------------
+
+
+def circle_track(radius=1, num_points=6, height=1, center=(0, 0, 0)):
+    angles = np.linspace(0, 2 * np.pi, num_points + 1, endpoint=True)
+    pts = np.zeros((num_points + 1, 3))
+    pts[:, 0] = center[0] + radius * np.cos(angles)
+    pts[:, 1] = center[1] + radius * np.sin(angles)
+    pts[:, 2] = center[2] + height
+    targets = list(pts)[1:]                       # circle=True pops the first (PBDroneSimulator.py:129-130)
+    return np.array(targets), np.array([[radius, 0, center[2] + radius]], dtype=np.float64), np.array([-2, -2, 0, 2, 2, 2])
+
+
+def reaching_track():
+    arr = np.array([[-2.5, 4.5, 3], [10, 3.5, 1], [8, -4.5, 1], [-4.5, -6, 2],
+                    [-5, -5, 2], [5, -1, 3], [2.5, 6, 3], [-2.5, 4.5, 3]], dtype=np.float64)
+    for i in range(len(arr)):
+        arr[i][2] += 3
+        arr[i] /= 5
+    return arr, np.array([arr[0]]), np.array([-4, -4, 0, 4, 4, 4])
+
+
+def make_reference_env(track="circle", pyb_freq=240, ctrl_freq=240, max_steps=4096, **kw) -> OracleDroneEnv:
+    """The env PBDroneSimulator.make_env builds (PBDroneSimulator.py:154-172)."""
+    if track == "circle":
+        targets, init, dim = circle_track()
+        circle = True
+    elif track == "reaching":
+        targets, init, dim = reaching_track()
+        circle = False
+    else:
+        raise ValueError(track)
+    args = dict(target_points=targets, threshold=0.3, discount=0.999, max_steps=max_steps,
+                aviary_dim=dim, initial_xyzs=init, pyb_freq=pyb_freq, ctrl_freq=ctrl_freq,
+                act=ACT_THRUST, cylinder=True, circle=circle, include_distance=True,
+                normalize_actions=True)
+    args.update(kw)
+    return OracleDroneEnv(**args)

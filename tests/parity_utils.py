@@ -1,0 +1,133 @@
+"""Helpers shared by the GPU parity tests: drive the CUDA path (through the C ABI) and the
+CPU oracle with the same seeded inputs and compare.
+
+Stated tolerances (FP32 CUDA path vs FP64 oracle):
+over a 240-substep (1 s) open-loop horizon  |dpos| <= 1e-4 m, |dvel| <= 1e-3 m/s,
+|dquat| <= 1e-4, |dobs| <= 1e-4, |dreward| <= 1e-3 (the shaped reward has a 3000x gain on
+the distance difference); discrete outputs (done bits, found_targets) exact, except where
+the oracle itself sits within MARGIN_TOL of a threshold (near-tie), which is counted,
+reported and excluded.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+POS_TOL, VEL_TOL, QUAT_TOL, OBS_TOL, REW_TOL = 1e-4, 1e-3, 1e-4, 1e-4, 1e-3
+MARGIN_TOL = 2e-5          # oracle margin below which an FP32/FP64 discrete disagreement is a near-tie
+HORIZON_SUBSTEPS = 240
+
+
+def oracle_state_arrays(envs):
+    """Stack oracle env states into the row-major arrays dn_set_state takes."""
+    keys = ("pos", "quat", "vel", "rpy_rates", "ang_v", "prev_vel", "prev_ang_v")
+    st = [e.get_state() for e in envs]
+    out = {k: np.stack([s[k] for s in st]).astype(np.float32) for k in keys}
+    out["dist"] = np.array([s["dist"] for s in st], np.float32)
+    out["prev_dist"] = np.array([s["prev_dist"] for s in st], np.float32)
+    out["target_idx"] = np.array([s["target_idx"] for s in st], np.int32)
+    out["steps"] = np.array([s["steps"] for s in st], np.int32)
+    out["just_found"] = np.array([s["just_found"] for s in st], np.uint8)
+    return out
+
+
+def upload_oracle_state(gpu_env, workers):
+    st = oracle_state_arrays([w.env for w in workers])
+    st["ep_return"] = np.array([w.ep_return for w in workers], np.float32)
+    st["ep_length"] = np.array([w.ep_len for w in workers], np.int32)
+    if gpu_env.uses_drag:
+        st["last_rpm_sum"] = np.array([float(np.sum(w.env.last_clipped_action)) for w in workers], np.float32)
+    gpu_env.set_state(st)
+
+
+def obs_error(a, b):
+    """max |a - b| over an observation row; the three Euler-angle entries (3..5, in units of pi) are
+    compared modulo 2 so that a +-pi wrap of atan2 on either side is not a discrepancy."""
+    d = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
+    d[3:6] = np.minimum(d[3:6], np.abs(2.0 - d[3:6]))
+    return float(d.max())
+
+
+def min_margin(env):
+    m = [abs(float(x)) for x in env.margins if np.isfinite(x)]
+    return min(m) if m else np.inf
+
+
+class ParityReport:
+    def __init__(self):
+        self.max_obs = self.max_rew = self.max_pos = self.max_vel = self.max_quat = 0.0
+        self.near_ties = 0
+        self.env_steps = 0
+        self.dones = 0
+        self.captures = 0
+
+    def __str__(self):
+        return (f"env_steps={self.env_steps} dones={self.dones} captures={self.captures} near_ties={self.near_ties} "
+                f"max|dobs|={self.max_obs:.2e} max|drew|={self.max_rew:.2e} max|dpos|={self.max_pos:.2e} "
+                f"max|dvel|={self.max_vel:.2e} max|dquat|={self.max_quat:.2e}")
+
+
+def run_lockstep(gpu_env, workers, actions, resync_every, report=None, check_state=True,
+                 obs_tol=OBS_TOL, rew_tol=REW_TOL):
+    """Steps the CUDA env and the oracle workers in lock-step on `actions` [T, N, 4].
+
+    Every `resync_every` control steps (= HORIZON_SUBSTEPS / S) the continuous state is
+    compared against the horizon tolerances and the oracle state is uploaded again, so
+    each comparison window is one stated horizon.  A discrete disagreement is accepted only
+    if the oracle's own threshold margin at that step is < MARGIN_TOL; the env is then
+    re-synchronised from the oracle.
+    """
+    rep = report or ParityReport()
+    T, N = actions.shape[0], actions.shape[1]
+    a_dev = torch.from_numpy(actions).to(gpu_env.device)
+    for t in range(T):
+        o, r, d, f = gpu_env.step(a_dev[t])
+        o, r, d, f = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), f.cpu().numpy()
+        term_obs = gpu_env.terminal_obs.cpu().numpy()
+        ep_r, ep_l = gpu_env.episode_return.cpu().numpy(), gpu_env.episode_length.cpu().numpy()
+        need_resync = False
+        for i, w in enumerate(workers):
+            prev_idx = w.env._current_target_index
+            oo, rr, dd, info = w.step(actions[t, i])
+            rep.env_steps += 1
+            want_bits = (1 if w.last_terminated else 0) | (2 if w.last_truncated else 0)
+            assert bool(want_bits) == bool(dd)
+            tie = min_margin(w.env) < MARGIN_TOL
+            discrete_ok = (int(d[i]) == want_bits) and (int(f[i]) == info["found_targets"])
+            if not discrete_ok:
+                assert tie, (f"discrete mismatch at t={t} env={i}: gpu done={d[i]} found={f[i]} vs oracle "
+                             f"{want_bits}/{info['found_targets']}, oracle margin={min_margin(w.env):.3e}")
+                rep.near_ties += 1
+                need_resync = True
+                continue
+            rew_err = abs(float(r[i]) - float(np.float32(rr)))
+            if rew_err > rew_tol:
+                # orientation / smoothness thresholds only change the reward, not the state
+                assert tie, f"reward mismatch at t={t} env={i}: {r[i]} vs {rr} (margin {min_margin(w.env):.3e})"
+                rep.near_ties += 1
+            else:
+                rep.max_rew = max(rep.max_rew, rew_err)
+            rep.max_obs = max(rep.max_obs, obs_error(o[i], oo))
+            assert rep.max_obs <= obs_tol, f"obs drift {rep.max_obs:.3e} at t={t} env={i}\n gpu {o[i]}\n ref {oo}"
+            if dd:
+                rep.dones += 1
+                e = obs_error(term_obs[i], info["terminal_observation"])
+                assert e <= obs_tol, f"terminal obs mismatch {e:.3e} at t={t} env={i}"
+                assert int(ep_l[i]) == info["episode"]["l"]
+                assert abs(float(ep_r[i]) - info["episode"]["r"]) <= max(5e-3, 1e-5 * abs(info["episode"]["r"]))
+            if info["found_targets"] > prev_idx:
+                rep.captures += 1
+        if check_state and ((t + 1) % resync_every == 0 or need_resync or t == T - 1):
+            st = {k: v.cpu().numpy() for k, v in gpu_env.get_state().items()}
+            ref = oracle_state_arrays([w.env for w in workers])
+            if not need_resync:
+                rep.max_pos = max(rep.max_pos, float(np.max(np.abs(st["pos"] - ref["pos"]))))
+                rep.max_vel = max(rep.max_vel, float(np.max(np.abs(st["vel"] - ref["vel"]))))
+                qd = np.minimum(np.abs(st["quat"] - ref["quat"]).max(axis=1), np.abs(st["quat"] + ref["quat"]).max(axis=1))
+                rep.max_quat = max(rep.max_quat, float(qd.max()))
+                assert rep.max_pos <= POS_TOL and rep.max_vel <= VEL_TOL and rep.max_quat <= QUAT_TOL, str(rep)
+                np.testing.assert_array_equal(st["target_idx"], ref["target_idx"])
+                np.testing.assert_array_equal(st["steps"], ref["steps"])
+                np.testing.assert_array_equal(st["just_found"], ref["just_found"])
+            upload_oracle_state(gpu_env, workers)
+    return rep

@@ -1,0 +1,250 @@
+"""Parity of the CUDA path (called through the C ABI) against the CPU oracle.  GPU only."""
+import numpy as np
+import pytest
+import torch
+
+from tests import parity_utils as PU
+
+pytestmark = pytest.mark.gpu
+
+HOVER = 0.092227
+
+
+def _make(track, N, S, normalize_obs=False, max_steps=4096, **kw):
+    from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
+    from oracle.dyn_oracle import OracleWorker, make_reference_env
+    ctrl = 240 // S
+    ref = make_reference_env(track, pyb_freq=240, ctrl_freq=ctrl, max_steps=max_steps)
+    env = BatchedDroneEnv(N, ref._target_points, threshold=0.3, discount=0.999, max_steps=max_steps,
+                          aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS, pyb_freq=240, ctrl_freq=ctrl,
+                          cylinder=True, circle=(track == "circle"), include_distance=True,
+                          normalize_actions=True, normalize_obs=normalize_obs, **kw)
+    workers = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=ctrl, max_steps=max_steps),
+                            normalize_obs=normalize_obs) for _ in range(N)]
+    return env, workers
+
+
+def _actions(mode, T, N, seed):
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(-1, 1, size=(T, N, 4))
+    if mode == "saturating":          # config 2(A): U(-1,1) -> near bang-bang, reset-heavy
+        a = u
+    elif mode == "hover_band":        # config 2(B): long episodes
+        a = HOVER + 0.002 * u
+    elif mode == "mixed":             # wider band: tumbles, leaves the tube within ~1 s
+        a = HOVER + 0.006 * u
+    else:
+        raise ValueError(mode)
+    return a.astype(np.float32)
+
+
+def _reset_both(env, workers):
+    obs = env.reset().cpu().numpy()
+    for i, w in enumerate(workers):
+        o, _ = w.reset()
+        np.testing.assert_allclose(obs[i], o, atol=1e-6)
+
+
+@pytest.mark.parametrize("track,S,mode,N,T", [
+    ("circle", 1, "saturating", 24, 400),
+    ("circle", 1, "hover_band", 16, 480),
+    ("circle", 8, "saturating", 24, 120),
+    ("circle", 8, "mixed", 24, 150),
+    ("reaching", 1, "mixed", 16, 480),
+    ("reaching", 8, "saturating", 16, 120),
+    ("reaching", 8, "hover_band", 16, 90),
+])
+def test_lockstep_parity(track, S, mode, N, T):
+    env, workers = _make(track, N, S)
+    _reset_both(env, workers)
+    rep = PU.run_lockstep(env, workers, _actions(mode, T, N, seed=hash((track, S, mode)) % 1000), resync_every=240 // S)
+    print(f"\n[{track} S={S} {mode}] {rep}")
+    assert rep.near_ties <= max(2, rep.env_steps // 200)
+    env.close()
+
+
+def test_reset_after_crash_uses_stale_position():
+    """SURVEY 8(c) scenario: max thrust -> -10 at step 53; the returned (reset) obs carries the stale
+    distance 0.26039 and the new distance is measured from the stale position."""
+    env, workers = _make("circle", 4, 1)
+    env.reset()
+    a = torch.ones(4, 4, device=env.device)
+    for k in range(1, 60):
+        o, r, d, f = env.step(a)
+        if int(d[0]):
+            break
+    assert k == 53 and float(r[0]) == -10.0 and int(d[0]) == 1
+    assert float(o[0, 12]) == pytest.approx(0.26039, abs=1e-5)
+    np.testing.assert_allclose(o[0, :3].cpu().numpy(), [0.5, 0, 0.5])
+    st = env.get_state()
+    assert float(st["dist"][0]) == pytest.approx(1.04157, abs=1e-5)
+    assert int(st["steps"][0]) == 0 and int(st["episode_count"][0]) == 1
+    stats = env.episode_stats()
+    assert stats["episodes"] == 4 and stats["crashes"] == 4 and stats["length_sum"] == 4 * 53
+    env.close()
+
+
+def test_truncation_step_and_time_limit_bit():
+    env, workers = _make("circle", 4, 1, max_steps=7)
+    env.reset()
+    a = torch.full((4, 4), HOVER, device=env.device)
+    bits = [int(env.step(a)[2][0]) for _ in range(8)]
+    assert bits == [0] * 7 + [2]
+    assert env.episode_stats()["truncations"] == 4
+    env.close()
+
+
+def test_single_step_random_states_all_branches():
+    """Differential single-step test from randomised mid-episode states placed near targets, tube walls,
+    box walls and the step limit, so that every branch of the reward / termination state machine fires."""
+    from oracle.dyn_oracle import bullet_quaternion_from_euler
+    N = 768
+    rng = np.random.default_rng(7)
+    total = PU.ParityReport()
+    for track, S in (("circle", 1), ("reaching", 8)):
+        env, workers = _make(track, N, S, max_steps=64)
+        _reset_both(env, workers)
+        T = len(workers[0].env._target_points)
+        for i, w in enumerate(workers):
+            e = w.env
+            steps = int(rng.choice([0, 1, 30, 63, 64]))
+            # steps == 0 means "no post-step since the last reset": target 0 and a distance that was
+            # measured from the (stale) current position -- the only such states the reference can be in
+            idx = 0 if steps == 0 else int(rng.integers(0, T))
+            tgt = e._target_points[idx]
+            kind = i % 4
+            if kind == 0:      # near the current target -> capture / final target
+                pos = tgt + rng.normal(0, 0.2, 3)
+            elif kind == 1:    # near the tube wall
+                prev = e.INIT_XYZS[0] if idx == 0 else e._target_points[idx - 1]
+                lam = rng.uniform(0, 1)
+                pos = prev + lam * (tgt - prev) + rng.normal(0, 0.25, 3)
+            elif kind == 2:    # near the box / ceiling
+                pos = np.array([rng.choice([-1, 1]) * (e._x_high - abs(rng.normal(0, 0.01))), rng.uniform(-1, 1),
+                                e._z_high - abs(rng.normal(0, 0.01))])
+            else:
+                pos = e.INIT_XYZS[0] + rng.normal(0, 0.05, 3)
+            rpy = rng.normal(0, 0.4, 3)
+            st = dict(pos=pos, quat=bullet_quaternion_from_euler(rpy), vel=rng.normal(0, 1.0, 3),
+                      rpy_rates=rng.normal(0, 2.0, 3), ang_v=rng.normal(0, 2.0, 3), prev_vel=rng.normal(0, 1.0, 3),
+                      prev_ang_v=rng.normal(0, 2.0, 3), dist=float(np.linalg.norm(tgt - pos) + rng.normal(0, 0.01)),
+                      prev_dist=float(np.linalg.norm(tgt - pos) + rng.normal(0, 0.02)), target_idx=idx,
+                      steps=steps, just_found=bool(rng.integers(0, 2)))
+            st["dist"] = abs(st["dist"])
+            if steps == 0:
+                st["dist"] = st["prev_dist"] = float(np.linalg.norm(pos - tgt))
+                st["just_found"] = False
+            e.set_state(st)
+        PU.upload_oracle_state(env, workers)
+        acts = _actions("mixed", 2, N, seed=3)
+        rep = PU.run_lockstep(env, workers, acts, resync_every=1, report=None)
+        print(f"\n[single-step {track} S={S}] {rep}")
+        assert rep.dones > N // 8 and rep.captures > N // 20
+        total.near_ties += rep.near_ties
+        env.close()
+    assert total.near_ties <= 8
+
+
+def test_step_many_matches_repeated_step():
+    """dn_step_many (T steps, state in registers) is bit-identical to T dn_step launches."""
+    envA, _ = _make("circle", 1000, 8)
+    envB, _ = _make("circle", 1000, 8)
+    envA.reset(); envB.reset()
+    T = 40
+    acts = torch.from_numpy(_actions("saturating", T, 1000, seed=11)).to(envA.device)
+    outs = envB.step_many(acts, per_step_outputs=True)
+    for t in range(T):
+        o, r, d, f = envA.step(acts[t])
+        assert torch.equal(o, outs["obs"][t]) and torch.equal(r, outs["reward"][t])
+        assert torch.equal(d, outs["done"][t]) and torch.equal(f, outs["found_targets"][t])
+    sa, sb = envA.get_state(), envB.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert envA.episode_stats()["episodes"] == envB.episode_stats()["episodes"] > 0
+    envA.close(); envB.close()
+
+
+def test_ragged_sizes_and_obs12():
+    """N not a multiple of the CTA size (tail CTA takes the non-TMA store path), N = 1, 12-dim obs."""
+    from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
+    from oracle.dyn_oracle import make_reference_env
+    ref = make_reference_env("circle")
+    outs = {}
+    for N in (1, 3, 127, 130, 1027):
+        for inc in (True, False):
+            env = BatchedDroneEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS,
+                                  circle=True, include_distance=inc, normalize_actions=True)
+            env.reset()
+            a = torch.full((N, 4), HOVER, device=env.device)
+            for _ in range(3):
+                o, r, d, f = env.step(a)
+            assert o.shape == (N, 13 if inc else 12)
+            outs[(N, inc)] = o.cpu().numpy()
+            env.close()
+    for (N, inc), o in outs.items():      # every env got the same actions -> identical rows, equal to N=1
+        np.testing.assert_array_equal(o, np.repeat(outs[(1, inc)], N, axis=0))
+
+
+def test_vec_env_protocol_against_oracle_workers():
+    """GpuDroneVecEnv (numpy, pinned host buffers) reproduces the SubprocVecEnv worker contract,
+    NormalizeObservation included (FP32 running statistics vs the reference's FP64: looser obs tolerance)."""
+    from drl_dronenavigation_b200.vec_env import GpuDroneVecEnv
+    from oracle.dyn_oracle import OracleWorker, make_reference_env
+    N, T = 12, 200
+    ref = make_reference_env("circle")
+    venv = GpuDroneVecEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS,
+                          circle=True, include_distance=True, normalize_actions=True, normalize_obs=True)
+    workers = [OracleWorker(make_reference_env("circle"), normalize_obs=True) for _ in range(N)]
+    obs = venv.reset()
+    assert obs.shape == (N, 13) and obs.dtype == np.float32
+    for i, w in enumerate(workers):
+        np.testing.assert_allclose(obs[i], w.reset()[0], atol=2e-4)
+    acts = _actions("saturating", T, N, seed=5)
+    n_done = 0
+    for t in range(T):
+        o, r, d, infos = venv.step(acts[t])
+        assert d.dtype == np.bool_ and len(infos) == N
+        for i, w in enumerate(workers):
+            oo, rr, dd, info = w.step(acts[t, i])
+            assert bool(d[i]) == dd and infos[i]["found_targets"] == info["found_targets"]
+            np.testing.assert_allclose(o[i], oo, atol=2e-3, rtol=2e-3)
+            assert abs(r[i] - rr) < 1e-3
+            if dd:
+                n_done += 1
+                assert infos[i]["episode"]["l"] == info["episode"]["l"]
+                assert infos[i]["TimeLimit.truncated"] == info["TimeLimit.truncated"]
+                np.testing.assert_allclose(infos[i]["terminal_observation"], info["terminal_observation"], atol=2e-3, rtol=2e-3)
+    assert n_done > 20
+    assert venv.env_is_wrapped(type("Monitor", (), {}))[0]
+    venv.close()
+
+
+def test_full_size_properties():
+    """BASELINE config sizes (4096 and 65536 envs, S = 8): size-independent properties --
+    identical action rows give identical env rows, unit quaternions, finite outputs, done <=> state reset,
+    statistics consistent with the done bits."""
+    from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
+    from oracle.dyn_oracle import make_reference_env
+    ref = make_reference_env("circle")
+    for N in (4096, 65536):
+        env = BatchedDroneEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS,
+                              pyb_freq=240, ctrl_freq=30, circle=True, include_distance=True, normalize_actions=True)
+        env.reset()
+        g = torch.Generator(device="cpu").manual_seed(N)
+        n_done = 0
+        for t in range(30):
+            half = (torch.rand(N // 2, 4, generator=g) * 2 - 1)
+            a = torch.cat([half, half]).to(env.device)               # env i and i + N/2 see the same actions
+            o, r, d, f = env.step(a)
+            assert torch.isfinite(o).all() and torch.isfinite(r).all()
+            assert torch.equal(o[: N // 2], o[N // 2:]) and torch.equal(r[: N // 2], r[N // 2:])
+            st = env.get_state()
+            qn = (st["quat"] ** 2).sum(dim=1)
+            assert float((qn - 1).abs().max()) < 1e-5
+            done = d != 0
+            n_done += int(done.sum())
+            assert bool((st["steps"][done] == 0).all()) and bool((st["target_idx"][done] == 0).all())
+            assert bool((st["steps"][~done] > 0).all())
+        stats = env.episode_stats()
+        assert stats["episodes"] == n_done and stats["crashes"] + stats["truncations"] + stats["successes"] == n_done
+        env.close()
