@@ -1,0 +1,473 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the fused drone-navigation control step on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1]): step-only throughput, 4096 CF2X envs per GPU, DYN physics,
+240 Hz physics / 30 Hz control (S = 8 substeps fused per launch), circle track, THRUST actions with
+normalize_actions, 13-dim observation, default reward, pre-generated saturating U(-1,1) actions
+(reset-heavy).  One "step" = one launch of the fused kernel over the whole batch.
+
+Printed JSON line (rank 0): see the task contract.  Extra keys:
+  value            device-timed, inputs resident in HBM, L2 flushed between the timed launches
+  l2_resident      same workload replayed back to back from a CUDA graph (state stays in the 126 MB L2,
+                   as it does in real use at this batch size) -- launch-latency regime
+  sweep            larger batches (65 536 / 1 Mi / 4 Mi envs): the HBM regime, with roofline fractions
+  roofline         dominant kernel (step_kernel) at the headline workload
+  roofline_hbm     the same kernel at the largest swept batch (state + outputs >> L2)
+  e2e              the same metric through the C-ABI host-buffer call (dn_step_host): pinned host
+                   actions -> H2D -> kernel -> D2H obs/reward/done/found every step
+  cpu_baseline     the CPU oracle (numpy port of the reference step) on the host cores, bounded sample
+`--impl reference` times that CPU path as its own arm (the reference is pure Python; pybullet / SB3 are
+not installable here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "env-steps/sec (fused substeps)"
+UNIT = "env-steps/s"
+BYTES_PER_ENV_STEP = 16 + 112 + 112 + 52 + 4 + 1 + 4   # action | state in | state out | obs | reward | done | found  
+HOVER = 0.092227
+
+
+def track_setup(track: str):
+    from drl_dronenavigation_b200 import Track, Waypoints, track_targets
+    if track == "circle":
+        tr = Track(Waypoints.circle(radius=1, num_points=6, height=1), circle=True)
+    else:
+        tr = Track(Waypoints.reaching(), circle=False)
+    return np.array(track_targets(tr)), np.array(tr.initial_xyzs, dtype=np.float64), np.array(tr.aviary_dim), tr.is_circle
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (recipe line of /opt/skills/guides/B200_PROFILING.md)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            if t0 is not None and not (t0 - 0.15 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:   # timed region shorter than one sample: take whatever was seen
+            for ts, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1])); smax = float(f[2])
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle (numpy port of the reference step), one env object per worker process slot,
+# exactly like SubprocVecEnv workers
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    track, S, n_envs, n_steps, seed = args
+    from oracle.dyn_oracle import OracleWorker, make_reference_env
+    ws = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S), normalize_obs=False) for _ in range(n_envs)]
+    for w in ws:
+        w.reset()
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(-1, 1, size=(n_steps, n_envs, 4)).astype(np.float32)
+    t0 = time.perf_counter()
+    for t in range(n_steps):
+        for i, w in enumerate(ws):
+            w.step(acts[t, i])
+    return time.perf_counter() - t0
+
+
+def cpu_oracle_rate(track, S, envs_per_proc, steps, procs):
+    """env-steps/s of the numpy oracle over `procs` processes (sum of per-process rates by max time)."""
+    with mp.get_context("fork").Pool(procs) as pool:
+        times = pool.map(_cpu_worker, [(track, S, envs_per_proc, steps, 100 + p) for p in range(procs)])
+    return procs * envs_per_proc * steps / max(times), max(times)
+
+
+def cpu_baseline(track, S, budget_s=12.0):
+    cores = os.cpu_count() or 1
+    rate1, _ = cpu_oracle_rate(track, S, 2, 40, cores)                       # calibration
+    steps = max(20, int(budget_s * rate1 / (cores * 4)))
+    rate, dt = cpu_oracle_rate(track, S, 4, steps, cores)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"numpy oracle (FP64 port of PBDroneEnv.step + BaseAviary._dynamics), {cores} processes x 4 envs x {steps} "
+                      f"control steps, S={S}, {track} track, saturating actions, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python on
+    PyBullet; neither pybullet nor gymnasium nor SB3 is installable here, and its own DYN branch is dead
+    code, so the arm times the oracle port of it with every host core, SubprocVecEnv-style."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S, track = args.substeps, args.track
+    cores = os.cpu_count() or 1
+    K, W = args.steps, args.warmup
+    rate1, _ = cpu_oracle_rate(track, S, 2, 20, cores)
+    budget = 120.0
+    envs_per_proc = int(max(1, min(args.envs // cores, budget * rate1 / (cores * (K + W)))))
+    n_envs = envs_per_proc * cores
+    # one "step" = one control step of a bounded sample of the workload's envs (n_envs of args.envs)
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_worker, [(track, S, envs_per_proc, max(W, 1), 7 + p) for p in range(cores)])          # warm-up
+        t0 = time.perf_counter()
+        times = pool.map(_cpu_worker, [(track, S, envs_per_proc, K, 100 + p) for p in range(cores)])
+        wall = time.perf_counter() - t0
+    value = n_envs * K / max(times)
+    sample = (f"{n_envs} of {args.envs} envs ({cores} processes x {envs_per_proc}), {K} control steps, S={S}, numpy oracle port "
+              f"of the reference step (pybullet/SB3 not installable; reference DYN branch is dead code)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * max(times) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "envs_in_sample": n_envs, "substeps": S, "track": track},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"step-only throughput: {args.envs} CF2X envs per GPU, Physics.DYN, 240 Hz physics / {240 // args.substeps} Hz control "
+            f"(S={args.substeps}), {args.track} track, THRUST+normalize_actions, obs13, default reward, {args.actions} actions")
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def make_env(n_envs, args, device, env_id_offset=0):
+    from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
+    targets, init, dim, is_circle = track_setup(args.track)
+    return BatchedDroneEnv(n_envs, targets, threshold=0.3, discount=0.999, max_steps=4096, aviary_dim=dim,
+                           initial_xyzs=init, pyb_freq=240, ctrl_freq=240 // args.substeps, cylinder=True, circle=is_circle,
+                           include_distance=True, normalize_actions=True, device=device, env_id_offset=env_id_offset)
+
+
+def make_actions(n_buf, n_envs, mode, device, seed):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    u = torch.rand(n_buf, n_envs, 4, generator=g, device=device) * 2 - 1
+    return u.contiguous() if mode == "saturating" else (HOVER + 0.002 * u).contiguous()
+
+
+def time_flushed(env, acts, K, W, flush_buf):
+    """K launches, each bracketed by its own CUDA-event pair on the launching stream, L2 flushed
+    (a write larger than L2) between them outside the timed brackets."""
+    import torch
+    A = acts.shape[0]
+    for k in range(W):
+        env.step(acts[k % A])
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for k in range(K):
+        flush_buf.fill_(k & 1)
+        starts[k].record()
+        env.step(acts[(W + k) % A])
+        ends[k].record()
+    torch.cuda.synchronize()
+    per = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])     # ms
+    return float(per.sum()) * 1e-3, per
+
+
+def time_graph(env, acts, K, W, group=None):
+    """K launches replayed from CUDA graphs of `group` steps each, back to back, one event pair around all."""
+    import torch
+    A = acts.shape[0]
+    group = group or min(K, A, 50)
+    while K % group:
+        group -= 1
+    s = torch.cuda.Stream(device=env.device)
+    s.wait_stream(torch.cuda.current_stream(env.device))
+    with torch.cuda.stream(s):
+        for k in range(max(W, 3)):
+            env.step(acts[k % A])
+    torch.cuda.current_stream(env.device).wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        for k in range(group):
+            env.step(acts[k % A])
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K // group):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3, group
+
+
+def time_plain(env, acts, K, W):
+    """K plain launches back to back (no graph), one event pair around all."""
+    import torch
+    A = acts.shape[0]
+    for k in range(W):
+        env.step(acts[k % A])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        env.step(acts[(W + k) % A])
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def roofline(n_envs, sec_per_launch, traffic=None):
+    peak, src = peaks()
+    achieved = BYTES_PER_ENV_STEP * n_envs / sec_per_launch / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "kernel": "dn::step_kernel<0,false>", "bytes_per_env_step": BYTES_PER_ENV_STEP, "envs_per_launch": n_envs,
+            "us_per_launch": sec_per_launch * 1e6, "peak_source": src}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    K, W = args.steps, max(args.warmup, 3)
+    N = args.envs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    env = make_env(N, args, dev, env_id_offset=rank * N)
+    env.reset()
+    A = max(8, min(1000, (64 << 20) // (N * 16)))
+    acts = make_actions(A, N, args.actions, dev, seed=1234 + rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+
+    # ---- headline: K launches, L2 flushed between them, per-launch CUDA events ------------------
+    barrier()
+    l0 = env.launch_count
+    t0 = time.time()
+    sec, per = time_flushed(env, acts, K, W, flush)
+    barrier()
+    t1 = time.time()
+    launches = env.launch_count - l0 - W
+    sec = max_over_ranks(sec)
+    value = world * N * K / sec
+    clocks = sampler.stop(t0, t1)
+
+    # ---- same workload, L2-resident, CUDA-graph replay (launch-latency regime) -------------------
+    barrier()
+    sec_g, group = time_graph(env, acts, K, W)
+    sec_g = max_over_ranks(sec_g)
+    barrier()
+    sec_p = max_over_ranks(time_plain(env, acts, K, W))
+    resident = {"value": world * N * K / sec_g, "unit": UNIT, "us_per_launch": 1e6 * sec_g / K, "cuda_graph_steps": group,
+                "plain_launch_value": world * N * K / sec_p, "plain_us_per_launch": 1e6 * sec_p / K,
+                "note": "state (0.9 MB) stays in L2 between launches, as in real use at this batch size"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * sec / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "envs_per_gpu": N, "substeps": args.substeps, "track": args.track,
+                       "actions": args.actions, "l2": "flushed between timed launches (256 MiB fill, outside the event brackets)",
+                       "parallelism": f"env-shard x{world} (no data-path collective)"},
+            "physics_steps_per_s": value * args.substeps,
+            "clocks": clocks, "gpu_launches": int(launches), "l2_resident": resident}
+
+    if rank == 0 or world > 1:
+        pass
+    # ---- single-GPU extras on rank 0 only: roofline, sweep, e2e, cpu baseline --------------------
+    if world == 1:
+        line["roofline"] = roofline(N, sec / K)
+        line["roofline"]["note"] = "launch/latency-bound at this batch size: 1.2 MB per launch is ~0.2 us of HBM time"
+        sweep = []
+        for n_big in args.sweep:
+            try:
+                e2 = make_env(n_big, args, dev)
+                e2.reset()
+                a2 = make_actions(4, n_big, args.actions, dev, seed=99)
+                k2 = max(10, min(K, int(2e8 // n_big)))
+                s2 = time_plain(e2, a2, k2, 3)
+                s1 = None
+                if args.substeps != 1:     # S = 1 (240/240 Hz, the reference default): the pure-HBM regime
+                    pass
+                rf = roofline(n_big, s2 / k2)
+                sweep.append({"envs": n_big, "value": n_big * k2 / s2, "us_per_launch": 1e6 * s2 / k2, "steps": k2,
+                              "roofline_frac": rf["frac"], "achieved_gbs": rf["achieved"],
+                              "working_set_mb": n_big * (BYTES_PER_ENV_STEP - 16) / 1e6, "l2": "inputs larger than L2" if n_big * 224 > 126e6 else "fits L2"})
+                if n_big == max(args.sweep):
+                    line["roofline_hbm"] = rf
+                e2.close()
+                del e2, a2
+                torch.cuda.empty_cache()
+            except Exception as ex:  # noqa: BLE001
+                sweep.append({"envs": n_big, "error": str(ex)[:200]})
+        line["sweep"] = sweep
+        # S = 1 variant of the largest batch (reference default 240/240 Hz): HBM-bound regime
+        try:
+            import copy
+            a1 = copy.copy(args); a1.substeps = 1
+            n_big = max(args.sweep)
+            e3 = make_env(n_big, a1, dev); e3.reset()
+            a3 = make_actions(4, n_big, args.actions, dev, seed=98)
+            k3 = max(10, min(K, int(2e8 // n_big)))
+            s3 = time_plain(e3, a3, k3, 3)
+            line["roofline_hbm_s1"] = roofline(n_big, s3 / k3)
+            line["roofline_hbm_s1"]["substeps"] = 1
+            e3.close(); del e3, a3
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            line["roofline_hbm_s1"] = {"error": str(ex)[:200]}
+
+    # ---- e2e: C-ABI host-buffer call, pinned host actions -> H2D -> kernel -> D2H results ---------
+    D = env.obs_dim
+    h_act = torch.empty(A, N, 4, dtype=torch.float32).pin_memory()
+    h_act.copy_(acts.cpu())
+    h_obs = torch.empty(N, D, dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(N, dtype=torch.uint8).pin_memory()
+    h_found = torch.empty(N, dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+    ios = [env._make_io(h_act[k], h_obs, h_rew, h_done, None, h_found) for k in range(A)]
+    for k in range(W):
+        env.step_host(ios[k % A])
+    barrier()
+    l0 = env.launch_count
+    t0 = time.perf_counter()
+    for k in range(K):
+        env.step_host(ios[(W + k) % A])
+    e2e_sec = time.perf_counter() - t0
+    e2e_launches = env.launch_count - l0
+    barrier()
+    e2e_sec = max_over_ranks(e2e_sec)
+    line["e2e"] = {"value": world * N * K / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": N * 16,
+                   "d2h_bytes_per_step": N * (D * 4 + 4 + 1 + 4), "us_per_step": 1e6 * e2e_sec / K,
+                   "api": "dn_step_host (C ABI, host buffers): pinned actions -> H2D -> step_kernel -> D2H obs,reward,done,found_targets",
+                   "gpu_launches": int(e2e_launches)}
+    if world == 1 and not args.no_vecenv:
+        # the SB3 VecEnv protocol on top of the same call (numpy in / numpy out + per-env info dicts)
+        from drl_dronenavigation_b200.vec_env import GpuDroneVecEnv
+        targets, init, dim, is_circle = track_setup(args.track)
+        venv = GpuDroneVecEnv(N, targets, aviary_dim=dim, initial_xyzs=init, pyb_freq=240, ctrl_freq=240 // args.substeps,
+                              circle=is_circle, include_distance=True, normalize_actions=True, normalize_obs=True, device=dev)
+        venv.reset()
+        a_np = h_act.numpy()
+        kv = min(K, 200)
+        for k in range(3):
+            venv.step(a_np[k % A])
+        t0 = time.perf_counter()
+        for k in range(kv):
+            venv.step(a_np[k % A])
+        dtv = time.perf_counter() - t0
+        line["e2e_vecenv"] = {"value": N * kv / dtv, "unit": UNIT, "us_per_step": 1e6 * dtv / kv,
+                              "api": "GpuDroneVecEnv.step (SB3 VecEnv protocol incl. NormalizeObservation, Monitor, info dicts)"}
+        venv.close()
+
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args.track, args.substeps, budget_s=args.cpu_budget)
+    elif world > 1:
+        line["cpu_baseline"] = None
+    env.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU (BASELINE configs[1]: 4096)")
+    ap.add_argument("--substeps", type=int, default=8, help="pyb_freq / ctrl_freq (240/30 Hz -> 8)")
+    ap.add_argument("--track", default="circle", choices=["circle", "reaching"])
+    ap.add_argument("--actions", default="saturating", choices=["saturating", "hover_band"])
+    ap.add_argument("--sweep", type=int, nargs="*", default=[65536, 1 << 20, 1 << 22])
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-vecenv", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

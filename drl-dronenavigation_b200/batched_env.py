@@ -154,6 +154,11 @@ class BatchedDroneEnv:
         L.check(self._lib.dn_step(self._handle, C.byref(self._io), self._stream()), "dn_step")
         return self.obs, self.reward, self.done, self.found_targets
 
+    def step_host(self, host_io) -> None:
+        """dn_step_host: one control step with HOST buffers (an ``_lib.dn_step_io`` of host pointers,
+        see :meth:`_make_io`); returns when the results are in the host buffers."""
+        L.check(self._lib.dn_step_host(self._handle, C.byref(host_io)), "dn_step_host")
+
     def step_many(self, actions: torch.Tensor, per_step_outputs: bool = True, out: Optional[Dict] = None):
         """T control steps in one launch (state stays in registers); actions [T, N, 4]."""
         T = int(actions.shape[0])

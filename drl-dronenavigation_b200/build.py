@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdronenav.so")
 SOURCES = ["dronenav.cu"]
-HEADERS = ["dn_params.h", "dn_device.cuh", os.path.join("..", "..", "include", "dronenav.h")]
+HEADERS = ["dn_params.h", "dn_device.cuh", "dn_host.h", os.path.join("..", "..", "include", "dronenav.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

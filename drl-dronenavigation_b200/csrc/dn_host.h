@@ -1,0 +1,152 @@
+// dn_host.h -- host-side derivation of the kernel parameter block from a dn_config:
+// CF2X constants, derived BaseAviary quantities, the spawn observation and the target /
+// segment tables, all computed in double and rounded once to FP32.
+// Shared by dronenav.cu (the product) and tests/host_emu (a g++ build of the same step
+// logic that lets the CPU test suite exercise the device code path without a GPU).
+#pragma once
+#include <cmath>
+#include <vector>
+#include "../../include/dronenav.h"
+#include "dn_params.h"
+
+namespace dn { namespace host {
+
+// CF2X constants: Sol/resources/safegym/cf2x.urdf:5,11-12,34 ; derived BaseAviary.py:76,163-176
+struct CF2X {
+    static constexpr double M = 0.027, L = 0.0397, T2W = 2.25;
+    static constexpr double IXX = 1.4e-5, IYY = 1.4e-5, IZZ = 2.17e-5;
+    static constexpr double KF = 3.16e-10, KM = 7.94e-12;
+    static constexpr double COLLISION_H = 0.025;
+    static constexpr double GND_EFF_COEFF = 11.36859, PROP_RADIUS = 2.31348e-2;
+    static constexpr double DRAG_XY = 9.1785e-7, DRAG_Z = 10.311e-7;
+    static constexpr double PWM2RPM_SCALE = 0.2685, PWM2RPM_CONST = 4070.3, MIN_PWM = 20000.0, MAX_PWM = 65535.0;
+    static constexpr double G = 9.8;
+};
+
+inline void quat_from_euler(const double rpy[3], double q[4]) {   // p.getQuaternionFromEuler (BaseAviary.py:567)
+    const double r = rpy[0] * 0.5, p = rpy[1] * 0.5, y = rpy[2] * 0.5;
+    const double cr = std::cos(r), sr = std::sin(r), cp = std::cos(p), sp = std::sin(p), cy = std::cos(y), sy = std::sin(y);
+    q[0] = sr * cp * cy - cr * sp * sy;
+    q[1] = cr * sp * cy + sr * cp * sy;
+    q[2] = cr * cp * sy - sr * sp * cy;
+    q[3] = cr * cp * cy + sr * sp * sy;
+    const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int k = 0; k < 4; ++k) q[k] /= n;
+}
+
+inline void euler_from_quat(const double q[4], double rpy[3]) {    // p.getEulerFromQuaternion (BaseAviary.py:597)
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double sarg = -2.0 * (x * z - w * y);
+    const double pi = 3.14159265358979323846;
+    if (sarg <= -0.99999) { rpy[0] = 0; rpy[1] = -0.5 * pi; rpy[2] = 2 * std::atan2(x, -y); }
+    else if (sarg >= 0.99999) { rpy[0] = 0; rpy[1] = 0.5 * pi; rpy[2] = 2 * std::atan2(-x, y); }
+    else {
+        rpy[0] = std::atan2(2 * (y * z + w * x), w * w - x * x - y * y + z * z);
+        rpy[1] = std::asin(sarg);
+        rpy[2] = std::atan2(2 * (x * y + w * z), w * w + x * x - y * y - z * z);
+    }
+}
+
+inline bool reward_table(int id, dn::RewardParams& w) {
+    switch (id) {
+        case DN_REWARD_DEFAULT:    // PBDroneEnv.py:475-607
+            w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.7f, 0.3f, 1.f, 25.f}; return true;
+        case DN_REWARD_DUMMY:      // dummy_env.py:446-550,587-598 (smoothness thresholds 0.1 / 0.1)
+            w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.1f, 0.1f, 1.f, 25.f}; return true;
+        case DN_REWARD_THRUSTENV:  // ThrustEnv.py:368-463 (-4 crash, +25 / +1000, 20 x progress, no orientation / smoothness)
+            w = {-4.f, 1000.f, 25.f, 0.f, 3.f, 2.f, 20.f, 0.f, 0.f, 0.f, 0.f, 25.f}; return true;
+        default: return false;
+    }
+}
+
+inline void fill_params(const dn_config& cfg, const RewardParams& rw, Params& P,
+                        std::vector<float4>& h_t, std::vector<float4>& h_s, float& d0) {
+    const int N = cfg.num_envs, T = cfg.num_targets;
+    P.n = N;
+    P.substeps = cfg.pyb_freq / cfg.ctrl_freq;
+    P.act_type = cfg.act_type;
+    P.normalize_actions = cfg.normalize_actions ? 1 : 0;
+    P.physics = cfg.physics;
+    P.obs_dim = cfg.include_distance ? 13 : 12;
+    P.cylinder = cfg.cylinder ? 1 : 0;
+    P.circle = cfg.circle ? 1 : 0;
+    P.max_steps = cfg.max_steps;
+    P.num_targets = T;
+    P.spawn_mode = cfg.spawn_mode;
+    P.reward_id = cfg.reward_id;
+    P.dt = static_cast<float>(1.0 / cfg.pyb_freq);
+    P.threshold = static_cast<float>(cfg.threshold);
+    const double* ad = cfg.aviary_dim;
+    P.x_low = (float)ad[0]; P.y_low = (float)ad[1]; P.z_low = (float)ad[2];
+    P.x_high = (float)ad[3]; P.y_high = (float)ad[4]; P.z_high = (float)ad[5];
+    const double mtd = std::fmax(std::fmax(std::fabs(ad[0]) + ad[3], std::fabs(ad[1]) + ad[4]), ad[5]);   // PBDroneEnv.py:91
+    P.max_target_dist = static_cast<float>(mtd);
+    double q0[4];
+    quat_from_euler(cfg.init_rpy, q0);
+    for (int k = 0; k < 3; ++k) { P.init_pos[k] = (float)cfg.init_xyz[k]; P.init_seg_base[k] = (float)cfg.init_xyz[k]; }
+    for (int k = 0; k < 4; ++k) P.init_quat[k] = (float)q0[k];
+    {   // observation of the spawn pose, entries 0..11 (PBDroneEnv.py:338-398), in double
+        double rpy[3];
+        euler_from_quat(q0, rpy);
+        const double pi = 3.14159265358979323846;
+        double o[12] = {cfg.init_xyz[0] / ad[3], cfg.init_xyz[1] / ad[4], cfg.init_xyz[2] / ad[5],
+                        std::fmin(std::fmax(rpy[0], -pi), pi) / pi, std::fmin(std::fmax(rpy[1], -pi), pi) / pi, rpy[2] / pi,
+                        0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < 12; ++k) P.init_obs[k] = (float)o[k];
+    }
+    // action map constants: float32 like the reference (PBDroneEnv.py:113-116)
+    const double a_low = CF2X::KF * std::pow(CF2X::PWM2RPM_SCALE * CF2X::MIN_PWM + CF2X::PWM2RPM_CONST, 2);
+    const double a_high = CF2X::KF * std::pow(CF2X::PWM2RPM_SCALE * CF2X::MAX_PWM + CF2X::PWM2RPM_CONST, 2);
+    P.a_low = (float)a_low; P.a_high = (float)a_high;
+    P.kf = (float)CF2X::KF; P.km = (float)CF2X::KM;
+    P.pwm_scale = (float)CF2X::PWM2RPM_SCALE; P.pwm_const = (float)CF2X::PWM2RPM_CONST;
+    P.pwm_min = (float)CF2X::MIN_PWM; P.pwm_max = (float)CF2X::MAX_PWM;
+    const double gravity = CF2X::G * CF2X::M;
+    const double hover_rpm = std::sqrt(gravity / (4 * CF2X::KF));
+    const double max_rpm = std::sqrt((CF2X::T2W * gravity) / (4 * CF2X::KF));
+    const double max_thrust = 4 * CF2X::KF * max_rpm * max_rpm;
+    P.hover_rpm = (float)hover_rpm;
+    P.gravity = (float)gravity; P.inv_m = (float)(1.0 / CF2X::M);
+    P.arm_over_sqrt2 = (float)(CF2X::L / std::sqrt(2.0));
+    P.ixx = (float)CF2X::IXX; P.iyy = (float)CF2X::IYY; P.izz = (float)CF2X::IZZ;
+    P.inv_ixx = (float)(1.0 / CF2X::IXX); P.inv_iyy = (float)(1.0 / CF2X::IYY); P.inv_izz = (float)(1.0 / CF2X::IZZ);
+    P.drag_xy = (float)CF2X::DRAG_XY; P.drag_z = (float)CF2X::DRAG_Z;
+    P.gnd_coeff = (float)CF2X::GND_EFF_COEFF; P.prop_radius = (float)CF2X::PROP_RADIUS;
+    P.gnd_h_clip = (float)(0.25 * CF2X::PROP_RADIUS * std::sqrt((15 * max_rpm * max_rpm * CF2X::KF * CF2X::GND_EFF_COEFF) / max_thrust));
+    P.collision_half_h = (float)(CF2X::COLLISION_H / 2);
+    const double px[4] = {0.028, -0.028, -0.028, 0.028}, py[4] = {0.028, 0.028, -0.028, -0.028};   // safegym/cf2x.urdf:42,54,66,78
+    for (int k = 0; k < 4; ++k) { P.prop_x[k] = (float)px[k]; P.prop_y[k] = (float)py[k]; }
+    P.rw = rw;
+    P.seed = cfg.seed;
+    P.env_id_offset = cfg.env_id_offset;
+
+    // target table + segment table for the non-circle cylinder (PBDroneEnv.py:746-786), in double
+    h_t.assign(T, float4{}); h_s.assign(2 * T, float4{});
+    for (int k = 0; k < T; ++k) {
+        const double* tk = cfg.targets + 3 * k;
+        h_t[k] = make_float4((float)tk[0], (float)tk[1], (float)tk[2], 0.f);
+        const double* b1 = (k == 0) ? cfg.init_xyz : cfg.targets + 3 * (k - 1);
+        double lv[3] = {tk[0] - b1[0], tk[1] - b1[1], tk[2] - b1[2]};
+        const double len = std::sqrt(lv[0] * lv[0] + lv[1] * lv[1] + lv[2] * lv[2]);
+        if (len == 0.0) {
+            h_s[2 * k] = make_float4((float)b1[0], (float)b1[1], (float)b1[2], 0.f);
+            h_s[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const double u[3] = {lv[0] / len, lv[1] / len, lv[2] / len};
+            const double e1[3] = {b1[0] - 0.2 * u[0], b1[1] - 0.2 * u[1], b1[2] - 0.2 * u[2]};
+            const double e2[3] = {tk[0] + 0.2 * u[0], tk[1] + 0.2 * u[1], tk[2] + 0.2 * u[2]};
+            const double el = std::sqrt((e2[0] - e1[0]) * (e2[0] - e1[0]) + (e2[1] - e1[1]) * (e2[1] - e1[1]) + (e2[2] - e1[2]) * (e2[2] - e1[2]));
+            h_s[2 * k] = make_float4((float)e1[0], (float)e1[1], (float)e1[2], (float)el);
+            h_s[2 * k + 1] = make_float4((float)u[0], (float)u[1], (float)u[2], (float)len);
+        }
+    }
+    // constructor distance: ||INIT_XYZS[0] - target[0]|| (PBDroneEnv.py:137-138)
+    {
+        const double* t0 = cfg.targets;
+        const double dx = cfg.init_xyz[0] - t0[0], dy = cfg.init_xyz[1] - t0[1], dz = cfg.init_xyz[2] - t0[2];
+        d0 = (float)std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+
+}
+
+}}  // namespace dn::host

@@ -7,7 +7,9 @@
 // pointers to the handle's HBM-resident state.
 #pragma once
 #include <stdint.h>
+#ifndef DN_HOST_EMU
 #include <cuda_runtime.h>
+#endif
 
 namespace dn {
 

@@ -24,11 +24,11 @@
 #include "../../include/dronenav.h"
 #include "dn_params.h"
 #include "dn_device.cuh"
+#include "dn_host.h"
 
 namespace dn {
 
 constexpr int kBlock = 128;
-constexpr int kMaxObs = 13;
 
 // ---------------------------------------------------------------------------
 // small PTX wrappers (TMA 1-D bulk store of the observation tile)
@@ -44,162 +44,6 @@ __device__ __forceinline__ void bulk_store_g2s_commit(void* gdst, const void* ss
 }
 __device__ __forceinline__ void bulk_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
-// ---------------------------------------------------------------------------
-// normalize.RunningMeanStd with a batch of one (normalize.py:19-47) followed by
-// NormalizeObservation.normalize (:94-97).  mean/var/count are per env, FP32 planes.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ float rms_update_normalize(float x, float& mean, float& var, float count) {
-    const float tot = count + 1.0f;
-    const float delta = x - mean;
-    mean = mean + delta / tot;
-    const float m2 = var * count + (delta * delta) * count / tot;
-    var = m2 / tot;
-    return (x - mean) / sqrtf(var + 1e-8f);
-}
-
-struct StepResult {
-    float reward;
-    uint8_t done;
-    int found;
-    bool finished;          // done (terminated or truncated)
-    float ep_ret;
-    int ep_len;
-    bool success, crash;
-};
-
-// One control step for one environment.  `obs_row` receives the observation the VecEnv
-// returns (the reset observation when the episode ended), `term_row` (may alias nothing)
-// the terminal observation.  Returns bookkeeping for outputs and statistics.
-template <int PHYS>
-__device__ __forceinline__ StepResult env_step(const Params& P, EnvState& s, const float4 act,
-                                               float& last_rpm_sum, float* obs_row, float* term_row) {
-    StepResult out;
-    const int T = P.num_targets;
-    int idx = static_cast<int>(s.bits >> kIdxShift);
-    int steps = static_cast<int>(s.bits & kStepsMask);
-    bool just_found = (s.bits & kJustFoundBit) != 0;
-
-    // state at step entry: PBDroneEnv.current_vel / current_ang_v and _current_position
-    const float evx = s.vx, evy = s.vy, evz = s.vz;
-    const float eax = s.ax, eay = s.ay, eaz = s.az;
-    const float epx = s.px, epy = s.py, epz = s.pz;
-
-    // ---- action -> rpm (PBDroneEnv.py:173-176,872-895) ----------------------
-    float rpm[4];
-    rpm[0] = action_to_rpm(P, act.x);
-    if (P.act_type == 2) { rpm[1] = rpm[2] = rpm[3] = rpm[0]; }
-    else { rpm[1] = action_to_rpm(P, act.y); rpm[2] = action_to_rpm(P, act.z); rpm[3] = action_to_rpm(P, act.w); }
-
-    // ---- physics (BaseAviary.py:410-444) -------------------------------------
-    integrate<PHYS>(P, s, rpm, last_rpm_sum);
-
-    // ---- observation (PBDroneEnv.py:296-336): new pose, STALE distance -------
-    kinematic_obs(P, s, term_row);
-    if (P.obs_dim == 13) term_row[12] = s.dist / P.max_target_dist;
-#pragma unroll
-    for (int k = 0; k < kMaxObs; ++k) if (k < P.obs_dim) term_row[k] = clip_f32_range(term_row[k]);
-
-    // ---- reward + waypoint state machine (PBDroneEnv.py:475-571) -------------
-    float fx, fy, fz;
-    forward_vector(s.qx, s.qy, s.qz, s.qw, fx, fy, fz);
-    const RewardParams& W = P.rw;
-    bool terminated;
-    bool is_done = false;
-    float reward;
-    out.crash = false;
-    if (collided(P, s.px, s.py, s.pz, idx)) {
-        reward = W.crash;                      // -10.0, not divided (:489-490)
-        terminated = true;
-        out.crash = true;
-    } else {
-        if (s.dist <= P.threshold) {           // stale distance (:539)
-            idx += 1;
-            if (idx == T) {
-                reward = W.final_bonus / W.divisor;
-                is_done = true;
-            } else {
-                const float4 tg = __ldg(&P.targets[idx]);
-                reward = (W.capture_bonus + W.capture_orient_w * orientation_term(fx, fy, fz, s.px, s.py, s.pz, tg)) / W.divisor;
-                just_found = true;
-            }
-        } else {
-            const float4 tg = __ldg(&P.targets[idx]);
-            float r = W.exp_w * expf(-W.exp_k * s.dist);
-            r += just_found ? 0.0f : (s.prev_dist - s.dist) * W.progress_w;
-            r += W.orient_w * orientation_term(fx, fy, fz, s.px, s.py, s.pz, tg);
-            if (W.smooth_w != 0.0f) {          // smoothness_reward (:599-607), one-step-stale velocities
-                const float lx = evx - s.pvx, ly = evy - s.pvy, lz = evz - s.pvz;
-                const float gx = eax - s.pax, gy = eay - s.pay, gz = eaz - s.paz;
-                const float lin = sqrtf(lx * lx + ly * ly + lz * lz);
-                const float ang = sqrtf(gx * gx + gy * gy + gz * gz);
-                r += W.smooth_w * ((lin > W.smooth_lin_thr ? -lin : 0.0f) + (ang > W.smooth_ang_thr ? -ang : 0.0f));
-            }
-            reward = r / W.divisor;
-            just_found = false;
-        }
-        s.prev_dist = s.dist;                  // :568
-        // _computeTerminated after the reward (:448,:456-473): index possibly advanced
-        terminated = is_done || collided(P, s.px, s.py, s.pz, idx);
-    }
-    const bool truncated = (P.max_steps <= steps);   // before this step's increment (:444-454)
-    out.found = idx;                                 // :434-442
-
-    // ---- _update_state_post_step (PBDroneEnv.py:196-223), skipped when terminated
-    if (!terminated) {
-        steps += 1;
-        s.pvx = evx; s.pvy = evy; s.pvz = evz;
-        s.pax = eax; s.pay = eay; s.paz = eaz;
-        const float4 tg = __ldg(&P.targets[idx]);
-        const float dx = tg.x - s.px, dy = tg.y - s.py, dz = tg.z - s.pz;
-        s.dist = sqrtf(dx * dx + dy * dy + dz * dz);
-    }
-
-    // ---- Monitor (SB3) --------------------------------------------------------
-    s.ep_ret += reward;
-    s.ep_len += 1;
-    out.reward = reward;
-    out.done = static_cast<uint8_t>((terminated ? DN_DONE_TERMINATED : 0) | (truncated ? DN_DONE_TRUNCATED : 0));
-    out.finished = terminated || truncated;
-    out.ep_ret = s.ep_ret;
-    out.ep_len = s.ep_len;
-    out.success = is_done;
-
-    if (!out.finished) {
-#pragma unroll
-        for (int k = 0; k < kMaxObs; ++k) if (k < P.obs_dim) obs_row[k] = term_row[k];
-    } else {
-        // ---- auto-reset: BaseAviary.reset (:276-320) then PBDroneEnv.reset (:609-665).
-        // The reset observation is taken BEFORE the distances are reset (:318 vs :651), and the
-        // new distance uses the stale _current_position: the position of the last non-terminal
-        // post-step (entry position if this step terminated, the new position if it was only
-        // truncated, unchanged if no post-step has run since the previous reset).
-        const float stale_dist = s.dist;
-        float D;
-        if (steps == 0) {
-            D = s.dist;
-        } else {
-            const float4 t0 = __ldg(&P.targets[0]);
-            const float cx = terminated ? epx : s.px, cy = terminated ? epy : s.py, cz = terminated ? epz : s.pz;
-            const float dx = cx - t0.x, dy = cy - t0.y, dz = cz - t0.z;
-            D = sqrtf(dx * dx + dy * dy + dz * dz);
-        }
-        s.px = P.init_pos[0]; s.py = P.init_pos[1]; s.pz = P.init_pos[2];
-        s.qx = P.init_quat[0]; s.qy = P.init_quat[1]; s.qz = P.init_quat[2]; s.qw = P.init_quat[3];
-        s.vx = s.vy = s.vz = 0.0f; s.wx = s.wy = s.wz = 0.0f; s.ax = s.ay = s.az = 0.0f;
-        s.pvx = s.pvy = s.pvz = 0.0f; s.pax = s.pay = s.paz = 0.0f;
-        s.dist = D; s.prev_dist = D;
-        idx = 0; steps = 0; just_found = false;
-        s.ep_ret = 0.0f; s.ep_len = 0; s.ep_count += 1u;
-        last_rpm_sum = 0.0f;                   // _housekeeping: last_clipped_action = 0 (BaseAviary.py:545)
-#pragma unroll
-        for (int k = 0; k < 12; ++k) obs_row[k] = P.init_obs[k];
-        if (P.obs_dim == 13) obs_row[12] = clip_f32_range(stale_dist / P.max_target_dist);
-    }
-    s.bits = (static_cast<uint32_t>(idx) << kIdxShift) | (just_found ? kJustFoundBit : 0u) |
-             (static_cast<uint32_t>(steps) & kStepsMask);
-    return out;
 }
 
 // ---------------------------------------------------------------------------
@@ -456,6 +300,9 @@ struct dn_env {
     dn::Stats* d_stats;
     int64_t launches;
     float d0;
+    // dn_step_host staging (allocated on first use)
+    cudaStream_t host_stream;
+    void* stage;            // device: actions | obs | terminal_obs | reward | ep_return | found | ep_length | done
 };
 
 static thread_local std::string g_err;
@@ -478,53 +325,6 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// CF2X constants: Sol/resources/safegym/cf2x.urdf:5,11-12,34 ; derived BaseAviary.py:76,163-176
-struct CF2X {
-    static constexpr double M = 0.027, L = 0.0397, T2W = 2.25;
-    static constexpr double IXX = 1.4e-5, IYY = 1.4e-5, IZZ = 2.17e-5;
-    static constexpr double KF = 3.16e-10, KM = 7.94e-12;
-    static constexpr double COLLISION_H = 0.025;
-    static constexpr double GND_EFF_COEFF = 11.36859, PROP_RADIUS = 2.31348e-2;
-    static constexpr double DRAG_XY = 9.1785e-7, DRAG_Z = 10.311e-7;
-    static constexpr double PWM2RPM_SCALE = 0.2685, PWM2RPM_CONST = 4070.3, MIN_PWM = 20000.0, MAX_PWM = 65535.0;
-    static constexpr double G = 9.8;
-};
-
-void quat_from_euler(const double rpy[3], double q[4]) {   // p.getQuaternionFromEuler (BaseAviary.py:567)
-    const double r = rpy[0] * 0.5, p = rpy[1] * 0.5, y = rpy[2] * 0.5;
-    const double cr = std::cos(r), sr = std::sin(r), cp = std::cos(p), sp = std::sin(p), cy = std::cos(y), sy = std::sin(y);
-    q[0] = sr * cp * cy - cr * sp * sy;
-    q[1] = cr * sp * cy + sr * cp * sy;
-    q[2] = cr * cp * sy - sr * sp * cy;
-    q[3] = cr * cp * cy + sr * sp * sy;
-    const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-    for (int k = 0; k < 4; ++k) q[k] /= n;
-}
-
-void euler_from_quat(const double q[4], double rpy[3]) {    // p.getEulerFromQuaternion (BaseAviary.py:597)
-    const double x = q[0], y = q[1], z = q[2], w = q[3];
-    const double sarg = -2.0 * (x * z - w * y);
-    const double pi = 3.14159265358979323846;
-    if (sarg <= -0.99999) { rpy[0] = 0; rpy[1] = -0.5 * pi; rpy[2] = 2 * std::atan2(x, -y); }
-    else if (sarg >= 0.99999) { rpy[0] = 0; rpy[1] = 0.5 * pi; rpy[2] = 2 * std::atan2(-x, y); }
-    else {
-        rpy[0] = std::atan2(2 * (y * z + w * x), w * w - x * x - y * y + z * z);
-        rpy[1] = std::asin(sarg);
-        rpy[2] = std::atan2(2 * (x * y + w * z), w * w + x * x - y * y - z * z);
-    }
-}
-
-bool reward_table(int id, dn::RewardParams& w) {
-    switch (id) {
-        case DN_REWARD_DEFAULT:    // PBDroneEnv.py:475-607
-            w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.7f, 0.3f, 1.f, 25.f}; return true;
-        case DN_REWARD_DUMMY:      // dummy_env.py:446-550,587-598 (smoothness thresholds 0.1 / 0.1)
-            w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.1f, 0.1f, 1.f, 25.f}; return true;
-        case DN_REWARD_THRUSTENV:  // ThrustEnv.py:368-463 (-4 crash, +25 / +1000, 20 x progress, no orientation / smoothness)
-            w = {-4.f, 1000.f, 25.f, 0.f, 3.f, 2.f, 20.f, 0.f, 0.f, 0.f, 0.f, 25.f}; return true;
-        default: return false;
-    }
-}
 }  // namespace
 
 extern "C" {
@@ -546,7 +346,7 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     if (cfg->spawn_mode != DN_SPAWN_FIXED) return fail(DN_EINVAL, "dn_create: spawn_mode not implemented");
     if (cfg->max_steps < 0 || cfg->max_steps > (int)dn::kStepsMask - 1) return fail(DN_EINVAL, "dn_create: max_steps out of range");
     dn::RewardParams rw;
-    if (!reward_table(cfg->reward_id, rw)) return fail(DN_EINVAL, "dn_create: reward_id not implemented");
+    if (!dn::host::reward_table(cfg->reward_id, rw)) return fail(DN_EINVAL, "dn_create: reward_id not implemented");
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -562,90 +362,8 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     e->normalize_obs = cfg->normalize_obs ? 1 : 0;
     Params& P = e->P;
     const int N = cfg->num_envs, T = cfg->num_targets;
-    P.n = N;
-    P.substeps = cfg->pyb_freq / cfg->ctrl_freq;
-    P.act_type = cfg->act_type;
-    P.normalize_actions = cfg->normalize_actions ? 1 : 0;
-    P.physics = cfg->physics;
-    P.obs_dim = cfg->include_distance ? 13 : 12;
-    P.cylinder = cfg->cylinder ? 1 : 0;
-    P.circle = cfg->circle ? 1 : 0;
-    P.max_steps = cfg->max_steps;
-    P.num_targets = T;
-    P.spawn_mode = cfg->spawn_mode;
-    P.reward_id = cfg->reward_id;
-    P.dt = static_cast<float>(1.0 / cfg->pyb_freq);
-    P.threshold = static_cast<float>(cfg->threshold);
-    const double* ad = cfg->aviary_dim;
-    P.x_low = (float)ad[0]; P.y_low = (float)ad[1]; P.z_low = (float)ad[2];
-    P.x_high = (float)ad[3]; P.y_high = (float)ad[4]; P.z_high = (float)ad[5];
-    const double mtd = std::fmax(std::fmax(std::fabs(ad[0]) + ad[3], std::fabs(ad[1]) + ad[4]), ad[5]);   // PBDroneEnv.py:91
-    P.max_target_dist = static_cast<float>(mtd);
-    double q0[4];
-    quat_from_euler(cfg->init_rpy, q0);
-    for (int k = 0; k < 3; ++k) { P.init_pos[k] = (float)cfg->init_xyz[k]; P.init_seg_base[k] = (float)cfg->init_xyz[k]; }
-    for (int k = 0; k < 4; ++k) P.init_quat[k] = (float)q0[k];
-    {   // observation of the spawn pose, entries 0..11 (PBDroneEnv.py:338-398), in double
-        double rpy[3];
-        euler_from_quat(q0, rpy);
-        const double pi = 3.14159265358979323846;
-        double o[12] = {cfg->init_xyz[0] / ad[3], cfg->init_xyz[1] / ad[4], cfg->init_xyz[2] / ad[5],
-                        std::fmin(std::fmax(rpy[0], -pi), pi) / pi, std::fmin(std::fmax(rpy[1], -pi), pi) / pi, rpy[2] / pi,
-                        0, 0, 0, 0, 0, 0};
-        for (int k = 0; k < 12; ++k) P.init_obs[k] = (float)o[k];
-    }
-    // action map constants: float32 like the reference (PBDroneEnv.py:113-116)
-    const double a_low = CF2X::KF * std::pow(CF2X::PWM2RPM_SCALE * CF2X::MIN_PWM + CF2X::PWM2RPM_CONST, 2);
-    const double a_high = CF2X::KF * std::pow(CF2X::PWM2RPM_SCALE * CF2X::MAX_PWM + CF2X::PWM2RPM_CONST, 2);
-    P.a_low = (float)a_low; P.a_high = (float)a_high;
-    P.kf = (float)CF2X::KF; P.km = (float)CF2X::KM;
-    P.pwm_scale = (float)CF2X::PWM2RPM_SCALE; P.pwm_const = (float)CF2X::PWM2RPM_CONST;
-    P.pwm_min = (float)CF2X::MIN_PWM; P.pwm_max = (float)CF2X::MAX_PWM;
-    const double gravity = CF2X::G * CF2X::M;
-    const double hover_rpm = std::sqrt(gravity / (4 * CF2X::KF));
-    const double max_rpm = std::sqrt((CF2X::T2W * gravity) / (4 * CF2X::KF));
-    const double max_thrust = 4 * CF2X::KF * max_rpm * max_rpm;
-    P.hover_rpm = (float)hover_rpm;
-    P.gravity = (float)gravity; P.inv_m = (float)(1.0 / CF2X::M);
-    P.arm_over_sqrt2 = (float)(CF2X::L / std::sqrt(2.0));
-    P.ixx = (float)CF2X::IXX; P.iyy = (float)CF2X::IYY; P.izz = (float)CF2X::IZZ;
-    P.inv_ixx = (float)(1.0 / CF2X::IXX); P.inv_iyy = (float)(1.0 / CF2X::IYY); P.inv_izz = (float)(1.0 / CF2X::IZZ);
-    P.drag_xy = (float)CF2X::DRAG_XY; P.drag_z = (float)CF2X::DRAG_Z;
-    P.gnd_coeff = (float)CF2X::GND_EFF_COEFF; P.prop_radius = (float)CF2X::PROP_RADIUS;
-    P.gnd_h_clip = (float)(0.25 * CF2X::PROP_RADIUS * std::sqrt((15 * max_rpm * max_rpm * CF2X::KF * CF2X::GND_EFF_COEFF) / max_thrust));
-    P.collision_half_h = (float)(CF2X::COLLISION_H / 2);
-    const double px[4] = {0.028, -0.028, -0.028, 0.028}, py[4] = {0.028, 0.028, -0.028, -0.028};   // safegym/cf2x.urdf:42,54,66,78
-    for (int k = 0; k < 4; ++k) { P.prop_x[k] = (float)px[k]; P.prop_y[k] = (float)py[k]; }
-    P.rw = rw;
-    P.seed = cfg->seed;
-    P.env_id_offset = cfg->env_id_offset;
-
-    // target table + segment table for the non-circle cylinder (PBDroneEnv.py:746-786), in double
-    std::vector<float4> h_t(T), h_s(2 * T);
-    for (int k = 0; k < T; ++k) {
-        const double* tk = cfg->targets + 3 * k;
-        h_t[k] = make_float4((float)tk[0], (float)tk[1], (float)tk[2], 0.f);
-        const double* b1 = (k == 0) ? cfg->init_xyz : cfg->targets + 3 * (k - 1);
-        double lv[3] = {tk[0] - b1[0], tk[1] - b1[1], tk[2] - b1[2]};
-        const double len = std::sqrt(lv[0] * lv[0] + lv[1] * lv[1] + lv[2] * lv[2]);
-        if (len == 0.0) {
-            h_s[2 * k] = make_float4((float)b1[0], (float)b1[1], (float)b1[2], 0.f);
-            h_s[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            const double u[3] = {lv[0] / len, lv[1] / len, lv[2] / len};
-            const double e1[3] = {b1[0] - 0.2 * u[0], b1[1] - 0.2 * u[1], b1[2] - 0.2 * u[2]};
-            const double e2[3] = {tk[0] + 0.2 * u[0], tk[1] + 0.2 * u[1], tk[2] + 0.2 * u[2]};
-            const double el = std::sqrt((e2[0] - e1[0]) * (e2[0] - e1[0]) + (e2[1] - e1[1]) * (e2[1] - e1[1]) + (e2[2] - e1[2]) * (e2[2] - e1[2]));
-            h_s[2 * k] = make_float4((float)e1[0], (float)e1[1], (float)e1[2], (float)el);
-            h_s[2 * k + 1] = make_float4((float)u[0], (float)u[1], (float)u[2], (float)len);
-        }
-    }
-    // constructor distance: ||INIT_XYZS[0] - target[0]|| (PBDroneEnv.py:137-138)
-    {
-        const double* t0 = cfg->targets;
-        const double dx = cfg->init_xyz[0] - t0[0], dy = cfg->init_xyz[1] - t0[1], dz = cfg->init_xyz[2] - t0[2];
-        e->d0 = (float)std::sqrt(dx * dx + dy * dy + dz * dz);
-    }
+    std::vector<float4> h_t, h_s;
+    dn::host::fill_params(*cfg, rw, P, h_t, h_s, e->d0);
 
     auto cleanup = [&](int code, const std::string& msg) {
         if (e->state_mem) cudaFree(e->state_mem);
@@ -692,6 +410,8 @@ int dn_destroy(dn_env* env) {
     if (!env) return DN_OK;
     DeviceGuard guard(env->device);
     cudaFree(env->state_mem); cudaFree(env->d_targets); cudaFree(env->d_segs); cudaFree(env->d_stats);
+    if (env->stage) cudaFree(env->stage);
+    if (env->host_stream) cudaStreamDestroy(env->host_stream);
     delete env;
     return DN_OK;
 }
@@ -744,6 +464,44 @@ int dn_step(dn_env* env, const dn_step_io* io, void* stream) { return launch_ste
 
 int dn_step_many(dn_env* env, const dn_step_io* io, int num_steps, int per_step_outputs, void* stream) {
     return launch_step(env, io, num_steps, per_step_outputs ? 1 : 0, stream);
+}
+
+int dn_step_host(dn_env* env, const dn_step_io* h) {
+    if (!env || !h) return fail(DN_EINVAL, "dn_step_host: null argument");
+    if (!h->actions || !h->obs || !h->reward || !h->done) return fail(DN_EINVAL, "dn_step_host: actions/obs/reward/done are required");
+    DeviceGuard guard(env->device);
+    const size_t N = env->P.n, D = env->P.obs_dim;
+    const size_t a256 = 255;
+    auto up = [&](size_t b) { return (b + a256) & ~a256; };
+    const size_t o_act = 0, o_obs = o_act + up(N * 16), o_term = o_obs + up(N * D * 4), o_rew = o_term + up(N * D * 4);
+    const size_t o_epr = o_rew + up(N * 4), o_fnd = o_epr + up(N * 4), o_epl = o_fnd + up(N * 4), o_done = o_epl + up(N * 4);
+    if (!env->stage) {
+        DN_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
+        DN_CUDA(cudaMalloc(&env->stage, o_done + up(N)));
+    }
+    char* d = static_cast<char*>(env->stage);
+    cudaStream_t st = env->host_stream;
+    DN_CUDA(cudaMemcpyAsync(d + o_act, h->actions, N * 16, cudaMemcpyHostToDevice, st));
+    dn_step_io io;
+    io.actions = reinterpret_cast<const float*>(d + o_act);
+    io.obs = reinterpret_cast<float*>(d + o_obs);
+    io.reward = reinterpret_cast<float*>(d + o_rew);
+    io.done = reinterpret_cast<uint8_t*>(d + o_done);
+    io.terminal_obs = h->terminal_obs ? reinterpret_cast<float*>(d + o_term) : nullptr;
+    io.found_targets = h->found_targets ? reinterpret_cast<int32_t*>(d + o_fnd) : nullptr;
+    io.episode_return = h->episode_return ? reinterpret_cast<float*>(d + o_epr) : nullptr;
+    io.episode_length = h->episode_length ? reinterpret_cast<int32_t*>(d + o_epl) : nullptr;
+    const int rc = launch_step(env, &io, 1, 1, st);
+    if (rc != DN_OK) return rc;
+    DN_CUDA(cudaMemcpyAsync(h->obs, d + o_obs, N * D * 4, cudaMemcpyDeviceToHost, st));
+    DN_CUDA(cudaMemcpyAsync(h->reward, d + o_rew, N * 4, cudaMemcpyDeviceToHost, st));
+    DN_CUDA(cudaMemcpyAsync(h->done, d + o_done, N, cudaMemcpyDeviceToHost, st));
+    if (h->found_targets) DN_CUDA(cudaMemcpyAsync(h->found_targets, d + o_fnd, N * 4, cudaMemcpyDeviceToHost, st));
+    if (h->terminal_obs) DN_CUDA(cudaMemcpyAsync(h->terminal_obs, d + o_term, N * D * 4, cudaMemcpyDeviceToHost, st));
+    if (h->episode_return) DN_CUDA(cudaMemcpyAsync(h->episode_return, d + o_epr, N * 4, cudaMemcpyDeviceToHost, st));
+    if (h->episode_length) DN_CUDA(cudaMemcpyAsync(h->episode_length, d + o_epl, N * 4, cudaMemcpyDeviceToHost, st));
+    DN_CUDA(cudaStreamSynchronize(st));
+    return DN_OK;
 }
 
 static int state_xfer(dn_env* env, const dn_state_view* v, bool set, void* stream) {

@@ -79,9 +79,11 @@ class GpuDroneVecEnv(_SB3VecEnv):
         self._h_found = pin(N, dtype=torch.int32)
         self._h_epr = pin(N, dtype=torch.float32)
         self._h_epl = pin(N, dtype=torch.int32)
-        self._d_actions = torch.zeros(N, 4, dtype=torch.float32, device=self.core.device)
-        self._stream = torch.cuda.Stream(device=self.core.device)
-        torch.cuda.synchronize(self.core.device)   # allocations above were made on the default stream
+        # one dn_step_host call per vector step: H2D(actions) -> fused kernel -> D2H(results), on the
+        # handle's own stream, into these pinned buffers
+        self._host_io = self.core._make_io(self._h_actions, self._h_obs, self._h_rew, self._h_done, self._h_term,
+                                           self._h_found, self._h_epr, self._h_epl)
+        torch.cuda.synchronize(self.core.device)
         self._t_start = time.time()
         self._pending = False
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
@@ -92,33 +94,20 @@ class GpuDroneVecEnv(_SB3VecEnv):
 
     # ------------------------------------------------------------- VecEnv API
     def reset(self) -> np.ndarray:
-        with torch.cuda.stream(self._stream):
-            obs = self.core.reset()
-            self._h_obs.copy_(obs, non_blocking=True)
-        self._stream.synchronize()
+        obs = self.core.reset()
+        self._h_obs.copy_(obs)
+        torch.cuda.current_stream(self.core.device).synchronize()
         return self._h_obs.numpy().copy()
 
     def step_async(self, actions: np.ndarray) -> None:
         a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 4)
         self._h_actions.numpy()[...] = a
-        c = self.core
-        with torch.cuda.stream(self._stream):
-            self._d_actions.copy_(self._h_actions, non_blocking=True)
-            c.step(self._d_actions)
-            self._h_obs.copy_(c.obs, non_blocking=True)
-            self._h_rew.copy_(c.reward, non_blocking=True)
-            self._h_done.copy_(c.done, non_blocking=True)
-            self._h_found.copy_(c.found_targets, non_blocking=True)
-            # rows of these three are only meaningful where done; tiny next to obs for small N
-            self._h_term.copy_(c.terminal_obs, non_blocking=True)
-            self._h_epr.copy_(c.episode_return, non_blocking=True)
-            self._h_epl.copy_(c.episode_length, non_blocking=True)
+        self.core.step_host(self._host_io)
         self._pending = True
 
     def step_wait(self):
         if not self._pending:
             raise RuntimeError("step_wait() called without step_async()")
-        self._stream.synchronize()
         self._pending = False
         obs = self._h_obs.numpy().copy()
         rews = self._h_rew.numpy().copy()

@@ -177,6 +177,13 @@ int dn_step(dn_env* env, const dn_step_io* io, void* stream);
  * ([N,...]).  Used for open-loop rollouts / the step-only throughput benchmark. */
 int dn_step_many(dn_env* env, const dn_step_io* io, int num_steps, int per_step_outputs, void* stream);
 
+/* dn_step with HOST buffers (pinned or pageable, caller-owned; same shapes as dn_step_io):
+ * copies the actions to the device, runs the fused step, copies obs / reward / done (and the
+ * optional outputs that are non-NULL) back and returns when they have landed.  This is the call
+ * an out-of-process / numpy caller such as SB3's VecEnv.step_wait makes; staging buffers and the
+ * stream belong to the handle. */
+int dn_step_host(dn_env* env, const dn_step_io* host_io);
+
 int dn_get_state(dn_env* env, const dn_state_view* view, void* stream);
 int dn_set_state(dn_env* env, const dn_state_view* view, void* stream);
 

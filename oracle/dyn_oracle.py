@@ -679,6 +679,7 @@ class OracleWorker:
     def step(self, action):
         obs, reward, terminated, truncated, info = self.env.step(action)
         self.last_terminated, self.last_truncated = bool(terminated), bool(truncated)
+        self.last_step_ang_v_norm = float(np.linalg.norm(self.env.ang_v))   # test instrumentation
         obs = self._normalize(obs)
         self.ep_return += float(reward)
         self.ep_len += 1

@@ -11,9 +11,12 @@ reported and excluded.
 from __future__ import annotations
 
 import numpy as np
-import torch
 
 POS_TOL, VEL_TOL, QUAT_TOL, OBS_TOL, REW_TOL = 1e-4, 1e-3, 1e-4, 1e-4, 1e-3
+# obs[9:12] is ang_v / |ang_v| (PBDroneEnv.py:383-384): the direction of a nearly-zero vector is
+# ill-conditioned (bang-bang torques cancel to ~1e-7 rad/s residues, in the reference too), so those
+# three entries are compared as  |d| <= OBS_TOL + ANGV_ABS_TOL / |ang_v_oracle|
+ANGV_ABS_TOL = 2e-6
 MARGIN_TOL = 2e-5          # oracle margin below which an FP32/FP64 discrete disagreement is a near-tie
 HORIZON_SUBSTEPS = 240
 
@@ -40,11 +43,18 @@ def upload_oracle_state(gpu_env, workers):
     gpu_env.set_state(st)
 
 
-def obs_error(a, b):
+def _np(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
+
+def obs_error(a, b, ang_v_norm=None):
     """max |a - b| over an observation row; the three Euler-angle entries (3..5, in units of pi) are
-    compared modulo 2 so that a +-pi wrap of atan2 on either side is not a discrepancy."""
+    compared modulo 2 so that a +-pi wrap of atan2 on either side is not a discrepancy; the ang_v
+    direction entries are de-weighted by their conditioning (see ANGV_ABS_TOL)."""
     d = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
     d[3:6] = np.minimum(d[3:6], np.abs(2.0 - d[3:6]))
+    if ang_v_norm is not None:
+        d[9:12] = np.maximum(d[9:12] - ANGV_ABS_TOL / max(ang_v_norm, 1e-30), 0.0)
     return float(d.max())
 
 
@@ -79,17 +89,22 @@ def run_lockstep(gpu_env, workers, actions, resync_every, report=None, check_sta
     """
     rep = report or ParityReport()
     T, N = actions.shape[0], actions.shape[1]
-    a_dev = torch.from_numpy(actions).to(gpu_env.device)
+    on_gpu = hasattr(gpu_env, "device")
+    if on_gpu:
+        import torch
+        a_dev = torch.from_numpy(actions).to(gpu_env.device)
     for t in range(T):
-        o, r, d, f = gpu_env.step(a_dev[t])
-        o, r, d, f = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), f.cpu().numpy()
-        term_obs = gpu_env.terminal_obs.cpu().numpy()
-        ep_r, ep_l = gpu_env.episode_return.cpu().numpy(), gpu_env.episode_length.cpu().numpy()
+        o, r, d, f = [_np(x).copy() for x in gpu_env.step(a_dev[t] if on_gpu else actions[t])]
+        term_obs = _np(gpu_env.terminal_obs)
+        has_ep = hasattr(gpu_env, "episode_return")
+        ep_r = _np(gpu_env.episode_return) if has_ep else None
+        ep_l = _np(gpu_env.episode_length) if has_ep else None
         need_resync = False
         for i, w in enumerate(workers):
             prev_idx = w.env._current_target_index
             oo, rr, dd, info = w.step(actions[t, i])
             rep.env_steps += 1
+            angn = w.last_step_ang_v_norm
             want_bits = (1 if w.last_terminated else 0) | (2 if w.last_truncated else 0)
             assert bool(want_bits) == bool(dd)
             tie = min_margin(w.env) < MARGIN_TOL
@@ -107,18 +122,19 @@ def run_lockstep(gpu_env, workers, actions, resync_every, report=None, check_sta
                 rep.near_ties += 1
             else:
                 rep.max_rew = max(rep.max_rew, rew_err)
-            rep.max_obs = max(rep.max_obs, obs_error(o[i], oo))
+            rep.max_obs = max(rep.max_obs, obs_error(o[i], oo, angn))
             assert rep.max_obs <= obs_tol, f"obs drift {rep.max_obs:.3e} at t={t} env={i}\n gpu {o[i]}\n ref {oo}"
             if dd:
                 rep.dones += 1
-                e = obs_error(term_obs[i], info["terminal_observation"])
+                e = obs_error(term_obs[i], info["terminal_observation"], angn)
                 assert e <= obs_tol, f"terminal obs mismatch {e:.3e} at t={t} env={i}"
-                assert int(ep_l[i]) == info["episode"]["l"]
-                assert abs(float(ep_r[i]) - info["episode"]["r"]) <= max(5e-3, 1e-5 * abs(info["episode"]["r"]))
+                if has_ep:
+                    assert int(ep_l[i]) == info["episode"]["l"]
+                    assert abs(float(ep_r[i]) - info["episode"]["r"]) <= max(5e-3, 1e-5 * abs(info["episode"]["r"]))
             if info["found_targets"] > prev_idx:
                 rep.captures += 1
         if check_state and ((t + 1) % resync_every == 0 or need_resync or t == T - 1):
-            st = {k: v.cpu().numpy() for k, v in gpu_env.get_state().items()}
+            st = {k: _np(v) for k, v in gpu_env.get_state().items()}
             ref = oracle_state_arrays([w.env for w in workers])
             if not need_resync:
                 rep.max_pos = max(rep.max_pos, float(np.max(np.abs(st["pos"] - ref["pos"]))))
