@@ -81,6 +81,10 @@ inline void fill_params(const dn_config& cfg, const RewardParams& rw, Params& P,
     P.x_high = (float)ad[3]; P.y_high = (float)ad[4]; P.z_high = (float)ad[5];
     const double mtd = std::fmax(std::fmax(std::fabs(ad[0]) + ad[3], std::fabs(ad[1]) + ad[4]), ad[5]);   // PBDroneEnv.py:91
     P.max_target_dist = static_cast<float>(mtd);
+    P.inv_x_high = (float)(1.0 / ad[3]); P.inv_y_high = (float)(1.0 / ad[4]); P.inv_z_high = (float)(1.0 / ad[5]);
+    P.inv_max_target_dist = (float)(1.0 / mtd);
+    P.thr2 = (float)(cfg.threshold * cfg.threshold);
+    P.cyl_limit2 = (float)((cfg.threshold + 0.2) * (cfg.threshold + 0.2));
     double q0[4];
     quat_from_euler(cfg.init_rpy, q0);
     for (int k = 0; k < 3; ++k) { P.init_pos[k] = (float)cfg.init_xyz[k]; P.init_seg_base[k] = (float)cfg.init_xyz[k]; }

@@ -65,6 +65,9 @@ struct Params {
     float threshold;
     float x_low, y_low, z_low, x_high, y_high, z_high;
     float max_target_dist;
+    float inv_x_high, inv_y_high, inv_z_high, inv_max_target_dist;   // reciprocals, computed in double
+    float thr2;              // threshold^2
+    float cyl_limit2;        // (threshold + 0.2)^2, segment tube (PBDroneEnv.py:786)
     float init_pos[3];
     float init_quat[4];
     float init_obs[12];      // observation of the spawn pose (entries 0..11)

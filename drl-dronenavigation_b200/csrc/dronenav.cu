@@ -75,36 +75,41 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
         r.finished = false; r.success = false; r.crash = false; r.done = 0; r.ep_ret = 0.f; r.ep_len = 0; r.found = 0; r.reward = 0.f;
         if (active) {
             const float4 act = __ldg(io.actions + static_cast<size_t>(t) * P.n + i);
-            float term_row[kMaxObs];
-            r = env_step<PHYS>(P, s, act, last_rpm_sum, obs_row, term_row);
+            r = env_step<PHYS>(P, s, act, last_rpm_sum, obs_row);      // obs_row = obs of the step (terminal obs if finished)
+            float* term_out = (write_out && r.finished && io.terminal_obs) ? io.terminal_obs + (orow + i) * D : nullptr;
             if (NORM) {
                 // NormalizeObservation sits inside Monitor and the worker's auto-reset
                 // (PBDroneSimulator.py:181): the terminal observation updates the running
                 // statistics in .step, the reset observation again in .reset (normalize.py:74-92).
                 const size_t N = P.n;
                 float* cnt_p = P.obs_rms + static_cast<size_t>(2 * D) * N + i;
-                float cnt = *cnt_p;
+                const float cnt = *cnt_p;
                 for (int k = 0; k < D; ++k) {
                     float* mp = P.obs_rms + static_cast<size_t>(k) * N + i;
                     float* vp = P.obs_rms + static_cast<size_t>(D + k) * N + i;
                     float m = *mp, v = *vp;
-                    const float tn = rms_update_normalize(term_row[k], m, v, cnt);
-                    term_row[k] = tn;
-                    if (r.finished) obs_row[k] = rms_update_normalize(obs_row[k], m, v, cnt + 1.0f);
-                    else obs_row[k] = tn;
+                    const float tn = rms_update_normalize(obs_row[k], m, v, cnt);
+                    float o = tn;
+                    if (r.finished) {
+                        if (term_out) term_out[k] = tn;
+                        const float raw = (k < 12) ? P.init_obs[k] : r.reset_obs_dist;
+                        o = rms_update_normalize(raw, m, v, cnt + 1.0f);
+                    }
+                    obs_row[k] = o;
                     *mp = m; *vp = v;
                 }
                 *cnt_p = cnt + (r.finished ? 2.0f : 1.0f);
+            } else if (r.finished) {
+                for (int k = 0; k < D; ++k) {
+                    if (term_out) term_out[k] = obs_row[k];
+                    obs_row[k] = (k < 12) ? P.init_obs[k] : r.reset_obs_dist;
+                }
             }
             if (write_out) {
                 io.reward[orow + i] = r.reward;
                 io.done[orow + i] = r.done;
                 if (io.found_targets) io.found_targets[orow + i] = r.found;
                 if (r.finished) {
-                    if (io.terminal_obs) {
-                        float* to = io.terminal_obs + (orow + i) * D;
-                        for (int k = 0; k < D; ++k) to[k] = term_row[k];
-                    }
                     if (io.episode_return) io.episode_return[orow + i] = r.ep_ret;
                     if (io.episode_length) io.episode_length[orow + i] = r.ep_len;
                 }
@@ -213,7 +218,7 @@ __global__ void reset_kernel(const __grid_constant__ Params P, const uint8_t* ma
     float o[kMaxObs];
 #pragma unroll
     for (int k = 0; k < 12; ++k) o[k] = P.init_obs[k];
-    o[12] = clip_f32_range(stale_dist / P.max_target_dist);
+    o[12] = stale_dist * P.inv_max_target_dist;
     if (NORM) {
         const size_t N = P.n;
         float* cnt_p = P.obs_rms + static_cast<size_t>(2 * D) * N + i;
@@ -278,6 +283,10 @@ __global__ void state_xfer_kernel(const __grid_constant__ Params P, const __grid
         }
     }
     if (SET) {
+        if (V.quat) {   // resetBasePositionAndOrientation -> read-back returns a unit quaternion
+            const float inv = rsqrtf(s.qx * s.qx + s.qy * s.qy + s.qz * s.qz + s.qw * s.qw);
+            s.qx *= inv; s.qy *= inv; s.qz *= inv; s.qw *= inv;
+        }
         s.bits = (static_cast<uint32_t>(idx) << kIdxShift) | (jf ? kJustFoundBit : 0u) | (static_cast<uint32_t>(steps) & kStepsMask);
         store_state(P, i, s);
     }

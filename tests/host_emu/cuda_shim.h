@@ -23,4 +23,5 @@ static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4);
 static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
+#define __expf(a) expf(a)
 template <typename T> static inline T __ldg(const T* p) { return *p; }

@@ -25,11 +25,14 @@ static void step_all(Emu* e, const float* actions, float* obs, float* reward, ui
         dn::EnvState s;
         dn::load_state(P, i, s);
         float lrs = (PHYS & 1) ? P.last_rpm_sum[i] : 0.f;
-        float term_row[dn::kMaxObs];
         const float4 a = make_float4(actions[4 * i], actions[4 * i + 1], actions[4 * i + 2], actions[4 * i + 3]);
-        dn::StepResult r = dn::env_step<PHYS>(P, s, a, lrs, obs + (size_t)i * P.obs_dim, term_row);
+        float* row = obs + (size_t)i * P.obs_dim;
+        dn::StepResult r = dn::env_step<PHYS>(P, s, a, lrs, row);
         reward[i] = r.reward; done[i] = r.done; found[i] = r.found;
-        if (r.finished) for (int k = 0; k < P.obs_dim; ++k) term_obs[(size_t)i * P.obs_dim + k] = term_row[k];
+        if (r.finished) for (int k = 0; k < P.obs_dim; ++k) {
+            term_obs[(size_t)i * P.obs_dim + k] = row[k];
+            row[k] = (k < 12) ? P.init_obs[k] : r.reset_obs_dist;
+        }
         dn::store_state(P, i, s);
         if (PHYS & 1) P.last_rpm_sum[i] = lrs;
     }
