@@ -347,8 +347,6 @@ def run_b200(args):
             "physics_steps_per_s": value * args.substeps,
             "clocks": clocks, "gpu_launches": int(launches), "l2_resident": resident}
 
-    if rank == 0 or world > 1:
-        pass
     # ---- single-GPU extras on rank 0 only: roofline, sweep, e2e, cpu baseline --------------------
     if world == 1:
         line["roofline"] = roofline(N, sec / K)
@@ -360,10 +358,7 @@ def run_b200(args):
                 e2.reset()
                 a2 = make_actions(4, n_big, args.actions, dev, seed=99)
                 k2 = max(10, min(K, int(2e8 // n_big)))
-                s2 = time_plain(e2, a2, k2, 3)
-                s1 = None
-                if args.substeps != 1:     # S = 1 (240/240 Hz, the reference default): the pure-HBM regime
-                    pass
+                s2 = time_plain(e2, a2, k2, 24)      # 24 warm-up steps: episodes are de-phased (steady-state reset mix)
                 rf = roofline(n_big, s2 / k2)
                 sweep.append({"envs": n_big, "value": n_big * k2 / s2, "us_per_launch": 1e6 * s2 / k2, "steps": k2,
                               "roofline_frac": rf["frac"], "achieved_gbs": rf["achieved"],
@@ -384,7 +379,7 @@ def run_b200(args):
             e3 = make_env(n_big, a1, dev); e3.reset()
             a3 = make_actions(4, n_big, args.actions, dev, seed=98)
             k3 = max(10, min(K, int(2e8 // n_big)))
-            s3 = time_plain(e3, a3, k3, 3)
+            s3 = time_plain(e3, a3, k3, 24)
             line["roofline_hbm_s1"] = roofline(n_big, s3 / k3)
             line["roofline_hbm_s1"]["substeps"] = 1
             e3.close(); del e3, a3

@@ -176,6 +176,14 @@ class BatchedDroneEnv:
                 "dn_step_many")
         return out
 
+    def action_to_rpm(self, actions: torch.Tensor) -> torch.Tensor:
+        """PBDroneEnv._preprocessAction(rescale_action(a)) elementwise (any shape, float32 CUDA)."""
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(a)
+        L.check(self._lib.dn_action_to_rpm(self._handle, a.data_ptr(), out.data_ptr(), a.numel(), self._stream()),
+                "dn_action_to_rpm")
+        return out
+
     def _state_view(self, tensors: Dict[str, torch.Tensor]):
         v = L.dn_state_view()
         for name in L.STATE_FIELDS:

@@ -50,11 +50,11 @@ inline void euler_from_quat(const double q[4], double rpy[3]) {    // p.getEuler
 inline bool reward_table(int id, dn::RewardParams& w) {
     switch (id) {
         case DN_REWARD_DEFAULT:    // PBDroneEnv.py:475-607
-            w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.7f, 0.3f, 1.f, 25.f}; return true;
+            w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.7f, 0.3f, 1.f, 25.f, 0.04f}; return true;
         case DN_REWARD_DUMMY:      // dummy_env.py:446-550,587-598 (smoothness thresholds 0.1 / 0.1)
-            w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.1f, 0.1f, 1.f, 25.f}; return true;
+            w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.1f, 0.1f, 1.f, 25.f, 0.04f}; return true;
         case DN_REWARD_THRUSTENV:  // ThrustEnv.py:368-463 (-4 crash, +25 / +1000, 20 x progress, no orientation / smoothness)
-            w = {-4.f, 1000.f, 25.f, 0.f, 3.f, 2.f, 20.f, 0.f, 0.f, 0.f, 0.f, 25.f}; return true;
+            w = {-4.f, 1000.f, 25.f, 0.f, 3.f, 2.f, 20.f, 0.f, 0.f, 0.f, 0.f, 25.f, 0.04f}; return true;
         default: return false;
     }
 }
@@ -105,6 +105,11 @@ inline void fill_params(const dn_config& cfg, const RewardParams& rw, Params& P,
     P.kf = (float)CF2X::KF; P.km = (float)CF2X::KM;
     P.pwm_scale = (float)CF2X::PWM2RPM_SCALE; P.pwm_const = (float)CF2X::PWM2RPM_CONST;
     P.pwm_min = (float)CF2X::MIN_PWM; P.pwm_max = (float)CF2X::MAX_PWM;
+    // divisors exactly as numpy forms them in float32, and their correctly rounded float32 reciprocals
+    P.a_span = P.a_high - P.a_low;                       // float32 subtraction (PBDroneEnv.py:968)
+    P.inv_a_span = (float)(1.0 / (double)P.a_span);
+    P.inv_kf = (float)(1.0 / (double)P.kf);
+    P.inv_pwm_scale = (float)(1.0 / (double)P.pwm_scale);
     const double gravity = CF2X::G * CF2X::M;
     const double hover_rpm = std::sqrt(gravity / (4 * CF2X::KF));
     const double max_rpm = std::sqrt((CF2X::T2W * gravity) / (4 * CF2X::KF));

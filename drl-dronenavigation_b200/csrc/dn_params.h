@@ -27,12 +27,14 @@ struct RewardParams {
     float smooth_lin_thr, smooth_ang_thr;  // :599
     float smooth_w;          // 1 = smoothness term on, 0 = off (ThrustEnv)
     float divisor;           // :571
+    float inv_divisor;       // 1 / divisor (host, double)
 };
 
 struct Stats {               // device mirror of dn_stats
     double             return_sum;
     unsigned long long length_sum, episodes, successes, found_targets, crashes, truncations;
 };
+typedef Stats BlockStats;    // one accumulation slot per CTA of the step grid (no atomics)
 
 // Per-env persistent state in HBM: seven float4 planes ("structure of float4 arrays"),
 // plane p of env i at s[p][i].  One LDG.128 / STG.128 per plane per env, consecutive
@@ -74,6 +76,7 @@ struct Params {
     float init_seg_base[3];  // INIT_XYZS[0], base of segment 0 (PBDroneEnv.py:746-748)
     // action map (PBDroneEnv.py:113-116,872-895,949-971; env_utils.py:8-59)
     float a_low, a_high, kf, km, pwm_scale, pwm_const, pwm_min, pwm_max, hover_rpm;
+    float a_span, inv_a_span, inv_kf, inv_pwm_scale;   // float32 divisors and their RN reciprocals (div_const_rn)
     // rigid body (BaseAviary.py:899-958)
     float gravity, inv_m, arm_over_sqrt2, ixx, iyy, izz, inv_ixx, inv_iyy, inv_izz;
     // add-ons (BaseAviary.py:798-865)
@@ -87,7 +90,7 @@ struct Params {
     float4* s[kPlanes];
     float* last_rpm_sum;     // [N], drag only
     float* obs_rms;          // [(2*obs_dim+1)][N] mean planes | var planes | count, normalize_obs only
-    Stats* stats;
+    BlockStats* block_stats; // [ceil(N / CTA)] Monitor statistics slots
 };
 
 struct StepIO {

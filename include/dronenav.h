@@ -184,6 +184,12 @@ int dn_step_many(dn_env* env, const dn_step_io* io, int num_steps, int per_step_
  * stream belong to the handle. */
 int dn_step_host(dn_env* env, const dn_step_io* host_io);
 
+/* The action map alone, elementwise over `n` action components (device pointers):
+ * PBDroneEnv._preprocessAction(rescale_action(a)) (PBDroneEnv.py:872-895,949-971) or the RPM map
+ * (BaseSingleAgentAviary.py:176-179), whichever the handle was created with.  Bit-identical to
+ * the reference's float32 numpy arithmetic; used by the parity tests and by callers that log RPMs. */
+int dn_action_to_rpm(dn_env* env, const float* actions, float* rpm_out, int64_t n, void* stream);
+
 int dn_get_state(dn_env* env, const dn_state_view* view, void* stream);
 int dn_set_state(dn_env* env, const dn_state_view* view, void* stream);
 

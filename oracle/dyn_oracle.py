@@ -215,6 +215,23 @@ def thrust_to_rpm(action, bounds, c: CF2XConstants = CF2X):
     return c.PWM2RPM_SCALE * pwm + c.PWM2RPM_CONST
 
 
+def thrust_to_rpm_batch(actions, bounds, c: CF2XConstants = CF2X):
+    """thrust_to_rpm for many 4-vectors at once ([M, 4] float32): the same float32 operations with
+    n_motor = 1 written out (the literal function derives n_motor from the array size, so it only
+    accepts one 4-vector).  tests/test_oracle_kat.py checks the two agree bit for bit."""
+    a = np.asarray(actions, dtype=np.float32).reshape(-1, 4)
+    thrust = np.clip(a, bounds[0], bounds[1])
+    thrust = np.clip(thrust, np.zeros_like(thrust), None)
+    pwm = (np.sqrt(thrust / 1 / c.KF) - c.PWM2RPM_CONST) / c.PWM2RPM_SCALE
+    pwm = np.clip(pwm, c.MIN_PWM, c.MAX_PWM)
+    return c.PWM2RPM_SCALE * pwm + c.PWM2RPM_CONST
+
+
+def rescale_action_batch(actions, bounds):
+    """rescale_action for [M, 4] float32 (numpy broadcasting makes the literal function batch-safe)."""
+    return rescale_action(np.asarray(actions, dtype=np.float32).reshape(-1, 4), bounds)
+
+
 def rpm_action_to_rpm(action, c: CF2XConstants = CF2X, numpy_legacy_cast: bool = True):
     """BaseSingleAgentAviary.py:176-179.  Under the reference's pinned numpy 1.26
     (uv.lock:231-232) ``np.float64 scalar * float32 array`` stays float32

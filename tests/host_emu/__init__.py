@@ -33,6 +33,8 @@ class HostEmuEnv:
         self.lib = C.CDLL(build())
         self.lib.emu_create.restype = C.c_void_p
         self.lib.emu_create.argtypes = [C.POINTER(L.dn_config)]
+        self.lib.emu_action_to_rpm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
+        self.lib.emu_action_to_rpm.restype = None
         for name, n in (("emu_step", 7), ("emu_get_planes", 2), ("emu_set_planes", 2), ("emu_set_last_rpm_sum", 2), ("emu_destroy", 1)):
             getattr(self.lib, name).argtypes = [C.c_void_p] * n
             getattr(self.lib, name).restype = None
@@ -68,6 +70,12 @@ class HostEmuEnv:
         self.lib.emu_step(self.h, self._p(a), self._p(self.obs), self._p(self.reward), self._p(self.done),
                           self._p(self.terminal_obs), self._p(self.found_targets))
         return self.obs.copy(), self.reward.copy(), self.done.copy(), self.found_targets.copy()
+
+    def action_to_rpm(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        out = np.empty_like(a)
+        self.lib.emu_action_to_rpm(self.h, self._p(a), self._p(out), a.size)
+        return out
 
     def _planes(self):
         pl = np.zeros((7, self.num_envs, 4), np.float32)

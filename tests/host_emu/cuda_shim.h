@@ -17,6 +17,7 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }

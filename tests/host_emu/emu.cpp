@@ -13,7 +13,6 @@ struct Emu {
     std::vector<float4> planes[dn::kPlanes];
     std::vector<float4> targets, segs;
     std::vector<float> last_rpm_sum, obs_rms;
-    dn::Stats stats;
     int normalize_obs;
     float d0;
 };
@@ -45,12 +44,11 @@ Emu* emu_create(const dn_config* cfg) {
     if (!dn::host::reward_table(cfg->reward_id, rw)) return nullptr;
     Emu* e = new Emu();
     memset(&e->P, 0, sizeof(e->P));
-    memset(&e->stats, 0, sizeof(e->stats));
     dn::host::fill_params(*cfg, rw, e->P, e->targets, e->segs, e->d0);
     const int N = cfg->num_envs;
     e->normalize_obs = cfg->normalize_obs;
     for (int k = 0; k < dn::kPlanes; ++k) { e->planes[k].assign(N, float4{0, 0, 0, 0}); e->P.s[k] = e->planes[k].data(); }
-    e->P.targets = e->targets.data(); e->P.segs = e->segs.data(); e->P.stats = &e->stats;
+    e->P.targets = e->targets.data(); e->P.segs = e->segs.data();
     if (cfg->physics & DN_PHYS_DRAG) { e->last_rpm_sum.assign(N, 0.f); e->P.last_rpm_sum = e->last_rpm_sum.data(); }
     for (int i = 0; i < N; ++i) {
         dn::EnvState s;
@@ -71,6 +69,10 @@ void emu_step(Emu* e, const float* actions, float* obs, float* reward, uint8_t* 
         case 2: step_all<2>(e, actions, obs, reward, done, term_obs, found); break;
         default: step_all<3>(e, actions, obs, reward, done, term_obs, found); break;
     }
+}
+
+void emu_action_to_rpm(Emu* e, const float* a, float* out, long long n) {
+    for (long long i = 0; i < n; ++i) out[i] = dn::action_to_rpm(e->P, a[i]);
 }
 
 // raw access to the packed planes: [7][N][4] floats

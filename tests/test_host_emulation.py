@@ -45,6 +45,22 @@ def test_device_logic_lockstep(track, S, mode, N, T):
     env.close()
 
 
+def test_device_action_map_bit_exact():
+    """Constant-divisor division by FMA residual (div_const_rn) == numpy's float32 division, bit for bit,
+    over every float32 in the pass-through band of the THRUST map and a random sample outside it."""
+    from oracle.dyn_oracle import physical_action_bounds, rescale_action_batch, thrust_to_rpm_batch
+    env, _ = _make("circle", 1, 1)
+    b = physical_action_bounds()
+    band = np.arange(np.float32(0.0895).view(np.int32), np.float32(0.0975).view(np.int32) + 1, dtype=np.int32).view(np.float32)
+    rnd = np.random.default_rng(0).uniform(-1.2, 1.2, size=200_000).astype(np.float32)
+    a = np.concatenate([band, rnd])
+    a = a[: (a.size // 4) * 4]
+    ref = thrust_to_rpm_batch(rescale_action_batch(a, b), b).reshape(-1)
+    got = env.action_to_rpm(a)
+    np.testing.assert_array_equal(got.view(np.int32), ref.view(np.int32))
+    env.close()
+
+
 @pytest.mark.parametrize("physics,oracle_physics", [(1, "dyn_drag"), (2, "dyn_gnd"), (3, "dyn_gnd_drag")])
 def test_device_logic_physics_addons(physics, oracle_physics):
     env, workers = _make("circle", 6, 8, physics=physics, oracle_physics=oracle_physics)

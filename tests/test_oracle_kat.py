@@ -40,6 +40,18 @@ def test_action_map_table():
         np.testing.assert_allclose(r, want, rtol=2e-7)
 
 
+def test_batched_action_map_equals_literal():
+    from oracle.dyn_oracle import rescale_action_batch, thrust_to_rpm_batch
+    b = physical_action_bounds()
+    rng = np.random.default_rng(3)
+    a = np.concatenate([rng.uniform(-1, 1, (200, 4)), 0.0935 + 0.005 * rng.uniform(-1, 1, (400, 4))]).astype(np.float32)
+    got = thrust_to_rpm_batch(rescale_action_batch(a, b), b)
+    assert got.dtype == np.float32
+    for i in range(a.shape[0]):
+        ref = thrust_to_rpm(rescale_action(a[i], b), b)
+        np.testing.assert_array_equal(got[i].view(np.int32), ref.view(np.int32))
+
+
 def test_rotation_and_euler_roundtrip():
     rng = np.random.default_rng(0)
     for _ in range(200):

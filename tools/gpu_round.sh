@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 20 --warmup 3 --no-cpu --no-vecenv --sweep 4194304 > gpurun_out/ncu_bench.log 2>&1
 for cfg in "4194304 8" "4194304 1" "4096 8"; do
   set -- $cfg
-  ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 3 -c 1 -f -o gpurun_out/prof_n$1_s$2 \
-      python tools/profile_step.py $1 $2 > gpurun_out/ncu_n$1_s$2.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 30 -c 1 -f -o gpurun_out/prof_n$1_s$2 \
+      python tools/profile_step.py $1 $2 34 > gpurun_out/ncu_n$1_s$2.log 2>&1
 done
 ls -la gpurun_out
