@@ -54,7 +54,7 @@ __device__ __forceinline__ void bulk_store_wait_read() {
 // loads/stores, and dn_episode_stats reduces the slots.  (A first version used one atomicAdd
 // per warp per counter on 7 global addresses; with ~12 % of the envs finishing per step that
 // serialised in L2 and doubled the step time at 4 Mi envs.)  Sums are deterministic.
-struct BlockAcc { float ret; int len, fnd, eps, suc, cra, tru; };
+struct BlockAcc { float ret; int len, fnd, eps_suc, cra_tru; };   // eps|suc and cra|tru packed 16:16 (<= 65535 steps per launch)
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
@@ -62,7 +62,8 @@ template <int PHYS, bool NORM>
 __global__ void __launch_bounds__(kBlock)
 step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int num_steps, int per_step) {
     __shared__ __align__(128) float tile[kBlock * kMaxObs];
-    __shared__ BlockAcc wacc[kBlock / 32];
+    __shared__ BlockAcc wacc[kBlock / 32];       // per-warp partials: ret, len, fnd, episodes, successes
+    __shared__ int2 wextra[kBlock / 32];         //                    crashes, truncations
     const int tid = threadIdx.x;
     const int base = blockIdx.x * kBlock;
     const int i = base + tid;
@@ -77,7 +78,7 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
         load_state(P, i, s);
         if (PHYS & 1) last_rpm_sum = P.last_rpm_sum[i];
     }
-    BlockAcc acc = {0.f, 0, 0, 0, 0, 0, 0};      // this thread's finished episodes over the launch
+    BlockAcc acc = {0.f, 0, 0, 0, 0};            // this thread's finished episodes over the launch
 
     for (int t = 0; t < num_steps; ++t) {
         const bool write_out = per_step || (t == num_steps - 1);
@@ -109,10 +110,14 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
                 }
                 *cnt_p = cnt + (r.finished ? 2.0f : 1.0f);
             } else if (r.finished) {
-                for (int k = 0; k < D; ++k) {
-                    if (term_out) term_out[k] = obs_row[k];
-                    obs_row[k] = (k < 12) ? P.init_obs[k] : r.reset_obs_dist;
+                if (term_out) {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) term_out[k] = obs_row[k];
+                    if (D == 13) term_out[12] = obs_row[12];
                 }
+#pragma unroll
+                for (int k = 0; k < 12; ++k) obs_row[k] = P.init_obs[k];
+                if (D == 13) obs_row[12] = r.reset_obs_dist;
             }
             if (write_out) {
                 io.reward[o] = r.reward;
@@ -124,8 +129,9 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
                 }
             }
             if (r.finished) {
-                acc.ret += r.ep_ret; acc.len += r.ep_len; acc.fnd += r.found; acc.eps += 1;
-                acc.suc += r.success ? 1 : 0; acc.cra += r.crash ? 1 : 0; acc.tru += (r.done == DN_DONE_TRUNCATED) ? 1 : 0;
+                acc.ret += r.ep_ret; acc.len += r.ep_len; acc.fnd += r.found;
+                acc.eps_suc += 1 + (r.success ? 0x10000 : 0);
+                acc.cra_tru += (r.crash ? 1 : 0) + ((r.done == DN_DONE_TRUNCATED) ? 0x10000 : 0);
             }
         }
         // ---- observation tile: shared memory -> one TMA bulk store per CTA ----------
@@ -153,21 +159,23 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
         if (PHYS & 1) P.last_rpm_sum[i] = last_rpm_sum;
     }
     // ---- Monitor statistics: warp shuffle -> shared -> this CTA's slot (no atomics) ----
-    const int eps_w = warp_sum(acc.eps);
+    // (per-lane counts are < 2^16 per launch, so a warp's packed 16:16 sums need the two halves summed apart)
+    const int eps_w = warp_sum(acc.eps_suc & 0xffff);
     if (__syncthreads_or(eps_w != 0)) {            // CTA-uniform: any finished episode in this CTA during the launch
         float ret = acc.ret;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) ret += __shfl_xor_sync(0xffffffffu, ret, d);
-        const int len = warp_sum(acc.len), fnd = warp_sum(acc.fnd), suc = warp_sum(acc.suc), cra = warp_sum(acc.cra), tru = warp_sum(acc.tru);
-        if ((tid & 31) == 0) wacc[tid >> 5] = BlockAcc{ret, len, fnd, eps_w, suc, cra, tru};
+        const int len = warp_sum(acc.len), fnd = warp_sum(acc.fnd), suc = warp_sum(acc.eps_suc >> 16);
+        const int cra = warp_sum(acc.cra_tru & 0xffff), tru = warp_sum(acc.cra_tru >> 16);
+        if ((tid & 31) == 0) { wacc[tid >> 5] = BlockAcc{ret, len, fnd, eps_w, suc}; wextra[tid >> 5] = make_int2(cra, tru); }
         __syncthreads();
         if (tid == 0) {
             BlockStats b = P.block_stats[blockIdx.x];
 #pragma unroll
             for (int w = 0; w < kBlock / 32; ++w) {
                 b.return_sum += static_cast<double>(wacc[w].ret);
-                b.length_sum += wacc[w].len; b.found_targets += wacc[w].fnd; b.episodes += wacc[w].eps;
-                b.successes += wacc[w].suc; b.crashes += wacc[w].cra; b.truncations += wacc[w].tru;
+                b.length_sum += wacc[w].len; b.found_targets += wacc[w].fnd; b.episodes += wacc[w].eps_suc;
+                b.successes += wacc[w].cra_tru; b.crashes += wextra[w].x; b.truncations += wextra[w].y;
             }
             P.block_stats[blockIdx.x] = b;
         }

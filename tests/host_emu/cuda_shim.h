@@ -25,4 +25,5 @@ static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; 
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
 #define __expf(a) expf(a)
+static inline float __fdividef(float a, float b) { return a / b; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
