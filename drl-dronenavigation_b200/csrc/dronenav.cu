@@ -58,24 +58,27 @@ struct BlockAcc { float ret; int len, fnd, eps_suc, cra_tru; };   // eps|suc and
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
-template <int PHYS, bool NORM>
-__global__ void __launch_bounds__(kBlock)
-step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int num_steps, int per_step) {
+// MULTI = false: exactly one control step per launch (dn_step): no step loop, no per-thread
+// statistics carried across steps, <= 64 registers (8 CTAs / SM).  MULTI = true: dn_step_many.
+template <int PHYS, bool NORM, bool MULTI>
+__global__ void __launch_bounds__(kBlock, MULTI ? 6 : 8)
+step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int num_steps_arg, int per_step_arg) {
     __shared__ __align__(128) float tile[kBlock * kMaxObs];
     __shared__ BlockAcc wacc[kBlock / 32];       // per-warp partials: ret, len, fnd, episodes, successes
     __shared__ int2 wextra[kBlock / 32];         //                    crashes, truncations
+    const int num_steps = MULTI ? num_steps_arg : 1;
+    const int per_step = MULTI ? per_step_arg : 1;
     const int tid = threadIdx.x;
     const int base = blockIdx.x * kBlock;
     const int i = base + tid;
     const bool active = i < P.n;
     const int D = P.obs_dim;
-    const int n_here = min(kBlock, P.n - base);
     float* const obs_row = tile + tid * D;
 
     EnvState s;
     float last_rpm_sum = 0.0f;
     if (active) {
-        load_state(P, i, s);
+        load_core(P, i, s);
         if (PHYS & 1) last_rpm_sum = P.last_rpm_sum[i];
     }
     BlockAcc acc = {0.f, 0, 0, 0, 0};            // this thread's finished episodes over the launch
@@ -85,7 +88,7 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
         const size_t o = (per_step ? static_cast<size_t>(t) * P.n : 0) + i;      // output element index of this env
         if (active) {
             const float4 act = __ldg(io.actions + static_cast<size_t>(t) * P.n + i);
-            const StepResult r = env_step<PHYS>(P, s, act, last_rpm_sum, obs_row);   // obs_row: obs of the step (terminal obs if finished)
+            const StepResult r = env_step<PHYS>(P, i, s, act, last_rpm_sum, obs_row);   // obs_row: obs of the step (terminal obs if finished)
             float* term_out = (write_out && r.finished && io.terminal_obs) ? io.terminal_obs + o * D : nullptr;
             if (NORM) {
                 // NormalizeObservation sits inside Monitor and the worker's auto-reset
@@ -133,9 +136,14 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
                 acc.eps_suc += 1 + (r.success ? 0x10000 : 0);
                 acc.cra_tru += (r.crash ? 1 : 0) + ((r.done == DN_DONE_TRUNCATED) ? 0x10000 : 0);
             }
+            // stored every step: the next step's epilogue (MULTI) re-reads the bookkeeping planes and, on a
+            // crash, the entry position from memory; the physics planes stay in registers across steps
+            store_state(P, i, s);
+            if ((PHYS & 1) && t == num_steps - 1) P.last_rpm_sum[i] = last_rpm_sum;
         }
         // ---- observation tile: shared memory -> one TMA bulk store per CTA ----------
         if (write_out) {
+            const int n_here = min(kBlock, P.n - base);
             float* gdst = io.obs + ((per_step ? static_cast<size_t>(t) * P.n : 0) + base) * D;
             const uint32_t bytes = static_cast<uint32_t>(n_here) * D * 4u;
             const bool bulk_ok = ((reinterpret_cast<uintptr_t>(gdst) & 15u) == 0) && ((bytes & 15u) == 0);
@@ -144,19 +152,15 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
                 __syncthreads();
                 if (tid == 0) {
                     bulk_store_g2s_commit(gdst, tile, bytes);
-                    if (t + 1 < num_steps) bulk_store_wait_read();   // tile is rewritten by the next step
+                    if (MULTI && t + 1 < num_steps) bulk_store_wait_read();   // tile is rewritten by the next step
                 }
-                if (t + 1 < num_steps) __syncthreads();
+                if (MULTI && t + 1 < num_steps) __syncthreads();
             } else {
                 __syncthreads();
                 for (int j = tid; j < n_here * D; j += kBlock) gdst[j] = tile[j];
-                if (t + 1 < num_steps) __syncthreads();
+                if (MULTI && t + 1 < num_steps) __syncthreads();
             }
         }
-    }
-    if (active) {
-        store_state(P, i, s);
-        if (PHYS & 1) P.last_rpm_sum[i] = last_rpm_sum;
     }
     // ---- Monitor statistics: warp shuffle -> shared -> this CTA's slot (no atomics) ----
     // (per-lane counts are < 2^16 per launch, so a warp's packed 16:16 sums need the two halves summed apart)
@@ -511,7 +515,11 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
     const int N = env->P.n;
     const dim3 grid((N + dn::kBlock - 1) / dn::kBlock), block(dn::kBlock);
     const int phys = env->P.physics & 3;
-#define DN_LAUNCH(PH, NO) dn::step_kernel<PH, NO><<<grid, block, 0, st>>>(env->P, k, num_steps, per_step)
+#define DN_LAUNCH(PH, NO)                                                                              \
+    do {                                                                                               \
+        if (num_steps == 1) dn::step_kernel<PH, NO, false><<<grid, block, 0, st>>>(env->P, k, 1, 1);   \
+        else dn::step_kernel<PH, NO, true><<<grid, block, 0, st>>>(env->P, k, num_steps, per_step);   \
+    } while (0)
     if (env->normalize_obs) {
         switch (phys) { case 0: DN_LAUNCH(0, true); break; case 1: DN_LAUNCH(1, true); break;
                         case 2: DN_LAUNCH(2, true); break; default: DN_LAUNCH(3, true); break; }

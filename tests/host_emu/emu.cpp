@@ -22,11 +22,11 @@ static void step_all(Emu* e, const float* actions, float* obs, float* reward, ui
     const dn::Params& P = e->P;
     for (int i = 0; i < P.n; ++i) {
         dn::EnvState s;
-        dn::load_state(P, i, s);
+        dn::load_core(P, i, s);
         float lrs = (PHYS & 1) ? P.last_rpm_sum[i] : 0.f;
         const float4 a = make_float4(actions[4 * i], actions[4 * i + 1], actions[4 * i + 2], actions[4 * i + 3]);
         float* row = obs + (size_t)i * P.obs_dim;
-        dn::StepResult r = dn::env_step<PHYS>(P, s, a, lrs, row);
+        dn::StepResult r = dn::env_step<PHYS>(P, i, s, a, lrs, row);
         reward[i] = r.reward; done[i] = r.done; found[i] = r.found;
         if (r.finished) for (int k = 0; k < P.obs_dim; ++k) {
             term_obs[(size_t)i * P.obs_dim + k] = row[k];

@@ -248,7 +248,7 @@ def test_vec_env_protocol_against_oracle_workers():
                 assert infos[i]["episode"]["l"] == info["episode"]["l"]
                 assert infos[i]["TimeLimit.truncated"] == info["TimeLimit.truncated"]
                 np.testing.assert_allclose(infos[i]["terminal_observation"], info["terminal_observation"], atol=2e-3, rtol=2e-3)
-    assert n_done > 20
+    assert n_done > 10
     assert venv.env_is_wrapped(type("Monitor", (), {}))[0]
     venv.close()
 
