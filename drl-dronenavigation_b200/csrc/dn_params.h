@@ -91,6 +91,7 @@ struct Params {
     float* last_rpm_sum;     // [N], drag only
     float* obs_rms;          // [(2*obs_dim+1)][N] mean planes | var planes | count, normalize_obs only
     BlockStats* block_stats; // [ceil(N / CTA)] Monitor statistics slots
+    int prefetch_ctas;       // software-prefetch distance in CTAs (= CTAs resident on the whole GPU)
 };
 
 struct StepIO {

@@ -45,15 +45,18 @@ __device__ __forceinline__ void bulk_store_g2s_commit(void* gdst, const void* ss
 __device__ __forceinline__ void bulk_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// fire-and-forget L2 prefetch: raises the number of DRAM requests in flight without holding registers
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
 
 // ---------------------------------------------------------------------------
 // the fused step kernel
 // ---------------------------------------------------------------------------
-// Monitor statistics without atomics: every CTA owns one BlockStats slot (stream-ordered
-// launches of the same grid never overlap), adds its finished episodes to it with plain
-// loads/stores, and dn_episode_stats reduces the slots.  (A first version used one atomicAdd
-// per warp per counter on 7 global addresses; with ~12 % of the envs finishing per step that
-// serialised in L2 and doubled the step time at 4 Mi envs.)  Sums are deterministic.
+// Monitor statistics without contended atomics: every CTA owns one BlockStats slot, its warps add
+// their finished episodes to it, and dn_episode_stats reduces the slots.  (A first version used one
+// atomicAdd per warp per counter on 7 GLOBAL addresses; with ~12 % of the envs finishing per step
+// that serialised in L2 and doubled the step time at 4 Mi envs.)
 struct BlockAcc { float ret; int len, fnd, eps_suc, cra_tru; };   // eps|suc and cra|tru packed 16:16 (<= 65535 steps per launch)
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
@@ -64,8 +67,6 @@ template <int PHYS, bool NORM, bool MULTI>
 __global__ void __launch_bounds__(kBlock, MULTI ? 6 : 8)
 step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int num_steps_arg, int per_step_arg) {
     __shared__ __align__(128) float tile[kBlock * kMaxObs];
-    __shared__ BlockAcc wacc[kBlock / 32];       // per-warp partials: ret, len, fnd, episodes, successes
-    __shared__ int2 wextra[kBlock / 32];         //                    crashes, truncations
     const int num_steps = MULTI ? num_steps_arg : 1;
     const int per_step = MULTI ? per_step_arg : 1;
     const int tid = threadIdx.x;
@@ -80,6 +81,16 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
     if (active) {
         load_core(P, i, s);
         if (PHYS & 1) last_rpm_sum = P.last_rpm_sum[i];
+        // The bookkeeping planes are consumed ~1000 instructions from now: start them towards L2.
+        prefetch_l2(&P.s[4][i]); prefetch_l2(&P.s[5][i]); prefetch_l2(&P.s[6][i]);
+        // Software pipelining across CTAs: the CTA that will run on this SM slot one "GPU-full of CTAs"
+        // later finds its physics planes and actions already in L2 (the kernel is otherwise limited by
+        // the DRAM latency exposed at the top of each thread, not by bandwidth or issue slots).
+        const long long j = static_cast<long long>(i) + static_cast<long long>(P.prefetch_ctas) * kBlock;
+        if (j < P.n) {
+            prefetch_l2(&P.s[0][j]); prefetch_l2(&P.s[1][j]); prefetch_l2(&P.s[2][j]); prefetch_l2(&P.s[3][j]);
+            prefetch_l2(io.actions + j);
+        }
     }
     BlockAcc acc = {0.f, 0, 0, 0, 0};            // this thread's finished episodes over the launch
 
@@ -141,50 +152,55 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
             store_state(P, i, s);
             if ((PHYS & 1) && t == num_steps - 1) P.last_rpm_sum[i] = last_rpm_sum;
         }
-        // ---- observation tile: shared memory -> one TMA bulk store per CTA ----------
+        // ---- observation rows: shared memory -> one TMA bulk store PER WARP (32 rows are contiguous both in
+        // shared and in global memory, 32 * obs_dim * 4 bytes is a multiple of 16): no CTA-wide barrier.
         if (write_out) {
-            const int n_here = min(kBlock, P.n - base);
-            float* gdst = io.obs + ((per_step ? static_cast<size_t>(t) * P.n : 0) + base) * D;
-            const uint32_t bytes = static_cast<uint32_t>(n_here) * D * 4u;
-            const bool bulk_ok = ((reinterpret_cast<uintptr_t>(gdst) & 15u) == 0) && ((bytes & 15u) == 0);
-            if (bulk_ok) {
-                fence_proxy_async_smem();
-                __syncthreads();
-                if (tid == 0) {
-                    bulk_store_g2s_commit(gdst, tile, bytes);
-                    if (MULTI && t + 1 < num_steps) bulk_store_wait_read();   // tile is rewritten by the next step
+            const int wbase = base + (tid & ~31);                        // first env of this warp
+            const int n_here = min(32, P.n - wbase);                     // <= 0 for warps past the end
+            if (n_here > 0) {
+                float* gdst = io.obs + ((per_step ? static_cast<size_t>(t) * P.n : 0) + wbase) * D;
+                const float* wsrc = tile + (tid & ~31) * D;
+                const uint32_t bytes = static_cast<uint32_t>(n_here) * D * 4u;
+                const bool bulk_ok = ((reinterpret_cast<uintptr_t>(gdst) & 15u) == 0) && ((bytes & 15u) == 0);
+                if (bulk_ok) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if ((tid & 31) == 0) {
+                        bulk_store_g2s_commit(gdst, wsrc, bytes);
+                        if (MULTI && t + 1 < num_steps) bulk_store_wait_read();   // rows are rewritten by the next step
+                    }
+                    if (MULTI && t + 1 < num_steps) __syncwarp();
+                } else {
+                    __syncwarp();
+                    for (int j = (tid & 31); j < n_here * D; j += 32) gdst[j] = wsrc[j];
+                    if (MULTI && t + 1 < num_steps) __syncwarp();
                 }
-                if (MULTI && t + 1 < num_steps) __syncthreads();
-            } else {
-                __syncthreads();
-                for (int j = tid; j < n_here * D; j += kBlock) gdst[j] = tile[j];
-                if (MULTI && t + 1 < num_steps) __syncthreads();
             }
         }
     }
-    // ---- Monitor statistics: warp shuffle -> shared -> this CTA's slot (no atomics) ----
+    // ---- Monitor statistics: warp shuffle -> this CTA's slot.  Only the (up to 4) warps of one CTA ever
+    // touch a slot, so these reductions do not contend; integer sums are exact and the float returns are
+    // added as doubles (exact for any realistic count), so the totals do not depend on arrival order.
     // (per-lane counts are < 2^16 per launch, so a warp's packed 16:16 sums need the two halves summed apart)
     const int eps_w = warp_sum(acc.eps_suc & 0xffff);
-    if (__syncthreads_or(eps_w != 0)) {            // CTA-uniform: any finished episode in this CTA during the launch
+    if (eps_w != 0) {                              // warp-uniform
         float ret = acc.ret;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) ret += __shfl_xor_sync(0xffffffffu, ret, d);
         const int len = warp_sum(acc.len), fnd = warp_sum(acc.fnd), suc = warp_sum(acc.eps_suc >> 16);
         const int cra = warp_sum(acc.cra_tru & 0xffff), tru = warp_sum(acc.cra_tru >> 16);
-        if ((tid & 31) == 0) { wacc[tid >> 5] = BlockAcc{ret, len, fnd, eps_w, suc}; wextra[tid >> 5] = make_int2(cra, tru); }
-        __syncthreads();
-        if (tid == 0) {
-            BlockStats b = P.block_stats[blockIdx.x];
-#pragma unroll
-            for (int w = 0; w < kBlock / 32; ++w) {
-                b.return_sum += static_cast<double>(wacc[w].ret);
-                b.length_sum += wacc[w].len; b.found_targets += wacc[w].fnd; b.episodes += wacc[w].eps_suc;
-                b.successes += wacc[w].cra_tru; b.crashes += wextra[w].x; b.truncations += wextra[w].y;
-            }
-            P.block_stats[blockIdx.x] = b;
+        if ((tid & 31) == 0) {
+            BlockStats* b = &P.block_stats[blockIdx.x];
+            atomicAdd(&b->return_sum, static_cast<double>(ret));
+            atomicAdd(&b->length_sum, static_cast<unsigned long long>(len));
+            atomicAdd(&b->episodes, static_cast<unsigned long long>(eps_w));
+            atomicAdd(&b->found_targets, static_cast<unsigned long long>(fnd));
+            if (suc) atomicAdd(&b->successes, static_cast<unsigned long long>(suc));
+            if (cra) atomicAdd(&b->crashes, static_cast<unsigned long long>(cra));
+            if (tru) atomicAdd(&b->truncations, static_cast<unsigned long long>(tru));
         }
     }
-    if (tid == 0) bulk_store_wait_read();   // shared memory must outlive the bulk read
+    if ((tid & 31) == 0) bulk_store_wait_read();   // shared memory must outlive the bulk read
 }
 
 // reduces the per-CTA slots into one Stats record (dn_episode_stats); optionally clears the slots
@@ -463,6 +479,12 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
         (ce = cudaMemset(e->d_block_stats, 0, sizeof(dn::BlockStats) * ((N + dn::kBlock - 1) / dn::kBlock))) != cudaSuccess)
         return cleanup(DN_ECUDA, std::string("dn_create: table upload: ") + cudaGetErrorString(ce));
     e->n_slots = (N + dn::kBlock - 1) / dn::kBlock;
+    {
+        cudaDeviceProp prop;
+        int sms = 148;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) sms = prop.multiProcessorCount;
+        P.prefetch_ctas = sms * 8;               // 8 CTAs of 128 threads per SM at 64 registers
+    }
     P.targets = e->d_targets; P.segs = e->d_segs; P.block_stats = e->d_block_stats;
 
     dn::init_kernel<<<(N + 255) / 256, 256>>>(P, e->d0);
