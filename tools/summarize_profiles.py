@@ -1,0 +1,97 @@
+"""Turns the ncu artefacts of one GPU visit (gpurun_out/) into the tracked summaries under profiles/.
+usage: summarize_profiles.py <round-tag>"""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+dst = os.path.join(ROOT, "profiles")
+os.makedirs(dst, exist_ok=True)
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__grid_size", "launch__block_size",
+        "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__warps_eligible.avg.per_cycle_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__sass_thread_inst_executed_op_ffma_pred_on.sum", "sm__sass_thread_inst_executed_op_fmul_pred_on.sum",
+        "sm__sass_thread_inst_executed_op_fadd_pred_on.sum", "lts__t_sector_hit_rate.pct"]
+
+lines = [f"# ncu summaries, {tag}", "",
+         "Captured on a B200 under `gpurun` with `ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 30 -c 1`",
+         "(launch 31 of `tools/profile_step.py ENVS SUBSTEPS 34`: steady-state reset mix, saturating actions). Times under ncu are",
+         "cold-cache and serialised; bench.py's CUDA-event numbers are the ones to quote.", ""]
+summary = {}
+for f in sorted(os.listdir(OUT)):
+    if not f.endswith(".ncu-rep"):
+        continue
+    raw = subprocess.run(["ncu", "-i", os.path.join(OUT, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+    lines += [f"## {f}  --  `{name}`", "", "| metric | value | unit |", "|---|---|---|"]
+    rec = {}
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            lines.append(f"| {k} | {vals[i]} | {units[i]} |")
+            rec[k] = vals[i]
+    try:
+        rd = float(rec["dram__bytes_read.sum"]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}[units[hdr.index("dram__bytes_read.sum")]]
+        wr = float(rec["dram__bytes_write.sum"]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}[units[hdr.index("dram__bytes_write.sum")]]
+        rec["traffic_bytes"] = rd + wr
+        lines.append(f"| dram traffic (read+write) | {rd + wr:.4g} | byte |")
+    except Exception:  # noqa: BLE001
+        pass
+    lines.append("")
+    summary[f] = rec
+    # warp stall sampling totals from the source page
+    src = subprocess.run(["ncu", "-i", os.path.join(OUT, f), "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(src.splitlines()))
+    if len(srows) > 2:
+        h = srows[1]
+        tot = collections.Counter()
+        for r in srows[2:]:
+            for i, c in enumerate(h):
+                if c.startswith("stall_") and "Not Issued" not in c:
+                    try:
+                        tot[c] += float(r[i])
+                    except (ValueError, IndexError):
+                        pass
+        allv = sum(tot.values()) or 1
+        lines.append("warp-stall samples: " + ", ".join(f"{c[6:]} {100 * v / allv:.1f}%" for c, v in tot.most_common(8)))
+        lines.append("")
+open(os.path.join(dst, f"ncu_summary_{tag}.md"), "w").write("\n".join(lines) + "\n")
+json.dump(summary, open(os.path.join(dst, f"ncu_summary_{tag}.json"), "w"), indent=1)
+
+# launch list: per-kernel totals and shares
+lp = os.path.join(OUT, "launches.csv")
+if os.path.exists(lp):
+    rows = [r for r in csv.reader(open(lp)) if len(r) > 5]
+    hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    h = rows[hi]
+    kn, mv = h.index("Kernel Name"), h.index("Metric Value")
+    agg, cnt = collections.Counter(), collections.Counter()
+    for r in rows[hi + 1:]:
+        try:
+            agg[r[kn]] += float(r[mv].replace(",", "")); cnt[r[kn]] += 1
+        except ValueError:
+            pass
+    tot = sum(agg.values()) or 1
+    with open(os.path.join(dst, f"launches_{tag}.md"), "w") as f:
+        f.write(f"# ncu launch list, {tag}\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 20 --warmup 3 "
+                f"--no-cpu --no-vecenv --sweep 4194304` (first 400 launches; cold-cache, serialised: compare shares)\n\n"
+                "| kernel | launches | total ns | share |\n|---|---|---|---|\n")
+        for k, v in agg.most_common():
+            f.write(f"| `{k[:110]}` | {cnt[k]} | {v:.0f} | {100 * v / tot:.1f}% |\n")
+bp = os.path.join(OUT, "bench.json")
+if os.path.exists(bp) and os.path.getsize(bp) > 10:
+    open(os.path.join(dst, f"bench_{tag}.json"), "w").write(open(bp).read())
+print("wrote", sorted(os.listdir(dst)))
