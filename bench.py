@@ -277,6 +277,39 @@ def roofline(n_envs, sec_per_launch, traffic=None):
             "us_per_launch": sec_per_launch * 1e6, "peak_source": src}
 
 
+def run_ppo(args, dev, world, rank, barrier, max_over_ranks):
+    """PPO samples/s end to end on `--ppo-envs` envs per GPU: rollout (policy inference + fused env step, all on
+    device) + GAE kernel + the PPO update (10 epochs, clipped losses, KL early stop) with ONE flat-gradient
+    NCCL all-reduce per optimiser step.  Reference hyper-parameters; rollout length and minibatch scaled."""
+    import torch
+    from drl_dronenavigation_b200.ppo import PPOConfig, PPOTrainer
+    import copy
+    a = copy.copy(args)
+    a.track = args.ppo_track
+    env = make_env(args.ppo_envs, a, dev, env_id_offset=rank * args.ppo_envs)
+    T = args.ppo_rollout
+    cfg = PPOConfig(n_steps=T, batch_size=max(512, (T * args.ppo_envs) // 32))
+    tr = PPOTrainer(env, cfg, rollout_steps=T)
+    tr.train_iteration()                                   # warm-up (cuBLAS heuristics, allocator)
+    barrier()
+    l0 = env.launch_count
+    t0 = time.perf_counter()
+    outs = [tr.train_iteration() for _ in range(args.ppo_iters)]
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    samples = world * args.ppo_envs * T * args.ppo_iters
+    res = {"value": samples / dt, "unit": "samples/s (env-steps/s incl. policy inference and PPO update)",
+           "envs_per_gpu": args.ppo_envs, "rollout_steps": T, "iterations": args.ppo_iters, "track": a.track, "substeps": args.substeps,
+           "minibatch": cfg.batch_size, "epochs_run": [o["epochs"] for o in outs], "minibatches_run": [o["minibatches"] for o in outs],
+           "rollout_s": sum(o["rollout_s"] for o in outs), "update_s": sum(o["update_s"] for o in outs),
+           "env_share_of_rollout": None, "allreduce_calls": tr.learner.allreduce_calls, "allreduce_bytes": tr.learner.n_params * 4,
+           "gpu_launches": int(env.launch_count - l0), "approx_kl": outs[-1]["approx_kl"],
+           "policy": "2 x MLP 13-512-512-256 (pi, vf), Tanh, TF32 GEMMs (cuBLAS)", "collective": "NCCL all-reduce of one flat FP32 gradient bucket per optimiser step" if world > 1 else "none (1 GPU)"}
+    env.close()
+    return res
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -431,6 +464,13 @@ def run_b200(args):
                               "api": "GpuDroneVecEnv.step (SB3 VecEnv protocol incl. NormalizeObservation, Monitor, info dicts)"}
         venv.close()
 
+    # ---- PPO SPS end to end (BASELINE configs[2]): device-resident rollout + update, NCCL gradient all-reduce ----
+    if not args.no_ppo:
+        try:
+            line["ppo"] = run_ppo(args, dev, world, rank, barrier, max_over_ranks)
+        except Exception as ex:  # noqa: BLE001
+            line["ppo"] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.track, args.substeps, budget_s=args.cpu_budget)
     elif world > 1:
@@ -455,6 +495,11 @@ def main():
     ap.add_argument("--actions", default="saturating", choices=["saturating", "hover_band"])
     ap.add_argument("--sweep", type=int, nargs="*", default=[65536, 1 << 20, 1 << 22])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true")
+    ap.add_argument("--ppo-envs", type=int, default=65536, help="BASELINE configs[2]: 65536 envs per GPU")
+    ap.add_argument("--ppo-rollout", type=int, default=16)
+    ap.add_argument("--ppo-iters", type=int, default=2)
+    ap.add_argument("--ppo-track", default="reaching", choices=["circle", "reaching"])
     ap.add_argument("--no-vecenv", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()

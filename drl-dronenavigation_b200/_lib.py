@@ -78,6 +78,8 @@ SYMBOLS = {
     "dn_step_many": (C.c_int, [C.c_void_p, C.POINTER(dn_step_io), C.c_int, C.c_int, C.c_void_p]),
     "dn_step_host": (C.c_int, [C.c_void_p, C.POINTER(dn_step_io)]),
     "dn_action_to_rpm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dn_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                         C.c_int32, C.c_int32, C.c_void_p]),
     "dn_get_state": (C.c_int, [C.c_void_p, C.POINTER(dn_state_view), C.c_void_p]),
     "dn_set_state": (C.c_int, [C.c_void_p, C.POINTER(dn_state_view), C.c_void_p]),
     "dn_episode_stats": (C.c_int, [C.c_void_p, C.POINTER(dn_stats), C.c_int, C.c_void_p]),

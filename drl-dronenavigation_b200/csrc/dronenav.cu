@@ -304,6 +304,24 @@ __global__ void action_map_kernel(const __grid_constant__ Params P, const float*
     if (i < n) out[i] = action_to_rpm(P, a[i]);
 }
 
+__global__ void gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const uint8_t* __restrict__ done,
+                           const float* __restrict__ last_val, float gamma, float lam, float* __restrict__ adv,
+                           float* __restrict__ ret, int T, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float next_v = last_val[n], gae = 0.0f;
+    for (int t = T - 1; t >= 0; --t) {
+        const size_t k = static_cast<size_t>(t) * N + n;
+        const float nnt = done[k] ? 0.0f : 1.0f;
+        const float v = val[k];
+        const float delta = rew[k] + gamma * next_v * nnt - v;
+        gae = delta + gamma * lam * nnt * gae;
+        adv[k] = gae;
+        ret[k] = gae + v;
+        next_v = v;
+    }
+}
+
 struct StateView {   // device mirror of dn_state_view
     float *pos, *quat, *vel, *rpy_rates, *ang_v, *prev_vel, *prev_ang_v, *dist, *prev_dist;
     int32_t *target_idx, *steps; uint8_t* just_found; float* ep_return; int32_t* ep_length;
@@ -606,6 +624,17 @@ int dn_action_to_rpm(dn_env* env, const float* actions, float* rpm_out, int64_t 
     dn::action_map_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(env->P, actions, rpm_out, n);
     DN_CUDA(cudaGetLastError());
     env->launches += 1;
+    return DN_OK;
+}
+
+int dn_gae(const float* rewards, const float* values, const uint8_t* done, const float* last_values,
+           float gamma, float gae_lambda, float* advantages_out, float* returns_out,
+           int32_t num_steps, int32_t num_envs, void* stream) {
+    if (!rewards || !values || !done || !last_values || !advantages_out || !returns_out || num_steps <= 0 || num_envs <= 0)
+        return fail(DN_EINVAL, "dn_gae: bad argument");
+    dn::gae_kernel<<<(num_envs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        rewards, values, done, last_values, gamma, gae_lambda, advantages_out, returns_out, num_steps, num_envs);
+    DN_CUDA(cudaGetLastError());
     return DN_OK;
 }
 

@@ -1,0 +1,281 @@
+"""Torch-native PPO on the device-resident environment.
+
+The update is the maths of the reference's ``PPO.train`` (Sol/Model/Algorithms/sb3_ppo.py:190-316:
+per-minibatch advantage normalisation, clipped surrogate, clipped value loss, entropy bonus,
+approx-KL early stop at 1.5 x target_kl, grad-norm clipping) with the hyper-parameters of
+``PBDroneSimulator.setup_agent`` (Sol/Model/PBDroneSimulator.py:251-286) and SB3's
+``ActorCriticPolicy`` defaults the reference relies on (separate pi / vf MLPs [512, 512, 256] with
+Tanh, diagonal Gaussian with a state-independent log-std initialised at 0, orthogonal init,
+Adam(eps=1e-5)).  What changes is where the data lives: observations, actions, rewards and dones
+never leave the GPU (no SB3 numpy hop), GAE is a CUDA kernel (``dn_gae``), and under ``torchrun``
+every optimiser step all-reduces ONE flat gradient bucket (~0.8 M parameters, 3.2 MB) over NCCL --
+the only collective in the system (the environment shards need none).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+@dataclass
+class PPOConfig:
+    """Defaults = PBDroneSimulator.setup_agent's PPO branch (PBDroneSimulator.py:251-286)."""
+    n_steps: int = 4096
+    batch_size: int = 512
+    n_epochs: int = 10
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    ent_coef: float = 0.02
+    vf_coef: float = 0.5
+    clip_range: float = 0.2
+    clip_range_vf: Optional[float] = 0.3
+    normalize_advantage: bool = True
+    max_grad_norm: float = 0.5
+    target_kl: Optional[float] = 0.05
+    learning_rate: float = 2.5e-4
+    pi_arch: tuple = (512, 512, 256)
+    vf_arch: tuple = (512, 512, 256)
+    log_std_init: float = 0.0
+    adam_eps: float = 1e-5
+    seed: int = 42                      # model.set_random_seed(42), PBDroneSimulator.py:690
+    matmul_precision: str = "tf32"      # "fp32" | "tf32": precision of the MLP GEMMs (cuBLAS)
+
+
+def _mlp(sizes, out_dim, out_gain):
+    layers: List[nn.Module] = []
+    for a, b in zip(sizes[:-1], sizes[1:]):
+        lin = nn.Linear(a, b)
+        nn.init.orthogonal_(lin.weight, gain=math.sqrt(2))
+        nn.init.zeros_(lin.bias)
+        layers += [lin, nn.Tanh()]
+    head = nn.Linear(sizes[-1], out_dim)
+    nn.init.orthogonal_(head.weight, gain=out_gain)
+    nn.init.zeros_(head.bias)
+    layers.append(head)
+    return nn.Sequential(*layers)
+
+
+class ActorCritic(nn.Module):
+    """SB3 ActorCriticPolicy with share_features_extractor=False and net_arch=dict(pi=..., vf=...)."""
+
+    def __init__(self, obs_dim: int, act_dim: int, cfg: PPOConfig):
+        super().__init__()
+        self.pi = _mlp((obs_dim,) + tuple(cfg.pi_arch), act_dim, 0.01)
+        self.vf = _mlp((obs_dim,) + tuple(cfg.vf_arch), 1, 1.0)
+        self.log_std = nn.Parameter(torch.full((act_dim,), float(cfg.log_std_init)))
+
+    def value(self, obs):
+        return self.vf(obs).squeeze(-1)
+
+    def act(self, obs, generator=None, deterministic=False):
+        mean = self.pi(obs)
+        if deterministic:
+            action = mean
+        else:
+            noise = torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
+            action = mean + noise * self.log_std.exp()
+        return action, self._log_prob(mean, action), self.value(obs)
+
+    def _log_prob(self, mean, action):
+        var = (2 * self.log_std).exp()
+        return (-((action - mean) ** 2) / (2 * var) - self.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+
+    def evaluate(self, obs, actions):
+        mean = self.pi(obs)
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + self.log_std).sum().expand(obs.shape[0])
+        return self.value(obs), self._log_prob(mean, actions), entropy
+
+
+def compute_gae_torch(rewards, values, dones, last_values, gamma, lam):
+    """Reference recursion (SB3 RolloutBuffer.compute_returns_and_advantage) as plain torch ops; used on
+    CPU tensors (gloo tests) and as the FP32 reference of the dn_gae kernel's numerics test."""
+    T = rewards.shape[0]
+    adv = torch.zeros_like(rewards)
+    gae = torch.zeros_like(last_values)
+    next_v = last_values
+    for t in range(T - 1, -1, -1):
+        nnt = 1.0 - (dones[t] != 0).to(rewards.dtype)
+        delta = rewards[t] + gamma * next_v * nnt - values[t]
+        gae = delta + gamma * lam * nnt * gae
+        adv[t] = gae
+        next_v = values[t]
+    return adv, adv + values
+
+
+def compute_gae(rewards, values, dones, last_values, gamma, lam):
+    """[T, N] tensors -> (advantages, returns).  CUDA tensors go through libdronenav's dn_gae kernel."""
+    if not rewards.is_cuda:
+        return compute_gae_torch(rewards, values, dones, last_values, gamma, lam)
+    from . import _lib as L
+    rewards, values, last_values = rewards.contiguous(), values.contiguous(), last_values.contiguous()
+    dones = dones.to(torch.uint8).contiguous()
+    adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+    T, N = rewards.shape
+    stream = C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream)
+    with torch.cuda.device(rewards.device):
+        L.check(L.lib().dn_gae(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), last_values.data_ptr(),
+                               float(gamma), float(lam), adv.data_ptr(), ret.data_ptr(), T, N, stream), "dn_gae")
+    return adv, ret
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class PPOLearner:
+    """Policy + optimiser + the PPO update; independent of the environment (works on any device, which
+    is what the world_size-2 gloo tests use)."""
+
+    def __init__(self, obs_dim: int, act_dim: int, cfg: PPOConfig = PPOConfig(), device="cpu"):
+        self.cfg, self.device = cfg, torch.device(device)
+        torch.manual_seed(cfg.seed)                     # same seed on every rank -> identical initial parameters
+        self.policy = ActorCritic(obs_dim, act_dim, cfg).to(self.device)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps)
+        self.params = [p for p in self.policy.parameters()]
+        self.n_params = sum(p.numel() for p in self.params)
+        # the one gradient bucket: every parameter's .grad is a view into it, so backward() writes the
+        # bucket in place and the all-reduce / norm clip are single operations on one contiguous tensor
+        self._flat = torch.zeros(self.n_params, device=self.device)
+        off = 0
+        for p in self.params:
+            p.grad = self._flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.n_updates = 0
+        self.allreduce_calls = 0
+        if self.device.type == "cuda" and cfg.matmul_precision == "tf32":
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
+
+    # ---- the only collective: one flat bucket per optimiser step (between backward and clip, sb3_ppo.py:291-293)
+    def _allreduce_grads(self):
+        w = _world()
+        if w == 1:
+            return
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+        self._flat.div_(w)
+        self.allreduce_calls += 1
+
+    def _sync_stop(self, stop: bool) -> bool:
+        """Ranks must leave the epoch loop together (sb3_ppo.py:283-287): all-reduce(MAX) of the decision."""
+        if _world() == 1:
+            return stop
+        t = torch.tensor([1.0 if stop else 0.0], device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(t.item() > 0)
+
+    def update(self, obs, actions, old_logp, old_values, advantages, returns, generator=None) -> Dict[str, float]:
+        """PPO.train (sb3_ppo.py:190-316) on flat [B, ...] tensors of this rank's rollout."""
+        cfg = self.cfg
+        B = obs.shape[0]
+        mb = min(cfg.batch_size, B)
+        n_mb = B // mb
+        stats = dict(pg=0.0, vf=0.0, ent=0.0, kl=0.0, clip=0.0, n=0)
+        acc = torch.zeros(5, device=self.device)
+        stop = False
+        epochs_run = 0
+        for epoch in range(cfg.n_epochs):
+            perm = torch.randperm(B, device=self.device, generator=generator)
+            for k in range(n_mb):
+                idx = perm[k * mb:(k + 1) * mb]
+                values, logp, entropy = self.policy.evaluate(obs[idx], actions[idx])
+                adv = advantages[idx]
+                if cfg.normalize_advantage and adv.numel() > 1:
+                    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+                ratio = torch.exp(logp - old_logp[idx])
+                pg_loss = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+                if cfg.clip_range_vf is None:
+                    v_pred = values
+                else:
+                    ov = old_values[idx]
+                    v_pred = ov + torch.clamp(values - ov, -cfg.clip_range_vf, cfg.clip_range_vf)
+                v_loss = torch.nn.functional.mse_loss(returns[idx], v_pred)
+                ent_loss = -entropy.mean()
+                loss = pg_loss + cfg.ent_coef * ent_loss + cfg.vf_coef * v_loss
+                with torch.no_grad():
+                    log_ratio = logp - old_logp[idx]
+                    approx_kl = ((torch.exp(log_ratio) - 1) - log_ratio).mean()
+                    clip_frac = ((ratio - 1).abs() > cfg.clip_range).float().mean()
+                    acc += torch.stack([pg_loss.detach(), v_loss.detach(), ent_loss.detach(), approx_kl, clip_frac])
+                stats["n"] += 1
+                if cfg.target_kl is not None:
+                    stop = self._sync_stop(bool(approx_kl.item() > 1.5 * cfg.target_kl))   # one host sync per minibatch, as in SB3
+                    if stop:
+                        break
+                self._flat.zero_()
+                loss.backward()
+                self._allreduce_grads()
+                # th.nn.utils.clip_grad_norm_(parameters, max_grad_norm) on the flat bucket
+                norm = torch.linalg.vector_norm(self._flat)
+                self._flat.mul_(torch.clamp(cfg.max_grad_norm / (norm + 1e-6), max=1.0))
+                self.opt.step()
+            self.n_updates += 1
+            epochs_run += 1
+            if stop:
+                break
+        a = (acc / max(stats["n"], 1)).tolist()
+        return {"policy_gradient_loss": a[0], "value_loss": a[1], "entropy_loss": a[2], "approx_kl": a[3],
+                "clip_fraction": a[4], "epochs": epochs_run, "minibatches": stats["n"], "early_stop": bool(stop),
+                "std": float(self.policy.log_std.detach().exp().mean())}
+
+    def flat_parameters(self) -> torch.Tensor:
+        return torch.cat([p.detach().reshape(-1) for p in self.params])
+
+
+class PPOTrainer:
+    """collect_rollouts + train on a BatchedDroneEnv shard (one process per GPU)."""
+
+    def __init__(self, env, cfg: PPOConfig = PPOConfig(), rollout_steps: Optional[int] = None):
+        self.env, self.cfg = env, cfg
+        self.dev = env.device
+        self.T = int(rollout_steps or cfg.n_steps)
+        self.learner = PPOLearner(env.obs_dim, 4, cfg, device=self.dev)
+        rank = dist.get_rank() if _world() > 1 else 0
+        self.gen = torch.Generator(device=self.dev).manual_seed(cfg.seed + 1000 * (rank + 1))   # exploration noise differs per shard
+        N, D, T = env.num_envs, env.obs_dim, self.T
+        f = dict(dtype=torch.float32, device=self.dev)
+        self.b_obs, self.b_act = torch.empty(T, N, D, **f), torch.empty(T, N, 4, **f)
+        self.b_logp, self.b_val, self.b_rew = torch.empty(T, N, **f), torch.empty(T, N, **f), torch.empty(T, N, **f)
+        self.b_done = torch.empty(T, N, dtype=torch.uint8, device=self.dev)
+        self.obs = env.reset().clone()
+        self.total_steps = 0
+        self.low, self.high = -1.0, 1.0           # Box(-1, 1) with normalize_actions (PBDroneEnv.py:230-236)
+
+    @torch.no_grad()
+    def collect_rollouts(self):
+        env, pol = self.env, self.learner.policy
+        for t in range(self.T):
+            action, logp, value = pol.act(self.obs, generator=self.gen)
+            self.b_obs[t], self.b_act[t], self.b_logp[t], self.b_val[t] = self.obs, action, logp, value
+            obs, rew, done, _ = env.step(action.clamp(self.low, self.high).contiguous())   # SB3 clips to the Box before env.step
+            self.b_rew[t], self.b_done[t] = rew, done
+            # bootstrap truncated episodes from the terminal observation (SB3 OnPolicyAlgorithm.collect_rollouts)
+            trunc_only = done == 2
+            if bool(trunc_only.any()):
+                tv = pol.value(env.terminal_obs[trunc_only])
+                self.b_rew[t][trunc_only] += self.cfg.gamma * tv
+            self.obs = obs.clone()
+        last_values = pol.value(self.obs)
+        adv, ret = compute_gae(self.b_rew, self.b_val, self.b_done, last_values, self.cfg.gamma, self.cfg.gae_lambda)
+        self.total_steps += self.T * env.num_envs
+        return adv, ret
+
+    def train_iteration(self) -> Dict[str, float]:
+        t0 = time.perf_counter()
+        adv, ret = self.collect_rollouts()
+        torch.cuda.synchronize(self.dev)
+        t1 = time.perf_counter()
+        N, D = self.env.num_envs, self.env.obs_dim
+        out = self.learner.update(self.b_obs.reshape(-1, D), self.b_act.reshape(-1, 4), self.b_logp.reshape(-1),
+                                  self.b_val.reshape(-1), adv.reshape(-1), ret.reshape(-1), generator=self.gen)
+        torch.cuda.synchronize(self.dev)
+        t2 = time.perf_counter()
+        out.update(rollout_s=t1 - t0, update_s=t2 - t1, samples=self.T * N * _world(),
+                   sps=self.T * N * _world() / (t2 - t0))
+        return out

@@ -1,0 +1,162 @@
+"""``PBDroneSimulator``: the reference's experiment manager (Sol/Model/PBDroneSimulator.py:108-995)
+with its vectorised environments resolved to the GPU environment.
+
+Kept: constructor signature, ``make_env`` keywords, ``setup_agent`` / ``run_full_training`` /
+``run_test`` / ``test_saved`` method names, the hyper-parameters of the PPO branch (:251-286), the
+evaluation protocol (stochastic actions, 10 episodes, :719-729).  The learner is the torch-native PPO
+of ``ppo.py`` (SB3 is not installable here; when it is, ``make_env(multi=True)`` returns a VecEnv that
+SB3's own PPO accepts unchanged).  Ray / CleanRL / TF-Agents launchers, wandb and plotting are out of
+scope.
+"""
+from __future__ import annotations
+
+import os
+import time
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from .batched_env import BatchedDroneEnv
+from .enums import ActionType
+from .ppo import PPOConfig, PPOTrainer
+from .vec_env import GpuDroneVecEnv
+from .waypoints import Track, dilate_targets
+from . import waypoints as Waypoints
+
+
+class PBDroneSimulator:
+    """Manage training and testing in the (GPU) PBDroneEnv environment."""
+
+    def __init__(self, args, track: Track, target_factor: int = 0, plot: bool = True, discount: float = 0.999):
+        self.args, self.plot, self.discount = args, plot, discount
+        self.threshold = 0.3
+        self.env_steps = args.max_env_steps
+        self.num_envs = args.num_envs
+        self.track = track
+        self.initial_xyzs = track.initial_xyzs
+        self.aviary_dim = track.aviary_dim
+        self.targets = dilate_targets(track.waypoints, target_factor)
+        if track.is_circle:
+            self.targets.pop(0)
+        self.pyb_freq = getattr(args, "pyb_freq", 240)
+        self.ctrl_freq = getattr(args, "ctrl_freq", 240)
+        print(track)
+
+    # ------------------------------------------------------------------ envs
+    def _env_kwargs(self, initial_xyzs, aviary_dim, include_distance, normalize_actions):
+        return dict(threshold=self.threshold, discount=self.discount, max_steps=self.env_steps,
+                    aviary_dim=aviary_dim, initial_xyzs=self.initial_xyzs if initial_xyzs is None else initial_xyzs,
+                    act=ActionType.THRUST, cylinder=True, circle=self.track.is_circle, include_distance=include_distance,
+                    normalize_actions=normalize_actions, pyb_freq=self.pyb_freq, ctrl_freq=self.ctrl_freq)
+
+    def make_env(self, multi=False, gui=False, initial_xyzs=None, aviary_dim=np.array([-1, -1, 0, 1, 1, 1]), rank: int = 0,
+                 save_path: str = None, include_distance: bool = True, normalize_actions: bool = True,
+                 collect_rollouts: bool = False, seed: int = 0, num_envs: int = 1):
+        """make_env of the reference (:136-204).  ``multi=True`` returns a thunk, like the reference's
+        SubprocVecEnv factories; calling it builds a ``GpuDroneVecEnv`` with the wrapper stack fused
+        (NormalizeObservation always, Monitor always)."""
+        if gui or collect_rollouts:
+            raise NotImplementedError("gui / rollout text dumps are outside the CUDA hot path")
+        kw = self._env_kwargs(initial_xyzs, aviary_dim, include_distance, normalize_actions)
+
+        def _init():
+            return GpuDroneVecEnv(num_envs, self.targets, normalize_obs=True, **kw)
+        return _init if multi else _init()
+
+    def make_device_env(self, num_envs: int, normalize_obs: bool = False, device=None, env_id_offset: int = 0):
+        """The device-resident shard the torch-native learner steps (no host hop)."""
+        kw = self._env_kwargs(None, self.aviary_dim, True, True)
+        return BatchedDroneEnv(num_envs, self.targets, normalize_obs=normalize_obs, device=device,
+                               env_id_offset=env_id_offset, **kw)
+
+    # ----------------------------------------------------------------- agent
+    def setup_agent(self, tensorboard_path=None, train_env=None, chkpt_path=None):
+        """PPO with the reference's hyper-parameters (:251-286).  The rollout length per env is n_steps=4096
+        for the reference's 12 envs; with thousands of envs it is scaled so that one rollout holds about the
+        same 12 x 4096 x (a few) samples per update unless --rollout_steps says otherwise."""
+        if self.args.agent != "PPO":
+            raise NotImplementedError(f"{self.args.agent}: only the PPO branch is built on the device path so far")
+        n = train_env.num_envs
+        T = getattr(self.args, "rollout_steps", None) or max(16, min(4096, (12 * 4096 * 8) // max(n, 1)))
+        cfg = PPOConfig(n_steps=T, batch_size=max(512, (T * n) // 32))
+        return PPOTrainer(train_env, cfg, rollout_steps=T)
+
+    # ------------------------------------------------------------------ runs
+    def evaluate(self, trainer: PPOTrainer, n_eval_episodes: int = 10, n_envs: int = 64, max_steps: int = 20000):
+        """EvalCallback's protocol (:719-729): stochastic actions, mean episode reward / length, plus the
+        success rate defined in BASELINE.md (episodes ending with all targets found)."""
+        env = self.make_device_env(n_envs, device=trainer.dev)
+        obs = env.reset()
+        gen = torch.Generator(device=trainer.dev).manual_seed(123)
+        with torch.no_grad():
+            for _ in range(max_steps):
+                a, _, _ = trainer.learner.policy.act(obs, generator=gen)
+                obs, _, _, _ = env.step(a.clamp(-1, 1).contiguous())
+                st = env.episode_stats()
+                if st["episodes"] >= n_eval_episodes:
+                    break
+        st = env.episode_stats()
+        env.close()
+        e = max(st["episodes"], 1)
+        return {"episodes": st["episodes"], "mean_reward": st["return_sum"] / e, "mean_ep_length": st["length_sum"] / e,
+                "success_rate": st["successes"] / e, "mean_found_targets": st["found_targets"] / e}
+
+    def run_full_training(self, max_seconds: float = None, log=print):
+        args = self.args
+        total = int(float(args.total_timesteps))
+        train_env = self.make_device_env(self.num_envs)
+        trainer = self.setup_agent(train_env=train_env)
+        chk = None
+        if args.savemodel:
+            chk = os.path.join("Sol", "model_chkpts", f"{args.agent}_save_{datetime.now().strftime('%m.%d.%Y_%H.%M.%S')}")
+            os.makedirs(chk, exist_ok=True)
+        t0, it, best = time.time(), 0, -np.inf
+        while trainer.total_steps < total and (max_seconds is None or time.time() - t0 < max_seconds):
+            out = trainer.train_iteration()
+            it += 1
+            if it % 5 == 0 or trainer.total_steps >= total:
+                st = train_env.episode_stats(clear=True)
+                e = max(st["episodes"], 1)
+                log(f"[{time.time() - t0:7.1f}s] steps {trainer.total_steps:>12d}  sps {out['sps']:.3g}  ep_rew {st['return_sum'] / e:8.3f}  "
+                    f"ep_len {st['length_sum'] / e:7.1f}  found {st['found_targets'] / e:5.2f}  success {st['successes'] / e:5.3f}  "
+                    f"kl {out['approx_kl']:.4f}  std {out['std']:.3f}")
+                if chk and st["return_sum"] / e > best:
+                    best = st["return_sum"] / e
+                    torch.save(trainer.learner.policy.state_dict(), os.path.join(chk, "best_model.pt"))
+        if chk:
+            torch.save(trainer.learner.policy.state_dict(), os.path.join(chk, "success_model.pt"))
+        ev = self.evaluate(trainer, n_eval_episodes=100)
+        log(f"final evaluation: {ev}")
+        train_env.close()
+        return trainer, ev
+
+    def run_test(self, max_steps: int = 2000, log=print):
+        """--run_type test (:390-436): constant action 0.1 on every motor on the `up` track until termination."""
+        from .env import PBDroneEnv
+        self.targets = Waypoints.up()[0]
+        env = PBDroneEnv(target_points=self.targets, threshold=self.threshold, discount=self.discount, max_steps=self.env_steps,
+                         aviary_dim=np.array([-2, -2, 0, 2, 2, 2]), initial_xyzs=np.array([[0, 0, 0.1]]), act=ActionType.THRUST,
+                         cylinder=True, circle=self.track.is_circle, include_distance=True, normalize_actions=True,
+                         pyb_freq=self.pyb_freq, ctrl_freq=self.ctrl_freq)
+        log(env.G); log(env.INIT_XYZS)
+        log(env.reset())
+        action = np.array([0.1, 0.1, 0.1, 0.1], dtype=np.float32)
+        rewards = []
+        for i in range(1, max_steps + 1):
+            ts = env.step(action)
+            rewards.append(ts[1])
+            log(f"step: {i} ------------------\n{ts}")
+            if ts[2]:
+                break
+        env.close()
+        return rewards
+
+    def test_saved(self, path: str, episodes: int = 50):
+        """--run_type saved (:438-572): roll a saved policy and report episode statistics."""
+        env = self.make_device_env(64)
+        trainer = self.setup_agent(train_env=env)
+        trainer.learner.policy.load_state_dict(torch.load(path, map_location=trainer.dev))
+        out = self.evaluate(trainer, n_eval_episodes=episodes)
+        env.close()
+        return out

@@ -196,6 +196,15 @@ int dn_set_state(dn_env* env, const dn_state_view* view, void* stream);
 /* Copies the aggregated statistics to host (synchronises `stream`); clears them if `clear`. */
 int dn_episode_stats(dn_env* env, dn_stats* host_out, int clear, void* stream);
 
+/* Generalised advantage estimation over a device-resident rollout, the recursion of SB3's
+ * RolloutBuffer.compute_returns_and_advantage that Sol/Model/Algorithms/sb3_ppo.py:190-316 consumes
+ * (advantages, returns).  Layout [T, N] row-major; `done[t, n] != 0` means the episode of env n ended
+ * with step t (so values[t+1, n] belongs to a new episode); `last_values[n]` is V(obs after step T-1).
+ * One thread per env walks its T steps backwards (coalesced across envs).  Runs on the current device. */
+int dn_gae(const float* rewards, const float* values, const uint8_t* done, const float* last_values,
+           float gamma, float gae_lambda, float* advantages_out, float* returns_out,
+           int32_t num_steps, int32_t num_envs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
