@@ -443,8 +443,30 @@ def run_b200(args):
     e2e_sec = max_over_ranks(e2e_sec)
     line["e2e"] = {"value": world * N * K / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": N * 16,
                    "d2h_bytes_per_step": N * (D * 4 + 4 + 1 + 4), "us_per_step": 1e6 * e2e_sec / K,
-                   "api": "dn_step_host (C ABI, host buffers): pinned actions -> H2D -> step_kernel -> D2H obs,reward,done,found_targets",
+                   "api": "dn_step_host (C ABI, pinned host buffers, zero copy): step_kernel reads the actions and writes obs,reward,done,"
+                          "found_targets in host memory over PCIe; one launch + one stream synchronise per step",
                    "gpu_launches": int(e2e_launches)}
+    if world == 1:
+        # the staged variant of the same call (pageable numpy buffers: H2D copy -> kernel -> D2H copies)
+        p_act = h_act.numpy().copy()
+        p_obs, p_rew = np.empty((N, D), np.float32), np.empty(N, np.float32)
+        p_done, p_found = np.empty(N, np.uint8), np.empty(N, np.int32)
+        from drl_dronenavigation_b200 import _lib as L
+        pios = []
+        for k in range(A):
+            io = L.dn_step_io()
+            io.actions, io.obs, io.reward, io.done, io.found_targets = (p_act[k].ctypes.data, p_obs.ctypes.data, p_rew.ctypes.data,
+                                                                        p_done.ctypes.data, p_found.ctypes.data)
+            pios.append(io)
+        ks = min(K, 300)
+        for k in range(5):
+            env.step_host(pios[k % A])
+        t0 = time.perf_counter()
+        for k in range(ks):
+            env.step_host(pios[k % A])
+        dts = time.perf_counter() - t0
+        line["e2e_staged"] = {"value": N * ks / dts, "unit": UNIT, "us_per_step": 1e6 * dts / ks,
+                              "api": "dn_step_host with pageable host buffers (staged H2D / D2H copies)"}
     if world == 1 and not args.no_vecenv:
         # the SB3 VecEnv protocol on top of the same call (numpy in / numpy out + per-env info dicts)
         from drl_dronenavigation_b200.vec_env import GpuDroneVecEnv

@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <cstdlib>
 
 #include "../../include/dronenav.h"
 #include "dn_params.h"
@@ -401,6 +402,9 @@ struct dn_env {
     // dn_step_host staging (allocated on first use)
     cudaStream_t host_stream;
     void* stage;            // device: actions | obs | terminal_obs | reward | ep_return | found | ep_length | done
+    dn_step_io host_seen;   // last host io whose pointers were classified
+    dn_step_io host_mapped; // device aliases of those pointers when all of them are pinned + mapped (UVA)
+    int host_direct;        // 1: the kernel reads / writes the caller's pinned buffers directly (zero copy)
 };
 
 static thread_local std::string g_err;
@@ -583,15 +587,44 @@ int dn_step_host(dn_env* env, const dn_step_io* h) {
     if (!env || !h) return fail(DN_EINVAL, "dn_step_host: null argument");
     if (!h->actions || !h->obs || !h->reward || !h->done) return fail(DN_EINVAL, "dn_step_host: actions/obs/reward/done are required");
     DeviceGuard guard(env->device);
+    if (!env->host_stream) DN_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
+    // Zero-copy path: if every buffer is pinned host memory mapped into the device address space (torch /
+    // cudaHostAlloc / cudaHostRegister), the fused kernel reads the actions and writes its outputs over
+    // PCIe itself -- one launch + one stream synchronise per step, no staging copies.  The classification
+    // is cached on the pointer set.  Pageable buffers take the staged path below.
+    if (std::memcmp(&env->host_seen, h, sizeof(*h)) != 0) {
+        env->host_seen = *h;
+        env->host_direct = getenv("DN_HOST_STAGED") ? 0 : 1;
+        const void* src[8] = {h->actions, h->obs, h->reward, h->done, h->terminal_obs, h->found_targets, h->episode_return, h->episode_length};
+        void* dst[8] = {nullptr};
+        for (int k = 0; k < 8 && env->host_direct; ++k) {
+            if (!src[k]) continue;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, src[k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                cudaGetLastError();
+                env->host_direct = 0;
+            } else {
+                dst[k] = at.devicePointer;
+            }
+        }
+        if (env->host_direct && (reinterpret_cast<uintptr_t>(dst[0]) & 15u)) env->host_direct = 0;
+        env->host_mapped.actions = static_cast<const float*>(dst[0]); env->host_mapped.obs = static_cast<float*>(dst[1]);
+        env->host_mapped.reward = static_cast<float*>(dst[2]); env->host_mapped.done = static_cast<uint8_t*>(dst[3]);
+        env->host_mapped.terminal_obs = static_cast<float*>(dst[4]); env->host_mapped.found_targets = static_cast<int32_t*>(dst[5]);
+        env->host_mapped.episode_return = static_cast<float*>(dst[6]); env->host_mapped.episode_length = static_cast<int32_t*>(dst[7]);
+    }
+    if (env->host_direct) {
+        const int rc = launch_step(env, &env->host_mapped, 1, 1, env->host_stream);
+        if (rc != DN_OK) return rc;
+        DN_CUDA(cudaStreamSynchronize(env->host_stream));
+        return DN_OK;
+    }
     const size_t N = env->P.n, D = env->P.obs_dim;
     const size_t a256 = 255;
     auto up = [&](size_t b) { return (b + a256) & ~a256; };
     const size_t o_act = 0, o_obs = o_act + up(N * 16), o_term = o_obs + up(N * D * 4), o_rew = o_term + up(N * D * 4);
     const size_t o_epr = o_rew + up(N * 4), o_fnd = o_epr + up(N * 4), o_epl = o_fnd + up(N * 4), o_done = o_epl + up(N * 4);
-    if (!env->stage) {
-        DN_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
-        DN_CUDA(cudaMalloc(&env->stage, o_done + up(N)));
-    }
+    if (!env->stage) DN_CUDA(cudaMalloc(&env->stage, o_done + up(N)));
     char* d = static_cast<char*>(env->stage);
     cudaStream_t st = env->host_stream;
     DN_CUDA(cudaMemcpyAsync(d + o_act, h->actions, N * 16, cudaMemcpyHostToDevice, st));

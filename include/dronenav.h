@@ -177,11 +177,12 @@ int dn_step(dn_env* env, const dn_step_io* io, void* stream);
  * ([N,...]).  Used for open-loop rollouts / the step-only throughput benchmark. */
 int dn_step_many(dn_env* env, const dn_step_io* io, int num_steps, int per_step_outputs, void* stream);
 
-/* dn_step with HOST buffers (pinned or pageable, caller-owned; same shapes as dn_step_io):
- * copies the actions to the device, runs the fused step, copies obs / reward / done (and the
- * optional outputs that are non-NULL) back and returns when they have landed.  This is the call
- * an out-of-process / numpy caller such as SB3's VecEnv.step_wait makes; staging buffers and the
- * stream belong to the handle. */
+/* dn_step with HOST buffers (caller-owned; same shapes as dn_step_io).  Returns when the results are in
+ * the host buffers.  Pinned, device-mapped buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+ * are read and written by the fused kernel directly over PCIe (zero copy: one launch + one stream
+ * synchronise); pageable buffers are staged (H2D actions -> kernel -> D2H outputs).  This is the call an
+ * out-of-process / numpy caller such as SB3's VecEnv.step_wait makes; staging buffers and the stream
+ * belong to the handle.  Set DN_HOST_STAGED=1 to force the staged path. */
 int dn_step_host(dn_env* env, const dn_step_io* host_io);
 
 /* The action map alone, elementwise over `n` action components (device pointers):

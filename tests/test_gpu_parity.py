@@ -194,6 +194,44 @@ def test_step_many_matches_repeated_step():
     envA.close(); envB.close()
 
 
+def test_step_host_zero_copy_and_staged_paths_equal_device_step():
+    """dn_step_host with pinned (zero-copy) and pageable (staged) host buffers == dn_step on device buffers."""
+    envs = [_make("circle", 777, 8)[0] for _ in range(3)]
+    for e in envs:
+        e.reset()
+    N, D = 777, 13
+    acts = _actions("saturating", 12, N, seed=4)
+    pin = lambda *s, dtype: torch.empty(*s, dtype=dtype).pin_memory()
+    h = dict(a=pin(N, 4, dtype=torch.float32), o=pin(N, D, dtype=torch.float32), r=pin(N, dtype=torch.float32),
+             d=pin(N, dtype=torch.uint8), t=pin(N, D, dtype=torch.float32), f=pin(N, dtype=torch.int32),
+             er=pin(N, dtype=torch.float32), el=pin(N, dtype=torch.int32))
+    io_pin = envs[1]._make_io(h["a"], h["o"], h["r"], h["d"], h["t"], h["f"], h["er"], h["el"])
+    p = dict(a=np.zeros((N, 4), np.float32), o=np.zeros((N, D), np.float32), r=np.zeros(N, np.float32), d=np.zeros(N, np.uint8),
+             f=np.zeros(N, np.int32))
+    from drl_dronenavigation_b200 import _lib as L
+    io_pg = L.dn_step_io()
+    io_pg.actions, io_pg.obs, io_pg.reward, io_pg.done, io_pg.found_targets = (p["a"].ctypes.data, p["o"].ctypes.data, p["r"].ctypes.data,
+                                                                               p["d"].ctypes.data, p["f"].ctypes.data)
+    n_done = 0
+    for t in range(12):
+        o, r, d, f = envs[0].step(torch.from_numpy(acts[t]).cuda())
+        h["a"].copy_(torch.from_numpy(acts[t]))
+        envs[1].step_host(io_pin)
+        p["a"][...] = acts[t]
+        envs[2].step_host(io_pg)
+        for name, dev_t in (("o", o), ("r", r), ("d", d), ("f", f)):
+            ref = dev_t.cpu().numpy()
+            np.testing.assert_array_equal(h[name].numpy(), ref)
+            np.testing.assert_array_equal(p[name], ref)
+        done = d.cpu().numpy() != 0
+        n_done += int(done.sum())
+        np.testing.assert_array_equal(h["t"].numpy()[done], envs[0].terminal_obs.cpu().numpy()[done])
+        np.testing.assert_array_equal(h["el"].numpy()[done], envs[0].episode_length.cpu().numpy()[done])
+    assert n_done > 100
+    for e in envs:
+        e.close()
+
+
 def test_ragged_sizes_and_obs12():
     """N not a multiple of the CTA size (tail CTA takes the non-TMA store path), N = 1, 12-dim obs."""
     from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
