@@ -5,15 +5,24 @@ A numpy restatement of the reference's per-environment control step for the
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
 reference`` legs may import this file; the product package never does.
 
-PARITY UNPINNED: the reference holds no golden vector, known-answer test or
-fixture for this path, its DYN branch is unreachable as
-shipped (``Sol/PyBullet/BaseAviary.py:418`` forces ``Physics.PYB``) and would
-crash on the undefined ``self.TIMESTEP`` (``BaseAviary.py:944``), and neither
-``pybullet`` nor ``gymnasium`` nor ``stable_baselines3`` is installable here
-(no network).  The oracle is therefore a restatement of the cited lines with
-``TIMESTEP := PYB_TIMESTEP``; the analytic known-answer tests in
-``tests/test_oracle_kat.py`` and the fixtures under ``tests/golden/`` are
-minted by us from this file.
+PARITY PIN: the reference holds no golden vector, known-answer test or fixture
+for this path, so the pin is the reference's own code run
+here: ``tests/golden/make_ref_golden.py`` imports ``/root/reference`` UNMODIFIED
+(behind import shims for the absent third-party packages, ``tests/golden/
+ref_shims.py``) and steps ``PBDroneEnv`` / ``BaseAviary._dynamics`` /
+``normalize.NormalizeObservation`` through nine scenarios; the committed outputs
+(``tests/golden/ref_*.npz``) are reproduced by this file to FP64 round-off
+(``tests/test_ref_golden.py``: observations identical as float32, reward 1e-12,
+state 1e-13, done bits / found_targets / episode lengths exact).  Two things the
+generator has to supply because the reference's DYN branch is unreachable as
+shipped: ``Sol/PyBullet/BaseAviary.py:418`` forces ``Physics.PYB`` (neutralised by a
+read-only ``PHYSICS`` property in a subclass) and ``BaseAviary.py:944`` reads the
+undefined ``self.TIMESTEP`` (defined as ``PYB_TIMESTEP``).  What remains unpinned
+is third-party: ``pybullet`` itself (unpinned by the reference, not installable
+here) -- its three quaternion helpers are restated from the published bullet3
+algorithms both in the shim and below.  The analytic known-answer tests in
+``tests/test_oracle_kat.py`` and the oracle-minted fixtures
+(``tests/golden/make_golden.py``: drag / ground-effect extension) complement it.
 
 What each piece follows (all paths relative to ``/root/reference``):
 
