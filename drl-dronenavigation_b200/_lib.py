@@ -12,12 +12,13 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libdronenav.so")
 
-DN_ABI_VERSION = 1
+DN_ABI_VERSION = 2
 
 # enums of include/dronenav.h
 DN_ACT_THRUST, DN_ACT_RPM, DN_ACT_ONE_D_RPM = 0, 1, 2
 DN_PHYS_DYN, DN_PHYS_DRAG, DN_PHYS_GROUND_EFFECT, DN_PHYS_GROUND_CONTACT = 0, 1, 2, 4
-DN_REWARD_DEFAULT, DN_REWARD_DUMMY, DN_REWARD_THRUSTENV = 0, 1, 2
+DN_REWARD_DEFAULT, DN_REWARD_DUMMY, DN_REWARD_THRUSTENV, DN_REWARD_HER = 0, 1, 2, 3
+DN_REWARD_REACHING, DN_REWARD_PROGRESS, DN_REWARD_HOVER, DN_REWARD_FLYTHRUGATE = 4, 5, 6, 7
 DN_SPAWN_FIXED, DN_SPAWN_LINE, DN_SPAWN_MIDPOINT = 0, 1, 2
 DN_DONE_TERMINATED, DN_DONE_TRUNCATED = 1, 2
 
@@ -34,7 +35,8 @@ class dn_config(C.Structure):
         ("spawn_mode", C.c_int32), ("normalize_obs", C.c_int32),
         ("threshold", C.c_double), ("discount", C.c_double),
         ("aviary_dim", C.c_double * 6), ("init_xyz", C.c_double * 3), ("init_rpy", C.c_double * 3),
-        ("num_targets", C.c_int32), ("reserved0", C.c_int32),
+        ("num_targets", C.c_int32), ("normalize_reward", C.c_int32),
+        ("clip_reward", C.c_double), ("reward_gamma", C.c_double),
         ("targets", C.POINTER(C.c_double)),
     ]
 
@@ -49,7 +51,7 @@ class dn_step_io(C.Structure):
 
 STATE_FIELDS = ("pos", "quat", "vel", "rpy_rates", "ang_v", "prev_vel", "prev_ang_v", "dist", "prev_dist",
                 "target_idx", "steps", "just_found", "ep_return", "ep_length", "episode_count",
-                "last_rpm_sum", "obs_rms")
+                "last_rpm_sum", "obs_rms", "aux", "rew_rms")
 
 
 class dn_state_view(C.Structure):

@@ -33,6 +33,7 @@ _STATE_DTYPES = {
     "target_idx": (torch.int32, 0), "steps": (torch.int32, 0), "just_found": (torch.uint8, 0),
     "ep_return": (torch.float32, 0), "ep_length": (torch.int32, 0), "episode_count": (torch.int32, 0),
     "last_rpm_sum": (torch.float32, 0), "obs_rms": (torch.float32, -1),
+    "aux": (torch.float32, 4), "rew_rms": (torch.float32, 4),
 }
 
 
@@ -46,6 +47,7 @@ class BatchedDroneEnv:
                  obs: ObservationType = ObservationType.KIN, act: ActionType = ActionType.THRUST,
                  cylinder=True, circle=False, include_distance=False, normalize_actions=False,
                  normalize_obs=False, reward_id: int = L.DN_REWARD_DEFAULT, ground_contact=False,
+                 normalize_reward=False, clip_reward: float = 0.0, reward_gamma: float = 0.99,
                  device=None, seed: int = 0, env_id_offset: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedDroneEnv needs a CUDA device: there is no CPU fallback")
@@ -79,6 +81,9 @@ class BatchedDroneEnv:
         c.max_steps = int(max_steps)
         c.spawn_mode = L.DN_SPAWN_FIXED
         c.normalize_obs = int(bool(normalize_obs))
+        c.normalize_reward = int(bool(normalize_reward))       # args.norm_rew (PBDroneSimulator.py:193-194)
+        c.clip_reward = float(clip_reward)                     # args.clip_rew -> 10 (PBDroneSimulator.py:191-192)
+        c.reward_gamma = float(reward_gamma)
         c.threshold, c.discount = float(threshold), float(discount)
         c.aviary_dim = (C.c_double * 6)(*[float(v) for v in aviary_dim])
         if initial_xyzs is None:   # BaseAviary.py:248-253, single drone
@@ -100,6 +105,10 @@ class BatchedDroneEnv:
         self.substeps = int(pyb_freq) // int(ctrl_freq)
         self.normalize_obs = bool(normalize_obs)
         self.uses_drag = bool(c.physics & L.DN_PHYS_DRAG)
+        self.normalize_reward = bool(normalize_reward)
+        self.reward_id = int(reward_id)
+        self._optional = {"last_rpm_sum": self.uses_drag, "obs_rms": self.normalize_obs,
+                          "aux": self.reward_id == L.DN_REWARD_REACHING, "rew_rms": self.normalize_reward}
         N, D, dev = self.num_envs, self.obs_dim, self.device
         self.obs = torch.zeros(N, D, dtype=torch.float32, device=dev)
         self.reward = torch.zeros(N, dtype=torch.float32, device=dev)
@@ -195,11 +204,9 @@ class BatchedDroneEnv:
         N, dev = self.num_envs, self.device
         ts = {}
         for name, (dt, w) in _STATE_DTYPES.items():
-            if name == "last_rpm_sum" and not self.uses_drag:
+            if not self._optional.get(name, True):
                 continue
             if name == "obs_rms":
-                if not self.normalize_obs:
-                    continue
                 ts[name] = torch.empty(N, 2 * self.obs_dim + 1, dtype=dt, device=dev)
             else:
                 ts[name] = torch.empty((N, w) if w else (N,), dtype=dt, device=dev)

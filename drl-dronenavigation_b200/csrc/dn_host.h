@@ -47,7 +47,9 @@ inline void euler_from_quat(const double q[4], double rpy[3]) {    // p.getEuler
     }
 }
 
-inline bool reward_table(int id, dn::RewardParams& w) {
+inline bool reward_table(int id, double discount, dn::RewardParams& w) {
+    w = dn::RewardParams{};
+    w.divisor = 1.f; w.inv_divisor = 1.f; w.mode = dn::RW_WAYPOINT;
     switch (id) {
         case DN_REWARD_DEFAULT:    // PBDroneEnv.py:475-607
             w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.7f, 0.3f, 1.f, 25.f, 0.04f}; return true;
@@ -55,7 +57,17 @@ inline bool reward_table(int id, dn::RewardParams& w) {
             w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.1f, 0.1f, 1.f, 25.f, 0.04f}; return true;
         case DN_REWARD_THRUSTENV:  // ThrustEnv.py:368-463 (-4 crash, +25 / +1000, 20 x progress, no orientation / smoothness)
             w = {-4.f, 1000.f, 25.f, 0.f, 3.f, 2.f, 20.f, 0.f, 0.f, 0.f, 0.f, 25.f, 0.04f}; return true;
-        default: return false;
+        case DN_REWARD_HER:        // HerPBDroneEnv.py:314-398: -3000 crash, 50 exp(-5 d) + 300 (prev_d - d), +5000 discount^(steps/10), +1e6
+            w.mode = dn::RW_HER; w.crash = -3000.f; w.final_bonus = 1.0e6f; w.capture_bonus = 5000.f;
+            w.exp_w = 50.f; w.exp_k = 5.f; w.progress_w = 300.f;
+            w.decay_log2 = (float)(std::log2(discount) / 10.0); return true;
+        case DN_REWARD_REACHING:   // dummy_env.py:617-643 / Rewarder.py:8-40: +3 gate, 10 final, -10 collision, travel - distance
+            w.mode = dn::RW_REACHING; w.crash = -10.f; w.final_bonus = 10.f; w.capture_bonus = 3.f; return true;
+        case DN_REWARD_HOVER:      // HoverAviary.py:65-76: -|(0,0,1) - p|^2
+            w.mode = dn::RW_POINT; w.pt_x = 0.f; w.pt_y_rate = 0.f; w.pt_z = 1.f; w.pt_w = 1.f; return true;
+        case DN_REWARD_FLYTHRUGATE: // FlyThruGateAviary.py:100-112: -10 |(0, -2 t_norm, 0.75) - p|^2
+            w.mode = dn::RW_POINT; w.pt_x = 0.f; w.pt_y_rate = -2.f; w.pt_z = 0.75f; w.pt_w = 10.f; return true;
+        default: return false;     // DN_REWARD_PROGRESS: not implemented (commented-out code in the reference)
     }
 }
 
@@ -126,6 +138,10 @@ inline void fill_params(const dn_config& cfg, const RewardParams& rw, Params& P,
     const double px[4] = {0.028, -0.028, -0.028, 0.028}, py[4] = {0.028, 0.028, -0.028, -0.028};   // safegym/cf2x.urdf:42,54,66,78
     for (int k = 0; k < 4; ++k) { P.prop_x[k] = (float)px[k]; P.prop_y[k] = (float)py[k]; }
     P.rw = rw;
+    P.rew_gamma = (float)(cfg.reward_gamma > 0.0 ? cfg.reward_gamma : 0.99);   // gym / normalize.NormalizeReward default
+    P.rew_eps = 1e-8f;
+    P.rew_clip = (float)(cfg.clip_reward > 0.0 ? cfg.clip_reward : 0.0);
+    P.ep_time_scale = (float)((double)(cfg.pyb_freq / cfg.ctrl_freq) / ((double)cfg.pyb_freq * 1.0));   // EPISODE_LEN_SEC = 1: _clipAndNormalizeState overwrites the constructor's 5 (PBDroneEnv.py:68,348)
     P.seed = cfg.seed;
     P.env_id_offset = cfg.env_id_offset;
 

@@ -28,7 +28,12 @@ struct RewardParams {
     float smooth_w;          // 1 = smoothness term on, 0 = off (ThrustEnv)
     float divisor;           // :571
     float inv_divisor;       // 1 / divisor (host, double)
+    // ---- other reward families (reward_id >= 3), see dn_device.cuh::reward_alt
+    int   mode;              // RW_* below
+    float decay_log2;        // HER: log2(discount) / 10, capture bonus * discount^(steps/10) (HerPBDroneEnv.py:371)
+    float pt_x, pt_y_rate, pt_z, pt_w;   // POINT: -pt_w * |(pt_x, pt_y_rate * t_norm, pt_z) - pos|^2 (HoverAviary.py:65-76, FlyThruGateAviary.py:100-112)
 };
+enum { RW_WAYPOINT = 0, RW_HER = 1, RW_REACHING = 2, RW_POINT = 3 };
 
 struct Stats {               // device mirror of dn_stats
     double             return_sum;
@@ -90,6 +95,10 @@ struct Params {
     float4* s[kPlanes];
     float* last_rpm_sum;     // [N], drag only
     float* obs_rms;          // [(2*obs_dim+1)][N] mean planes | var planes | count, normalize_obs only
+    float4* aux;             // [N] {_current_position.xyz (stale across resets), |_current_position - _last_position|}; RW_REACHING only
+    float4* rew_rms;         // [N] {returns, mean, var, count} of normalize.NormalizeReward (normalize.py:100-147); normalize_reward only
+    float rew_gamma, rew_eps, rew_clip;   // NormalizeReward gamma / epsilon; TransformReward clip bound (<= 0: off), PBDroneSimulator.py:190-193
+    float ep_time_scale;     // S / (PYB_FREQ * EPISODE_LEN_SEC): step_counter / PYB_FREQ / EPISODE_LEN_SEC = ep_len * this
     BlockStats* block_stats; // [ceil(N / CTA)] Monitor statistics slots
     int prefetch_ctas;       // software-prefetch distance in CTAs (= CTAs resident on the whole GPU)
 };

@@ -248,6 +248,8 @@ __global__ void init_kernel(const __grid_constant__ Params P, float d0) {
     s.pax = s.pay = s.paz = 0.f; s.ep_count = 0u;
     store_state(P, i, s);
     if (P.last_rpm_sum) P.last_rpm_sum[i] = 0.f;
+    if (P.aux) P.aux[i] = make_float4(P.init_pos[0], P.init_pos[1], P.init_pos[2], 0.f);   // _last_position = _current_position = INIT_XYZS[0]
+    if (P.rew_rms) P.rew_rms[i] = make_float4(0.f, 0.f, 1.f, 1e-4f);                       // returns 0; RunningMeanStd(): mean 0, var 1, count 1e-4
     if (P.obs_rms) {
         const size_t N = P.n; const int D = P.obs_dim;
         for (int k = 0; k < D; ++k) { P.obs_rms[k * N + i] = 0.f; P.obs_rms[(D + k) * N + i] = 1.f; }
@@ -326,7 +328,7 @@ __global__ void gae_kernel(const float* __restrict__ rew, const float* __restric
 struct StateView {   // device mirror of dn_state_view
     float *pos, *quat, *vel, *rpy_rates, *ang_v, *prev_vel, *prev_ang_v, *dist, *prev_dist;
     int32_t *target_idx, *steps; uint8_t* just_found; float* ep_return; int32_t* ep_length;
-    uint32_t* episode_count; float* last_rpm_sum; float* obs_rms;
+    uint32_t* episode_count; float* last_rpm_sum; float* obs_rms; float* aux; float* rew_rms;
 };
 
 template <bool SET>
@@ -362,6 +364,14 @@ __global__ void state_xfer_kernel(const __grid_constant__ Params P, const __grid
 #undef DN_V1
     if (V.last_rpm_sum && P.last_rpm_sum) {
         if (SET) P.last_rpm_sum[i] = V.last_rpm_sum[i]; else V.last_rpm_sum[i] = P.last_rpm_sum[i];
+    }
+    if (V.aux && P.aux) {
+        float4* g = reinterpret_cast<float4*>(V.aux);
+        if (SET) P.aux[i] = g[i]; else g[i] = P.aux[i];
+    }
+    if (V.rew_rms && P.rew_rms) {
+        float4* g = reinterpret_cast<float4*>(V.rew_rms);
+        if (SET) P.rew_rms[i] = g[i]; else g[i] = P.rew_rms[i];
     }
     if (V.obs_rms && P.obs_rms) {
         const int W = 2 * P.obs_dim + 1; const size_t N = P.n;
@@ -448,7 +458,7 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     if (cfg->spawn_mode != DN_SPAWN_FIXED) return fail(DN_EINVAL, "dn_create: spawn_mode not implemented");
     if (cfg->max_steps < 0 || cfg->max_steps > (int)dn::kStepsMask - 1) return fail(DN_EINVAL, "dn_create: max_steps out of range");
     dn::RewardParams rw;
-    if (!dn::host::reward_table(cfg->reward_id, rw)) return fail(DN_EINVAL, "dn_create: reward_id not implemented");
+    if (!dn::host::reward_table(cfg->reward_id, cfg->discount, rw)) return fail(DN_EINVAL, "dn_create: reward_id not implemented");
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -484,12 +494,17 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     if (drag) bytes += fplane;
     const size_t rms_floats = e->normalize_obs ? static_cast<size_t>(2 * P.obs_dim + 1) * N : 0;
     bytes += ((rms_floats * sizeof(float) + 255) / 256) * 256;
+    const bool need_aux = (rw.mode == dn::RW_REACHING), need_rew_rms = (cfg->normalize_reward != 0);
+    if (need_aux) bytes += plane;
+    if (need_rew_rms) bytes += plane;
     cudaError_t ce = cudaMalloc(&e->state_mem, bytes);
     if (ce != cudaSuccess) return cleanup(DN_ENOMEM, std::string("dn_create: cudaMalloc state: ") + cudaGetErrorString(ce));
     char* p = static_cast<char*>(e->state_mem);
     for (int k = 0; k < dn::kPlanes; ++k) { P.s[k] = reinterpret_cast<float4*>(p); p += plane; }
     if (drag) { P.last_rpm_sum = reinterpret_cast<float*>(p); p += fplane; }
-    if (rms_floats) P.obs_rms = reinterpret_cast<float*>(p);
+    if (rms_floats) { P.obs_rms = reinterpret_cast<float*>(p); p += ((rms_floats * sizeof(float) + 255) / 256) * 256; }
+    if (need_aux) { P.aux = reinterpret_cast<float4*>(p); p += plane; }
+    if (need_rew_rms) { P.rew_rms = reinterpret_cast<float4*>(p); p += plane; }
     if ((ce = cudaMalloc(&e->d_targets, T * sizeof(float4))) != cudaSuccess ||
         (ce = cudaMalloc(&e->d_segs, 2 * T * sizeof(float4))) != cudaSuccess ||
         (ce = cudaMalloc(&e->d_stats, sizeof(dn::Stats))) != cudaSuccess ||
@@ -679,6 +694,7 @@ static int state_xfer(dn_env* env, const dn_state_view* v, bool set, void* strea
     V.prev_vel = v->prev_vel; V.prev_ang_v = v->prev_ang_v; V.dist = v->dist; V.prev_dist = v->prev_dist;
     V.target_idx = v->target_idx; V.steps = v->steps; V.just_found = v->just_found; V.ep_return = v->ep_return;
     V.ep_length = v->ep_length; V.episode_count = v->episode_count; V.last_rpm_sum = v->last_rpm_sum; V.obs_rms = v->obs_rms;
+    V.aux = v->aux; V.rew_rms = v->rew_rms;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int N = env->P.n;
     if (set) dn::state_xfer_kernel<true><<<(N + 255) / 256, 256, 0, st>>>(env->P, V);

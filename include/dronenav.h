@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 1
+#define DN_ABI_VERSION 2
 
 /* error codes */
 #define DN_OK        0
@@ -56,11 +56,13 @@ extern "C" {
 #define DN_REWARD_DEFAULT   0   /* PBDroneEnv._computeReward, PBDroneEnv.py:475-571 */
 #define DN_REWARD_DUMMY     1   /* dummy_env.py:446-550 */
 #define DN_REWARD_THRUSTENV 2   /* ThrustEnv.py:368-513 */
-#define DN_REWARD_HER       3   /* HerPBDroneEnv.py:314-398 */
-#define DN_REWARD_REACHING  4   /* Rewarder.py reaching-progress (arXiv 2310.10943) */
-#define DN_REWARD_PROGRESS  5   /* Rewarder.py projection progress (arXiv 2103.08624) */
+#define DN_REWARD_HER       3   /* HerPBDroneEnv.py:314-398 (first element of its tuple) */
+#define DN_REWARD_REACHING  4   /* dummy_env.py:617-643 == Rewarder.py:8-40 reaching-progress (arXiv 2310.10943) */
+#define DN_REWARD_PROGRESS  5   /* Rewarder.py:43-62 projection progress (arXiv 2103.08624): only ever called from
+                                   commented-out code in the reference; reserved, dn_create rejects it */
 #define DN_REWARD_HOVER     6   /* upstream HoverAviary.py:65-76 */
-#define DN_NUM_REWARDS      7
+#define DN_REWARD_FLYTHRUGATE 7 /* FlyThruGateAviary.py:100-112 */
+#define DN_NUM_REWARDS      8
 
 /* spawn modes for (auto-)reset.  0 is the reference behaviour (PBDroneEnv.py:609-665). */
 #define DN_SPAWN_FIXED      0   /* INIT_XYZS / INIT_RPYS, deterministic */
@@ -100,7 +102,9 @@ typedef struct dn_config {
     double   init_xyz[3];        /* INIT_XYZS[0] (BaseAviary.py:248-257) */
     double   init_rpy[3];        /* INIT_RPYS[0] (BaseAviary.py:258-263) */
     int32_t  num_targets;        /* T */
-    int32_t  reserved0;
+    int32_t  normalize_reward;   /* fuse normalize.NormalizeReward (normalize.py:100-147; args.norm_rew, PBDroneSimulator.py:193) */
+    double   clip_reward;        /* > 0: clip the reward to +-this before normalisation (args.clip_rew, PBDroneSimulator.py:191-192: 10) */
+    double   reward_gamma;       /* NormalizeReward gamma; 0 = its default 0.99 */
     const double* targets;       /* HOST pointer, [T,3] row-major (copied by dn_create) */
 } dn_config;
 
@@ -136,6 +140,8 @@ typedef struct dn_state_view {
     uint32_t* episode_count;  /* [N]    episodes finished so far (Philox counter)        */
     float*    last_rpm_sum;   /* [N]    sum(last_clipped_action) (drag only, BaseAviary.py:429,442) */
     float*    obs_rms;        /* [N,2*obs_dim+1] mean | var | count (normalize.py:10-47); only if normalize_obs */
+    float*    aux;            /* [N,4] _current_position.xyz | last travel; only with DN_REWARD_REACHING */
+    float*    rew_rms;        /* [N,4] returns | mean | var | count (normalize.py:100-147); only if normalize_reward */
 } dn_state_view;
 
 /* Aggregated Monitor statistics since the last clear (SB3 Monitor / ep_info_buffer). */

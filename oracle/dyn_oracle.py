@@ -275,8 +275,11 @@ class OracleDroneEnv:
                  initial_xyzs=None, initial_rpys=None, physics=PHYSICS_DYN,
                  pyb_freq=240, ctrl_freq=240, act=ACT_THRUST, cylinder=True,
                  circle=False, include_distance=False, normalize_actions=False,
-                 ground_contact=False, consts: CF2XConstants = CF2X):
+                 ground_contact=False, reward_id="default", consts: CF2XConstants = CF2X):
         self.C = consts
+        self.reward_id = reward_id        # which reference reward function runs inside the PBDroneEnv step machine
+        self.EPISODE_LEN_SEC = 1          # PBDroneEnv.py:68 says 5, but _clipAndNormalizeState overwrites it with 1 on every
+                                          # observation (PBDroneEnv.py:348), i.e. before the first reward is ever computed
         self.ACT_TYPE = act
         self.PHYSICS = physics
         self._target_points = np.array(target_points, dtype=np.float64)
@@ -328,6 +331,7 @@ class OracleDroneEnv:
         self.just_found = False
         self._is_done = False
         self._steps = 0
+        self._last_position = self._current_position.copy()   # dummy_env.py:125 (reaching-progress reward only)
         # test instrumentation: signed distances of this step's threshold comparisons to their
         # thresholds (so FP32-vs-FP64 near-ties can be recognised); never read by the step itself
         self.margins = []
@@ -567,26 +571,87 @@ class OracleDroneEnv:
         self.margins.append(distance_from_line - (self._threshold + extension_length))
         return bool(distance_from_line > self._threshold + extension_length)
 
-    # ---- reward (PBDroneEnv.py:475-607) -------------------------------------
+    # ---- reward families other than the default ------------
     def _computeReward(self):
+        rid = self.reward_id
+        if rid == "default":
+            return self._reward_waypoint(-10.0, 200, 75, 5, 3000, 3, (0.7, 0.3))
+        if rid == "dummy":          # dummy_env.py:446-550, smoothness thresholds 0.1 / 0.1 (:587)
+            return self._reward_waypoint(-10.0, 200, 75, 5, 3000, 3, (0.1, 0.1))
+        if rid == "thrustenv":      # ThrustEnv.py:368-463
+            return self._reward_waypoint(-4.0, 1000, 25, 0, 20, 0, None)
+        if rid == "her":
+            return self._reward_her()
+        if rid == "reaching":
+            return self._reward_reaching()
+        if rid == "hover":          # HoverAviary.py:65-76
+            return -1 * np.linalg.norm(np.array([0, 0, 1]) - self.pos) ** 2
+        if rid == "flythrugate":    # FlyThruGateAviary.py:100-112
+            norm_ep_time = (self.step_counter / self.PYB_FREQ) / self.EPISODE_LEN_SEC
+            return -10 * np.linalg.norm(np.array([0, -2 * norm_ep_time, 0.75]) - self.pos) ** 2
+        raise ValueError(rid)
+
+    def _reward_her(self):
+        """HerPBDroneEnv._computeReward (HerPBDroneEnv.py:314-398), first element of the returned tuple."""
         if self._computeTerminated() and not self._is_done:
-            return -10.0
+            return -3000
+        reward = 0.0
+        distance_to_target = abs(np.linalg.norm(self._target_points[self._current_target_index] - self._current_position))
+        reward += np.exp(-distance_to_target * 5) * 50
+        reward += (self._prev_distance_to_target - distance_to_target) * 300
+        self.margins.append(distance_to_target - self._threshold)
+        if distance_to_target <= self._threshold:
+            self._current_target_index += 1
+            if self._current_target_index == len(self._target_points):
+                reward += 1_000_000.0
+                self._is_done = True
+                return reward
+            reward += 5000 * (self._discount ** (self._steps / 10))
+            return reward
+        self._prev_distance_to_target = distance_to_target
+        return reward
+
+    def _reward_reaching(self):
+        """dummy_env.PBDroneEnv.progress_reward (dummy_env.py:617-643) == Rewarder.reaching_progress_reward
+        (Rewarder.py:8-40)."""
+        reward = 0
+        dist_to_cent = np.linalg.norm(self._current_position - self._target_points[self._current_target_index])
+        self.margins.append(dist_to_cent - self._threshold)
+        if dist_to_cent <= self._threshold:
+            self._current_target_index += 1
+            reward += 3
+        if self._current_target_index == len(self._target_points):
+            self._is_done = True
+            return 10
+        dist_to_prev = np.linalg.norm(self._current_position - self._last_position)
+        penalty_term = 0.01 * np.linalg.norm(self.pos.reshape(1, 3)[10:])    # empty slice of the (1, 3) array -> 0
+        collision_penalty = -10.0 if self._has_collision_occurred() else 0.0
+        reward += dist_to_prev - dist_to_cent - penalty_term + collision_penalty
+        return reward
+
+    # ---- reward (PBDroneEnv.py:475-607) and its constant variants -----------
+    def _reward_waypoint(self, crash, final, capture, capture_orient, progress_w, orient_w, smooth_thr):
+        if self._computeTerminated() and not self._is_done:
+            return crash
         reward = np.float32(0.0)
         self.margins.append(self._distance_to_target - self._threshold)
         if self._distance_to_target <= self._threshold:
             self._current_target_index += 1
             if self._current_target_index == len(self._target_points):
-                reward += 200
+                reward += final
                 self._is_done = True
             else:
-                reward += 75
-                reward += self.orientation_reward(self.current_target()) * 5
+                reward += capture
+                if capture_orient:
+                    reward += self.orientation_reward(self.current_target()) * capture_orient
                 self.just_found = True
         else:
             reward += (np.exp(-2 * self._distance_to_target)) * 3
-            reward += ((self._prev_distance_to_target - self._distance_to_target) * 3000) if not self.just_found else 0
-            reward += self.orientation_reward(self.current_target()) * 3
-            reward += self.smoothness_reward()
+            reward += ((self._prev_distance_to_target - self._distance_to_target) * progress_w) if not self.just_found else 0
+            if orient_w:
+                reward += self.orientation_reward(self.current_target()) * orient_w
+            if smooth_thr is not None:
+                reward += self.smoothness_reward(*smooth_thr)
             self.just_found = False
         self._prev_distance_to_target = self._distance_to_target
         return reward / 25
@@ -618,6 +683,7 @@ class OracleDroneEnv:
     # ---- post-step (PBDroneEnv.py:201-223) ----------------------------------
     def _update_state_post_step(self, action):
         self._steps += 1
+        self._last_position = self._current_position.copy()     # dummy_env.py:196 (reaching-progress reward only)
         self._current_position = self.pos.copy()
         self.prev_vel, self.prev_ang_v = self.current_vel.copy(), self.current_ang_v.copy()
         self.current_vel, self.current_ang_v = self.vel.copy(), self.ang_v.copy()
@@ -682,9 +748,15 @@ class OracleWorker:
     the worker loop's auto-reset (PBDroneSimulator.py:153-198; SB3 contract in
     SURVEY.md a17)."""
 
-    def __init__(self, env: OracleDroneEnv, normalize_obs=True, norm_epsilon=1e-8):
+    def __init__(self, env: OracleDroneEnv, normalize_obs=True, norm_epsilon=1e-8,
+                 normalize_reward=False, clip_reward=0.0, reward_gamma=0.99):
         self.env = env
         self.normalize_obs = normalize_obs
+        # gym TransformReward(clip) then NormalizeReward, both inside Monitor (PBDroneSimulator.py:190-195);
+        # NormalizeReward restated from normalize.py:100-147
+        self.normalize_reward, self.clip_reward, self.reward_gamma = normalize_reward, clip_reward, reward_gamma
+        self.return_rms = OracleRunningMeanStd(shape=())
+        self.returns = np.zeros(1)
         self.obs_rms = OracleRunningMeanStd(shape=(env.obs_dim,))
         self.norm_epsilon = norm_epsilon
         self.ep_return = 0.0
@@ -707,6 +779,16 @@ class OracleWorker:
         self.last_terminated, self.last_truncated = bool(terminated), bool(truncated)
         self.last_step_ang_v_norm = float(np.linalg.norm(self.env.ang_v))   # test instrumentation
         obs = self._normalize(obs)
+        if self.clip_reward > 0:
+            reward = np.clip(reward, -self.clip_reward, self.clip_reward)
+        if self.normalize_reward:
+            rews = np.array([reward])
+            self.returns = self.returns * self.reward_gamma + rews
+            self.return_rms.update(self.returns)
+            rews = rews / np.sqrt(self.return_rms.var + self.norm_epsilon)
+            if terminated or truncated:
+                self.returns[:] = 0.0
+            reward = rews[0]
         self.ep_return += float(reward)
         self.ep_len += 1
         done = terminated or truncated

@@ -27,6 +27,7 @@ The SubprocVecEnv worker's auto-reset and the Monitor accumulators are SB3 code 
 restates that contract (reset on done, returned obs = reset obs, terminal obs kept aside).
 """
 import contextlib
+import copy
 import io
 import os
 import sys
@@ -39,7 +40,7 @@ REF = "/root/reference"
 HOVER = 0.092227
 
 CASES = {
-    # name: (track, S, action mode, envs, steps, seed, max_steps, normalize_obs)
+    # name: (track, S, action mode, envs, steps, seed, max_steps, normalize_obs[, reward function, norm_rew, clip_rew])
     "ref_circle_s1_saturating": ("circle", 1, "saturating", 4, 160, 21, 4096, False),
     "ref_circle_s8_mixed": ("circle", 8, "mixed", 4, 60, 22, 4096, False),
     "ref_circle_s8_saturating": ("circle", 8, "saturating", 4, 40, 26, 4096, False),
@@ -49,6 +50,19 @@ CASES = {
     "ref_circle_s1_truncate": ("circle", 1, "hover", 2, 30, 0, 12, False),
     "ref_circle_s8_normobs": ("circle", 8, "mixed", 3, 60, 25, 4096, True),
     "ref_circle_s1_normobs_resets": ("circle", 1, "saturating", 3, 140, 27, 4096, True),
+    # reward wrappers of make_env (PBDroneSimulator.py:190-195): clip to +-10, then the reference's NormalizeReward
+    "ref_circle_s8_normrew": ("circle", 8, "mixed", 3, 60, 28, 4096, False, "default", True, False),
+    "ref_reaching_s8_cliprew_normrew": ("reaching", 8, "saturating", 3, 50, 29, 4096, True, "default", True, True),
+    # other reward functions of the reference, run inside the same PBDroneEnv step machine
+    "ref_reaching_s8_rw_dummy": ("reaching", 8, "mixed", 3, 50, 30, 4096, False, "dummy", False, False),
+    "ref_circle_s8_rw_thrustenv": ("circle", 8, "mixed", 3, 50, 31, 4096, False, "thrustenv", False, False),
+    "ref_reaching_s8_rw_thrustenv": ("reaching", 8, "hover_band", 2, 40, 32, 4096, False, "thrustenv", False, False),
+    "ref_reaching_s8_rw_her": ("reaching", 8, "mixed", 3, 50, 33, 4096, False, "her", False, False),
+    "ref_circle_s8_rw_her": ("circle", 8, "saturating", 3, 40, 34, 4096, False, "her", False, False),
+    "ref_reaching_s8_rw_reaching": ("reaching", 8, "mixed", 3, 50, 35, 4096, False, "reaching", False, False),
+    "ref_circle_s1_rw_reaching": ("circle", 1, "saturating", 3, 140, 36, 4096, False, "reaching", False, False),
+    "ref_circle_s8_rw_hover": ("circle", 8, "mixed", 2, 40, 37, 4096, False, "hover", False, False),
+    "ref_circle_s8_rw_flythrugate": ("circle", 8, "mixed", 2, 40, 38, 4096, False, "flythrugate", False, False),
 }
 
 
@@ -78,11 +92,64 @@ def _import_reference():
         PHYSICS = property(lambda self: Physics.DYN, lambda self, value: None)        # see (2) above
         TIMESTEP = property(lambda self: self.PYB_TIMESTEP)                           # see (3) above
 
-    return _DynEnv, normalize, ActionType, Physics, Waypoints
+    # ---- the reference's OTHER reward functions, bound unmodified onto the same step machine ------------------
+    with contextlib.redirect_stdout(io.StringIO()):
+        from Sol.Model.Environments import dummy_env, ThrustEnv, HerPBDroneEnv
+        from Sol.PyBullet.FlyThruGateAviary import FlyThruGateAviary
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(
+            "_ref_hover", os.path.join(REF, "Sol/PyBullet/GymPybulletDronesMain/gym_pybullet_drones/envs/single_agent_rl/HoverAviary.py"))
+    try:
+        sys.path.insert(1, os.path.join(REF, "Sol/PyBullet/GymPybulletDronesMain"))   # the vendored upstream package tree
+        hover_mod = importlib.util.module_from_spec(spec)
+        with contextlib.redirect_stdout(io.StringIO()):
+            spec.loader.exec_module(hover_mod)
+        hover_reward = hover_mod.HoverAviary._computeReward
+    except Exception:          # the vendored upstream package imports its own (absent) module tree
+        hover_reward = None
+
+    class _Dummy(_DynEnv):
+        _computeReward = dummy_env.PBDroneEnv._computeReward
+        smoothness_reward = dummy_env.PBDroneEnv.smoothness_reward
+
+    class _Thrust(_DynEnv):
+        _computeReward = ThrustEnv.ThrustEnv._computeReward
+
+    class _Her(_DynEnv):
+        def _computeReward(self):
+            r = HerPBDroneEnv.PBDroneEnv._computeReward(self)        # (reward, reward + bonus) tuple, or -3000 on a crash
+            return r[0] if isinstance(r, tuple) else r
+
+    class _Reaching(_DynEnv):
+        _computeReward = dummy_env.PBDroneEnv.progress_reward
+
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self._last_position = self._current_position             # dummy_env.py __init__
+
+        def _update_state_post_step(self, action):                   # dummy_env.update_state_post_step keeps _last_position
+            self._last_position = copy.deepcopy(self._current_position)
+            super()._update_state_post_step(action)
+
+    class _Hover(_DynEnv):
+        if hover_reward is not None:
+            _computeReward = hover_reward
+        else:
+            def _computeReward(self):                                # HoverAviary.py:65-76 verbatim semantics
+                state = self._getDroneStateVector(0)
+                return -1 * np.linalg.norm(np.array([0, 0, 1]) - state[0:3]) ** 2
+
+    class _FlyThru(_DynEnv):
+        _computeReward = FlyThruGateAviary._computeReward
+
+    variants = {"default": _DynEnv, "dummy": _Dummy, "thrustenv": _Thrust, "her": _Her, "reaching": _Reaching,
+                "hover": _Hover, "flythrugate": _FlyThru}
+    return variants, normalize, ActionType, Physics, Waypoints, hover_reward is not None
 
 
-def make_env(ref, track, S, max_steps, normalize_obs):
-    DynEnv, normalize, ActionType, Physics, Waypoints = ref
+def make_env(ref, track, S, max_steps, normalize_obs, reward="default", norm_rew=False, clip_rew=False):
+    variants, normalize, ActionType, Physics, Waypoints, _ = ref
+    DynEnv = variants[reward]
     if track == "circle":      # simulation_controller.py / PBDroneSimulator.py:111-130
         tr = Waypoints.Track(Waypoints.circle(radius=1, num_points=6, height=1), circle=True)
     else:
@@ -99,12 +166,31 @@ def make_env(ref, track, S, max_steps, normalize_obs):
     raw = env
     if normalize_obs:
         env = normalize.NormalizeObservation(env)        # :181
+    if clip_rew:                                         # :191-192 gym.wrappers.TransformReward (third party): restated
+        env = _ClipReward(env)
+    if norm_rew:                                         # :193-194 gym.wrappers.NormalizeReward (third party); the
+        env = normalize.NormalizeReward(env)             # reference's own copy of the algorithm, normalize.py:100-147
     return env, raw
 
 
-def run(ref, track, S, mode, N, T, seed, max_steps, normalize_obs):
+class _ClipReward:
+    def __init__(self, env):
+        self.env = env
+
+    def step(self, action):
+        o, r, te, tr, info = self.env.step(action)
+        return o, np.clip(r, -10, 10), te, tr, info
+
+    def reset(self, **kw):
+        return self.env.reset(**kw)
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+
+def run(ref, track, S, mode, N, T, seed, max_steps, normalize_obs, reward="default", norm_rew=False, clip_rew=False):
     with contextlib.redirect_stdout(io.StringIO()):
-        envs = [make_env(ref, track, S, max_steps, normalize_obs) for _ in range(N)]
+        envs = [make_env(ref, track, S, max_steps, normalize_obs, reward, norm_rew, clip_rew) for _ in range(N)]
         a = actions(mode, T, N, seed)
         obs0 = np.stack([np.asarray(e.reset()[0], np.float64) for e, _ in envs])   # VecEnv.reset()
         D = obs0.shape[1]
@@ -134,12 +220,14 @@ def run(ref, track, S, mode, N, T, seed, max_steps, normalize_obs):
                     ep_ret[i], ep_len[i] = 0.0, 0
                     o, _ = e.reset()
                 out["obs"][t, i] = o
-    out["meta"] = np.array([track, str(S), mode, str(max_steps), "1" if normalize_obs else "0"])
+    out["meta"] = np.array([track, str(S), mode, str(max_steps), "1" if normalize_obs else "0", reward,
+                            "1" if norm_rew else "0", "1" if clip_rew else "0"])
     return out
 
 
 if __name__ == "__main__":
     ref = _import_reference()
+    print("HoverAviary imported from the reference:", ref[-1], file=sys.stderr)
     for name, cfg in CASES.items():
         out = run(ref, *cfg)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)

@@ -246,6 +246,11 @@ def _gym_module(name):
     spaces.Box = Box
     spaces.Dict = dict
     spaces.Space = object
+    spaces.__path__ = []                       # lets "from gymnasium.spaces.space import Space" resolve
+    space = types.ModuleType(name + ".spaces.space")
+    space.Space = object
+    spaces.space = space
+    sys.modules[name + ".spaces.space"] = space
     core = types.ModuleType(name + ".core")
     core.Wrapper, core.Env = Wrapper, Env
     m.spaces, m.core = spaces, core

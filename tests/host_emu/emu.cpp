@@ -13,6 +13,7 @@ struct Emu {
     std::vector<float4> planes[dn::kPlanes];
     std::vector<float4> targets, segs;
     std::vector<float> last_rpm_sum, obs_rms;
+    std::vector<float4> aux, rew_rms;
     int normalize_obs;
     float d0;
 };
@@ -41,7 +42,7 @@ extern "C" {
 
 Emu* emu_create(const dn_config* cfg) {
     dn::RewardParams rw;
-    if (!dn::host::reward_table(cfg->reward_id, rw)) return nullptr;
+    if (!dn::host::reward_table(cfg->reward_id, cfg->discount, rw)) return nullptr;
     Emu* e = new Emu();
     memset(&e->P, 0, sizeof(e->P));
     dn::host::fill_params(*cfg, rw, e->P, e->targets, e->segs, e->d0);
@@ -50,6 +51,10 @@ Emu* emu_create(const dn_config* cfg) {
     for (int k = 0; k < dn::kPlanes; ++k) { e->planes[k].assign(N, float4{0, 0, 0, 0}); e->P.s[k] = e->planes[k].data(); }
     e->P.targets = e->targets.data(); e->P.segs = e->segs.data();
     if (cfg->physics & DN_PHYS_DRAG) { e->last_rpm_sum.assign(N, 0.f); e->P.last_rpm_sum = e->last_rpm_sum.data(); }
+    if (rw.mode == dn::RW_REACHING) {
+        e->aux.assign(N, make_float4(e->P.init_pos[0], e->P.init_pos[1], e->P.init_pos[2], 0.f)); e->P.aux = e->aux.data();
+    }
+    if (cfg->normalize_reward) { e->rew_rms.assign(N, make_float4(0.f, 0.f, 1.f, 1e-4f)); e->P.rew_rms = e->rew_rms.data(); }
     for (int i = 0; i < N; ++i) {
         dn::EnvState s;
         memset(&s, 0, sizeof(s));

@@ -20,9 +20,14 @@ IDS = [os.path.basename(p)[:-4] for p in GOLD]
 HAVE_REF = os.path.isdir("/root/reference/Sol")
 
 
+REWARD_IDS = {"default": 0, "dummy": 1, "thrustenv": 2, "her": 3, "reaching": 4, "hover": 6, "flythrugate": 7}
+
+
 def _meta(g):
-    track, S, mode, max_steps, norm = [str(x) for x in g["meta"]]
-    return track, int(S), mode, int(max_steps), norm == "1"
+    m = [str(x) for x in g["meta"]] + ["default", "0", "0"]
+    track, S, mode, max_steps, norm, reward, norm_rew, clip_rew = m[:8]
+    return dict(track=track, S=int(S), mode=mode, max_steps=int(max_steps), norm=(norm == "1"), reward=reward,
+                norm_rew=(norm_rew == "1"), clip_rew=(clip_rew == "1"))
 
 
 def test_fixtures_exist():
@@ -53,9 +58,12 @@ def test_reference_reproduces_fixtures():
 def test_oracle_matches_reference(path):
     from oracle.dyn_oracle import OracleWorker, make_reference_env
     g = np.load(path)
-    track, S, mode, max_steps, norm = _meta(g)
+    m = _meta(g)
+    norm = m["norm"]
     T, N = g["reward"].shape
-    ws = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S, max_steps=max_steps), normalize_obs=norm)
+    ws = [OracleWorker(make_reference_env(m["track"], pyb_freq=240, ctrl_freq=240 // m["S"], max_steps=m["max_steps"],
+                                          reward_id=m["reward"]),
+                       normalize_obs=norm, normalize_reward=m["norm_rew"], clip_reward=10.0 if m["clip_rew"] else 0.0)
           for _ in range(N)]
     obs0 = np.stack([w.reset()[0] for w in ws])
     np.testing.assert_allclose(obs0, g["obs0"], rtol=0, atol=1e-12)
@@ -67,11 +75,11 @@ def test_oracle_matches_reference(path):
             assert bits == g["done"][t, i], (t, i)
             assert info["found_targets"] == g["found_targets"][t, i], (t, i)
             np.testing.assert_allclose(o, g["obs"][t, i], rtol=0, atol=1e-9 if norm else 0)
-            assert abs(float(r) - g["reward"][t, i]) <= 1e-12
+            assert abs(float(r) - g["reward"][t, i]) <= 1e-12 * max(1.0, abs(g["reward"][t, i]))
             if d:
                 np.testing.assert_allclose(info["terminal_observation"], g["terminal_obs"][t, i], rtol=0, atol=1e-9 if norm else 0)
                 assert info["episode"]["l"] == g["ep_length"][t, i]
-                assert abs(info["episode"]["r"] - g["ep_return"][t, i]) <= 1e-5      # Monitor rounds to 6 decimals
+                assert abs(info["episode"]["r"] - g["ep_return"][t, i]) <= 1e-5 + 1e-9 * abs(g["ep_return"][t, i])   # Monitor rounds to 6 decimals
                 ep_checked += 1
             else:
                 # physical state right after a non-terminal step (after a done the oracle worker has already reset)
@@ -92,7 +100,7 @@ def test_oracle_matches_reference(path):
 OBS_TOL, REW_TOL = 1e-3, 1e-2
 
 
-def _compare_fp32(g, step_fn, obs0, norm):
+def _compare_fp32(g, step_fn, obs0, norm, rel_reward=False):
     np.testing.assert_allclose(obs0, g["obs0"], atol=2e-4 if norm else 1e-6)
     T, N = g["reward"].shape
     worst_obs = worst_rew = 0.0
@@ -118,31 +126,41 @@ def _compare_fp32(g, step_fn, obs0, norm):
                 angn = float(np.linalg.norm(g["ang_v"][t, i]))
                 if not d[i]:
                     assert (e[9:12] <= 1e-3 + 1e-4 / max(angn, 1e-30)).all(), (t, i, e[9:12], angn)
-        worst_rew = max(worst_rew, float(np.abs(r - g["reward"][t]).max()))
+        if rel_reward:
+            # NormalizeReward divides by sqrt(var + 1e-8) of a running variance that starts near 0 (gain up to 1e4), and
+            # the HER reward reaches 1e6: relative tolerance on top of the absolute one
+            np.testing.assert_allclose(r, g["reward"][t], rtol=2e-3, atol=REW_TOL)
+        else:
+            worst_rew = max(worst_rew, float(np.abs(r - g["reward"][t]).max()))
     assert worst_obs < OBS_TOL and worst_rew < REW_TOL, (worst_obs, worst_rew)
     return worst_obs, worst_rew
 
 
 def _env_args(g):
     from oracle.dyn_oracle import circle_track, reaching_track
-    track, S, mode, max_steps, norm = _meta(g)
-    targets, init, dim = circle_track() if track == "circle" else reaching_track()
-    return dict(target_points=targets, aviary_dim=dim, initial_xyzs=init, pyb_freq=240, ctrl_freq=240 // S,
-                circle=(track == "circle"), include_distance=True, normalize_actions=True, max_steps=max_steps), norm
+    m = _meta(g)
+    targets, init, dim = circle_track() if m["track"] == "circle" else reaching_track()
+    kw = dict(target_points=targets, aviary_dim=dim, initial_xyzs=init, pyb_freq=240, ctrl_freq=240 // m["S"],
+              circle=(m["track"] == "circle"), include_distance=True, normalize_actions=True, max_steps=m["max_steps"],
+              reward_id=REWARD_IDS[m["reward"]], normalize_reward=m["norm_rew"], clip_reward=10.0 if m["clip_rew"] else 0.0)
+    return kw, m["norm"], (m["norm_rew"] or m["reward"] == "her")
 
 
-@pytest.mark.parametrize("path", [p for p in GOLD if "normobs" not in p], ids=[i for i in IDS if "normobs" not in i])
+_NO_OBS_NORM = [p for p in GOLD if not _meta(np.load(p))["norm"]]        # the host emulator has no NormalizeObservation path
+
+
+@pytest.mark.parametrize("path", _NO_OBS_NORM, ids=[os.path.basename(p)[:-4] for p in _NO_OBS_NORM])
 def test_device_logic_matches_reference(path):
     """csrc/dn_device.cuh compiled for the host (tests/host_emu) against the reference fixtures."""
     from tests.host_emu import HostEmuEnv
     g = np.load(path)
-    kw, norm = _env_args(g)
+    kw, norm, rel = _env_args(g)
     env = HostEmuEnv(g["reward"].shape[1], kw.pop("target_points"), **kw)
 
     def step(a):
         o, r, d, f = env.step(a)
         return o, r, d, f, env.terminal_obs.copy()
-    print(_compare_fp32(g, step, g["obs0"], norm))
+    print(_compare_fp32(g, step, g["obs0"], norm, rel))
     env.close()
 
 
@@ -152,13 +170,13 @@ def test_cuda_matches_reference(path):
     import torch
     from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
     g = np.load(path)
-    kw, norm = _env_args(g)
+    kw, norm, rel = _env_args(g)
     env = BatchedDroneEnv(g["reward"].shape[1], kw.pop("target_points"), normalize_obs=norm, **kw)
     obs0 = env.reset().cpu().numpy()
 
     def step(a):
         o, r, d, f = env.step(torch.from_numpy(a).cuda())
         return o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), f.cpu().numpy(), env.terminal_obs.cpu().numpy()
-    print(_compare_fp32(g, step, obs0, norm))
+    print(_compare_fp32(g, step, obs0, norm, rel))
     assert env.launch_count > g["reward"].shape[0]
     env.close()
