@@ -54,6 +54,8 @@ def build_parser() -> argparse.ArgumentParser:
     # additions of this implementation
     p.add_argument("--pyb_freq", type=int, default=240)
     p.add_argument("--ctrl_freq", type=int, default=240)
+    p.add_argument("--reward_id", type=int, default=0, help="DN_REWARD_* (include/dronenav.h): 0 PBDroneEnv, 1 dummy_env, "
+                   "2 ThrustEnv, 3 HER, 4 reaching-progress, 6 hover, 7 fly-thru-gate")
     p.add_argument("--rollout_steps", type=int, default=None, help="steps per env per PPO rollout (default: n_steps=4096 / scaled)")
     return p
 

@@ -48,7 +48,11 @@ class PBDroneSimulator:
         return dict(threshold=self.threshold, discount=self.discount, max_steps=self.env_steps,
                     aviary_dim=aviary_dim, initial_xyzs=self.initial_xyzs if initial_xyzs is None else initial_xyzs,
                     act=ActionType.THRUST, cylinder=True, circle=self.track.is_circle, include_distance=include_distance,
-                    normalize_actions=normalize_actions, pyb_freq=self.pyb_freq, ctrl_freq=self.ctrl_freq)
+                    normalize_actions=normalize_actions, pyb_freq=self.pyb_freq, ctrl_freq=self.ctrl_freq,
+                    # the reward wrappers make_env stacks between the env and Monitor (:190-195), fused into the kernel
+                    clip_reward=10.0 if getattr(self.args, "clip_rew", False) else 0.0,
+                    normalize_reward=bool(getattr(self.args, "norm_rew", False)),
+                    reward_id=int(getattr(self.args, "reward_id", 0)))
 
     def make_env(self, multi=False, gui=False, initial_xyzs=None, aviary_dim=np.array([-1, -1, 0, 1, 1, 1]), rank: int = 0,
                  save_path: str = None, include_distance: bool = True, normalize_actions: bool = True,
