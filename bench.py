@@ -269,8 +269,28 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def roofline(n_envs, sec_per_launch, traffic=None):
+def ncu_traffic(n_envs, substeps):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of step_kernel from the committed `ncu --set full`
+    capture of the same (envs, substeps) configuration (profiles/ncu_summary_r*.json, written by
+    tools/summarize_profiles.py from the .ncu-rep files); None if that configuration was not captured."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_summary_r*.json"))):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            rec = d.get(f"prof_n{n_envs}_s{substeps}.ncu-rep")
+            if rec and "traffic_bytes" in rec:
+                best = float(rec["traffic_bytes"])
+        except Exception:  # noqa: BLE001
+            pass
+    return best
+
+
+def roofline(n_envs, sec_per_launch, traffic=None, substeps=None):
     peak, src = peaks()
+    if traffic is None and substeps is not None:
+        traffic = ncu_traffic(n_envs, substeps)
     achieved = BYTES_PER_ENV_STEP * n_envs / sec_per_launch / 1e9
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "kernel": "dn::step_kernel<0,false>", "bytes_per_env_step": BYTES_PER_ENV_STEP, "envs_per_launch": n_envs,
@@ -382,7 +402,7 @@ def run_b200(args):
 
     # ---- single-GPU extras on rank 0 only: roofline, sweep, e2e, cpu baseline --------------------
     if world == 1:
-        line["roofline"] = roofline(N, sec / K)
+        line["roofline"] = roofline(N, sec / K, substeps=args.substeps)
         line["roofline"]["note"] = "launch/latency-bound at this batch size: 1.2 MB per launch is ~0.2 us of HBM time"
         sweep = []
         for n_big in args.sweep:
@@ -392,7 +412,7 @@ def run_b200(args):
                 a2 = make_actions(4, n_big, args.actions, dev, seed=99)
                 k2 = max(10, min(K, int(2e8 // n_big)))
                 s2 = time_plain(e2, a2, k2, 24)      # 24 warm-up steps: episodes are de-phased (steady-state reset mix)
-                rf = roofline(n_big, s2 / k2)
+                rf = roofline(n_big, s2 / k2, substeps=args.substeps)
                 sweep.append({"envs": n_big, "value": n_big * k2 / s2, "us_per_launch": 1e6 * s2 / k2, "steps": k2,
                               "roofline_frac": rf["frac"], "achieved_gbs": rf["achieved"],
                               "working_set_mb": n_big * (BYTES_PER_ENV_STEP - 16) / 1e6, "l2": "inputs larger than L2" if n_big * 224 > 126e6 else "fits L2"})
@@ -413,7 +433,7 @@ def run_b200(args):
             a3 = make_actions(4, n_big, args.actions, dev, seed=98)
             k3 = max(10, min(K, int(2e8 // n_big)))
             s3 = time_plain(e3, a3, k3, 24)
-            line["roofline_hbm_s1"] = roofline(n_big, s3 / k3)
+            line["roofline_hbm_s1"] = roofline(n_big, s3 / k3, substeps=1)
             line["roofline_hbm_s1"]["substeps"] = 1
             e3.close(); del e3, a3
             torch.cuda.empty_cache()

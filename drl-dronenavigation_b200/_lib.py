@@ -51,7 +51,7 @@ class dn_step_io(C.Structure):
 
 STATE_FIELDS = ("pos", "quat", "vel", "rpy_rates", "ang_v", "prev_vel", "prev_ang_v", "dist", "prev_dist",
                 "target_idx", "steps", "just_found", "ep_return", "ep_length", "episode_count",
-                "last_rpm_sum", "obs_rms", "aux", "rew_rms")
+                "last_rpm_sum", "obs_rms", "aux", "rew_rms", "spawn")
 
 
 class dn_state_view(C.Structure):

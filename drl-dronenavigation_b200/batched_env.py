@@ -33,7 +33,7 @@ _STATE_DTYPES = {
     "target_idx": (torch.int32, 0), "steps": (torch.int32, 0), "just_found": (torch.uint8, 0),
     "ep_return": (torch.float32, 0), "ep_length": (torch.int32, 0), "episode_count": (torch.int32, 0),
     "last_rpm_sum": (torch.float32, 0), "obs_rms": (torch.float32, -1),
-    "aux": (torch.float32, 4), "rew_rms": (torch.float32, 4),
+    "aux": (torch.float32, 4), "rew_rms": (torch.float32, 4), "spawn": (torch.float32, 4),
 }
 
 
@@ -48,7 +48,7 @@ class BatchedDroneEnv:
                  cylinder=True, circle=False, include_distance=False, normalize_actions=False,
                  normalize_obs=False, reward_id: int = L.DN_REWARD_DEFAULT, ground_contact=False,
                  normalize_reward=False, clip_reward: float = 0.0, reward_gamma: float = 0.99,
-                 device=None, seed: int = 0, env_id_offset: int = 0):
+                 random_spawn=False, device=None, seed: int = 0, env_id_offset: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedDroneEnv needs a CUDA device: there is no CPU fallback")
         if drone_model != DroneModel.CF2X:
@@ -79,7 +79,8 @@ class BatchedDroneEnv:
         c.include_distance = int(bool(include_distance))
         c.cylinder, c.circle = int(bool(cylinder)), int(bool(circle))
         c.max_steps = int(max_steps)
-        c.spawn_mode = L.DN_SPAWN_FIXED
+        # random_spawn=True: the reference's (commented-out) spawn around a random target-pair line (PBDroneEnv.py:622-629)
+        c.spawn_mode = L.DN_SPAWN_LINE if random_spawn else L.DN_SPAWN_FIXED
         c.normalize_obs = int(bool(normalize_obs))
         c.normalize_reward = int(bool(normalize_reward))       # args.norm_rew (PBDroneSimulator.py:193-194)
         c.clip_reward = float(clip_reward)                     # args.clip_rew -> 10 (PBDroneSimulator.py:191-192)
@@ -108,7 +109,8 @@ class BatchedDroneEnv:
         self.normalize_reward = bool(normalize_reward)
         self.reward_id = int(reward_id)
         self._optional = {"last_rpm_sum": self.uses_drag, "obs_rms": self.normalize_obs,
-                          "aux": self.reward_id == L.DN_REWARD_REACHING, "rew_rms": self.normalize_reward}
+                          "aux": self.reward_id == L.DN_REWARD_REACHING, "rew_rms": self.normalize_reward,
+                          "spawn": bool(random_spawn)}
         N, D, dev = self.num_envs, self.obs_dim, self.device
         self.obs = torch.zeros(N, D, dtype=torch.float32, device=dev)
         self.reward = torch.zeros(N, dtype=torch.float32, device=dev)

@@ -95,6 +95,7 @@ struct Params {
     float4* s[kPlanes];
     float* last_rpm_sum;     // [N], drag only
     float* obs_rms;          // [(2*obs_dim+1)][N] mean planes | var planes | count, normalize_obs only
+    float4* spawn;           // [N] {spawn point of the current episode, 0}; DN_SPAWN_LINE only (segment 0 of the tube starts there)
     float4* aux;             // [N] {_current_position.xyz (stale across resets), |_current_position - _last_position|}; RW_REACHING only
     float4* rew_rms;         // [N] {returns, mean, var, count} of normalize.NormalizeReward (normalize.py:100-147); normalize_reward only
     float rew_gamma, rew_eps, rew_clip;   // NormalizeReward gamma / epsilon; TransformReward clip bound (<= 0: off), PBDroneSimulator.py:190-193

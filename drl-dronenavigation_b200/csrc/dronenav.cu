@@ -117,7 +117,7 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
                     float ob = tn;
                     if (r.finished) {
                         if (term_out) term_out[k] = tn;
-                        const float raw = (k < 12) ? P.init_obs[k] : r.reset_obs_dist;
+                        const float raw = (k < 3) ? r.spawn_obs[k] : ((k < 12) ? P.init_obs[k] : r.reset_obs_dist);
                         ob = rms_update_normalize(raw, m, v, cnt + 1.0f);
                     }
                     obs_row[k] = ob;
@@ -131,7 +131,8 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
                     if (D == 13) term_out[12] = obs_row[12];
                 }
 #pragma unroll
-                for (int k = 0; k < 12; ++k) obs_row[k] = P.init_obs[k];
+                for (int k = 3; k < 12; ++k) obs_row[k] = P.init_obs[k];
+                obs_row[0] = r.spawn_obs[0]; obs_row[1] = r.spawn_obs[1]; obs_row[2] = r.spawn_obs[2];
                 if (D == 13) obs_row[12] = r.reset_obs_dist;
             }
             if (write_out) {
@@ -248,6 +249,7 @@ __global__ void init_kernel(const __grid_constant__ Params P, float d0) {
     s.pax = s.pay = s.paz = 0.f; s.ep_count = 0u;
     store_state(P, i, s);
     if (P.last_rpm_sum) P.last_rpm_sum[i] = 0.f;
+    if (P.spawn) P.spawn[i] = make_float4(P.init_pos[0], P.init_pos[1], P.init_pos[2], 0.f);
     if (P.aux) P.aux[i] = make_float4(P.init_pos[0], P.init_pos[1], P.init_pos[2], 0.f);   // _last_position = _current_position = INIT_XYZS[0]
     if (P.rew_rms) P.rew_rms[i] = make_float4(0.f, 0.f, 1.f, 1e-4f);                       // returns 0; RunningMeanStd(): mean 0, var 1, count 1e-4
     if (P.obs_rms) {
@@ -274,6 +276,15 @@ __global__ void reset_kernel(const __grid_constant__ Params P, const uint8_t* ma
         D0 = sqrtf(dx * dx + dy * dy + dz * dz);
     }
     s.px = P.init_pos[0]; s.py = P.init_pos[1]; s.pz = P.init_pos[2];
+    if (P.spawn_mode == DN_SPAWN_LINE) {        // see env_step; the Philox counter advances on explicit resets too
+        s.ep_count += 1u;
+        spawn_line(P, i, s.ep_count, s.px, s.py, s.pz);
+        P.spawn[i] = make_float4(s.px, s.py, s.pz, 0.f);
+        if (P.aux) { float4 ax = P.aux[i]; ax.x = s.px; ax.y = s.py; ax.z = s.pz; P.aux[i] = ax; }
+        const float4 t0 = __ldg(&P.targets[0]);
+        const float dx = s.px - t0.x, dy = s.py - t0.y, dz = s.pz - t0.z;
+        D0 = sqrtf(dx * dx + dy * dy + dz * dz);
+    }
     s.qx = P.init_quat[0]; s.qy = P.init_quat[1]; s.qz = P.init_quat[2]; s.qw = P.init_quat[3];
     s.vx = s.vy = s.vz = 0.f; s.wx = s.wy = s.wz = 0.f; s.ax = s.ay = s.az = 0.f;
     s.pvx = s.pvy = s.pvz = 0.f; s.pax = s.pay = s.paz = 0.f;
@@ -285,6 +296,7 @@ __global__ void reset_kernel(const __grid_constant__ Params P, const uint8_t* ma
     float o[kMaxObs];
 #pragma unroll
     for (int k = 0; k < 12; ++k) o[k] = P.init_obs[k];
+    if (P.spawn_mode == DN_SPAWN_LINE) { o[0] = s.px * P.inv_x_high; o[1] = s.py * P.inv_y_high; o[2] = s.pz * P.inv_z_high; }
     o[12] = stale_dist * P.inv_max_target_dist;
     if (NORM) {
         const size_t N = P.n;
@@ -328,7 +340,7 @@ __global__ void gae_kernel(const float* __restrict__ rew, const float* __restric
 struct StateView {   // device mirror of dn_state_view
     float *pos, *quat, *vel, *rpy_rates, *ang_v, *prev_vel, *prev_ang_v, *dist, *prev_dist;
     int32_t *target_idx, *steps; uint8_t* just_found; float* ep_return; int32_t* ep_length;
-    uint32_t* episode_count; float* last_rpm_sum; float* obs_rms; float* aux; float* rew_rms;
+    uint32_t* episode_count; float* last_rpm_sum; float* obs_rms; float* aux; float* rew_rms; float* spawn;
 };
 
 template <bool SET>
@@ -368,6 +380,10 @@ __global__ void state_xfer_kernel(const __grid_constant__ Params P, const __grid
     if (V.aux && P.aux) {
         float4* g = reinterpret_cast<float4*>(V.aux);
         if (SET) P.aux[i] = g[i]; else g[i] = P.aux[i];
+    }
+    if (V.spawn && P.spawn) {
+        float4* g = reinterpret_cast<float4*>(V.spawn);
+        if (SET) P.spawn[i] = g[i]; else g[i] = P.spawn[i];
     }
     if (V.rew_rms && P.rew_rms) {
         float4* g = reinterpret_cast<float4*>(V.rew_rms);
@@ -455,7 +471,9 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
         return fail(DN_EINVAL, "dn_create: need 1..2046 targets");
     if (cfg->act_type < 0 || cfg->act_type > DN_ACT_ONE_D_RPM) return fail(DN_EINVAL, "dn_create: unsupported act_type");
     if (cfg->physics & ~7) return fail(DN_EINVAL, "dn_create: unknown physics flags");
-    if (cfg->spawn_mode != DN_SPAWN_FIXED) return fail(DN_EINVAL, "dn_create: spawn_mode not implemented");
+    if (cfg->spawn_mode != DN_SPAWN_FIXED && cfg->spawn_mode != DN_SPAWN_LINE)
+        return fail(DN_EINVAL, "dn_create: spawn_mode not implemented (DN_SPAWN_MIDPOINT is reserved)");
+    if (cfg->spawn_mode == DN_SPAWN_LINE && cfg->num_targets < 2) return fail(DN_EINVAL, "dn_create: DN_SPAWN_LINE needs >= 2 targets");
     if (cfg->max_steps < 0 || cfg->max_steps > (int)dn::kStepsMask - 1) return fail(DN_EINVAL, "dn_create: max_steps out of range");
     dn::RewardParams rw;
     if (!dn::host::reward_table(cfg->reward_id, cfg->discount, rw)) return fail(DN_EINVAL, "dn_create: reward_id not implemented");
@@ -495,8 +513,10 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     const size_t rms_floats = e->normalize_obs ? static_cast<size_t>(2 * P.obs_dim + 1) * N : 0;
     bytes += ((rms_floats * sizeof(float) + 255) / 256) * 256;
     const bool need_aux = (rw.mode == dn::RW_REACHING), need_rew_rms = (cfg->normalize_reward != 0);
+    const bool need_spawn = (cfg->spawn_mode == DN_SPAWN_LINE);
     if (need_aux) bytes += plane;
     if (need_rew_rms) bytes += plane;
+    if (need_spawn) bytes += plane;
     cudaError_t ce = cudaMalloc(&e->state_mem, bytes);
     if (ce != cudaSuccess) return cleanup(DN_ENOMEM, std::string("dn_create: cudaMalloc state: ") + cudaGetErrorString(ce));
     char* p = static_cast<char*>(e->state_mem);
@@ -505,6 +525,7 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     if (rms_floats) { P.obs_rms = reinterpret_cast<float*>(p); p += ((rms_floats * sizeof(float) + 255) / 256) * 256; }
     if (need_aux) { P.aux = reinterpret_cast<float4*>(p); p += plane; }
     if (need_rew_rms) { P.rew_rms = reinterpret_cast<float4*>(p); p += plane; }
+    if (need_spawn) { P.spawn = reinterpret_cast<float4*>(p); p += plane; }
     if ((ce = cudaMalloc(&e->d_targets, T * sizeof(float4))) != cudaSuccess ||
         (ce = cudaMalloc(&e->d_segs, 2 * T * sizeof(float4))) != cudaSuccess ||
         (ce = cudaMalloc(&e->d_stats, sizeof(dn::Stats))) != cudaSuccess ||
@@ -694,7 +715,7 @@ static int state_xfer(dn_env* env, const dn_state_view* v, bool set, void* strea
     V.prev_vel = v->prev_vel; V.prev_ang_v = v->prev_ang_v; V.dist = v->dist; V.prev_dist = v->prev_dist;
     V.target_idx = v->target_idx; V.steps = v->steps; V.just_found = v->just_found; V.ep_return = v->ep_return;
     V.ep_length = v->ep_length; V.episode_count = v->episode_count; V.last_rpm_sum = v->last_rpm_sum; V.obs_rms = v->obs_rms;
-    V.aux = v->aux; V.rew_rms = v->rew_rms;
+    V.aux = v->aux; V.rew_rms = v->rew_rms; V.spawn = v->spawn;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int N = env->P.n;
     if (set) dn::state_xfer_kernel<true><<<(N + 255) / 256, 256, 0, st>>>(env->P, V);

@@ -66,8 +66,10 @@ extern "C" {
 
 /* spawn modes for (auto-)reset.  0 is the reference behaviour (PBDroneEnv.py:609-665). */
 #define DN_SPAWN_FIXED      0   /* INIT_XYZS / INIT_RPYS, deterministic */
-#define DN_SPAWN_LINE       1   /* Philox: within 0.1 m of a random target-pair line (PBDroneEnv.py:622-629) */
-#define DN_SPAWN_MIDPOINT   2   /* Philox: segment midpoint with rolled target order (PBDroneEnv.py:641-648) */
+#define DN_SPAWN_LINE       1   /* Philox: within 0.1 m of a random target-pair line (PBDroneEnv.py:622-629,
+                                   position_generator.py:121-152); commented out in the reference, offered as an option */
+#define DN_SPAWN_MIDPOINT   2   /* segment midpoint with rolled target order (PBDroneEnv.py:641-648, commented out);
+                                   reserved, dn_create rejects it */
 
 /* done byte written by dn_step */
 #define DN_DONE_TERMINATED  1
@@ -142,6 +144,7 @@ typedef struct dn_state_view {
     float*    obs_rms;        /* [N,2*obs_dim+1] mean | var | count (normalize.py:10-47); only if normalize_obs */
     float*    aux;            /* [N,4] _current_position.xyz | last travel; only with DN_REWARD_REACHING */
     float*    rew_rms;        /* [N,4] returns | mean | var | count (normalize.py:100-147); only if normalize_reward */
+    float*    spawn;          /* [N,4] INIT_XYZS[0] of the current episode | 0; only with DN_SPAWN_LINE */
 } dn_state_view;
 
 /* Aggregated Monitor statistics since the last clear (SB3 Monitor / ep_info_buffer). */

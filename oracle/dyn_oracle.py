@@ -262,6 +262,57 @@ PHYSICS_DYN_DRAG = "dyn_drag"
 PHYSICS_DYN_GND = "dyn_gnd"
 PHYSICS_DYN_GND_DRAG = "dyn_gnd_drag"
 
+# --------------------------------------------------------------------------
+# random spawn (optional; PBDroneEnv.py:622-629 is commented out in the reference)
+# --------------------------------------------------------------------------
+
+
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al., SC'11).  counter: 4 uint32, key: 2 uint32 -> 4 uint32."""
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c = [int(v) & MASK for v in counter]
+    k0, k1 = int(key[0]) & MASK, int(key[1]) & MASK
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & MASK, p1 & MASK, ((p0 >> 32) ^ c[3] ^ k1) & MASK, p0 & MASK]
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return c
+
+
+def spawn_line(targets, aviary_dim, seed, global_env_id, counter, max_distance=0.1):
+    """PositionGenerator.generate_random_point_around_line (position_generator.py:121-152) between two distinct
+    random targets (PBDroneEnv.py:623-624), with the draws taken from Philox(seed; counter, block, env id)
+    instead of numpy's / random's global generators (the mapping of draws to variables is ours; it is the same
+    in csrc/dn_device.cuh::spawn_line)."""
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    gid = (global_env_id & 0xFFFFFFFF, (global_env_id >> 32) & 0xFFFFFFFF)
+    a = philox4x32_10((counter, 0, gid[0], gid[1]), key)
+    b = philox4x32_10((counter, 1, gid[0], gid[1]), key)
+    u01 = lambda x: float(np.float32(x >> 8) * np.float32(1.0 / 16777216.0))
+    u01_open = lambda x: float((np.float32(x >> 8) + np.float32(1.0)) * np.float32(1.0 / 16777216.0))
+    T = len(targets)
+    ia = min(int(np.float32(u01(a[0])) * np.float32(T)), T - 1)
+    ib = min(int(np.float32(u01(a[1])) * np.float32(T - 1)), T - 2)
+    if ib >= ia:
+        ib += 1
+    from_point, to_point = np.asarray(targets[ia], np.float64), np.asarray(targets[ib], np.float64)
+    t = u01(a[2])
+    point = from_point + t * (to_point - from_point)
+    direction_vector = to_point - from_point
+    r1, r2 = math.sqrt(-2.0 * math.log(u01_open(a[3]))), math.sqrt(-2.0 * math.log(u01_open(b[1])))
+    random_vector = np.array([r1 * math.cos(2 * math.pi * u01(b[0])), r1 * math.sin(2 * math.pi * u01(b[0])),
+                              r2 * math.cos(2 * math.pi * u01(b[2]))])
+    perpendicular_vector = np.cross(direction_vector, random_vector)
+    n = np.linalg.norm(perpendicular_vector)
+    # identical end points (the reaching track's first and last gate coincide) make this 0/0 in the reference;
+    # defined here, and in the kernel, as "no perpendicular offset"
+    perpendicular_vector = perpendicular_vector / n if n > 0 else np.zeros(3)
+    offset = (2.0 * u01(b[3]) - 1.0) * max_distance
+    point = point + offset * perpendicular_vector
+    lo, hi = np.asarray(aviary_dim[:3], np.float64), np.asarray(aviary_dim[3:], np.float64)
+    return np.minimum(np.maximum(point, lo), hi)
+
+
 ACT_THRUST = "thrust"
 ACT_RPM = "rpm"
 ACT_ONE_D_RPM = "one_d_rpm"
@@ -275,8 +326,10 @@ class OracleDroneEnv:
                  initial_xyzs=None, initial_rpys=None, physics=PHYSICS_DYN,
                  pyb_freq=240, ctrl_freq=240, act=ACT_THRUST, cylinder=True,
                  circle=False, include_distance=False, normalize_actions=False,
-                 ground_contact=False, reward_id="default", consts: CF2XConstants = CF2X):
+                 ground_contact=False, reward_id="default", random_spawn=False, seed=0, global_env_id=0,
+                 consts: CF2XConstants = CF2X):
         self.C = consts
+        self.random_spawn, self.seed, self.global_env_id, self._reset_counter = random_spawn, seed, global_env_id, 0
         self.reward_id = reward_id        # which reference reward function runs inside the PBDroneEnv step machine
         self.EPISODE_LEN_SEC = 1          # PBDroneEnv.py:68 says 5, but _clipAndNormalizeState overwrites it with 1 on every
                                           # observation (PBDroneEnv.py:348), i.e. before the first reward is ever computed
@@ -354,6 +407,12 @@ class OracleDroneEnv:
 
     # ---- reset (BaseAviary.py:276-320 then PBDroneEnv.py:609-665) ----------
     def reset(self, seed=None, options=None):
+        self._reset_counter += 1
+        if self.random_spawn:
+            # OUR semantics for the reference's commented-out block (PBDroneEnv.py:622-629): the point is drawn first,
+            # the episode starts there, the reset observation shows it and the distances are measured from it
+            self.INIT_XYZS[0] = spawn_line(self._target_points, self._aviary_dim, self.seed, self.global_env_id, self._reset_counter)
+            self._current_position = self.INIT_XYZS[0].copy()
         self._housekeeping()
         initial_obs = self._computeObs()      # BEFORE the distances are reset
         initial_info = self._computeInfo()    # found_targets of the previous episode

@@ -28,7 +28,8 @@ class HostEmuEnv:
     def __init__(self, num_envs, target_points, threshold=0.3, discount=0.999, max_steps=4096,
                  aviary_dim=(-1, -1, 0, 1, 1, 1), initial_xyzs=None, pyb_freq=240, ctrl_freq=240,
                  act_type=0, cylinder=True, circle=False, include_distance=False, normalize_actions=False,
-                 physics=0, reward_id=0, normalize_reward=False, clip_reward=0.0, reward_gamma=0.99):
+                 physics=0, reward_id=0, normalize_reward=False, clip_reward=0.0, reward_gamma=0.99,
+                 random_spawn=False, seed=0, env_id_offset=0):
         from drl_dronenavigation_b200 import _lib as L
         self.lib = C.CDLL(build())
         self.lib.emu_create.restype = C.c_void_p
@@ -45,6 +46,7 @@ class HostEmuEnv:
         c.normalize_actions, c.physics, c.reward_id = int(normalize_actions), physics, reward_id
         c.include_distance, c.cylinder, c.circle, c.max_steps = int(include_distance), int(cylinder), int(circle), max_steps
         c.threshold, c.discount = threshold, discount
+        c.spawn_mode, c.seed, c.env_id_offset = (1 if random_spawn else 0), seed, env_id_offset
         c.normalize_reward, c.clip_reward, c.reward_gamma = int(normalize_reward), float(clip_reward), float(reward_gamma)
         c.aviary_dim = (C.c_double * 6)(*[float(v) for v in aviary_dim])
         c.init_xyz = (C.c_double * 3)(*np.array(initial_xyzs, dtype=np.float64).reshape(-1)[:3])

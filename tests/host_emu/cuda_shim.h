@@ -27,3 +27,4 @@ static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f
 #define __expf(a) expf(a)
 static inline float __fdividef(float a, float b) { return a / b; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline int min(int a, int b) { return a < b ? a : b; }

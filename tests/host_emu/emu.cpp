@@ -13,7 +13,7 @@ struct Emu {
     std::vector<float4> planes[dn::kPlanes];
     std::vector<float4> targets, segs;
     std::vector<float> last_rpm_sum, obs_rms;
-    std::vector<float4> aux, rew_rms;
+    std::vector<float4> aux, rew_rms, spawn;
     int normalize_obs;
     float d0;
 };
@@ -31,7 +31,7 @@ static void step_all(Emu* e, const float* actions, float* obs, float* reward, ui
         reward[i] = r.reward; done[i] = r.done; found[i] = r.found;
         if (r.finished) for (int k = 0; k < P.obs_dim; ++k) {
             term_obs[(size_t)i * P.obs_dim + k] = row[k];
-            row[k] = (k < 12) ? P.init_obs[k] : r.reset_obs_dist;
+            row[k] = (k < 3) ? r.spawn_obs[k] : ((k < 12) ? P.init_obs[k] : r.reset_obs_dist);
         }
         dn::store_state(P, i, s);
         if (PHYS & 1) P.last_rpm_sum[i] = lrs;
@@ -53,6 +53,9 @@ Emu* emu_create(const dn_config* cfg) {
     if (cfg->physics & DN_PHYS_DRAG) { e->last_rpm_sum.assign(N, 0.f); e->P.last_rpm_sum = e->last_rpm_sum.data(); }
     if (rw.mode == dn::RW_REACHING) {
         e->aux.assign(N, make_float4(e->P.init_pos[0], e->P.init_pos[1], e->P.init_pos[2], 0.f)); e->P.aux = e->aux.data();
+    }
+    if (cfg->spawn_mode == DN_SPAWN_LINE) {
+        e->spawn.assign(N, make_float4(e->P.init_pos[0], e->P.init_pos[1], e->P.init_pos[2], 0.f)); e->P.spawn = e->spawn.data();
     }
     if (cfg->normalize_reward) { e->rew_rms.assign(N, make_float4(0.f, 0.f, 1.f, 1e-4f)); e->P.rew_rms = e->rew_rms.data(); }
     for (int i = 0; i < N; ++i) {

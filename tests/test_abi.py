@@ -33,7 +33,7 @@ def test_struct_layouts_match_header(built_lib):
     from drl_dronenavigation_b200 import _lib
     # sizes implied by include/dronenav.h on LP64
     assert C.sizeof(_lib.dn_step_io) == 8 * 8
-    assert C.sizeof(_lib.dn_state_view) == 19 * 8
+    assert C.sizeof(_lib.dn_state_view) == 20 * 8
     assert C.sizeof(_lib.dn_stats) == 7 * 8
     assert C.sizeof(_lib.dn_config) == 4 + 4 + 8 + 8 + 12 * 4 + 2 * 8 + 12 * 8 + 4 + 4 + 2 * 8 + 8
 

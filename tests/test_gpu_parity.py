@@ -320,3 +320,40 @@ def test_full_size_properties():
         stats = env.episode_stats()
         assert stats["episodes"] == n_done and stats["crashes"] + stats["truncations"] + stats["successes"] == n_done
         env.close()
+
+
+@pytest.mark.parametrize("track", ["circle", "reaching"])
+def test_random_spawn_philox_matches_oracle_and_is_shard_invariant(track):
+    """DN_SPAWN_LINE (Philox-seeded auto-reset): the CUDA path against the oracle's restatement of the same draws,
+    and invariance to sharding -- env g of a shard with env_id_offset = k behaves exactly like env k + g of one big
+    handle (Philox subsequence = GLOBAL env id)."""
+    from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
+    from oracle.dyn_oracle import OracleWorker, make_reference_env
+    from tests.test_host_emulation import _open_loop
+    N, T, S, seed = 8, 120, 8, 0x1234ABCD5678
+    ref = make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S)
+    mk = lambda n, off: BatchedDroneEnv(n, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS,
+                                        pyb_freq=240, ctrl_freq=240 // S, circle=(track == "circle"), include_distance=True,
+                                        normalize_actions=True, random_spawn=True, seed=seed, env_id_offset=off)
+    big, shard = mk(N, 100), mk(N // 2, 100 + N // 2)
+    workers = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S, random_spawn=True, seed=seed,
+                                               global_env_id=100 + i), normalize_obs=False) for i in range(N)]
+    o_big, o_sh = big.reset().cpu().numpy(), shard.reset().cpu().numpy()
+    np.testing.assert_array_equal(o_big[N // 2:], o_sh)
+    for i, w in enumerate(workers):
+        np.testing.assert_allclose(o_big[i], w.reset()[0], atol=2e-6)
+    acts = _actions("saturating", T, N, seed=5)
+
+    def step(a):
+        o, r, d, f = [x.cpu().numpy().copy() for x in big.step(torch.from_numpy(a).cuda())]
+        o2, r2, d2, f2 = [x.cpu().numpy() for x in shard.step(torch.from_numpy(np.ascontiguousarray(a[N // 2:])).cuda())]
+        np.testing.assert_array_equal(o[N // 2:], o2)
+        np.testing.assert_array_equal(r[N // 2:], r2)
+        np.testing.assert_array_equal(d[N // 2:], d2)
+        return o, r, d, f
+    resets = _open_loop(step, workers, acts)
+    assert resets >= 10
+    sp = big.get_state()["spawn"].cpu().numpy()[:, :3]
+    want = np.stack([w.env.INIT_XYZS[0] for w in workers])
+    np.testing.assert_allclose(sp, want, atol=2e-6)
+    big.close(); shard.close()

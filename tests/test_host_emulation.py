@@ -67,3 +67,52 @@ def test_device_logic_physics_addons(physics, oracle_physics):
     rep = PU.run_lockstep(env, workers, _actions("mixed", 45, 6, seed=physics), resync_every=30)
     print(f"\n[emu physics={physics}] {rep}")
     env.close()
+
+
+def _open_loop(env_step, workers, actions, obs_tol=1e-3, rew_tol=1e-2):
+    """Open-loop comparison without re-synchronisation: every episode restarts from a (random) spawn, so FP32 drift
+    does not carry over; discrete outputs exact."""
+    T, N = actions.shape[:2]
+    resets = 0
+    for t in range(T):
+        o, r, d, f = env_step(actions[t])
+        for i, w in enumerate(workers):
+            oo, rr, dd, info = w.step(actions[t, i])
+            bits = (1 if w.last_terminated else 0) | (2 if w.last_truncated else 0)
+            assert int(d[i]) == bits and int(f[i]) == info["found_targets"], (t, i, d[i], bits, f[i], info["found_targets"])
+            e = np.abs(o[i].astype(np.float64) - oo)
+            e[3:6] = np.minimum(e[3:6], np.abs(2 - e[3:6]))
+            assert max(e[:9].max(), e[12]) < obs_tol, (t, i, e)
+            assert abs(float(r[i]) - float(rr)) < rew_tol, (t, i, r[i], rr)
+            resets += int(dd)
+    return resets
+
+
+@pytest.mark.parametrize("track", ["circle", "reaching"])
+def test_device_logic_random_spawn_philox(track):
+    """DN_SPAWN_LINE: Philox-seeded spawn around a random target-pair line at every auto-reset; the draws, the spawn
+    point, the per-env tube segment 0 and the reset observation must agree with the oracle's restatement."""
+    from oracle.dyn_oracle import OracleWorker, make_reference_env
+    from tests.host_emu import HostEmuEnv
+    N, T, S, seed, off = 6, 120, 8, 0x1234ABCD5678, 1000
+    ref = make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S)
+    env = HostEmuEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS, pyb_freq=240,
+                     ctrl_freq=240 // S, circle=(track == "circle"), include_distance=True, normalize_actions=True,
+                     random_spawn=True, seed=seed, env_id_offset=off)
+    workers = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S, random_spawn=True, seed=seed,
+                                               global_env_id=off + i), normalize_obs=False) for i in range(N)]
+    resets = _open_loop(env.step, workers, _actions("saturating", T, N, seed=5))
+    assert resets >= 10
+    # spawn points differ between envs and between episodes
+    sp = np.stack([w.env.INIT_XYZS[0] for w in workers])
+    assert len({tuple(np.round(p, 6)) for p in sp}) >= N // 2      # (envs that have not reset yet still sit at INIT_XYZS)
+    env.close()
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer vectors of the Random123 distribution (kat_vectors)."""
+    from oracle.dyn_oracle import philox4x32_10
+    assert philox4x32_10((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert philox4x32_10((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
