@@ -27,17 +27,18 @@ class PBDroneEnv:
                  gui=False, record=False, obs: ObservationType = ObservationType.KIN,
                  act: ActionType = ActionType.THRUST, vision_attributes=False, user_debug_gui=False,
                  obstacles=False, random_spawn=False, cylinder=True, circle=False, include_target=False,
-                 include_distance=False, normalize_actions=False, collect_rollouts=False, device=None):
+                 include_distance=False, normalize_actions=False, collect_rollouts=False, device=None, seed: int = 0):
         if gui or record or vision_attributes or obstacles:
             raise NotImplementedError("rendering / vision / obstacles are outside the CUDA hot path")
-        if random_spawn:
-            raise NotImplementedError("random_spawn: the reference disables it (PBDroneSimulator.py:166)")
         self._core = BatchedDroneEnv(1, target_points, threshold=threshold, discount=discount, max_steps=max_steps,
                                      aviary_dim=aviary_dim, initial_xyzs=initial_xyzs, initial_rpys=initial_rpys,
                                      drone_model=drone_model, physics=physics, pyb_freq=pyb_freq, ctrl_freq=ctrl_freq,
                                      obs=obs, act=act, cylinder=cylinder, circle=circle,
                                      include_distance=include_distance, normalize_actions=normalize_actions,
-                                     normalize_obs=False, device=device)
+                                     normalize_obs=False, device=device,
+                                     # the reference's make_env passes False (PBDroneSimulator.py:166); True selects the
+                                     # Philox version of its commented-out spawn around a target-pair line (PBDroneEnv.py:622-629)
+                                     random_spawn=random_spawn, seed=seed)
         self.ACT_TYPE, self.OBS_TYPE, self.PHYSICS = act, obs, physics
         self.normalize_actions, self.include_distance = normalize_actions, include_distance
         self.action_space = action_space(normalize_actions)

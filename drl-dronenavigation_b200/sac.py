@@ -1,0 +1,265 @@
+"""Torch-native SAC on the device-resident environment (BASELINE config 4).
+
+Hyper-parameters are the SAC branch of ``PBDroneSimulator.setup_agent`` (Sol/Model/PBDroneSimulator.py:290-331:
+qf [256, 256, 128], pi [256, 256], ReLU, batch 1024, buffer 1 048 576, learning_starts 8192, train_freq 3,
+gradient_steps 5, tau 0.005, lr 2.5e-4, gamma 0.99, ent_coef "auto", target_entropy "auto"); the update is the
+maths of SB3's ``SAC.train`` that the reference relies on (squashed diagonal Gaussian actor with log-std clamped to
+[-20, 2], twin critics, entropy-coefficient auto-tuning towards -|A|, Polyak targets every gradient step, time-limit
+truncations not treated as terminal, next observation of a finished episode = its terminal observation).
+What changes is where the data lives: the replay buffer is a set of device tensors filled straight from the fused
+step kernel's outputs (no numpy hop, no per-env Python), and under ``torchrun`` every gradient step all-reduces two
+flat buckets (critics + log-alpha, actor) over NCCL -- the environment shards need no collective.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+LOG_STD_MIN, LOG_STD_MAX = -20.0, 2.0      # SB3 sac/policies.py
+
+
+@dataclass
+class SACConfig:
+    """Defaults = PBDroneSimulator.setup_agent's SAC branch (PBDroneSimulator.py:304-327)."""
+    learning_starts: int = 8192
+    train_freq: int = 3            # env.step calls (x num_envs transitions) between update phases
+    gradient_steps: int = 5
+    batch_size: int = 1024
+    tau: float = 0.005
+    target_update_interval: int = 1
+    buffer_size: int = 1_048_576   # transitions in total (SB3 divides by n_envs)
+    learning_rate: float = 2.5e-4
+    gamma: float = 0.99
+    pi_arch: tuple = (256, 256)
+    qf_arch: tuple = (256, 256, 128)
+    n_critics: int = 2
+    ent_coef_init: float = 1.0     # ent_coef="auto" -> log_ent_coef = log(1.0)
+    target_entropy: Optional[float] = None   # "auto" -> -|A|
+    seed: int = 42
+    matmul_precision: str = "tf32"
+
+
+def _relu_mlp(sizes, out_dim=None):
+    layers = []
+    for a, b in zip(sizes[:-1], sizes[1:]):
+        layers += [nn.Linear(a, b), nn.ReLU()]
+    if out_dim is not None:
+        layers.append(nn.Linear(sizes[-1], out_dim))
+    return nn.Sequential(*layers)
+
+
+class Actor(nn.Module):
+    """SB3 sac.policies.Actor: latent MLP -> (mu, log_std) heads, tanh-squashed Gaussian."""
+
+    def __init__(self, obs_dim, act_dim, arch):
+        super().__init__()
+        self.latent = _relu_mlp((obs_dim,) + tuple(arch))
+        self.mu = nn.Linear(arch[-1], act_dim)
+        self.log_std = nn.Linear(arch[-1], act_dim)
+
+    def forward(self, obs, generator=None, deterministic=False):
+        h = self.latent(obs)
+        mu, log_std = self.mu(h), self.log_std(h).clamp(LOG_STD_MIN, LOG_STD_MAX)
+        if deterministic:
+            return torch.tanh(mu), None
+        std = log_std.exp()
+        eps = torch.randn(mu.shape, device=mu.device, dtype=mu.dtype, generator=generator)
+        g = mu + std * eps
+        a = torch.tanh(g)
+        # Normal(mu, std).log_prob(g).sum - sum log(1 - tanh(g)^2 + eps)   (SquashedDiagGaussianDistribution, epsilon 1e-6)
+        logp = (-0.5 * eps.pow(2) - log_std - 0.5 * math.log(2 * math.pi)).sum(-1) - torch.log(1 - a.pow(2) + 1e-6).sum(-1)
+        return a, logp
+
+
+class Critics(nn.Module):
+    """n_critics independent Q(s, a) MLPs (SB3 ContinuousCritic, share_features_extractor=False)."""
+
+    def __init__(self, obs_dim, act_dim, arch, n):
+        super().__init__()
+        self.qs = nn.ModuleList([_relu_mlp((obs_dim + act_dim,) + tuple(arch), 1) for _ in range(n)])
+
+    def forward(self, obs, act):
+        x = torch.cat([obs, act], dim=-1)
+        return [q(x).squeeze(-1) for q in self.qs]
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class _FlatGrads:
+    """All gradients of a parameter list as views into ONE tensor (one all-reduce per optimiser step)."""
+
+    def __init__(self, params, device):
+        self.params = list(params)
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.calls = 0
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce(self):
+        w = _world()
+        if w > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(w)
+            self.calls += 1
+
+
+class ReplayBuffer:
+    """Device-resident circular buffer, [capacity_steps, N, ...] (SB3 ReplayBuffer with n_envs = N,
+    handle_timeout_termination=True, optimize_memory_usage=False)."""
+
+    def __init__(self, capacity_transitions: int, num_envs: int, obs_dim: int, act_dim: int, device):
+        self.cap = max(capacity_transitions // num_envs, 1)
+        self.N, self.pos, self.full = num_envs, 0, False
+        f = dict(dtype=torch.float32, device=device)
+        self.obs = torch.empty(self.cap, num_envs, obs_dim, **f)
+        self.next_obs = torch.empty(self.cap, num_envs, obs_dim, **f)
+        self.act = torch.empty(self.cap, num_envs, act_dim, **f)
+        self.rew = torch.empty(self.cap, num_envs, **f)
+        self.done = torch.empty(self.cap, num_envs, **f)        # 1 only for true terminations (timeouts excluded)
+
+    def add(self, obs, next_obs, act, rew, done_bits, terminal_obs):
+        p = self.pos
+        finished = done_bits != 0
+        self.obs[p].copy_(obs)
+        # the VecEnv returns the RESET observation on done; the transition's successor is the terminal observation
+        self.next_obs[p].copy_(torch.where(finished.unsqueeze(-1), terminal_obs, next_obs))
+        self.act[p].copy_(act)
+        self.rew[p].copy_(rew)
+        self.done[p].copy_(((done_bits & 1) != 0).to(torch.float32))      # DN_DONE_TERMINATED; truncated-only -> bootstrap
+        self.pos = (p + 1) % self.cap
+        self.full = self.full or self.pos == 0
+
+    def __len__(self):
+        return (self.cap if self.full else self.pos) * self.N
+
+    def sample(self, batch_size: int, generator=None):
+        n = len(self)
+        idx = torch.randint(0, n, (batch_size,), device=self.obs.device, generator=generator)
+        flat = lambda t: t.reshape(self.cap * self.N, *t.shape[2:])
+        return flat(self.obs)[idx], flat(self.act)[idx], flat(self.rew)[idx], flat(self.next_obs)[idx], flat(self.done)[idx]
+
+
+class SACLearner:
+    """Actor, twin critics + targets, log-alpha and the SAC update; independent of the environment."""
+
+    def __init__(self, obs_dim: int, act_dim: int, cfg: SACConfig = SACConfig(), device="cpu"):
+        self.cfg, self.device = cfg, torch.device(device)
+        torch.manual_seed(cfg.seed)                         # same seed on every rank -> identical initial parameters
+        self.actor = Actor(obs_dim, act_dim, cfg.pi_arch).to(self.device)
+        self.critic = Critics(obs_dim, act_dim, cfg.qf_arch, cfg.n_critics).to(self.device)
+        self.critic_target = Critics(obs_dim, act_dim, cfg.qf_arch, cfg.n_critics).to(self.device)
+        self.critic_target.load_state_dict(self.critic.state_dict())
+        for p in self.critic_target.parameters():
+            p.requires_grad_(False)
+        self.log_ent_coef = torch.log(torch.ones(1, device=self.device) * cfg.ent_coef_init).requires_grad_(True)
+        self.target_entropy = float(-act_dim) if cfg.target_entropy is None else float(cfg.target_entropy)
+        lr = cfg.learning_rate
+        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=lr)
+        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=lr)
+        self.ent_opt = torch.optim.Adam([self.log_ent_coef], lr=lr)
+        # bucket 1: critics + log-alpha (their losses do not depend on each other's step); bucket 2: actor
+        self.g_critic = _FlatGrads(list(self.critic.parameters()) + [self.log_ent_coef], self.device)
+        self.g_actor = _FlatGrads(self.actor.parameters(), self.device)
+        self.n_updates = 0
+        if self.device.type == "cuda" and cfg.matmul_precision == "tf32":
+            torch.backends.cuda.matmul.allow_tf32 = True
+
+    @torch.no_grad()
+    def act(self, obs, generator=None, deterministic=False):
+        return self.actor(obs, generator=generator, deterministic=deterministic)[0]
+
+    def update(self, batch, generator=None) -> Dict[str, torch.Tensor]:
+        """One gradient step of SB3's SAC.train on a sampled batch (obs, act, rew, next_obs, done)."""
+        obs, act, rew, next_obs, done = batch
+        cfg = self.cfg
+        actions_pi, log_prob = self.actor(obs, generator=generator)
+        ent_coef = self.log_ent_coef.detach().exp()
+        ent_loss = -(self.log_ent_coef * (log_prob + self.target_entropy).detach()).mean()
+        with torch.no_grad():
+            next_a, next_logp = self.actor(next_obs, generator=generator)
+            next_q = torch.stack(self.critic_target(next_obs, next_a), 0).min(0).values - ent_coef * next_logp
+            target_q = rew + (1.0 - done) * cfg.gamma * next_q
+        cur_q = self.critic(obs, act)
+        critic_loss = 0.5 * sum(torch.nn.functional.mse_loss(q, target_q) for q in cur_q)
+        self.g_critic.zero()
+        (critic_loss + ent_loss).backward(inputs=self.g_critic.params)
+        self.g_critic.allreduce()
+        self.ent_opt.step()
+        self.critic_opt.step()
+        # actor: min_i Q_i(s, pi(s)) with the UPDATED critics, as in SB3
+        q_pi = torch.stack(self.critic(obs, actions_pi), 0).min(0).values
+        actor_loss = (ent_coef * log_prob - q_pi).mean()
+        self.g_actor.zero()
+        actor_loss.backward(inputs=self.g_actor.params)
+        self.g_actor.allreduce()
+        self.actor_opt.step()
+        self.n_updates += 1
+        if self.n_updates % cfg.target_update_interval == 0:
+            with torch.no_grad():                            # polyak_update(critic, critic_target, tau)
+                tp, sp = list(self.critic_target.parameters()), list(self.critic.parameters())
+                torch._foreach_mul_(tp, 1.0 - cfg.tau)
+                torch._foreach_add_(tp, sp, alpha=cfg.tau)
+        return {"critic_loss": critic_loss.detach(), "actor_loss": actor_loss.detach(), "ent_coef": ent_coef.squeeze(0),
+                "ent_coef_loss": ent_loss.detach()}
+
+    def flat_parameters(self) -> torch.Tensor:
+        ps = list(self.actor.parameters()) + list(self.critic.parameters()) + [self.log_ent_coef]
+        return torch.cat([p.detach().reshape(-1) for p in ps])
+
+
+class SACTrainer:
+    """Off-policy loop on a BatchedDroneEnv shard: train_freq env steps, then gradient_steps updates."""
+
+    def __init__(self, env, cfg: SACConfig = SACConfig()):
+        self.env, self.cfg, self.dev = env, cfg, env.device
+        self.learner = SACLearner(env.obs_dim, 4, cfg, device=self.dev)
+        rank = dist.get_rank() if _world() > 1 else 0
+        self.gen = torch.Generator(device=self.dev).manual_seed(cfg.seed + 1000 * (rank + 1))
+        self.buffer = ReplayBuffer(cfg.buffer_size, env.num_envs, env.obs_dim, 4, self.dev)
+        self.obs = env.reset().clone()
+        self.total_steps = 0
+
+    @torch.no_grad()
+    def collect(self, n_steps: int):
+        env, N = self.env, self.env.num_envs
+        for _ in range(n_steps):
+            if self.total_steps < self.cfg.learning_starts:      # SB3: uniform random actions before learning_starts
+                a = torch.rand(N, 4, device=self.dev, generator=self.gen) * 2 - 1
+            else:
+                a = self.learner.act(self.obs, generator=self.gen)
+            a = a.contiguous()
+            obs, rew, done, _ = env.step(a)
+            self.buffer.add(self.obs, obs, a, rew, done, env.terminal_obs)
+            self.obs = obs.clone()
+            self.total_steps += N * _world()
+
+    def train_iteration(self) -> Dict[str, float]:
+        cfg = self.cfg
+        t0 = time.perf_counter()
+        self.collect(cfg.train_freq)
+        out = {}
+        grad_steps = 0
+        if self.total_steps >= cfg.learning_starts and len(self.buffer) >= cfg.batch_size:
+            for _ in range(cfg.gradient_steps):
+                out = self.learner.update(self.buffer.sample(cfg.batch_size, generator=self.gen), generator=self.gen)
+                grad_steps += 1
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+        dt = time.perf_counter() - t0
+        res = {k: float(v) for k, v in out.items()}
+        res.update(samples=cfg.train_freq * self.env.num_envs * _world(), gradient_steps=grad_steps, seconds=dt,
+                   sps=cfg.train_freq * self.env.num_envs * _world() / dt)
+        return res

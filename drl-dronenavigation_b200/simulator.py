@@ -79,8 +79,11 @@ class PBDroneSimulator:
         """PPO with the reference's hyper-parameters (:251-286).  The rollout length per env is n_steps=4096
         for the reference's 12 envs; with thousands of envs it is scaled so that one rollout holds about the
         same 12 x 4096 x (a few) samples per update unless --rollout_steps says otherwise."""
+        if self.args.agent == "SAC":            # :290-331
+            from .sac import SACConfig, SACTrainer
+            return SACTrainer(train_env, SACConfig())
         if self.args.agent != "PPO":
-            raise NotImplementedError(f"{self.args.agent}: only the PPO branch is built on the device path so far")
+            raise NotImplementedError(f"{self.args.agent}: the PPO and SAC branches are built on the device path")
         n = train_env.num_envs
         T = getattr(self.args, "rollout_steps", None) or max(16, min(4096, (12 * 4096 * 8) // max(n, 1)))
         cfg = PPOConfig(n_steps=T, batch_size=max(512, (T * n) // 32))

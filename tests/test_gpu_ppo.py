@@ -57,3 +57,25 @@ def test_simulator_manager_short_training_and_test_run():
     venv.close()
     rewards = sim.run_test(log=lambda *_: None)
     assert len(rewards) >= 1 and rewards[-1] in (-10.0,) or len(rewards) > 1
+
+
+def test_sac_trainer_runs_on_device_with_drag_and_ground_effect():
+    """BASELINE config 4 at test size: SAC on the circle track with the drag + ground-effect physics extension."""
+    import bench
+    from drl_dronenavigation_b200 import Physics
+    from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
+    from drl_dronenavigation_b200.sac import SACConfig, SACTrainer
+    targets, init, dim, is_circle = bench.track_setup("circle")
+    env = BatchedDroneEnv(1024, targets, aviary_dim=dim, initial_xyzs=init, pyb_freq=240, ctrl_freq=30, circle=is_circle,
+                          include_distance=True, normalize_actions=True, physics=Physics.PYB_GND_DRAG_DW)
+    tr = SACTrainer(env, SACConfig(learning_starts=4096, buffer_size=65536))
+    p0 = tr.learner.flat_parameters().clone()
+    outs = [tr.train_iteration() for _ in range(6)]
+    assert outs[0]["gradient_steps"] == 0 and outs[-1]["gradient_steps"] == 5      # learning_starts respected
+    assert np.isfinite([outs[-1]["critic_loss"], outs[-1]["actor_loss"], outs[-1]["ent_coef"]]).all()
+    assert len(tr.buffer) == 6 * 3 * 1024 and tr.total_steps == 6 * 3 * 1024
+    assert not torch.equal(p0, tr.learner.flat_parameters())
+    # time-limit handling: only true terminations are stored as done
+    assert float(tr.buffer.done[:tr.buffer.pos].max()) <= 1.0
+    assert env.launch_count >= 18
+    env.close()
