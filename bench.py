@@ -323,6 +323,7 @@ def run_ppo(args, dev, world, rank, barrier, max_over_ranks):
            "envs_per_gpu": args.ppo_envs, "rollout_steps": T, "iterations": args.ppo_iters, "track": a.track, "substeps": args.substeps,
            "minibatch": cfg.batch_size, "epochs_run": [o["epochs"] for o in outs], "minibatches_run": [o["minibatches"] for o in outs],
            "rollout_s": sum(o["rollout_s"] for o in outs), "update_s": sum(o["update_s"] for o in outs),
+           "rollout_s_each": [round(o["rollout_s"], 5) for o in outs], "update_s_each": [round(o["update_s"], 5) for o in outs],
            "env_share_of_rollout": None, "allreduce_calls": tr.learner.allreduce_calls, "allreduce_bytes": tr.learner.n_params * 4,
            "gpu_launches": int(env.launch_count - l0), "approx_kl": outs[-1]["approx_kl"],
            "policy": "2 x MLP 13-512-512-256 (pi, vf), Tanh, TF32 GEMMs (cuBLAS)", "collective": "NCCL all-reduce of one flat FP32 gradient bucket per optimiser step" if world > 1 else "none (1 GPU)"}

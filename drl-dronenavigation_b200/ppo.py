@@ -46,6 +46,7 @@ class PPOConfig:
     adam_eps: float = 1e-5
     seed: int = 42                      # model.set_random_seed(42), PBDroneSimulator.py:690
     matmul_precision: str = "tf32"      # "fp32" | "tf32": precision of the MLP GEMMs (cuBLAS)
+    cuda_graph: bool = True             # replay each minibatch step from two captured CUDA graphs (CUDA devices only)
 
 
 def _mlp(sizes, out_dim, out_gain):
@@ -137,7 +138,10 @@ class PPOLearner:
         self.cfg, self.device = cfg, torch.device(device)
         torch.manual_seed(cfg.seed)                     # same seed on every rank -> identical initial parameters
         self.policy = ActorCritic(obs_dim, act_dim, cfg).to(self.device)
-        self.opt = torch.optim.Adam(self.policy.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps)
+        self._graphs = None                             # (shape key, graph A, graph B, static tensors); built lazily
+        self.use_graph = bool(cfg.cuda_graph) and self.device.type == "cuda"
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps,
+                                    capturable=self.use_graph)
         self.params = [p for p in self.policy.parameters()]
         self.n_params = sum(p.numel() for p in self.params)
         # the one gradient bucket: every parameter's .grad is a view into it, so backward() writes the
@@ -149,9 +153,9 @@ class PPOLearner:
             off += p.numel()
         self.n_updates = 0
         self.allreduce_calls = 0
-        if self.device.type == "cuda" and cfg.matmul_precision == "tf32":
-            torch.backends.cuda.matmul.allow_tf32 = True
-            torch.backends.cudnn.allow_tf32 = True
+        if self.device.type == "cuda":                  # process-wide switches: set both ways so "fp32" means FP32
+            torch.backends.cuda.matmul.allow_tf32 = (cfg.matmul_precision == "tf32")
+            torch.backends.cudnn.allow_tf32 = (cfg.matmul_precision == "tf32")
 
     # ---- the only collective: one flat bucket per optimiser step (between backward and clip, sb3_ppo.py:291-293)
     def _allreduce_grads(self):
@@ -170,58 +174,139 @@ class PPOLearner:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return bool(t.item() > 0)
 
+    # ---- one minibatch, in two halves around the gradient all-reduce --------------------------------------
+    def _forward_backward(self, obs, actions, old_logp, old_values, advantages, returns, acc):
+        """losses of sb3_ppo.py:225-281 + backward into the flat bucket; returns approx_kl (0-d tensor)."""
+        cfg = self.cfg
+        values, logp, entropy = self.policy.evaluate(obs, actions)
+        adv = advantages
+        if cfg.normalize_advantage and adv.numel() > 1:
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        ratio = torch.exp(logp - old_logp)
+        pg_loss = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+        if cfg.clip_range_vf is None:
+            v_pred = values
+        else:
+            v_pred = old_values + torch.clamp(values - old_values, -cfg.clip_range_vf, cfg.clip_range_vf)
+        v_loss = torch.nn.functional.mse_loss(returns, v_pred)
+        ent_loss = -entropy.mean()
+        loss = pg_loss + cfg.ent_coef * ent_loss + cfg.vf_coef * v_loss
+        with torch.no_grad():
+            log_ratio = logp - old_logp
+            approx_kl = ((torch.exp(log_ratio) - 1) - log_ratio).mean()
+            clip_frac = ((ratio - 1).abs() > cfg.clip_range).float().mean()
+            acc += torch.stack([pg_loss.detach(), v_loss.detach(), ent_loss.detach(), approx_kl, clip_frac])
+        self._flat.zero_()
+        loss.backward()
+        return approx_kl
+
+    def _clip_and_step(self):
+        # th.nn.utils.clip_grad_norm_(parameters, max_grad_norm) on the flat bucket, then Adam
+        norm = torch.linalg.vector_norm(self._flat)
+        self._flat.mul_(torch.clamp(self.cfg.max_grad_norm / (norm + 1e-6), max=1.0))
+        self.opt.step()
+
+    def _capture(self, B, mb, D, A):
+        """Two CUDA graphs per minibatch step: [gather -> forward -> losses -> backward] and [clip -> Adam], split
+        where the gradient all-reduce (and the KL early-stop decision of sb3_ppo.py:283-287) sits.  The eager
+        loop is CPU-bound (~200 small kernels per minibatch); replay makes it one launch per half."""
+        dev = self.device
+        f = dict(dtype=torch.float32, device=dev)
+        st = dict(obs=torch.zeros(B, D, **f), act=torch.zeros(B, A, **f), logp=torch.zeros(B, **f), val=torch.zeros(B, **f),
+                  adv=torch.zeros(B, **f), ret=torch.zeros(B, **f), idx=torch.zeros(mb, dtype=torch.long, device=dev),
+                  acc=torch.zeros(5, **f), kl=torch.zeros((), **f))
+
+        def half_a():
+            i = st["idx"]
+            kl = self._forward_backward(st["obs"][i], st["act"][i], st["logp"][i], st["val"][i], st["adv"][i], st["ret"][i], st["acc"])
+            st["kl"].copy_(kl)
+        # warm-up on a side stream (allocator, cuBLAS workspaces, Adam state) with the real parameters saved around it
+        saved = [p.detach().clone() for p in self.params]
+        opt_state = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            st["idx"].copy_(torch.arange(mb, device=dev) % B)
+            st["obs"].normal_(); st["act"].uniform_(-1, 1); st["adv"].normal_(); st["ret"].normal_()
+            for _ in range(3):
+                half_a()
+                self._clip_and_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            half_a()
+        with torch.cuda.graph(gb):
+            self._clip_and_step()
+        # undo the warm-up: parameters and the Adam moments / step counters back to their pre-capture values
+        with torch.no_grad():
+            for p, q in zip(self.params, saved):
+                p.copy_(q)
+            for p in self.params:
+                stt = self.opt.state[p]
+                stt["exp_avg"].zero_(); stt["exp_avg_sq"].zero_(); stt["step"].zero_()
+            if self._pending_opt_state is not None:
+                self._restore_opt(self._pending_opt_state)
+        self._graphs = ((B, mb, D, A), ga, gb, st)
+
+    _pending_opt_state = None
+
+    def _snapshot_opt(self):
+        return [{k: v.clone() for k, v in self.opt.state[p].items() if torch.is_tensor(v)} for p in self.params if p in self.opt.state]
+
+    def _restore_opt(self, snap):
+        for p, sn in zip(self.params, snap):
+            for k, v in sn.items():
+                self.opt.state[p][k].copy_(v)
+
     def update(self, obs, actions, old_logp, old_values, advantages, returns, generator=None) -> Dict[str, float]:
         """PPO.train (sb3_ppo.py:190-316) on flat [B, ...] tensors of this rank's rollout."""
         cfg = self.cfg
         B = obs.shape[0]
         mb = min(cfg.batch_size, B)
         n_mb = B // mb
-        stats = dict(pg=0.0, vf=0.0, ent=0.0, kl=0.0, clip=0.0, n=0)
-        acc = torch.zeros(5, device=self.device)
+        graphed = self.use_graph and obs.is_cuda
+        if graphed:
+            key = (B, mb, obs.shape[1], actions.shape[1])
+            if self._graphs is None or self._graphs[0] != key:
+                self._pending_opt_state = self._snapshot_opt() if self.n_updates > 0 else None
+                self._capture(*key)
+            _, ga, gb, st = self._graphs
+            st["obs"].copy_(obs); st["act"].copy_(actions); st["logp"].copy_(old_logp); st["val"].copy_(old_values)
+            st["adv"].copy_(advantages); st["ret"].copy_(returns)
+            acc = st["acc"].zero_()
+        else:
+            acc = torch.zeros(5, device=self.device)
+        n_done = 0
         stop = False
         epochs_run = 0
         for epoch in range(cfg.n_epochs):
             perm = torch.randperm(B, device=self.device, generator=generator)
             for k in range(n_mb):
                 idx = perm[k * mb:(k + 1) * mb]
-                values, logp, entropy = self.policy.evaluate(obs[idx], actions[idx])
-                adv = advantages[idx]
-                if cfg.normalize_advantage and adv.numel() > 1:
-                    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-                ratio = torch.exp(logp - old_logp[idx])
-                pg_loss = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
-                if cfg.clip_range_vf is None:
-                    v_pred = values
+                if graphed:
+                    st["idx"].copy_(idx)
+                    ga.replay()
+                    approx_kl = st["kl"]
                 else:
-                    ov = old_values[idx]
-                    v_pred = ov + torch.clamp(values - ov, -cfg.clip_range_vf, cfg.clip_range_vf)
-                v_loss = torch.nn.functional.mse_loss(returns[idx], v_pred)
-                ent_loss = -entropy.mean()
-                loss = pg_loss + cfg.ent_coef * ent_loss + cfg.vf_coef * v_loss
-                with torch.no_grad():
-                    log_ratio = logp - old_logp[idx]
-                    approx_kl = ((torch.exp(log_ratio) - 1) - log_ratio).mean()
-                    clip_frac = ((ratio - 1).abs() > cfg.clip_range).float().mean()
-                    acc += torch.stack([pg_loss.detach(), v_loss.detach(), ent_loss.detach(), approx_kl, clip_frac])
-                stats["n"] += 1
+                    approx_kl = self._forward_backward(obs[idx], actions[idx], old_logp[idx], old_values[idx],
+                                                       advantages[idx], returns[idx], acc)
+                n_done += 1
                 if cfg.target_kl is not None:
                     stop = self._sync_stop(bool(approx_kl.item() > 1.5 * cfg.target_kl))   # one host sync per minibatch, as in SB3
                     if stop:
                         break
-                self._flat.zero_()
-                loss.backward()
                 self._allreduce_grads()
-                # th.nn.utils.clip_grad_norm_(parameters, max_grad_norm) on the flat bucket
-                norm = torch.linalg.vector_norm(self._flat)
-                self._flat.mul_(torch.clamp(cfg.max_grad_norm / (norm + 1e-6), max=1.0))
-                self.opt.step()
+                if graphed:
+                    gb.replay()
+                else:
+                    self._clip_and_step()
             self.n_updates += 1
             epochs_run += 1
             if stop:
                 break
-        a = (acc / max(stats["n"], 1)).tolist()
+        a = (acc / max(n_done, 1)).tolist()
         return {"policy_gradient_loss": a[0], "value_loss": a[1], "entropy_loss": a[2], "approx_kl": a[3],
-                "clip_fraction": a[4], "epochs": epochs_run, "minibatches": stats["n"], "early_stop": bool(stop),
+                "clip_fraction": a[4], "epochs": epochs_run, "minibatches": n_done, "early_stop": bool(stop),
                 "std": float(self.policy.log_std.detach().exp().mean())}
 
     def flat_parameters(self) -> torch.Tensor:

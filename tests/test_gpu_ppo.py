@@ -79,3 +79,40 @@ def test_sac_trainer_runs_on_device_with_drag_and_ground_effect():
     assert float(tr.buffer.done[:tr.buffer.pos].max()) <= 1.0
     assert env.launch_count >= 18
     env.close()
+
+
+def test_ppo_update_cuda_graph_equals_eager():
+    """The two-graph replay of the minibatch step must be the same computation as the eager loop (same seeds ->
+    same minibatch order; same kernels -> same parameters up to FP32 reduction-order noise), including the
+    KL early stop and a second update (Adam state carried across replays)."""
+    from drl_dronenavigation_b200.ppo import PPOConfig, PPOLearner
+    g = torch.Generator(device="cuda").manual_seed(0)
+    B = 8192
+    obs, act = torch.randn(B, 13, device="cuda", generator=g), torch.rand(B, 4, device="cuda", generator=g) * 2 - 1
+    adv, ret = torch.randn(B, device="cuda", generator=g), torch.randn(B, device="cuda", generator=g)
+    outs = {}
+    for graph in (False, True):
+        L = PPOLearner(13, 4, PPOConfig(batch_size=1024, n_epochs=3, target_kl=None, cuda_graph=graph, matmul_precision="fp32"), device="cuda")
+        assert L.use_graph == graph
+        with torch.no_grad():
+            v, logp, _ = L.policy.evaluate(obs, act)
+        p0 = L.flat_parameters().clone()
+        r1 = L.update(obs, act, logp, v, adv, ret, generator=torch.Generator(device="cuda").manual_seed(1))
+        r2 = L.update(obs, act, logp, v, adv, ret, generator=torch.Generator(device="cuda").manual_seed(2))
+        outs[graph] = (p0, L.flat_parameters().clone(), r1, r2)
+    assert torch.equal(outs[False][0], outs[True][0])                 # capture warm-up left the parameters untouched
+    # Adam normalises every coordinate's step to ~lr, so coordinates whose gradient is rounding noise may move by up to
+    # lr per step in either direction; compare in aggregate (48 steps of lr 2.5e-4 = 1.2e-2 worst case)
+    d = (outs[True][1] - outs[False][1]).abs()
+    moved = (outs[False][1] - outs[False][0]).abs()
+    print("graph-vs-eager: max", float(d.max()), "mean", float(d.mean()), "mean movement", float(moved.mean()))
+    assert float(d.mean()) < 0.02 * float(moved.mean()) and float(d.max()) < 2e-3
+    for k in ("policy_gradient_loss", "value_loss", "approx_kl", "clip_fraction"):
+        assert abs(outs[True][2][k] - outs[False][2][k]) < 1e-4 and abs(outs[True][3][k] - outs[False][3][k]) < 1e-3
+    assert outs[True][2]["minibatches"] == outs[False][2]["minibatches"] == 24
+    # early stop path under replay
+    L = PPOLearner(13, 4, PPOConfig(batch_size=1024, n_epochs=30, target_kl=1e-4, learning_rate=1e-2, cuda_graph=True), device="cuda")
+    with torch.no_grad():
+        v, logp, _ = L.policy.evaluate(obs, act)
+    out = L.update(obs, act, logp, v, adv, ret, generator=torch.Generator(device="cuda").manual_seed(1))
+    assert out["early_stop"] and out["epochs"] < 30
