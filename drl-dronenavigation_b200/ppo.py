@@ -268,7 +268,7 @@ class PPOLearner:
         if graphed:
             key = (B, mb, obs.shape[1], actions.shape[1])
             if self._graphs is None or self._graphs[0] != key:
-                self._pending_opt_state = self._snapshot_opt() if self.n_updates > 0 else None
+                self._pending_opt_state = self._snapshot_opt() if len(self.opt.state) > 0 else None
                 self._capture(*key)
             _, ga, gb, st = self._graphs
             st["obs"].copy_(obs); st["act"].copy_(actions); st["logp"].copy_(old_logp); st["val"].copy_(old_values)

@@ -19,6 +19,7 @@ import torch
 
 from .batched_env import BatchedDroneEnv
 from .enums import ActionType
+from .checkpoint import load_sb3_zip, save_sb3_zip
 from .ppo import PPOConfig, PPOTrainer
 from .vec_env import GpuDroneVecEnv
 from .waypoints import Track, dilate_targets
@@ -60,12 +61,12 @@ class PBDroneSimulator:
         """make_env of the reference (:136-204).  ``multi=True`` returns a thunk, like the reference's
         SubprocVecEnv factories; calling it builds a ``GpuDroneVecEnv`` with the wrapper stack fused
         (NormalizeObservation always, Monitor always)."""
-        if gui or collect_rollouts:
-            raise NotImplementedError("gui / rollout text dumps are outside the CUDA hot path")
+        if gui:
+            raise NotImplementedError("the PyBullet GUI is outside the CUDA hot path")
         kw = self._env_kwargs(initial_xyzs, aviary_dim, include_distance, normalize_actions)
 
         def _init():
-            return GpuDroneVecEnv(num_envs, self.targets, normalize_obs=True, **kw)
+            return GpuDroneVecEnv(num_envs, self.targets, normalize_obs=True, collect_rollouts=collect_rollouts, **kw)
         return _init if multi else _init()
 
     def make_device_env(self, num_envs: int, normalize_obs: bool = False, device=None, env_id_offset: int = 0):
@@ -128,11 +129,11 @@ class PBDroneSimulator:
                 log(f"[{time.time() - t0:7.1f}s] steps {trainer.total_steps:>12d}  sps {out['sps']:.3g}  ep_rew {st['return_sum'] / e:8.3f}  "
                     f"ep_len {st['length_sum'] / e:7.1f}  found {st['found_targets'] / e:5.2f}  success {st['successes'] / e:5.3f}  "
                     f"kl {out['approx_kl']:.4f}  std {out['std']:.3f}")
-                if chk and st["return_sum"] / e > best:
+                if chk and st["return_sum"] / e > best and hasattr(trainer.learner, "policy"):
                     best = st["return_sum"] / e
-                    torch.save(trainer.learner.policy.state_dict(), os.path.join(chk, "best_model.pt"))
-        if chk:
-            torch.save(trainer.learner.policy.state_dict(), os.path.join(chk, "success_model.pt"))
+                    save_sb3_zip(os.path.join(chk, "best_model.zip"), trainer.learner)     # EvalCallback(best_model_save_path), :719-729
+        if chk and hasattr(trainer.learner, "policy"):
+            save_sb3_zip(os.path.join(chk, "success_model.zip"), trainer.learner)          # model.save(...), :741-746
         ev = self.evaluate(trainer, n_eval_episodes=100)
         log(f"final evaluation: {ev}")
         train_env.close()
@@ -163,7 +164,10 @@ class PBDroneSimulator:
         """--run_type saved (:438-572): roll a saved policy and report episode statistics."""
         env = self.make_device_env(64)
         trainer = self.setup_agent(train_env=env)
-        trainer.learner.policy.load_state_dict(torch.load(path, map_location=trainer.dev))
+        if path.endswith(".zip"):            # an SB3 archive: the reference's best_model.zip / success_model.zip or one of ours
+            load_sb3_zip(path, trainer.learner)
+        else:
+            trainer.learner.policy.load_state_dict(torch.load(path, map_location=trainer.dev))
         out = self.evaluate(trainer, n_eval_episodes=episodes)
         env.close()
         return out

@@ -58,11 +58,16 @@ class GpuDroneVecEnv(_SB3VecEnv):
 
     def __init__(self, num_envs: int, target_points, threshold=0.3, discount=0.999, max_steps=4096,
                  aviary_dim=(-1, -1, 0, 1, 1, 1), include_distance=True, normalize_actions=True,
-                 normalize_obs=True, device=None, **env_kwargs):
+                 normalize_obs=True, device=None, collect_rollouts=False, rollout_dir="Sol/rollouts", **env_kwargs):
+        # collect_rollouts (PBDroneEnv.py:152-157,811-821): every env appends "<13 obs floats>,<reward>" lines of the RAW
+        # observation to its own Sol/rollouts/rollout_<n>.txt.  The raw rows are only on the host when the fused
+        # NormalizeObservation is off, so in this (analysis) mode the wrapper runs on the host in numpy instead.
+        self.collect_rollouts = bool(collect_rollouts)
+        self._host_norm = bool(normalize_obs) and self.collect_rollouts
         self.core = BatchedDroneEnv(num_envs, target_points, threshold=threshold, discount=discount,
                                     max_steps=max_steps, aviary_dim=aviary_dim,
                                     include_distance=include_distance, normalize_actions=normalize_actions,
-                                    normalize_obs=normalize_obs, device=device, **env_kwargs)
+                                    normalize_obs=bool(normalize_obs) and not self.collect_rollouts, device=device, **env_kwargs)
         obs_space, act_space = observation_space(include_distance), action_space(normalize_actions)
         if _HAVE_SB3:  # pragma: no cover
             super().__init__(num_envs, obs_space, act_space)
@@ -83,6 +88,13 @@ class GpuDroneVecEnv(_SB3VecEnv):
         # handle's own stream, into these pinned buffers
         self._host_io = self.core._make_io(self._h_actions, self._h_obs, self._h_rew, self._h_done, self._h_term,
                                            self._h_found, self._h_epr, self._h_epl)
+        if self.collect_rollouts:
+            import os
+            os.makedirs(rollout_dir, exist_ok=True)
+            base = sum(len(files) for _, _, files in os.walk(rollout_dir))          # PBDroneEnv.py:154-156
+            self.rollout_paths = [os.path.join(rollout_dir, f"rollout_{base + 1 + i}.txt") for i in range(N)]
+            self._rms_mean, self._rms_var = np.zeros((N, D)), np.ones((N, D))         # normalize.RunningMeanStd per env
+            self._rms_count = np.full(N, 1e-4)
         torch.cuda.synchronize(self.core.device)
         self._t_start = time.time()
         self._pending = False
@@ -93,11 +105,33 @@ class GpuDroneVecEnv(_SB3VecEnv):
                        "G": CF2X.G}
 
     # ------------------------------------------------------------- VecEnv API
+    def _host_normalize(self, rows: np.ndarray, idx: np.ndarray) -> np.ndarray:
+        """normalize.NormalizeObservation.normalize (normalize.py:94-97) for the envs `idx`: RunningMeanStd.update with
+        a batch of one (:19-47), then (obs - mean) / sqrt(var + 1e-8); float64 statistics like the reference."""
+        x = rows.astype(np.float64)
+        mean, var, count = self._rms_mean[idx], self._rms_var[idx], self._rms_count[idx][:, None]
+        delta, tot = x - mean, count + 1.0
+        new_mean = mean + delta / tot
+        new_var = (var * count + np.square(delta) * count / tot) / tot
+        self._rms_mean[idx], self._rms_var[idx], self._rms_count[idx] = new_mean, new_var, tot[:, 0]
+        return ((x - new_mean) / np.sqrt(new_var + 1e-8)).astype(np.float32)
+
+    def _write_rollout_lines(self, raw: np.ndarray, rews: np.ndarray) -> None:
+        for i, path in enumerate(self.rollout_paths):                # PBDroneEnv.collect_rollout, :811-821
+            with open(path, mode="a+") as f:
+                for x in raw[i].tolist():
+                    f.write(str(np.format_float_positional(np.float32(x), unique=False, precision=32)) + ",")
+                f.write(str(float(rews[i])))
+                f.write("\n")
+
     def reset(self) -> np.ndarray:
         obs = self.core.reset()
         self._h_obs.copy_(obs)
         torch.cuda.current_stream(self.core.device).synchronize()
-        return self._h_obs.numpy().copy()
+        out = self._h_obs.numpy().copy()
+        if self._host_norm:
+            out = self._host_normalize(out, np.arange(self.num_envs))
+        return out
 
     def step_async(self, actions: np.ndarray) -> None:
         a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 4)
@@ -115,8 +149,20 @@ class GpuDroneVecEnv(_SB3VecEnv):
         dones = bits != 0
         found = self._h_found.numpy()
         infos: List[dict] = [{"found_targets": int(found[i]), "TimeLimit.truncated": False} for i in range(self.num_envs)]
+        term = self._h_term.numpy()
+        if self.collect_rollouts:
+            raw = np.where(dones[:, None], term, obs)                # env.step's own observation (terminal one where done)
+            self._write_rollout_lines(raw, rews)
+            if self._host_norm:                                      # NormalizeObservation.step, then .reset where done
+                all_idx = np.arange(self.num_envs)
+                normed = self._host_normalize(raw, all_idx)
+                d_idx = np.nonzero(dones)[0]
+                if d_idx.size:
+                    term = term.copy()
+                    term[d_idx] = normed[d_idx]
+                    normed[d_idx] = self._host_normalize(obs[d_idx], d_idx)
+                obs = normed
         if dones.any():
-            term = self._h_term.numpy()
             epr, epl = self._h_epr.numpy(), self._h_epl.numpy()
             now = round(time.time() - self._t_start, 6)
             for i in np.nonzero(dones)[0]:

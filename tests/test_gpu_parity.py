@@ -357,3 +357,47 @@ def test_random_spawn_philox_matches_oracle_and_is_shard_invariant(track):
     want = np.stack([w.env.INIT_XYZS[0] for w in workers])
     np.testing.assert_allclose(sp, want, atol=2e-6)
     big.close(); shard.close()
+
+
+def test_vec_env_collect_rollouts_text_format(tmp_path):
+    """collect_rollouts=True (PBDroneEnv.py:152-157,811-821): one text file per env, each line the 13 raw observation
+    floats formatted with np.format_float_positional(np.float32(x), unique=False, precision=32) then the reward; the
+    NormalizeObservation wrapper then runs on the host with the reference's float64 per-env statistics."""
+    from drl_dronenavigation_b200.vec_env import GpuDroneVecEnv
+    from oracle.dyn_oracle import OracleWorker, make_reference_env
+    N, T = 3, 40
+    ref = make_reference_env("circle")
+    venv = GpuDroneVecEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS, circle=True,
+                          include_distance=True, normalize_actions=True, normalize_obs=True, collect_rollouts=True,
+                          rollout_dir=str(tmp_path / "rollouts"))
+    workers = [OracleWorker(make_reference_env("circle"), normalize_obs=True) for _ in range(N)]
+    raw_workers = [OracleWorker(make_reference_env("circle"), normalize_obs=False) for _ in range(N)]
+    obs = venv.reset()
+    for i, w in enumerate(workers):
+        np.testing.assert_allclose(obs[i], w.reset()[0], atol=2e-5)
+        raw_workers[i].reset()
+    acts = _actions("saturating", T, N, seed=3)
+    want_lines = [[] for _ in range(N)]
+    for t in range(T):
+        o, r, d, infos = venv.step(acts[t])
+        for i, w in enumerate(workers):
+            oo, rr, dd, info = w.step(acts[t, i])
+            ro, _, rd, rinfo = raw_workers[i].step(acts[t, i])
+            want_lines[i].append((rinfo["terminal_observation"] if rd else ro, rr))
+            assert bool(d[i]) == bool(dd)
+            np.testing.assert_allclose(o[i][:9], oo[:9], atol=2e-3, rtol=2e-3)
+            if dd:
+                np.testing.assert_allclose(infos[i]["terminal_observation"][:9], info["terminal_observation"][:9], atol=2e-3, rtol=2e-3)
+    venv.close()
+    assert [p.split("rollout_")[-1] for p in venv.rollout_paths] == ["1.txt", "2.txt", "3.txt"]
+    for i, path in enumerate(venv.rollout_paths):
+        lines = open(path).read().strip().split("\n")
+        assert len(lines) == T
+        for line, (wo, wr) in zip(lines, want_lines[i]):
+            cells = line.split(",")
+            assert len(cells) == 14                                   # 13 observation floats + reward
+            got = np.array([float(c) for c in cells])
+            e = np.abs(got[:13] - wo)
+            e[3:6] = np.minimum(e[3:6], np.abs(2 - e[3:6]))
+            assert max(e[:9].max(), e[12]) < 2e-4 and abs(got[13] - float(wr)) < 2e-3
+            assert all("e" not in c.lower() for c in cells[:13])      # positional notation, as the reference writes it
