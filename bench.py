@@ -181,12 +181,52 @@ def workload_name(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def make_env(n_envs, args, device, env_id_offset=0):
+def make_env(n_envs, args, device, env_id_offset=0, **kw):
     from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
     targets, init, dim, is_circle = track_setup(args.track)
     return BatchedDroneEnv(n_envs, targets, threshold=0.3, discount=0.999, max_steps=4096, aviary_dim=dim,
                            initial_xyzs=init, pyb_freq=240, ctrl_freq=240 // args.substeps, cylinder=True, circle=is_circle,
-                           include_distance=True, normalize_actions=True, device=device, env_id_offset=env_id_offset)
+                           include_distance=True, normalize_actions=True, device=device, env_id_offset=env_id_offset, **kw)
+
+
+def baseline_configs(args, dev, K):
+    """Step-only throughput of the fused kernel on the env shape of every BASELINE.json config, one
+    GPU's share each, replayed from CUDA graphs (no host launch cost; working sets below 126 MB stay in L2, as they do
+    in real use at these sizes).  The headline `value` above is config 2 measured the strict way (L2 flushed, per-launch
+    events); these lines are context for the other four and are NOT headline numbers."""
+    import copy
+    import torch
+    from drl_dronenavigation_b200 import Physics
+    from drl_dronenavigation_b200 import _lib as L
+    specs = [
+        (1, "README PPO run: 12 envs, 240/240 Hz, circle, per-env NormalizeObservation", 12, 1, "circle", dict(normalize_obs=True)),
+        (2, "4096 envs, 240/30 Hz, circle", 4096, 8, "circle", {}),
+        (3, "65536 envs per GPU, 240/30 Hz, reaching track (segment tube)", 65536, 8, "reaching", {}),
+        (4, "16384 envs, 240/30 Hz, circle, drag + ground effect", 16384, 8, "circle", dict(physics=Physics.PYB_GND_DRAG_DW)),
+    ] + [(5, f"131072 envs per GPU (1 Mi / 8), 240/30 Hz, circle, reward_id={rid}", 131072, 8, "circle", dict(reward_id=rid))
+         for rid in (L.DN_REWARD_DEFAULT, L.DN_REWARD_DUMMY, L.DN_REWARD_THRUSTENV, L.DN_REWARD_HER, L.DN_REWARD_REACHING,
+                     L.DN_REWARD_HOVER, L.DN_REWARD_FLYTHRUGATE)]
+    out = []
+    for cid, name, n, S, track, kw in specs:
+        try:
+            a = copy.copy(args); a.substeps, a.track = S, track
+            env = make_env(n, a, dev, **kw)
+            env.reset()
+            acts = make_actions(8, n, args.actions, dev, seed=50 + cid)
+            k = max(50, min(K, int(5e7 // n)))
+            k -= k % 50
+            sec, group = time_graph(env, acts, k, 24, group=50)
+            st = env.episode_stats()
+            bytes_per = BYTES_PER_ENV_STEP + (216 if kw.get("normalize_obs") else 0) + (8 if kw.get("physics") else 0)
+            out.append({"config": cid, "shape": name, "envs": n, "substeps": S, "value": n * k / sec, "unit": UNIT,
+                        "us_per_launch": 1e6 * sec / k, "achieved_gbs": bytes_per * n * k / sec / 1e9, "steps": k,
+                        "episodes_finished": int(st["episodes"]), "timing": "CUDA-graph replay, 50 steps per graph"})
+            env.close()
+            del env, acts
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            out.append({"config": cid, "shape": name, "error": str(ex)[:200]})
+    return out
 
 
 def make_actions(n_buf, n_envs, mode, device, seed):
@@ -214,6 +254,52 @@ def time_flushed(env, acts, K, W, flush_buf):
     torch.cuda.synchronize()
     per = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])     # ms
     return float(per.sum()) * 1e-3, per
+
+
+def time_launch_floor(env, K, flush_buf):
+    """The same two measurement harnesses around a (near-)empty kernel of the same library -- action_map_kernel over 4
+    floats: (a) per-launch CUDA-event brackets with the L2 flush in between, (b) CUDA-graph replay back to back.  What
+    is left of a 4096-env step after subtracting these is the step kernel's own time."""
+    import torch
+    a = torch.zeros(4, dtype=torch.float32, device=env.device)
+    for _ in range(10):
+        env.action_to_rpm(a)
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for k in range(K):
+        flush_buf.fill_(k & 1)
+        starts[k].record()
+        env.action_to_rpm(a)
+        ends[k].record()
+    torch.cuda.synchronize()
+    bracket = float(np.mean([s.elapsed_time(e) for s, e in zip(starts, ends)])) * 1e3
+    s = torch.cuda.Stream(device=env.device)
+    s.wait_stream(torch.cuda.current_stream(env.device))
+    out = torch.empty_like(a)
+    import ctypes as C
+    from drl_dronenavigation_b200 import _lib as L
+
+    def tiny():
+        L.check(env._lib.dn_action_to_rpm(env._handle, a.data_ptr(), out.data_ptr(), 4,
+                                          C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)))
+    with torch.cuda.stream(s):
+        tiny()
+    torch.cuda.current_stream(env.device).wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        for _ in range(50):
+            tiny()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(max(K // 50, 1)):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return {"event_bracket_us": bracket, "graph_replay_us": e0.elapsed_time(e1) * 1e3 / (max(K // 50, 1) * 50),
+            "kernel": "dn::action_map_kernel over 4 floats (empty-kernel stand-in)"}
 
 
 def time_graph(env, acts, K, W, group=None):
@@ -405,6 +491,10 @@ def run_b200(args):
     if world == 1:
         line["roofline"] = roofline(N, sec / K, substeps=args.substeps)
         line["roofline"]["note"] = "launch/latency-bound at this batch size: 1.2 MB per launch is ~0.2 us of HBM time"
+        try:
+            line["launch_floor"] = time_launch_floor(env, min(K, 300), flush)
+        except Exception as ex:  # noqa: BLE001
+            line["launch_floor"] = {"error": str(ex)[:200]}
         sweep = []
         for n_big in args.sweep:
             try:
@@ -425,6 +515,8 @@ def run_b200(args):
             except Exception as ex:  # noqa: BLE001
                 sweep.append({"envs": n_big, "error": str(ex)[:200]})
         line["sweep"] = sweep
+        if not args.no_configs:
+            line["baseline_configs"] = baseline_configs(args, dev, K)
         # S = 1 variant of the largest batch (reference default 240/240 Hz): HBM-bound regime
         try:
             import copy
@@ -544,6 +636,7 @@ def main():
     ap.add_argument("--ppo-iters", type=int, default=2)
     ap.add_argument("--ppo-track", default="reaching", choices=["circle", "reaching"])
     ap.add_argument("--no-vecenv", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-BASELINE-config step-only lines")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
     if args.impl == "reference":

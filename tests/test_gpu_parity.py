@@ -291,35 +291,71 @@ def test_vec_env_protocol_against_oracle_workers():
     venv.close()
 
 
-def test_full_size_properties():
-    """BASELINE config sizes (4096 and 65536 envs, S = 8): size-independent properties --
-    identical action rows give identical env rows, unit quaternions, finite outputs, done <=> state reset,
-    statistics consistent with the done bits."""
+FULL_SIZE = [
+    # BASELINE.json configs at their full per-GPU sizes: (id, envs, track, env kwargs)
+    ("cfg2_4096_circle", 4096, "circle", {}),
+    ("cfg3_65536_reaching", 65536, "reaching", {}),
+    ("cfg4_16384_drag_gnd", 16384, "circle", {"physics": "PYB_GND_DRAG_DW"}),
+    ("cfg5_131072_reward_her", 131072, "circle", {"reward_id": 3}),
+    ("cfg5_131072_reward_reaching", 131072, "circle", {"reward_id": 4}),
+    ("cfg5_131072_reward_flythru_normrew", 131072, "circle", {"reward_id": 7, "normalize_reward": True, "clip_reward": 10.0}),
+]
+
+
+@pytest.mark.parametrize("name,N,track,kw", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_properties(name, N, track, kw):
+    """BASELINE config sizes (S = 8): size-independent properties -- identical action rows give identical env rows
+    (bit for bit), unit quaternions, finite outputs, done <=> state reset, Monitor statistics consistent with the
+    done bits, and a seeded sample of 16 envs agrees with the oracle stepped on the same actions."""
+    from drl_dronenavigation_b200 import Physics
     from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
-    from oracle.dyn_oracle import make_reference_env
-    ref = make_reference_env("circle")
-    for N in (4096, 65536):
-        env = BatchedDroneEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS,
-                              pyb_freq=240, ctrl_freq=30, circle=True, include_distance=True, normalize_actions=True)
-        env.reset()
-        g = torch.Generator(device="cpu").manual_seed(N)
-        n_done = 0
-        for t in range(30):
-            half = (torch.rand(N // 2, 4, generator=g) * 2 - 1)
-            a = torch.cat([half, half]).to(env.device)               # env i and i + N/2 see the same actions
-            o, r, d, f = env.step(a)
-            assert torch.isfinite(o).all() and torch.isfinite(r).all()
-            assert torch.equal(o[: N // 2], o[N // 2:]) and torch.equal(r[: N // 2], r[N // 2:])
-            st = env.get_state()
-            qn = (st["quat"] ** 2).sum(dim=1)
-            assert float((qn - 1).abs().max()) < 1e-5
-            done = d != 0
-            n_done += int(done.sum())
-            assert bool((st["steps"][done] == 0).all()) and bool((st["target_idx"][done] == 0).all())
-            assert bool((st["steps"][~done] > 0).all())
-        stats = env.episode_stats()
-        assert stats["episodes"] == n_done and stats["crashes"] + stats["truncations"] + stats["successes"] == n_done
-        env.close()
+    from oracle.dyn_oracle import OracleWorker, make_reference_env
+    kw = dict(kw)
+    okw = {}
+    if "physics" in kw:
+        kw["physics"] = getattr(Physics, kw["physics"])
+        okw["physics"] = "dyn_gnd_drag"
+    rid = {0: "default", 3: "her", 4: "reaching", 7: "flythrugate"}[kw.get("reward_id", 0)]
+    ref = make_reference_env(track, pyb_freq=240, ctrl_freq=30)
+    env = BatchedDroneEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS,
+                          pyb_freq=240, ctrl_freq=30, circle=(track == "circle"), include_distance=True, normalize_actions=True, **kw)
+    sample = np.linspace(0, N // 2 - 1, 16).astype(int)
+    workers = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=30, reward_id=rid, **okw), normalize_obs=False,
+                            normalize_reward=kw.get("normalize_reward", False), clip_reward=kw.get("clip_reward", 0.0)) for _ in sample]
+    env.reset()
+    for w in workers:
+        w.reset()
+    g = torch.Generator(device="cpu").manual_seed(N)
+    n_done = 0
+    for t in range(24):
+        half = (torch.rand(N // 2, 4, generator=g) * 2 - 1)
+        if t % 3:
+            half = HOVER + 0.006 * half                                 # mix of saturating and near-hover steps
+        a = torch.cat([half, half]).to(env.device)                      # env i and i + N/2 see the same actions
+        o, r, d, f = env.step(a)
+        assert torch.isfinite(o).all() and torch.isfinite(r).all()
+        assert torch.equal(o[: N // 2], o[N // 2:]) and torch.equal(r[: N // 2], r[N // 2:]) and torch.equal(d[: N // 2], d[N // 2:])
+        st = env.get_state()
+        qn = (st["quat"] ** 2).sum(dim=1)
+        assert float((qn - 1).abs().max()) < 1e-5
+        done = d != 0
+        n_done += int(done.sum())
+        assert bool((st["steps"][done] == 0).all()) and bool((st["target_idx"][done] == 0).all())
+        assert bool((st["steps"][~done] > 0).all())
+        on, rn, dn, an = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), half.numpy()
+        for j, w in zip(sample, workers):
+            oo, rr, dd, info = w.step(an[j])
+            bits = (1 if w.last_terminated else 0) | (2 if w.last_truncated else 0)
+            if int(dn[j]) != bits:
+                assert PU.min_margin(w.env) < 10 * PU.MARGIN_TOL, (name, t, j)   # open loop over 24 steps: near-tie only
+                pytest.skip("near-tie between FP32 and FP64 on a sampled env (open loop)")
+            assert PU.obs_error(on[j], oo, w.last_step_ang_v_norm) < 1e-3, (name, t, j)
+            assert abs(float(rn[j]) - float(rr)) <= 1e-2 + 2e-3 * abs(float(rr)), (name, t, j, rn[j], rr)
+    stats = env.episode_stats()
+    assert stats["episodes"] == n_done and n_done > 0
+    if rid in ("default", "her"):
+        assert stats["crashes"] + stats["truncations"] + stats["successes"] == n_done
+    env.close()
 
 
 @pytest.mark.parametrize("track", ["circle", "reaching"])
