@@ -256,6 +256,58 @@ def time_flushed(env, acts, K, W, flush_buf):
     return float(per.sum()) * 1e-3, per
 
 
+def time_rotating(args, dev, N, K, W, rank, n_handles=None, on_timed=None):
+    """`inputs larger than L2`: M independent N-env handles (state + actions + outputs of all of them > 126 MB L2) are
+    stepped round-robin, one launch per handle, replayed from CUDA graphs on one stream; one event pair around
+    EXACTLY K launches.  Every launch therefore finds its state, its actions and its output lines in HBM, not in
+    L2, without a flush kernel between launches and without per-launch event records in the timed region."""
+    import torch
+    per_handle = N * (BYTES_PER_ENV_STEP - 112)          # state planes once + actions + outputs, bytes resident per handle
+    M = n_handles or max(8, int(np.ceil(160e6 / per_handle)))
+    envs = [make_env(N, args, dev, env_id_offset=rank * N) for _ in range(M)]
+    for e in envs:
+        e.reset()
+    acts = make_actions(M, N, args.actions, dev, seed=4321 + rank)
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s):
+        for _ in range(max(3, -(-W // M))):              # >= W untimed warm-up steps (whole rotations)
+            for m, e in enumerate(envs):
+                e.step(acts[m])
+    torch.cuda.current_stream(dev).wait_stream(s)
+    torch.cuda.synchronize()
+    full, rem = divmod(K, M)
+    g_full, g_rem = torch.cuda.CUDAGraph(), (torch.cuda.CUDAGraph() if rem else None)
+    with torch.cuda.graph(g_full, stream=s):
+        for m, e in enumerate(envs):
+            e.step(acts[m])
+    if rem:
+        with torch.cuda.graph(g_rem, stream=s):
+            for m, e in enumerate(envs[:rem]):
+                e.step(acts[m])
+    g_full.replay()                                      # one more untimed rotation through the graph path
+    torch.cuda.synchronize()
+    if on_timed:
+        on_timed(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(full):
+        g_full.replay()
+    if rem:
+        g_rem.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    if on_timed:
+        on_timed(False)
+    sec = e0.elapsed_time(e1) * 1e-3
+    eps = sum(int(e.episode_stats()["episodes"]) for e in envs[:4])
+    for e in envs:
+        e.close()
+    del envs, acts
+    torch.cuda.empty_cache()
+    return sec, full * M + rem, M, per_handle * M, eps
+
+
 def time_launch_floor(env, K, flush_buf):
     """The same two measurement harnesses around a (near-)empty kernel of the same library -- action_map_kernel over 4
     floats: (a) per-launch CUDA-event brackets with the L2 flush in between, (b) CUDA-graph replay back to back.  What
@@ -456,17 +508,31 @@ def run_b200(args):
     sampler.start()
     time.sleep(0.3)
 
-    # ---- headline: K launches, L2 flushed between them, per-launch CUDA events ------------------
+    # ---- headline: EXACTLY K launches on inputs larger than L2 (rotating handles), one event pair -------------
+    # (timing rule: "flush L2 between timed iterations OR use inputs larger than L2" -- this is the second form; the
+    #  first form is reported below as `flushed_event_bracket`, where two event records per launch cost ~6 us of
+    #  harness time against a ~3 us kernel, see `launch_floor`)
     barrier()
-    l0 = env.launch_count
-    t0 = time.time()
-    sec, per = time_flushed(env, acts, K, W, flush)
+    win = {}
+    sec, k_r, m_r, bytes_r, eps_r = time_rotating(args, dev, N, K, W, rank,
+                                                  on_timed=lambda start: win.__setitem__("t0" if start else "t1", time.time()))
+    assert k_r == K
     barrier()
-    t1 = time.time()
-    launches = env.launch_count - l0 - W
     sec = max_over_ranks(sec)
     value = world * N * K / sec
-    clocks = sampler.stop(t0, t1)
+    launches = K
+    l2_note = (f"inputs larger than L2: {m_r} independent {N}-env handles = {bytes_r / 1e6:.0f} MB of state + actions + outputs "
+               "(> 126 MB L2) stepped round-robin from CUDA graphs on one stream, so every launch reads its inputs from HBM; "
+               "no flush kernel, one CUDA-event pair around the K launches")
+
+    # ---- the other sanctioned form: L2 flushed between launches, per-launch CUDA-event brackets ----------------
+    barrier()
+    sec_f, per = time_flushed(env, acts, K, W, flush)
+    barrier()
+    sec_f = max_over_ranks(sec_f)
+    clocks = sampler.stop(win.get("t0", time.time() - 1), max(win.get("t1", time.time()), win.get("t0", 0) + 0.05))
+    flushed = {"value": world * N * K / sec_f, "unit": UNIT, "us_per_launch": 1e6 * sec_f / K,
+               "l2": "flushed between timed launches (256 MiB fill, outside the per-launch event brackets)"}
 
     # ---- same workload, L2-resident, CUDA-graph replay (launch-latency regime) -------------------
     barrier()
@@ -482,10 +548,11 @@ def run_b200(args):
             "ms_per_step": 1e3 * sec / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "envs_per_gpu": N, "substeps": args.substeps, "track": args.track,
-                       "actions": args.actions, "l2": "flushed between timed launches (256 MiB fill, outside the event brackets)",
+                       "actions": args.actions, "l2": l2_note, "handles": m_r,
                        "parallelism": f"env-shard x{world} (no data-path collective)"},
             "physics_steps_per_s": value * args.substeps,
-            "clocks": clocks, "gpu_launches": int(launches), "l2_resident": resident}
+            "clocks": clocks, "gpu_launches": int(launches), "l2_resident": resident, "flushed_event_bracket": flushed,
+            "episodes_finished_sample": eps_r}
 
     # ---- single-GPU extras on rank 0 only: roofline, sweep, e2e, cpu baseline --------------------
     if world == 1:

@@ -65,7 +65,7 @@ __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffff
 // MULTI = false: exactly one control step per launch (dn_step): no step loop, no per-thread
 // statistics carried across steps, <= 64 registers (8 CTAs / SM).  MULTI = true: dn_step_many.
 template <int PHYS, bool NORM, bool MULTI>
-__global__ void __launch_bounds__(kBlock, MULTI ? 6 : 8)
+__global__ void __launch_bounds__(kBlock, (MULTI || NORM) ? 6 : 8)
 step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int num_steps_arg, int per_step_arg) {
     __shared__ __align__(128) float tile[kBlock * kMaxObs];
     const int num_steps = MULTI ? num_steps_arg : 1;
@@ -102,26 +102,43 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
             const float4 act = __ldg(io.actions + static_cast<size_t>(t) * P.n + i);
             const StepResult r = env_step<PHYS>(P, i, s, act, last_rpm_sum, obs_row);   // obs_row: obs of the step (terminal obs if finished)
             float* term_out = (write_out && r.finished && io.terminal_obs) ? io.terminal_obs + o * D : nullptr;
+            if (!MULTI) {
+                // single-step kernel: the state is final here; storing it now frees its registers for the
+                // wrapper code below (the multi-step variant keeps the physics planes in registers across steps)
+                store_state(P, i, s);
+                if (PHYS & 1) P.last_rpm_sum[i] = last_rpm_sum;
+            }
             if (NORM) {
                 // NormalizeObservation sits inside Monitor and the worker's auto-reset
                 // (PBDroneSimulator.py:181): the terminal observation updates the running
                 // statistics in .step, the reset observation again in .reset (normalize.py:74-92).
+                // All 2 x obs_dim statistics are fetched first (independent loads in flight together; a
+                // load -> update -> store loop per entry serialised 13 L2 round trips: 9 us for a 12-env launch).
                 const size_t N = P.n;
                 float* cnt_p = P.obs_rms + static_cast<size_t>(2 * D) * N + i;
                 const float cnt = *cnt_p;
-                for (int k = 0; k < D; ++k) {
-                    float* mp = P.obs_rms + static_cast<size_t>(k) * N + i;
-                    float* vp = P.obs_rms + static_cast<size_t>(D + k) * N + i;
-                    float m = *mp, v = *vp;
-                    const float tn = rms_update_normalize(obs_row[k], m, v, cnt);
-                    float ob = tn;
-                    if (r.finished) {
-                        if (term_out) term_out[k] = tn;
-                        const float raw = (k < 3) ? r.spawn_obs[k] : ((k < 12) ? P.init_obs[k] : r.reset_obs_dist);
-                        ob = rms_update_normalize(raw, m, v, cnt + 1.0f);
+                float m[kMaxObs], v[kMaxObs];
+#pragma unroll
+                for (int k = 0; k < kMaxObs; ++k) {
+                    if (k < D) {
+                        m[k] = P.obs_rms[static_cast<size_t>(k) * N + i];
+                        v[k] = P.obs_rms[static_cast<size_t>(D + k) * N + i];
                     }
-                    obs_row[k] = ob;
-                    *mp = m; *vp = v;
+                }
+#pragma unroll
+                for (int k = 0; k < kMaxObs; ++k) {
+                    if (k < D) {
+                        const float tn = rms_update_normalize(obs_row[k], m[k], v[k], cnt);
+                        float ob = tn;
+                        if (r.finished) {
+                            if (term_out) term_out[k] = tn;
+                            const float raw = (k < 3) ? r.spawn_obs[k] : ((k < 12) ? P.init_obs[k] : r.reset_obs_dist);
+                            ob = rms_update_normalize(raw, m[k], v[k], cnt + 1.0f);
+                        }
+                        obs_row[k] = ob;
+                        P.obs_rms[static_cast<size_t>(k) * N + i] = m[k];
+                        P.obs_rms[static_cast<size_t>(D + k) * N + i] = v[k];
+                    }
                 }
                 *cnt_p = cnt + (r.finished ? 2.0f : 1.0f);
             } else if (r.finished) {
@@ -149,10 +166,12 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
                 acc.eps_suc += 1 + (r.success ? 0x10000 : 0);
                 acc.cra_tru += (r.crash ? 1 : 0) + ((r.done == DN_DONE_TRUNCATED) ? 0x10000 : 0);
             }
-            // stored every step: the next step's epilogue (MULTI) re-reads the bookkeeping planes and, on a
-            // crash, the entry position from memory; the physics planes stay in registers across steps
-            store_state(P, i, s);
-            if ((PHYS & 1) && t == num_steps - 1) P.last_rpm_sum[i] = last_rpm_sum;
+            // MULTI: stored every step -- the next step's epilogue re-reads the bookkeeping planes and, on a crash, the
+            // entry position from memory; the physics planes stay in registers across steps
+            if (MULTI) {
+                store_state(P, i, s);
+                if ((PHYS & 1) && t == num_steps - 1) P.last_rpm_sum[i] = last_rpm_sum;
+            }
         }
         // ---- observation rows: shared memory -> one TMA bulk store PER WARP (32 rows are contiguous both in
         // shared and in global memory, 32 * obs_dim * 4 bytes is a multiple of 16): no CTA-wide barrier.
