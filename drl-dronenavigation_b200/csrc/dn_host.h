@@ -165,6 +165,10 @@ inline void fill_params(const dn_config& cfg, const RewardParams& rw, Params& P,
             h_s[2 * k + 1] = make_float4((float)u[0], (float)u[1], (float)u[2], (float)len);
         }
     }
+    P.const_tables = (T <= kConstTargets) ? 1 : 0;
+    if (P.const_tables) {
+        for (int k = 0; k < T; ++k) { P.tgt_c[k] = h_t[k]; P.seg_c[2 * k] = h_s[2 * k]; P.seg_c[2 * k + 1] = h_s[2 * k + 1]; }
+    }
     // constructor distance: ||INIT_XYZS[0] - target[0]|| (PBDroneEnv.py:137-138)
     {
         const double* t0 = cfg.targets;

@@ -54,6 +54,7 @@ typedef Stats BlockStats;    // one accumulation slot per CTA of the step grid (
 // current_vel / current_ang_v of the reference are vel / ang_v at step entry and are
 // not stored.  112 B read + 112 B written per env-step.
 constexpr int kPlanes = 7;
+constexpr int kConstTargets = 16;
 
 struct Params {
     int   n;
@@ -90,6 +91,12 @@ struct Params {
     RewardParams rw;
     unsigned long long seed;
     long long env_id_offset;
+    // Tracks of up to kConstTargets targets (circle: 6, reaching: 8) travel in the constant bank with the rest of
+    // this block: a dependent global load of targets[idx] in the middle of the epilogue costs an L2 round trip per
+    // thread, an indexed constant load does not.  Longer tracks use the global tables below.
+    int   const_tables;      // 1: tgt_c / seg_c hold the tables
+    float4 tgt_c[16];
+    float4 seg_c[32];
     const float4* targets;   // [T] (x,y,z,0)
     const float4* segs;      // [T][2] {ext_p1.xyz, ext_len} {unit.xyz, seg_len}; non-circle cylinder
     float4* s[kPlanes];

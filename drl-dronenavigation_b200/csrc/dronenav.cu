@@ -68,8 +68,16 @@ template <int PHYS, bool NORM, bool MULTI>
 __global__ void __launch_bounds__(kBlock, (MULTI || NORM) ? 6 : 8)
 step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int num_steps_arg, int per_step_arg) {
     __shared__ __align__(128) float tile[kBlock * kMaxObs];
+    // bookkeeping planes 4..6 of this CTA's environments, staged by cp.async at kernel entry and consumed after the
+    // last substep: the copy is in flight during the whole physics loop without holding registers, and the epilogue
+    // starts with a shared-memory read instead of an L2 / HBM round trip (single-step kernel only)
+    __shared__ __align__(16) float4 aux_stage[MULTI ? 1 : 3 * kBlock];
     const int num_steps = MULTI ? num_steps_arg : 1;
     const int per_step = MULTI ? per_step_arg : 1;
+    // programmatic dependent launch (see launch_step): let the next kernel of the stream be scheduled now, and do not
+    // touch global memory before the previous kernel has completed.  Both are no-ops for a normal launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const int base = blockIdx.x * kBlock;
     const int i = base + tid;
@@ -82,8 +90,17 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
     if (active) {
         load_core(P, i, s);
         if (PHYS & 1) last_rpm_sum = P.last_rpm_sum[i];
-        // The bookkeeping planes are consumed ~1000 instructions from now: start them towards L2.
-        prefetch_l2(&P.s[4][i]); prefetch_l2(&P.s[5][i]); prefetch_l2(&P.s[6][i]);
+        // The bookkeeping planes are consumed ~1000 instructions from now.
+        if (MULTI) {
+            prefetch_l2(&P.s[4][i]); prefetch_l2(&P.s[5][i]); prefetch_l2(&P.s[6][i]);
+        } else {
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(&aux_stage[p * kBlock + tid]));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(&P.s[4 + p][i]) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         // Software pipelining across CTAs: the CTA that will run on this SM slot one "GPU-full of CTAs"
         // later finds its physics planes and actions already in L2 (the kernel is otherwise limited by
         // the DRAM latency exposed at the top of each thread, not by bandwidth or issue slots).
@@ -100,7 +117,8 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
         const size_t o = (per_step ? static_cast<size_t>(t) * P.n : 0) + i;      // output element index of this env
         if (active) {
             const float4 act = __ldg(io.actions + static_cast<size_t>(t) * P.n + i);
-            const StepResult r = env_step<PHYS>(P, i, s, act, last_rpm_sum, obs_row);   // obs_row: obs of the step (terminal obs if finished)
+            const StepResult r = env_step<PHYS>(P, i, s, act, last_rpm_sum, obs_row,     // obs_row: obs of the step (terminal obs if finished)
+                                                MULTI ? nullptr : &aux_stage[tid], kBlock);
             float* term_out = (write_out && r.finished && io.terminal_obs) ? io.terminal_obs + o * D : nullptr;
             if (!MULTI) {
                 // single-step kernel: the state is final here; storing it now frees its registers for the
@@ -290,7 +308,7 @@ __global__ void reset_kernel(const __grid_constant__ Params P, const uint8_t* ma
     const float stale_dist = s.dist;
     float D0 = s.dist;
     if (steps != 0) {                           // _current_position == pos of the last post-step
-        const float4 t0 = __ldg(&P.targets[0]);
+        const float4 t0 = target_at(P, 0);
         const float dx = s.px - t0.x, dy = s.py - t0.y, dz = s.pz - t0.z;
         D0 = sqrtf(dx * dx + dy * dy + dz * dz);
     }
@@ -300,7 +318,7 @@ __global__ void reset_kernel(const __grid_constant__ Params P, const uint8_t* ma
         spawn_line(P, i, s.ep_count, s.px, s.py, s.pz);
         P.spawn[i] = make_float4(s.px, s.py, s.pz, 0.f);
         if (P.aux) { float4 ax = P.aux[i]; ax.x = s.px; ax.y = s.py; ax.z = s.pz; P.aux[i] = ax; }
-        const float4 t0 = __ldg(&P.targets[0]);
+        const float4 t0 = target_at(P, 0);
         const float dx = s.px - t0.x, dy = s.py - t0.y, dz = s.pz - t0.z;
         D0 = sqrtf(dx * dx + dy * dy + dz * dz);
     }
@@ -614,10 +632,22 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
     const int N = env->P.n;
     const dim3 grid((N + dn::kBlock - 1) / dn::kBlock), block(dn::kBlock);
     const int phys = env->P.physics & 3;
-#define DN_LAUNCH(PH, NO)                                                                              \
-    do {                                                                                               \
-        if (num_steps == 1) dn::step_kernel<PH, NO, false><<<grid, block, 0, st>>>(env->P, k, 1, 1);   \
-        else dn::step_kernel<PH, NO, true><<<grid, block, 0, st>>>(env->P, k, num_steps, per_step);   \
+    // Programmatic dependent launch: the step kernel may be scheduled while the previous kernel of the stream is still
+    // running (its CTAs trigger at entry); it then waits (griddepcontrol.wait, before its first global access) until that
+    // kernel has completed and flushed.  Back-to-back steps -- plain or replayed from a CUDA graph -- thereby hide
+    // the launch / CTA-scheduling latency, which is a third of a 4096-env step.  DN_NO_PDL=1 disables it.
+    static const bool use_pdl = (getenv("DN_NO_PDL") == nullptr);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = 0; lc.stream = st;
+    lc.attrs = attr; lc.numAttrs = use_pdl ? 1 : 0;
+    cudaError_t lerr = cudaSuccess;
+#define DN_LAUNCH(PH, NO)                                                                                          \
+    do {                                                                                                           \
+        if (num_steps == 1) lerr = cudaLaunchKernelEx(&lc, dn::step_kernel<PH, NO, false>, env->P, k, 1, 1);       \
+        else lerr = cudaLaunchKernelEx(&lc, dn::step_kernel<PH, NO, true>, env->P, k, num_steps, per_step);        \
     } while (0)
     if (env->normalize_obs) {
         switch (phys) { case 0: DN_LAUNCH(0, true); break; case 1: DN_LAUNCH(1, true); break;
@@ -627,6 +657,7 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
                         case 2: DN_LAUNCH(2, false); break; default: DN_LAUNCH(3, false); break; }
     }
 #undef DN_LAUNCH
+    DN_CUDA(lerr);
     DN_CUDA(cudaGetLastError());
     env->launches += 1;
     return DN_OK;
