@@ -87,7 +87,8 @@ class PBDroneSimulator:
             raise NotImplementedError(f"{self.args.agent}: the PPO and SAC branches are built on the device path")
         n = train_env.num_envs
         T = getattr(self.args, "rollout_steps", None) or max(16, min(4096, (12 * 4096 * 8) // max(n, 1)))
-        cfg = PPOConfig(n_steps=T, batch_size=max(512, (T * n) // 32))
+        cfg = PPOConfig(n_steps=T, batch_size=getattr(self.args, "minibatch", None) or max(512, (T * n) // 32),
+                        n_epochs=getattr(self.args, "n_epochs", 10))
         return PPOTrainer(train_env, cfg, rollout_steps=T)
 
     # ------------------------------------------------------------------ runs
@@ -98,11 +99,12 @@ class PBDroneSimulator:
         obs = env.reset()
         gen = torch.Generator(device=trainer.dev).manual_seed(123)
         with torch.no_grad():
-            for _ in range(max_steps):
+            for k in range(max_steps):
                 a, _, _ = trainer.learner.policy.act(obs, generator=gen)
                 obs, _, _, _ = env.step(a.clamp(-1, 1).contiguous())
-                st = env.episode_stats()
-                if st["episodes"] >= n_eval_episodes:
+                # statistics are read (one host sync) every 64 steps; run at least one full time-limit horizon so that
+                # long (successful / truncated) episodes are not under-represented against quick crashes
+                if k % 64 == 63 and k >= min(self.env_steps, max_steps - 1) and env.episode_stats()["episodes"] >= n_eval_episodes:
                     break
         st = env.episode_stats()
         env.close()
@@ -120,12 +122,29 @@ class PBDroneSimulator:
             chk = os.path.join("Sol", "model_chkpts", f"{args.agent}_save_{datetime.now().strftime('%m.%d.%Y_%H.%M.%S')}")
             os.makedirs(chk, exist_ok=True)
         t0, it, best = time.time(), 0, -np.inf
+        max_seconds = max_seconds if max_seconds is not None else getattr(args, "max_seconds", None)
+        # TensorBoard scalars under SB3's tag names (what Sol/Utilities/TensorboardManager.py reads back), SURVEY f.4
+        tb = None
+        if getattr(args, "tensorboard", None):
+            from torch.utils.tensorboard import SummaryWriter
+            tb = SummaryWriter(args.tensorboard)
         while trainer.total_steps < total and (max_seconds is None or time.time() - t0 < max_seconds):
             out = trainer.train_iteration()
             it += 1
             if it % 5 == 0 or trainer.total_steps >= total:
                 st = train_env.episode_stats(clear=True)
                 e = max(st["episodes"], 1)
+                if tb is not None:
+                    step = trainer.total_steps
+                    tb.add_scalar("rollout/ep_rew_mean", st["return_sum"] / e, step)
+                    tb.add_scalar("rollout/ep_len_mean", st["length_sum"] / e, step)
+                    tb.add_scalar("rollout/success_rate", st["successes"] / e, step)
+                    tb.add_scalar("time/fps", out.get("sps", 0.0), step)
+                    for k_src, k_dst in (("approx_kl", "train/approx_kl"), ("clip_fraction", "train/clip_fraction"),
+                                         ("entropy_loss", "train/entropy_loss"), ("policy_gradient_loss", "train/policy_gradient_loss"),
+                                         ("value_loss", "train/value_loss"), ("std", "train/std")):
+                        if k_src in out:
+                            tb.add_scalar(k_dst, out[k_src], step)
                 log(f"[{time.time() - t0:7.1f}s] steps {trainer.total_steps:>12d}  sps {out['sps']:.3g}  ep_rew {st['return_sum'] / e:8.3f}  "
                     f"ep_len {st['length_sum'] / e:7.1f}  found {st['found_targets'] / e:5.2f}  success {st['successes'] / e:5.3f}  "
                     f"kl {out['approx_kl']:.4f}  std {out['std']:.3f}")
@@ -134,7 +153,9 @@ class PBDroneSimulator:
                     save_sb3_zip(os.path.join(chk, "best_model.zip"), trainer.learner)     # EvalCallback(best_model_save_path), :719-729
         if chk and hasattr(trainer.learner, "policy"):
             save_sb3_zip(os.path.join(chk, "success_model.zip"), trainer.learner)          # model.save(...), :741-746
-        ev = self.evaluate(trainer, n_eval_episodes=100)
+        if tb is not None:
+            tb.close()
+        ev = self.evaluate(trainer, n_eval_episodes=1000, n_envs=256) if hasattr(trainer.learner, "policy") else {}
         log(f"final evaluation: {ev}")
         train_env.close()
         return trainer, ev
