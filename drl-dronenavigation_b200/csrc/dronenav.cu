@@ -62,6 +62,31 @@ struct BlockAcc { float ret; int len, fnd, eps_suc, cra_tru; };   // eps|suc and
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
+// ---- Monitor statistics: warp shuffle -> this CTA's slot.  Only the (up to 4) warps of one CTA ever
+// touch a slot, so these reductions do not contend; integer sums are exact and the float returns are
+// added as doubles (exact for any realistic count), so the totals do not depend on arrival order.
+// (per-lane counts are < 2^16 per launch, so a warp's packed 16:16 sums need the two halves summed apart)
+__device__ __forceinline__ void flush_stats(const Params& P, const BlockAcc& acc, const int tid) {
+    const int eps_w = warp_sum(acc.eps_suc & 0xffff);
+    if (eps_w != 0) {                              // warp-uniform
+        float ret = acc.ret;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) ret += __shfl_xor_sync(0xffffffffu, ret, d);
+        const int len = warp_sum(acc.len), fnd = warp_sum(acc.fnd), suc = warp_sum(acc.eps_suc >> 16);
+        const int cra = warp_sum(acc.cra_tru & 0xffff), tru = warp_sum(acc.cra_tru >> 16);
+        if ((tid & 31) == 0) {
+            BlockStats* b = &P.block_stats[blockIdx.x];
+            atomicAdd(&b->return_sum, static_cast<double>(ret));
+            atomicAdd(&b->length_sum, static_cast<unsigned long long>(len));
+            atomicAdd(&b->episodes, static_cast<unsigned long long>(eps_w));
+            atomicAdd(&b->found_targets, static_cast<unsigned long long>(fnd));
+            if (suc) atomicAdd(&b->successes, static_cast<unsigned long long>(suc));
+            if (cra) atomicAdd(&b->crashes, static_cast<unsigned long long>(cra));
+            if (tru) atomicAdd(&b->truncations, static_cast<unsigned long long>(tru));
+        }
+    }
+}
+
 // MULTI = false: exactly one control step per launch (dn_step): no step loop, no per-thread
 // statistics carried across steps, <= 64 registers (8 CTAs / SM).  MULTI = true: dn_step_many.
 template <int PHYS, bool NORM, bool MULTI>
@@ -217,29 +242,142 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
             }
         }
     }
-    // ---- Monitor statistics: warp shuffle -> this CTA's slot.  Only the (up to 4) warps of one CTA ever
-    // touch a slot, so these reductions do not contend; integer sums are exact and the float returns are
-    // added as doubles (exact for any realistic count), so the totals do not depend on arrival order.
-    // (per-lane counts are < 2^16 per launch, so a warp's packed 16:16 sums need the two halves summed apart)
-    const int eps_w = warp_sum(acc.eps_suc & 0xffff);
-    if (eps_w != 0) {                              // warp-uniform
-        float ret = acc.ret;
+    flush_stats(P, acc, tid);
+    if ((tid & 31) == 0) bulk_store_wait_read();   // shared memory must outlive the bulk read
+}
+
+// ---------------------------------------------------------------------------
+// EXPERIMENTAL (opt-in with DN_PIPE=1; measured SLOWER than step_kernel so far: 4 Mi envs, S = 8: 297 vs 235 us,
+// S = 1: 231 vs 196 us -- ncu: 15 % of SMSP time without a resident warp and 53 % DRAM utilisation, i.e. the
+// statically scheduled persistent CTAs stay phase-locked and leave a tail).
+// Persistent, software-pipelined variant of the single-step kernel for large batches (>= 2 tiles per resident CTA).
+// In step_kernel all CTAs of an SM start together, load together, compute together and retire together, so the
+// load phase of every wave is exposed (ncu, 4 Mi envs, S = 8: no eligible warp in 20 % of the cycles although HBM is
+// at 69 % and the issue slots at 80 %).  Here each CTA walks tiles blockIdx.x, + gridDim.x, ... and keeps the NEXT
+// tile's inputs in flight with cp.async (LDGSTS) while it computes the current one:
+//   group C(t): actions + physics planes 0..3 of tile t  -> core_stage   (consumed at the top of iteration t)
+//   group A(t): bookkeeping planes 4..6 of tile t        -> aux_stage    (consumed after the last substep)
+// Every thread only ever touches its own 16-byte slots, so the pipeline needs no barrier: cp.async.wait_group 1
+// always leaves exactly the younger group in flight (order of commits: C(t0) A(t0) | C(t1) A(t1) | ...).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+template <int PHYS>
+__global__ void __launch_bounds__(kBlock, 7)
+step_kernel_pipe(const __grid_constant__ Params P, const __grid_constant__ StepIO io, const int num_tiles) {
+    __shared__ __align__(128) float tile2[2][kBlock * kMaxObs];   // observation rows, double-buffered across iterations
+    __shared__ __align__(16) float4 core_stage[5 * kBlock];     // action | planes 0..3
+    __shared__ __align__(16) float4 aux_stage[3 * kBlock];      // planes 4..6
+    __shared__ __align__(16) float4 entry_stage[kBlock];        // plane 0 at step entry (the reset path needs the old position)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int tid = threadIdx.x;
+    const int D = P.obs_dim;
+    int parity = 0;
+    BlockAcc acc = {0.f, 0, 0, 0, 0};
+
+    auto issue_core = [&](int t) {
+        const int j = t * kBlock + tid;
+        if (t < num_tiles && j < P.n) {
+            cp_async16(&core_stage[tid], io.actions + j);
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) ret += __shfl_xor_sync(0xffffffffu, ret, d);
-        const int len = warp_sum(acc.len), fnd = warp_sum(acc.fnd), suc = warp_sum(acc.eps_suc >> 16);
-        const int cra = warp_sum(acc.cra_tru & 0xffff), tru = warp_sum(acc.cra_tru >> 16);
-        if ((tid & 31) == 0) {
-            BlockStats* b = &P.block_stats[blockIdx.x];
-            atomicAdd(&b->return_sum, static_cast<double>(ret));
-            atomicAdd(&b->length_sum, static_cast<unsigned long long>(len));
-            atomicAdd(&b->episodes, static_cast<unsigned long long>(eps_w));
-            atomicAdd(&b->found_targets, static_cast<unsigned long long>(fnd));
-            if (suc) atomicAdd(&b->successes, static_cast<unsigned long long>(suc));
-            if (cra) atomicAdd(&b->crashes, static_cast<unsigned long long>(cra));
-            if (tru) atomicAdd(&b->truncations, static_cast<unsigned long long>(tru));
+            for (int p = 0; p < 4; ++p) cp_async16(&core_stage[(p + 1) * kBlock + tid], &P.s[p][j]);
+        }
+        cp_async_commit();                                  // committed even when empty: keeps the group count uniform
+    };
+    auto issue_aux = [&](int t) {
+        const int j = t * kBlock + tid;
+        if (t < num_tiles && j < P.n) {
+#pragma unroll
+            for (int p = 0; p < 3; ++p) cp_async16(&aux_stage[p * kBlock + tid], &P.s[4 + p][j]);
+        }
+        cp_async_commit();
+    };
+    issue_core(blockIdx.x);
+    issue_aux(blockIdx.x);
+
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int base = t * kBlock;
+        const int i = base + tid;
+        const bool active = i < P.n;
+        float* const tile = tile2[parity];
+        float* const obs_row = tile + tid * D;
+        parity ^= 1;
+        asm volatile("cp.async.wait_group 1;" ::: "memory");            // C(t) has landed; A(t) may still be in flight
+        EnvState s;
+        float last_rpm_sum = 0.0f;
+        if (active) {
+            const float4 act = core_stage[tid];
+            const float4 a = core_stage[kBlock + tid], b = core_stage[2 * kBlock + tid];
+            const float4 c = core_stage[3 * kBlock + tid], d = core_stage[4 * kBlock + tid];
+            s.px = a.x; s.py = a.y; s.pz = a.z; s.dist = a.w;
+            s.qx = b.x; s.qy = b.y; s.qz = b.z; s.qw = b.w;
+            s.vx = c.x; s.vy = c.y; s.vz = c.z; s.prev_dist = c.w;
+            s.wx = d.x; s.wy = d.y; s.wz = d.z; s.ep_ret = d.w;
+            if (PHYS & 1) last_rpm_sum = P.last_rpm_sum[i];
+            entry_stage[tid] = a;
+            issue_core(t + gridDim.x);                                  // this thread's slots are free again
+            const StepResult r = env_step<PHYS>(P, i, s, act, last_rpm_sum, obs_row, &aux_stage[tid], kBlock, 1, &entry_stage[tid]);
+            issue_aux(t + gridDim.x);                                   // A(t) was consumed inside env_step
+            store_state(P, i, s);
+            if (PHYS & 1) P.last_rpm_sum[i] = last_rpm_sum;
+            if (r.finished) {
+                if (io.terminal_obs) {
+                    float* term_out = io.terminal_obs + static_cast<size_t>(i) * D;
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) term_out[k] = obs_row[k];
+                    if (D == 13) term_out[12] = obs_row[12];
+                }
+#pragma unroll
+                for (int k = 3; k < 12; ++k) obs_row[k] = P.init_obs[k];
+                obs_row[0] = r.spawn_obs[0]; obs_row[1] = r.spawn_obs[1]; obs_row[2] = r.spawn_obs[2];
+                if (D == 13) obs_row[12] = r.reset_obs_dist;
+                if (io.episode_return) io.episode_return[i] = r.ep_ret;
+                if (io.episode_length) io.episode_length[i] = r.ep_len;
+                acc.ret += r.ep_ret; acc.len += r.ep_len; acc.fnd += r.found;
+                acc.eps_suc += 1 + (r.success ? 0x10000 : 0);
+                acc.cra_tru += (r.crash ? 1 : 0) + ((r.done == DN_DONE_TRUNCATED) ? 0x10000 : 0);
+            }
+            io.reward[i] = r.reward;
+            io.done[i] = r.done;
+            if (io.found_targets) io.found_targets[i] = r.found;
+        } else {                                                        // keep the group accounting of idle lanes uniform
+            issue_core(t + gridDim.x);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            issue_aux(t + gridDim.x);
+        }
+        // observation rows of this warp: one TMA bulk store.  The two row buffers alternate, so before the next
+        // iteration only the store issued ONE ITERATION AGO must have been read by the bulk engine (wait_group.read 1):
+        // the warp never waits for the store it has just issued
+        const int wbase = base + (tid & ~31);
+        const int n_here = min(32, P.n - wbase);
+        if (n_here > 0) {
+            float* gdst = io.obs + static_cast<size_t>(wbase) * D;
+            const float* wsrc = tile + (tid & ~31) * D;
+            const uint32_t bytes = static_cast<uint32_t>(n_here) * D * 4u;
+            const bool bulk_ok = ((reinterpret_cast<uintptr_t>(gdst) & 15u) == 0) && ((bytes & 15u) == 0);
+            if (bulk_ok) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if ((tid & 31) == 0) {
+                    bulk_store_g2s_commit(gdst, wsrc, bytes);
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                }
+                __syncwarp();
+            } else {
+                __syncwarp();
+                for (int j = (tid & 31); j < n_here * D; j += 32) gdst[j] = wsrc[j];
+                __syncwarp();
+            }
         }
     }
-    if ((tid & 31) == 0) bulk_store_wait_read();   // shared memory must outlive the bulk read
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    flush_stats(P, acc, tid);
+    if ((tid & 31) == 0) bulk_store_wait_read();   // shared memory must outlive the bulk reads
 }
 
 // reduces the per-CTA slots into one Stats record (dn_episode_stats); optionally clears the slots
@@ -461,6 +599,8 @@ struct dn_env {
     dn::BlockStats* d_block_stats; // one slot per CTA of the step grid
     int n_slots;
     int64_t launches;
+    int pipe_ctas;          // grid of the persistent pipelined kernel: SMs x resident CTAs per SM
+    int use_pipe;           // DN_PIPE=1 at dn_create: opt into step_kernel_pipe for large batches (experimental)
     float d0;
     // dn_step_host staging (allocated on first use)
     cudaStream_t host_stream;
@@ -579,6 +719,8 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
         int sms = 148;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) sms = prop.multiProcessorCount;
         P.prefetch_ctas = sms * 8;               // 8 CTAs of 128 threads per SM at 64 registers
+        e->pipe_ctas = sms * 7;                  // step_kernel_pipe: __launch_bounds__(128, 7)
+        e->use_pipe = getenv("DN_PIPE") != nullptr;
     }
     P.targets = e->d_targets; P.segs = e->d_segs; P.block_stats = e->d_block_stats;
 
@@ -644,6 +786,21 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
     lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = 0; lc.stream = st;
     lc.attrs = attr; lc.numAttrs = use_pdl ? 1 : 0;
     cudaError_t lerr = cudaSuccess;
+    // large batches: persistent software-pipelined kernel (>= 2 tiles per resident CTA, single step, no fused obs-RMS)
+    const int tiles = (N + dn::kBlock - 1) / dn::kBlock;
+    if (env->use_pipe && num_steps == 1 && !env->normalize_obs && tiles >= 2 * env->pipe_ctas) {
+        lc.gridDim = dim3(env->pipe_ctas);
+        switch (phys) {
+            case 0: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<0>, env->P, k, tiles); break;
+            case 1: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<1>, env->P, k, tiles); break;
+            case 2: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<2>, env->P, k, tiles); break;
+            default: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<3>, env->P, k, tiles); break;
+        }
+        DN_CUDA(lerr);
+        DN_CUDA(cudaGetLastError());
+        env->launches += 1;
+        return DN_OK;
+    }
 #define DN_LAUNCH(PH, NO)                                                                                          \
     do {                                                                                                           \
         if (num_steps == 1) lerr = cudaLaunchKernelEx(&lc, dn::step_kernel<PH, NO, false>, env->P, k, 1, 1);       \
