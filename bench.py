@@ -435,6 +435,40 @@ def roofline(n_envs, sec_per_launch, traffic=None, substeps=None):
             "us_per_launch": sec_per_launch * 1e6, "peak_source": src}
 
 
+def run_sac(args, dev, world, rank, barrier, max_over_ranks):
+    """SAC samples/s end to end on BASELINE configs[3]: 16384 envs per GPU, circle track, drag + ground-effect physics,
+    reference SAC-branch hyper-parameters (train_freq 3 env steps, 5 gradient steps of batch 1024, twin critics
+    [256,256,128], actor [256,256]); two flat-bucket NCCL all-reduces per gradient step under torchrun."""
+    import copy
+    import torch
+    from drl_dronenavigation_b200 import Physics
+    from drl_dronenavigation_b200.sac import SACConfig, SACTrainer
+    a = copy.copy(args)
+    a.track = "circle"
+    n = args.sac_envs
+    env = make_env(n, a, dev, env_id_offset=rank * n, physics=Physics.PYB_GND_DRAG_DW)
+    tr = SACTrainer(env, SACConfig(learning_starts=2 * 3 * n * world))     # two collection-only iterations, then updates
+    for _ in range(4):
+        tr.train_iteration()                                               # warm-up (past learning_starts)
+    barrier()
+    l0 = env.launch_count
+    t0 = time.perf_counter()
+    outs = [tr.train_iteration() for _ in range(args.sac_iters)]
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    samples = sum(o["samples"] for o in outs)
+    res = {"value": samples / dt, "unit": "samples/s (env-steps/s incl. actor inference and SAC updates)", "envs_per_gpu": n,
+           "iterations": args.sac_iters, "train_freq": tr.cfg.train_freq, "gradient_steps": tr.cfg.gradient_steps,
+           "batch_size": tr.cfg.batch_size, "gradient_steps_run": sum(o["gradient_steps"] for o in outs),
+           "physics": "DYN + drag + ground effect", "track": "circle", "substeps": args.substeps,
+           "critic_loss": outs[-1].get("critic_loss"), "ent_coef": outs[-1].get("ent_coef"),
+           "allreduce_calls": tr.learner.g_critic.calls + tr.learner.g_actor.calls, "gpu_launches": int(env.launch_count - l0),
+           "replay_transitions": len(tr.buffer)}
+    env.close()
+    return res
+
+
 def run_ppo(args, dev, world, rank, barrier, max_over_ranks):
     """PPO samples/s end to end on `--ppo-envs` envs per GPU: rollout (policy inference + fused env step, all on
     device) + GAE kernel + the PPO update (10 epochs, clipped losses, KL early stop) with ONE flat-gradient
@@ -673,6 +707,12 @@ def run_b200(args):
         except Exception as ex:  # noqa: BLE001
             line["ppo"] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
 
+    if not args.no_ppo:
+        try:
+            line["sac"] = run_sac(args, dev, world, rank, barrier, max_over_ranks)
+        except Exception as ex:  # noqa: BLE001
+            line["sac"] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.track, args.substeps, budget_s=args.cpu_budget)
     elif world > 1:
@@ -702,6 +742,8 @@ def main():
     ap.add_argument("--ppo-rollout", type=int, default=16)
     ap.add_argument("--ppo-iters", type=int, default=2)
     ap.add_argument("--ppo-track", default="reaching", choices=["circle", "reaching"])
+    ap.add_argument("--sac-envs", type=int, default=16384, help="BASELINE configs[3]: 16384 envs")
+    ap.add_argument("--sac-iters", type=int, default=20)
     ap.add_argument("--no-vecenv", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-BASELINE-config step-only lines")
     ap.add_argument("--cpu-budget", type=float, default=12.0)

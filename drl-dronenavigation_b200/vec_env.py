@@ -148,7 +148,9 @@ class GpuDroneVecEnv(_SB3VecEnv):
         bits = self._h_done.numpy()
         dones = bits != 0
         found = self._h_found.numpy()
-        infos: List[dict] = [{"found_targets": int(found[i]), "TimeLimit.truncated": False} for i in range(self.num_envs)]
+        # one dict per env, as SB3 expects; built from Python ints (tolist) -- per-element numpy scalar conversion was
+        # the most expensive line of the whole vector step at 4096 envs
+        infos: List[dict] = [{"found_targets": f, "TimeLimit.truncated": False} for f in found.tolist()]
         term = self._h_term.numpy()
         if self.collect_rollouts:
             raw = np.where(dones[:, None], term, obs)                # env.step's own observation (terminal one where done)
