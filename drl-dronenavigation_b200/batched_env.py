@@ -112,13 +112,22 @@ class BatchedDroneEnv:
                           "aux": self.reward_id == L.DN_REWARD_REACHING, "rew_rms": self.normalize_reward,
                           "spawn": bool(random_spawn)}
         N, D, dev = self.num_envs, self.obs_dim, self.device
-        self.obs = torch.zeros(N, D, dtype=torch.float32, device=dev)
-        self.reward = torch.zeros(N, dtype=torch.float32, device=dev)
-        self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self.terminal_obs = torch.zeros(N, D, dtype=torch.float32, device=dev)
-        self.found_targets = torch.zeros(N, dtype=torch.int32, device=dev)
-        self.episode_return = torch.zeros(N, dtype=torch.float32, device=dev)
-        self.episode_length = torch.zeros(N, dtype=torch.int32, device=dev)
+        # the persistent output lines of dn_step, carved out of ONE zero-filled allocation (one fill kernel per handle)
+        up = lambda b: (b + 255) & ~255
+        sizes = [("obs", N * D * 4), ("terminal_obs", N * D * 4), ("reward", N * 4), ("found_targets", N * 4),
+                 ("episode_return", N * 4), ("episode_length", N * 4), ("done", N)]
+        self._out_mem = torch.zeros(sum(up(b) for _, b in sizes), dtype=torch.uint8, device=dev)
+        views, off = {}, 0
+        for name, b in sizes:
+            views[name] = self._out_mem[off:off + b]
+            off += up(b)
+        self.obs = views["obs"].view(torch.float32).view(N, D)
+        self.terminal_obs = views["terminal_obs"].view(torch.float32).view(N, D)
+        self.reward = views["reward"].view(torch.float32)
+        self.found_targets = views["found_targets"].view(torch.int32)
+        self.episode_return = views["episode_return"].view(torch.float32)
+        self.episode_length = views["episode_length"].view(torch.int32)
+        self.done = views["done"]
         self._io = self._make_io(None, self.obs, self.reward, self.done, self.terminal_obs,
                                  self.found_targets, self.episode_return, self.episode_length)
 

@@ -86,8 +86,12 @@ if os.path.exists(lp):
             pass
     tot = sum(agg.values()) or 1
     with open(os.path.join(dst, f"launches_{tag}.md"), "w") as f:
-        f.write(f"# ncu launch list, {tag}\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 20 --warmup 3 "
-                f"--no-cpu --no-vecenv --sweep 4194304` (first 400 launches; cold-cache, serialised: compare shares)\n\n"
+        f.write(f"# ncu launch list, {tag}\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 64 --warmup 3 "
+                f"--no-cpu --no-vecenv --no-ppo --no-configs --rotating-handles 8 --sweep 4194304` (first 400 launches; cold-cache, serialised: "
+                "compare shares).  `--rotating-handles 8` keeps the set-up of the headline measurement (one init / reset / zero-fill per handle) "
+                "short enough for the 400-launch window to cover the timed region: 8 warm-up rotations + 64 timed step launches replayed from "
+                "CUDA graphs, then the flushed-bracket pass (one 256 MiB fill + one step per iteration).  In the timed region of the headline "
+                "the step kernel is the ONLY kernel launched.\n\n"
                 "| kernel | launches | total ns | share |\n|---|---|---|---|\n")
         for k, v in agg.most_common():
             f.write(f"| `{k[:110]}` | {cnt[k]} | {v:.0f} | {100 * v / tot:.1f}% |\n")
