@@ -622,13 +622,23 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 namespace {
-struct DeviceGuard {
-    int prev = -1; bool ok = false;
+struct DeviceGuard {   // switches the calling thread to the handle's device only when it is on another one
+    int prev = -1; bool ok = false, switched = false;
     explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        if (prev == dev) { ok = true; return; }
+        if (cudaSetDevice(dev) == cudaSuccess) { ok = true; switched = true; }
     }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
 };
+
+// Lowest-latency completion wait for the host-buffer call: poll the stream instead of blocking in
+// cudaStreamSynchronize (the caller is a single-threaded step loop that has nothing else to do).
+inline cudaError_t spin_until_done(cudaStream_t st) {
+    cudaError_t e;
+    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {}
+    return e;
+}
 
 }  // namespace
 
@@ -859,7 +869,7 @@ int dn_step_host(dn_env* env, const dn_step_io* h) {
     if (env->host_direct) {
         const int rc = launch_step(env, &env->host_mapped, 1, 1, env->host_stream);
         if (rc != DN_OK) return rc;
-        DN_CUDA(cudaStreamSynchronize(env->host_stream));
+        DN_CUDA(spin_until_done(env->host_stream));
         return DN_OK;
     }
     const size_t N = env->P.n, D = env->P.obs_dim;

@@ -22,6 +22,10 @@ def main(argv=None):
         sim.run_full_training()
     elif args.run_type == "test":
         sim.run_test()
+    elif args.run_type == "saved":
+        print(sim.test_saved())
+    elif args.run_type == "learning":
+        sim.test_learning()
     else:
         raise NotImplementedError(f"--run_type {args.run_type}")
 

@@ -42,6 +42,8 @@ class PBDroneSimulator:
             self.targets.pop(0)
         self.pyb_freq = getattr(args, "pyb_freq", 240)
         self.ctrl_freq = getattr(args, "ctrl_freq", 240)
+        # Example agent loaded from checkpoint by --run_type cont / saved (PBDroneSimulator.py:132-134)
+        self.continued_agent = getattr(args, "model_path", None) or "Sol/model_chkpts/PPO_save_05.31.2024_03.06.57/best_model.zip"
         print(track)
 
     # ------------------------------------------------------------------ envs
@@ -117,6 +119,10 @@ class PBDroneSimulator:
         total = int(float(args.total_timesteps))
         train_env = self.make_device_env(self.num_envs)
         trainer = self.setup_agent(train_env=train_env)
+        if args.run_type == "cont":              # continue from an SB3-format archive (:701-712)
+            if not os.path.exists(self.continued_agent):
+                raise FileNotFoundError(f"--run_type cont: {self.continued_agent} not found (pass --model_path)")
+            load_sb3_zip(self.continued_agent, trainer.learner, load_optimizer=True)
         chk = None
         if args.savemodel:
             chk = os.path.join("Sol", "model_chkpts", f"{args.agent}_save_{datetime.now().strftime('%m.%d.%Y_%H.%M.%S')}")
@@ -181,8 +187,24 @@ class PBDroneSimulator:
         env.close()
         return rewards
 
-    def test_saved(self, path: str, episodes: int = 50):
+    def test_learning(self, total_timesteps: int = 500, log=print):
+        """--run_type learning (:574-612): a 500-timestep PPO smoke run on ONE environment with the wider/deeper policy
+        of that method (net_arch=[512, 512, dict(vf=[256, 128], pi=[256, 128])]; the shared trunk of old SB3 versions
+        is unrolled into the two separate networks newer SB3 builds), n_steps = max_env_steps, batch_size = --batch_size."""
+        env = self.make_device_env(1)
+        T = min(int(self.args.max_env_steps), total_timesteps)
+        cfg = PPOConfig(n_steps=T, batch_size=min(int(self.args.batch_size), T), pi_arch=(512, 512, 256, 128), vf_arch=(512, 512, 256, 128))
+        trainer = PPOTrainer(env, cfg, rollout_steps=T)
+        log(trainer.learner.policy)
+        out = None
+        while trainer.total_steps < total_timesteps:
+            out = trainer.train_iteration()
+        env.close()
+        return trainer, out
+
+    def test_saved(self, path: str = None, episodes: int = 50):
         """--run_type saved (:438-572): roll a saved policy and report episode statistics."""
+        path = path or self.continued_agent
         env = self.make_device_env(64)
         trainer = self.setup_agent(train_env=env)
         if path.endswith(".zip"):            # an SB3 archive: the reference's best_model.zip / success_model.zip or one of ours

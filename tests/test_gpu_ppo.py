@@ -116,3 +116,29 @@ def test_ppo_update_cuda_graph_equals_eager():
         v, logp, _ = L.policy.evaluate(obs, act)
     out = L.update(obs, act, logp, v, adv, ret, generator=torch.Generator(device="cuda").manual_seed(1))
     assert out["early_stop"] and out["epochs"] < 30
+
+
+def test_manager_saved_cont_and_learning_run_types(tmp_path):
+    """--run_type learning (500-step smoke run with the deeper policy), a checkpoint written as an SB3 archive,
+    --run_type saved on it, and --run_type cont resuming from it (PBDroneSimulator.py:438-612,701-712)."""
+    from drl_dronenavigation_b200 import Track, Waypoints
+    from drl_dronenavigation_b200.argparser import parse_args
+    from drl_dronenavigation_b200.checkpoint import save_sb3_zip
+    from drl_dronenavigation_b200.simulator import PBDroneSimulator
+    track = Track(Waypoints.circle(radius=1, num_points=6, height=1), circle=True)
+    args = parse_args(["--num_envs", "256", "--total_timesteps", "8192", "--savemodel", "f", "--rollout_steps", "16",
+                       "--max_env_steps", "64", "--batch_size", "32"])
+    sim = PBDroneSimulator(args, track)
+    trainer, out = sim.test_learning(log=lambda *_: None)
+    assert trainer.total_steps >= 500 and np.isfinite(out["value_loss"])
+    # the deeper architecture: 13-512-512-256-128-4
+    assert sum(p.numel() for p in trainer.learner.policy.pi.parameters()) == 13 * 512 + 512 + 512 * 512 + 512 + 512 * 256 + 256 + 256 * 128 + 128 + 128 * 4 + 4
+    tr, _ = sim.run_full_training(log=lambda *_: None)
+    path = save_sb3_zip(str(tmp_path / "best_model.zip"), tr.learner)
+    ev = sim.test_saved(path, episodes=20)
+    assert ev["episodes"] >= 20
+    args2 = parse_args(["--num_envs", "256", "--total_timesteps", "8192", "--savemodel", "f", "--rollout_steps", "16",
+                        "--run_type", "cont", "--model_path", path])
+    sim2 = PBDroneSimulator(args2, track)
+    tr2, _ = sim2.run_full_training(log=lambda *_: None)
+    assert tr2.total_steps >= 8192
