@@ -22,6 +22,14 @@
  *     the step path, CUDA-graph capturable;
  *   - one handle per device shard; a handle is not thread-safe; handles are independent;
  *   - there is NO CPU fallback: without a CUDA device dn_create fails with DN_ECUDA.
+ *
+ * Launch behaviour
+ *   - dn_step / dn_step_many launch with programmatic stream serialization (PDL): the grid may be scheduled
+ *     while the previous kernel of the stream is still running, but it executes griddepcontrol.wait before
+ *     its first global memory access, so stream-order semantics of all buffers are unchanged;
+ *   - environment variables read by the library: DN_NO_PDL=1 (plain launches), DN_HOST_STAGED=1 (dn_step_host
+ *     always stages through device buffers), DN_PIPE=1 at dn_create (experimental persistent pipelined kernel for
+ *     batches of >= 2 tiles per resident CTA; slower than the default in all measurements so far).
  */
 #ifndef DRONENAV_H_
 #define DRONENAV_H_
