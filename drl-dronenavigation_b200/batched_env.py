@@ -80,7 +80,8 @@ class BatchedDroneEnv:
         c.cylinder, c.circle = int(bool(cylinder)), int(bool(circle))
         c.max_steps = int(max_steps)
         # random_spawn=True: the reference's (commented-out) spawn around a random target-pair line (PBDroneEnv.py:622-629)
-        c.spawn_mode = L.DN_SPAWN_LINE if random_spawn else L.DN_SPAWN_FIXED
+        # "midpoint": the other commented-out variant (PBDroneEnv.py:641-648)
+        c.spawn_mode = {False: L.DN_SPAWN_FIXED, True: L.DN_SPAWN_LINE, "line": L.DN_SPAWN_LINE, "midpoint": L.DN_SPAWN_MIDPOINT}[random_spawn]
         c.normalize_obs = int(bool(normalize_obs))
         c.normalize_reward = int(bool(normalize_reward))       # args.norm_rew (PBDroneSimulator.py:193-194)
         c.clip_reward = float(clip_reward)                     # args.clip_rew -> 10 (PBDroneSimulator.py:191-192)

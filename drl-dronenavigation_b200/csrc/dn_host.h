@@ -67,7 +67,10 @@ inline bool reward_table(int id, double discount, dn::RewardParams& w) {
             w.mode = dn::RW_POINT; w.pt_x = 0.f; w.pt_y_rate = 0.f; w.pt_z = 1.f; w.pt_w = 1.f; return true;
         case DN_REWARD_FLYTHRUGATE: // FlyThruGateAviary.py:100-112: -10 |(0, -2 t_norm, 0.75) - p|^2
             w.mode = dn::RW_POINT; w.pt_x = 0.f; w.pt_y_rate = -2.f; w.pt_z = 0.75f; w.pt_w = 10.f; return true;
-        default: return false;     // DN_REWARD_PROGRESS: not implemented (commented-out code in the reference)
+        case DN_REWARD_PROGRESS:   // PBDroneEnv._computeReward with the progress term of Rewarder.py:43-62, weight 2000 (ThrustEnv.py:416-421)
+            w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.7f, 0.3f, 1.f, 25.f, 0.04f};
+            w.proj_w = 2000.f; return true;
+        default: return false;
     }
 }
 

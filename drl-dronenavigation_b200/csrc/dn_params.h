@@ -31,6 +31,7 @@ struct RewardParams {
     // ---- other reward families (reward_id >= 3), see dn_device.cuh::reward_alt
     int   mode;              // RW_* below
     float decay_log2;        // HER: log2(discount) / 10, capture bonus * discount^(steps/10) (HerPBDroneEnv.py:371)
+    float proj_w;            // DN_REWARD_PROGRESS: weight of the projection progress that replaces (prev_d - d) * progress_w; 0 = off
     float pt_x, pt_y_rate, pt_z, pt_w;   // POINT: -pt_w * |(pt_x, pt_y_rate * t_norm, pt_z) - pos|^2 (HoverAviary.py:65-76, FlyThruGateAviary.py:100-112)
 };
 enum { RW_WAYPOINT = 0, RW_HER = 1, RW_REACHING = 2, RW_POINT = 3 };

@@ -451,12 +451,14 @@ __global__ void reset_kernel(const __grid_constant__ Params P, const uint8_t* ma
         D0 = sqrtf(dx * dx + dy * dy + dz * dz);
     }
     s.px = P.init_pos[0]; s.py = P.init_pos[1]; s.pz = P.init_pos[2];
-    if (P.spawn_mode == DN_SPAWN_LINE) {        // see env_step; the Philox counter advances on explicit resets too
+    if (P.spawn_mode != DN_SPAWN_FIXED) {       // see env_step; the Philox counter advances on explicit resets too
         s.ep_count += 1u;
-        spawn_line(P, i, s.ep_count, s.px, s.py, s.pz);
-        P.spawn[i] = make_float4(s.px, s.py, s.pz, 0.f);
+        int roll = 0;
+        if (P.spawn_mode == DN_SPAWN_LINE) spawn_line(P, i, s.ep_count, s.px, s.py, s.pz);
+        else spawn_midpoint(P, i, s.ep_count, s.px, s.py, s.pz, roll);
+        P.spawn[i] = make_float4(s.px, s.py, s.pz, static_cast<float>(roll));
         if (P.aux) { float4 ax = P.aux[i]; ax.x = s.px; ax.y = s.py; ax.z = s.pz; P.aux[i] = ax; }
-        const float4 t0 = target_at(P, 0);
+        const float4 t0 = target_at(P, roll);
         const float dx = s.px - t0.x, dy = s.py - t0.y, dz = s.pz - t0.z;
         D0 = sqrtf(dx * dx + dy * dy + dz * dz);
     }
@@ -471,7 +473,7 @@ __global__ void reset_kernel(const __grid_constant__ Params P, const uint8_t* ma
     float o[kMaxObs];
 #pragma unroll
     for (int k = 0; k < 12; ++k) o[k] = P.init_obs[k];
-    if (P.spawn_mode == DN_SPAWN_LINE) { o[0] = s.px * P.inv_x_high; o[1] = s.py * P.inv_y_high; o[2] = s.pz * P.inv_z_high; }
+    if (P.spawn_mode != DN_SPAWN_FIXED) { o[0] = s.px * P.inv_x_high; o[1] = s.py * P.inv_y_high; o[2] = s.pz * P.inv_z_high; }
     o[12] = stale_dist * P.inv_max_target_dist;
     if (NORM) {
         const size_t N = P.n;
@@ -658,9 +660,8 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
         return fail(DN_EINVAL, "dn_create: need 1..2046 targets");
     if (cfg->act_type < 0 || cfg->act_type > DN_ACT_ONE_D_RPM) return fail(DN_EINVAL, "dn_create: unsupported act_type");
     if (cfg->physics & ~7) return fail(DN_EINVAL, "dn_create: unknown physics flags");
-    if (cfg->spawn_mode != DN_SPAWN_FIXED && cfg->spawn_mode != DN_SPAWN_LINE)
-        return fail(DN_EINVAL, "dn_create: spawn_mode not implemented (DN_SPAWN_MIDPOINT is reserved)");
-    if (cfg->spawn_mode == DN_SPAWN_LINE && cfg->num_targets < 2) return fail(DN_EINVAL, "dn_create: DN_SPAWN_LINE needs >= 2 targets");
+    if (cfg->spawn_mode < DN_SPAWN_FIXED || cfg->spawn_mode > DN_SPAWN_MIDPOINT) return fail(DN_EINVAL, "dn_create: unknown spawn_mode");
+    if (cfg->spawn_mode != DN_SPAWN_FIXED && cfg->num_targets < 2) return fail(DN_EINVAL, "dn_create: random spawn needs >= 2 targets");
     if (cfg->max_steps < 0 || cfg->max_steps > (int)dn::kStepsMask - 1) return fail(DN_EINVAL, "dn_create: max_steps out of range");
     dn::RewardParams rw;
     if (!dn::host::reward_table(cfg->reward_id, cfg->discount, rw)) return fail(DN_EINVAL, "dn_create: reward_id not implemented");
@@ -700,7 +701,7 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     const size_t rms_floats = e->normalize_obs ? static_cast<size_t>(2 * P.obs_dim + 1) * N : 0;
     bytes += ((rms_floats * sizeof(float) + 255) / 256) * 256;
     const bool need_aux = (rw.mode == dn::RW_REACHING), need_rew_rms = (cfg->normalize_reward != 0);
-    const bool need_spawn = (cfg->spawn_mode == DN_SPAWN_LINE);
+    const bool need_spawn = (cfg->spawn_mode != DN_SPAWN_FIXED);
     if (need_aux) bytes += plane;
     if (need_rew_rms) bytes += plane;
     if (need_spawn) bytes += plane;

@@ -66,8 +66,9 @@ extern "C" {
 #define DN_REWARD_THRUSTENV 2   /* ThrustEnv.py:368-513 */
 #define DN_REWARD_HER       3   /* HerPBDroneEnv.py:314-398 (first element of its tuple) */
 #define DN_REWARD_REACHING  4   /* dummy_env.py:617-643 == Rewarder.py:8-40 reaching-progress (arXiv 2310.10943) */
-#define DN_REWARD_PROGRESS  5   /* Rewarder.py:43-62 projection progress (arXiv 2103.08624): only ever called from
-                                   commented-out code in the reference; reserved, dn_create rejects it */
+#define DN_REWARD_PROGRESS  5   /* PBDroneEnv reward with the projection progress of Rewarder.py:43-62 (arXiv 2103.08624) x 2000
+                                   in place of the distance difference (the reference only calls it from commented-out
+                                   code, ThrustEnv.py:416-421; p_t / p_t-1 = position after / before the step) */
 #define DN_REWARD_HOVER     6   /* upstream HoverAviary.py:65-76 */
 #define DN_REWARD_FLYTHRUGATE 7 /* FlyThruGateAviary.py:100-112 */
 #define DN_NUM_REWARDS      8
@@ -76,8 +77,8 @@ extern "C" {
 #define DN_SPAWN_FIXED      0   /* INIT_XYZS / INIT_RPYS, deterministic */
 #define DN_SPAWN_LINE       1   /* Philox: within 0.1 m of a random target-pair line (PBDroneEnv.py:622-629,
                                    position_generator.py:121-152); commented out in the reference, offered as an option */
-#define DN_SPAWN_MIDPOINT   2   /* segment midpoint with rolled target order (PBDroneEnv.py:641-648, commented out);
-                                   reserved, dn_create rejects it */
+#define DN_SPAWN_MIDPOINT   2   /* Philox: midpoint of a random track segment, target order rolled to start behind it
+                                   (PBDroneEnv.py:641-648, commented out in the reference, offered as an option) */
 
 /* done byte written by dn_step */
 #define DN_DONE_TERMINATED  1
@@ -152,7 +153,7 @@ typedef struct dn_state_view {
     float*    obs_rms;        /* [N,2*obs_dim+1] mean | var | count (normalize.py:10-47); only if normalize_obs */
     float*    aux;            /* [N,4] _current_position.xyz | last travel; only with DN_REWARD_REACHING */
     float*    rew_rms;        /* [N,4] returns | mean | var | count (normalize.py:100-147); only if normalize_reward */
-    float*    spawn;          /* [N,4] INIT_XYZS[0] of the current episode | 0; only with DN_SPAWN_LINE */
+    float*    spawn;          /* [N,4] INIT_XYZS[0] of the current episode | target roll; only with a random spawn mode */
 } dn_state_view;
 
 /* Aggregated Monitor statistics since the last clear (SB3 Monitor / ep_info_buffer). */

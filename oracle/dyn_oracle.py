@@ -313,6 +313,18 @@ def spawn_line(targets, aviary_dim, seed, global_env_id, counter, max_distance=0
     return np.minimum(np.maximum(point, lo), hi)
 
 
+def spawn_midpoint(targets, seed, global_env_id, counter):
+    """PBDroneEnv.py:641-648 (commented out in the reference): a random segment of the track, its midpoint, and the
+    target order rolled to start behind it.  Returns (spawn point, roll)."""
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    a = philox4x32_10((counter, 0, global_env_id & 0xFFFFFFFF, (global_env_id >> 32) & 0xFFFFFFFF), key)
+    T = len(targets)
+    u = np.float32(a[0] >> 8) * np.float32(1.0 / 16777216.0)
+    segment_index = min(int(u * np.float32(T - 1)), T - 2)                     # np.random.randint(T - 1)
+    segment_center = (np.asarray(targets[segment_index], np.float64) + np.asarray(targets[segment_index + 1], np.float64)) / 2
+    return segment_center, segment_index + 1
+
+
 ACT_THRUST = "thrust"
 ACT_RPM = "rpm"
 ACT_ONE_D_RPM = "one_d_rpm"
@@ -336,6 +348,7 @@ class OracleDroneEnv:
         self.ACT_TYPE = act
         self.PHYSICS = physics
         self._target_points = np.array(target_points, dtype=np.float64)
+        self._or_target_points = self._target_points.copy()          # PBDroneEnv.py:73
         self._threshold = threshold
         self._discount = discount
         self._max_steps = max_steps
@@ -409,9 +422,14 @@ class OracleDroneEnv:
     def reset(self, seed=None, options=None):
         self._reset_counter += 1
         if self.random_spawn:
-            # OUR semantics for the reference's commented-out block (PBDroneEnv.py:622-629): the point is drawn first,
-            # the episode starts there, the reset observation shows it and the distances are measured from it
-            self.INIT_XYZS[0] = spawn_line(self._target_points, self._aviary_dim, self.seed, self.global_env_id, self._reset_counter)
+            # OUR semantics for the reference's commented-out blocks (PBDroneEnv.py:622-629 / :641-648): the point is
+            # drawn first, the episode starts there, the reset observation shows it and the distances are measured from it
+            if self.random_spawn == "midpoint":
+                center, roll = spawn_midpoint(self._or_target_points, self.seed, self.global_env_id, self._reset_counter)
+                self.INIT_XYZS[0] = center
+                self._target_points = np.concatenate((self._or_target_points[roll:], self._or_target_points[:roll]), axis=0)
+            else:
+                self.INIT_XYZS[0] = spawn_line(self._target_points, self._aviary_dim, self.seed, self.global_env_id, self._reset_counter)
             self._current_position = self.INIT_XYZS[0].copy()
         self._housekeeping()
         initial_obs = self._computeObs()      # BEFORE the distances are reset
@@ -430,6 +448,7 @@ class OracleDroneEnv:
     def step(self, action):
         action = np.asarray(action)
         self.margins = []
+        self._pos_at_entry = self.pos.copy()
         a = self.rescale_action(action) if self.normalize_actions else action
         rpm = np.reshape(self._preprocessAction(a), 4)
         for _ in range(self.PYB_STEPS_PER_CTRL):
@@ -637,6 +656,8 @@ class OracleDroneEnv:
             return self._reward_waypoint(-10.0, 200, 75, 5, 3000, 3, (0.7, 0.3))
         if rid == "dummy":          # dummy_env.py:446-550, smoothness thresholds 0.1 / 0.1 (:587)
             return self._reward_waypoint(-10.0, 200, 75, 5, 3000, 3, (0.1, 0.1))
+        if rid == "progress":       # PBDroneEnv reward with Rewarder.calculate_progress_reward x 2000 in place of the distance difference
+            return self._reward_waypoint(-10.0, 200, 75, 5, 3000, 3, (0.7, 0.3), proj_w=2000)
         if rid == "thrustenv":      # ThrustEnv.py:368-463
             return self._reward_waypoint(-4.0, 1000, 25, 0, 20, 0, None)
         if rid == "her":
@@ -689,7 +710,14 @@ class OracleDroneEnv:
         return reward
 
     # ---- reward (PBDroneEnv.py:475-607) and its constant variants -----------
-    def _reward_waypoint(self, crash, final, capture, capture_orient, progress_w, orient_w, smooth_thr):
+    def calculate_progress_reward(self, pc_t, pc_t_minus_1, g1, g2):
+        """Rewarder.py:43-62 / dummy_env.py:599-615."""
+        def s(p):
+            g_diff = g2 - g1
+            return np.dot(p - g1, g_diff) / np.linalg.norm(g_diff) ** 2
+        return s(pc_t) - s(pc_t_minus_1)
+
+    def _reward_waypoint(self, crash, final, capture, capture_orient, progress_w, orient_w, smooth_thr, proj_w=0):
         if self._computeTerminated() and not self._is_done:
             return crash
         reward = np.float32(0.0)
@@ -706,7 +734,14 @@ class OracleDroneEnv:
                 self.just_found = True
         else:
             reward += (np.exp(-2 * self._distance_to_target)) * 3
-            reward += ((self._prev_distance_to_target - self._distance_to_target) * progress_w) if not self.just_found else 0
+            if proj_w:
+                idx = self._current_target_index
+                g1 = np.array(self.INIT_XYZS[0]) if idx == 0 else np.array(self._target_points[idx - 1])
+                g2 = np.array(self._target_points[idx])
+                prog = 0.0 if np.linalg.norm(g2 - g1) == 0 else proj_w * self.calculate_progress_reward(self.pos, self._pos_at_entry, g1, g2)
+            else:
+                prog = (self._prev_distance_to_target - self._distance_to_target) * progress_w
+            reward += prog if not self.just_found else 0
             if orient_w:
                 reward += self.orientation_reward(self.current_target()) * orient_w
             if smooth_thr is not None:

@@ -46,7 +46,7 @@ class HostEmuEnv:
         c.normalize_actions, c.physics, c.reward_id = int(normalize_actions), physics, reward_id
         c.include_distance, c.cylinder, c.circle, c.max_steps = int(include_distance), int(cylinder), int(circle), max_steps
         c.threshold, c.discount = threshold, discount
-        c.spawn_mode, c.seed, c.env_id_offset = (1 if random_spawn else 0), seed, env_id_offset
+        c.spawn_mode, c.seed, c.env_id_offset = ({False: 0, True: 1, "line": 1, "midpoint": 2}[random_spawn]), seed, env_id_offset
         c.normalize_reward, c.clip_reward, c.reward_gamma = int(normalize_reward), float(clip_reward), float(reward_gamma)
         c.aviary_dim = (C.c_double * 6)(*[float(v) for v in aviary_dim])
         c.init_xyz = (C.c_double * 3)(*np.array(initial_xyzs, dtype=np.float64).reshape(-1)[:3])

@@ -54,7 +54,7 @@ Emu* emu_create(const dn_config* cfg) {
     if (rw.mode == dn::RW_REACHING) {
         e->aux.assign(N, make_float4(e->P.init_pos[0], e->P.init_pos[1], e->P.init_pos[2], 0.f)); e->P.aux = e->aux.data();
     }
-    if (cfg->spawn_mode == DN_SPAWN_LINE) {
+    if (cfg->spawn_mode != DN_SPAWN_FIXED) {
         e->spawn.assign(N, make_float4(e->P.init_pos[0], e->P.init_pos[1], e->P.init_pos[2], 0.f)); e->P.spawn = e->spawn.data();
     }
     if (cfg->normalize_reward) { e->rew_rms.assign(N, make_float4(0.f, 0.f, 1.f, 1e-4f)); e->P.rew_rms = e->rew_rms.data(); }

@@ -297,6 +297,7 @@ FULL_SIZE = [
     ("cfg3_65536_reaching", 65536, "reaching", {}),
     ("cfg4_16384_drag_gnd", 16384, "circle", {"physics": "PYB_GND_DRAG_DW"}),
     ("cfg5_131072_reward_her", 131072, "circle", {"reward_id": 3}),
+    ("cfg5_131072_reward_progress", 131072, "circle", {"reward_id": 5}),
     ("cfg5_131072_reward_reaching", 131072, "circle", {"reward_id": 4}),
     ("cfg5_131072_reward_flythru_normrew", 131072, "circle", {"reward_id": 7, "normalize_reward": True, "clip_reward": 10.0}),
 ]
@@ -315,7 +316,7 @@ def test_full_size_properties(name, N, track, kw):
     if "physics" in kw:
         kw["physics"] = getattr(Physics, kw["physics"])
         okw["physics"] = "dyn_gnd_drag"
-    rid = {0: "default", 3: "her", 4: "reaching", 7: "flythrugate"}[kw.get("reward_id", 0)]
+    rid = {0: "default", 3: "her", 4: "reaching", 5: "progress", 7: "flythrugate"}[kw.get("reward_id", 0)]
     ref = make_reference_env(track, pyb_freq=240, ctrl_freq=30)
     env = BatchedDroneEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS,
                           pyb_freq=240, ctrl_freq=30, circle=(track == "circle"), include_distance=True, normalize_actions=True, **kw)
@@ -353,13 +354,14 @@ def test_full_size_properties(name, N, track, kw):
             assert abs(float(rn[j]) - float(rr)) <= 1e-2 + 2e-3 * abs(float(rr)), (name, t, j, rn[j], rr)
     stats = env.episode_stats()
     assert stats["episodes"] == n_done and n_done > 0
-    if rid in ("default", "her"):
+    if rid in ("default", "her", "progress"):
         assert stats["crashes"] + stats["truncations"] + stats["successes"] == n_done
     env.close()
 
 
+@pytest.mark.parametrize("mode", ["line", "midpoint"])
 @pytest.mark.parametrize("track", ["circle", "reaching"])
-def test_random_spawn_philox_matches_oracle_and_is_shard_invariant(track):
+def test_random_spawn_philox_matches_oracle_and_is_shard_invariant(track, mode):
     """DN_SPAWN_LINE (Philox-seeded auto-reset): the CUDA path against the oracle's restatement of the same draws,
     and invariance to sharding -- env g of a shard with env_id_offset = k behaves exactly like env k + g of one big
     handle (Philox subsequence = GLOBAL env id)."""
@@ -370,9 +372,9 @@ def test_random_spawn_philox_matches_oracle_and_is_shard_invariant(track):
     ref = make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S)
     mk = lambda n, off: BatchedDroneEnv(n, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS,
                                         pyb_freq=240, ctrl_freq=240 // S, circle=(track == "circle"), include_distance=True,
-                                        normalize_actions=True, random_spawn=True, seed=seed, env_id_offset=off)
+                                        normalize_actions=True, random_spawn=mode, seed=seed, env_id_offset=off)
     big, shard = mk(N, 100), mk(N // 2, 100 + N // 2)
-    workers = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S, random_spawn=True, seed=seed,
+    workers = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S, random_spawn=mode, seed=seed,
                                                global_env_id=100 + i), normalize_obs=False) for i in range(N)]
     o_big, o_sh = big.reset().cpu().numpy(), shard.reset().cpu().numpy()
     np.testing.assert_array_equal(o_big[N // 2:], o_sh)

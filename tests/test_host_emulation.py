@@ -116,3 +116,73 @@ def test_philox_known_answer():
     assert philox4x32_10((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+@pytest.mark.parametrize("track", ["circle", "reaching"])
+def test_device_logic_midpoint_spawn_rolled_targets(track):
+    """DN_SPAWN_MIDPOINT: spawn at the midpoint of a random track segment with the target order rolled to start behind
+    it (PBDroneEnv.py:641-648): rolled target lookups, the on-the-fly tube segments (spawn -> first target, last track
+    target -> track target 0) and found_targets must agree with the oracle."""
+    from oracle.dyn_oracle import OracleWorker, make_reference_env
+    from tests.host_emu import HostEmuEnv
+    N, T, S, seed, off = 6, 150, 8, 987654321, 40
+    ref = make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S)
+    env = HostEmuEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS, pyb_freq=240,
+                     ctrl_freq=240 // S, circle=(track == "circle"), include_distance=True, normalize_actions=True,
+                     random_spawn="midpoint", seed=seed, env_id_offset=off)
+    workers = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S, random_spawn="midpoint", seed=seed,
+                                               global_env_id=off + i), normalize_obs=False) for i in range(N)]
+    a = _actions("saturating", T, N, seed=8)
+    a[T // 2:] = _actions("mixed", T - T // 2, N, seed=9)          # longer episodes in the second half: targets get captured
+    resets = _open_loop(env.step, workers, a)
+    assert resets >= 10
+    assert len({tuple(np.round(w.env.INIT_XYZS[0], 6)) for w in workers}) >= 2
+    env.close()
+
+
+@pytest.mark.parametrize("track,S", [("circle", 1), ("reaching", 8)])
+def test_device_logic_projection_progress_reward(track, S):
+    """DN_REWARD_PROGRESS: the default reward with Rewarder.calculate_progress_reward x 2000 as the progress term."""
+    from oracle.dyn_oracle import OracleWorker, make_reference_env
+    from tests.host_emu import HostEmuEnv
+    N, T = 6, 120
+    ref = make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S)
+    env = HostEmuEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS, pyb_freq=240,
+                     ctrl_freq=240 // S, circle=(track == "circle"), include_distance=True, normalize_actions=True, reward_id=5)
+    workers = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S, reward_id="progress"), normalize_obs=False)
+               for _ in range(N)]
+    resets = _open_loop(env.step, workers, _actions("mixed", T, N, seed=21), rew_tol=2e-2)
+    assert resets >= 3
+    env.close()
+
+
+def test_device_logic_midpoint_spawn_captures_on_a_tight_track():
+    """Same, on a tight 5-gate loop (chord 0.53 m, threshold 0.3 m) flown in the segment tube: every episode captures
+    its first (rolled) target on step 1, so target indices > 0, the rolled segment table and its wrap-around entry
+    (last track target -> track target 0) are all exercised."""
+    from oracle.dyn_oracle import OracleDroneEnv, OracleWorker
+    from tests.host_emu import HostEmuEnv
+    N, T, S, seed = 12, 90, 8, 4242
+    ang = np.linspace(0, 2 * np.pi, 6)[:-1]
+    targets = np.stack([0.45 * np.cos(ang), 0.45 * np.sin(ang), np.ones(5)], axis=1)
+    dim, init = np.array([-2, -2, 0, 2, 2, 2]), np.array([[0.45, 0.0, 1.0]])
+    kw = dict(threshold=0.3, discount=0.999, max_steps=4096, aviary_dim=dim, initial_xyzs=init, pyb_freq=240, ctrl_freq=240 // S,
+              cylinder=True, circle=False, include_distance=True, normalize_actions=True)
+    env = HostEmuEnv(N, targets, random_spawn="midpoint", seed=seed, **kw)
+    workers = [OracleWorker(OracleDroneEnv(targets, random_spawn="midpoint", seed=seed, global_env_id=i, **kw), normalize_obs=False)
+               for i in range(N)]
+    a = _actions("mixed", T, N, seed=3)
+    a[:6] = _actions("saturating", 6, N, seed=4)                  # crash the constructor-state episodes quickly
+    T_, found_max = a.shape[0], 0
+    for t in range(T_):
+        o, r, d, f = env.step(a[t])
+        for i, w in enumerate(workers):
+            oo, rr, dd, info = w.step(a[t, i])
+            bits = (1 if w.last_terminated else 0) | (2 if w.last_truncated else 0)
+            assert int(d[i]) == bits and int(f[i]) == info["found_targets"], (t, i)
+            assert abs(float(r[i]) - float(rr)) < 1e-2, (t, i, r[i], rr)
+            found_max = max(found_max, info["found_targets"])
+    assert found_max >= 1
+    rolls = {int(np.argmin(np.linalg.norm(targets - w.env._target_points[0], axis=1))) for w in workers}
+    assert len(rolls) >= 3                                        # several different rolled orders were in play
+    env.close()
