@@ -24,7 +24,8 @@
  *   - there is NO CPU fallback: without a CUDA device dn_create fails with DN_ECUDA.
  *
  * Launch behaviour
- *   - dn_step / dn_step_many launch with programmatic stream serialization (PDL): the grid may be scheduled
+ *   - dn_step / dn_step_many launch small grids (at most half the SMs) with programmatic stream serialization
+ *     (PDL): the grid may be scheduled
  *     while the previous kernel of the stream is still running, but it executes griddepcontrol.wait before
  *     its first global memory access, so stream-order semantics of all buffers are unchanged;
  *   - environment variables read by the library: DN_NO_PDL=1 (plain launches), DN_HOST_STAGED=1 (dn_step_host
