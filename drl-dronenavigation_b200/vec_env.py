@@ -216,8 +216,20 @@ class GpuDroneVecEnv(_SB3VecEnv):
     def render(self, mode: Optional[str] = None):
         return None
 
-    # the reference calls eval_env.save(path) (PBDroneSimulator.py:746): persist the obs-RMS state
+    # the reference calls eval_env.save(path) (PBDroneSimulator.py:746): persist the running statistics of the wrappers
     def save(self, path: str) -> None:
         state = {k: v.cpu().numpy() for k, v in self.core.get_state().items()}
         with open(path, "wb") as f:
-            pickle.dump({"obs_rms": state.get("obs_rms"), "obs_dim": self.core.obs_dim}, f)
+            pickle.dump({"obs_rms": state.get("obs_rms"), "rew_rms": state.get("rew_rms"), "obs_dim": self.core.obs_dim,
+                         "num_envs": self.num_envs}, f)
+
+    def load_running_stats(self, path: str) -> None:
+        """Counterpart of save(): restores the per-env NormalizeObservation / NormalizeReward statistics (what
+        VecNormalize.load(stats_path, env) does for the reference's evaluation runs, PBDroneSimulator.py:745-746)."""
+        with open(path, "rb") as f:
+            d = pickle.load(f)
+        if d.get("num_envs") != self.num_envs or d.get("obs_dim") != self.core.obs_dim:
+            raise ValueError("running statistics were saved for a different num_envs / observation size")
+        st = {k: d[k] for k in ("obs_rms", "rew_rms") if d.get(k) is not None and self.core._optional.get(k)}
+        if st:
+            self.core.set_state(st)

@@ -59,3 +59,31 @@ def test_no_cpu_fallback_in_product_code():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_config_validation_messages(built_lib):
+    """dn_create validates the whole configuration before it looks for a device, so these run without a GPU."""
+    import numpy as np
+    from drl_dronenavigation_b200 import _lib
+    targets = np.ascontiguousarray([[0.0, 0.0, 1.0], [1.0, 0.0, 1.0]], dtype=np.float64)
+
+    def cfg(**kw):
+        c = _lib.dn_config()
+        c.abi_version, c.num_envs, c.pyb_freq, c.ctrl_freq = _lib.DN_ABI_VERSION, 4, 240, 30
+        c.num_targets, c.targets, c.max_steps = 2, targets.ctypes.data_as(C.POINTER(C.c_double)), 4096
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+    h = C.c_void_p()
+    for kw, msg in ((dict(num_envs=0), b"num_envs"), (dict(num_targets=0), b"targets"), (dict(act_type=7), b"act_type"),
+                    (dict(physics=64), b"physics"), (dict(spawn_mode=9), b"spawn_mode"), (dict(reward_id=99), b"reward_id"),
+                    (dict(max_steps=1 << 21), b"max_steps"), (dict(spawn_mode=1, num_targets=1), b"random spawn")):
+        assert built_lib.dn_create(C.byref(cfg(**kw)), 0, C.byref(h)) == -1, kw
+        assert msg in built_lib.dn_last_error(), (kw, built_lib.dn_last_error())
+    # a valid configuration passes validation and then fails on the missing device (no CPU fallback) -- or succeeds on a GPU box
+    rc = built_lib.dn_create(C.byref(cfg()), 0, C.byref(h))
+    assert rc in (0, -2)
+    if rc == 0:
+        built_lib.dn_destroy(h)
+    else:
+        assert b"no CUDA device" in built_lib.dn_last_error() or b"CUDA" in built_lib.dn_last_error()

@@ -480,3 +480,25 @@ def test_pipelined_kernel_matches_single_step_kernel(monkeypatch):
     assert st["episodes"] == n_done > 0 and st["crashes"] + st["truncations"] + st["successes"] == n_done
     for e in (big, head, tail):
         e.close()
+
+
+def test_vec_env_save_and_load_running_stats(tmp_path):
+    """eval_env.save(path) (PBDroneSimulator.py:746) and its counterpart: the per-env obs / reward statistics survive a
+    round trip, so a restored env normalises the next observation exactly like the one that was saved."""
+    from drl_dronenavigation_b200.vec_env import GpuDroneVecEnv
+    from oracle.dyn_oracle import make_reference_env
+    ref = make_reference_env("circle")
+    mk = lambda: GpuDroneVecEnv(5, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS, circle=True,
+                                include_distance=True, normalize_actions=True, normalize_obs=True, normalize_reward=True)
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    acts = _actions("mixed", 30, 5, seed=2)
+    for t in range(20):
+        a.step(acts[t])
+    path = str(tmp_path / "vec_normalize.pkl")
+    a.save(path)
+    b.load_running_stats(path)
+    sa, sb = a.core.get_state(), b.core.get_state()
+    assert torch.equal(sa["obs_rms"], sb["obs_rms"]) and torch.equal(sa["rew_rms"], sb["rew_rms"])
+    assert float(sa["obs_rms"][:, -1].min()) > 20          # counts advanced
+    a.close(); b.close()
