@@ -21,6 +21,7 @@
 #include <vector>
 #include <new>
 #include <cstdlib>
+#include <algorithm>
 
 #include "../../include/dronenav.h"
 #include "dn_params.h"
@@ -249,7 +250,8 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
 // ---------------------------------------------------------------------------
 // EXPERIMENTAL (opt-in with DN_PIPE=1; measured SLOWER than step_kernel so far: 4 Mi envs, S = 8: 297 vs 235 us,
 // S = 1: 231 vs 196 us -- ncu: 15 % of SMSP time without a resident warp and 53 % DRAM utilisation, i.e. the
-// statically scheduled persistent CTAs stay phase-locked and leave a tail).
+// statically scheduled persistent CTAs stay phase-locked and leave a tail; DN_PIPE=k > 1 runs k contiguous tiles per
+// CTA on a normal grid instead: k = 2 is 1-3 % faster than step_kernel, k >= 4 slower).
 // Persistent, software-pipelined variant of the single-step kernel for large batches (>= 2 tiles per resident CTA).
 // In step_kernel all CTAs of an SM start together, load together, compute together and retire together, so the
 // load phase of every wave is exposed (ncu, 4 Mi envs, S = 8: no eligible warp in 20 % of the cycles although HBM is
@@ -268,7 +270,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 
 template <int PHYS>
 __global__ void __launch_bounds__(kBlock, 7)
-step_kernel_pipe(const __grid_constant__ Params P, const __grid_constant__ StepIO io, const int num_tiles) {
+step_kernel_pipe(const __grid_constant__ Params P, const __grid_constant__ StepIO io, const int num_tiles, const int tiles_per_cta) {
     __shared__ __align__(128) float tile2[2][kBlock * kMaxObs];   // observation rows, double-buffered across iterations
     __shared__ __align__(16) float4 core_stage[5 * kBlock];     // action | planes 0..3
     __shared__ __align__(16) float4 aux_stage[3 * kBlock];      // planes 4..6
@@ -280,9 +282,15 @@ step_kernel_pipe(const __grid_constant__ Params P, const __grid_constant__ StepI
     int parity = 0;
     BlockAcc acc = {0.f, 0, 0, 0, 0};
 
+    // tiles_per_cta > 0: this CTA owns the contiguous tiles [blockIdx.x * tiles_per_cta, +tiles_per_cta) and the grid is
+    // ceil(num_tiles / tiles_per_cta) (CTAs come and go, the hardware balances them); 0: persistent grid-stride walk
+    const int t_first = tiles_per_cta > 0 ? blockIdx.x * tiles_per_cta : blockIdx.x;
+    const int t_step = tiles_per_cta > 0 ? 1 : static_cast<int>(gridDim.x);
+    const int t_end = tiles_per_cta > 0 ? min(num_tiles, t_first + tiles_per_cta) : num_tiles;
+
     auto issue_core = [&](int t) {
         const int j = t * kBlock + tid;
-        if (t < num_tiles && j < P.n) {
+        if (t < t_end && j < P.n) {
             cp_async16(&core_stage[tid], io.actions + j);
 #pragma unroll
             for (int p = 0; p < 4; ++p) cp_async16(&core_stage[(p + 1) * kBlock + tid], &P.s[p][j]);
@@ -291,16 +299,16 @@ step_kernel_pipe(const __grid_constant__ Params P, const __grid_constant__ StepI
     };
     auto issue_aux = [&](int t) {
         const int j = t * kBlock + tid;
-        if (t < num_tiles && j < P.n) {
+        if (t < t_end && j < P.n) {
 #pragma unroll
             for (int p = 0; p < 3; ++p) cp_async16(&aux_stage[p * kBlock + tid], &P.s[4 + p][j]);
         }
         cp_async_commit();
     };
-    issue_core(blockIdx.x);
-    issue_aux(blockIdx.x);
+    issue_core(t_first);
+    issue_aux(t_first);
 
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = t_first; t < t_end; t += t_step) {
         const int base = t * kBlock;
         const int i = base + tid;
         const bool active = i < P.n;
@@ -320,9 +328,9 @@ step_kernel_pipe(const __grid_constant__ Params P, const __grid_constant__ StepI
             s.wx = d.x; s.wy = d.y; s.wz = d.z; s.ep_ret = d.w;
             if (PHYS & 1) last_rpm_sum = P.last_rpm_sum[i];
             entry_stage[tid] = a;
-            issue_core(t + gridDim.x);                                  // this thread's slots are free again
+            issue_core(t + t_step);                                     // this thread's slots are free again
             const StepResult r = env_step<PHYS>(P, i, s, act, last_rpm_sum, obs_row, &aux_stage[tid], kBlock, 1, &entry_stage[tid]);
-            issue_aux(t + gridDim.x);                                   // A(t) was consumed inside env_step
+            issue_aux(t + t_step);                                      // A(t) was consumed inside env_step
             store_state(P, i, s);
             if (PHYS & 1) P.last_rpm_sum[i] = last_rpm_sum;
             if (r.finished) {
@@ -346,9 +354,9 @@ step_kernel_pipe(const __grid_constant__ Params P, const __grid_constant__ StepI
             io.done[i] = r.done;
             if (io.found_targets) io.found_targets[i] = r.found;
         } else {                                                        // keep the group accounting of idle lanes uniform
-            issue_core(t + gridDim.x);
+            issue_core(t + t_step);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
-            issue_aux(t + gridDim.x);
+            issue_aux(t + t_step);
         }
         // observation rows of this warp: one TMA bulk store.  The two row buffers alternate, so before the next
         // iteration only the store issued ONE ITERATION AGO must have been read by the bulk engine (wait_group.read 1):
@@ -733,7 +741,7 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
         P.prefetch_ctas = sms * 8;               // 8 CTAs of 128 threads per SM at 64 registers
         e->sms = sms;
         e->pipe_ctas = sms * 7;                  // step_kernel_pipe: __launch_bounds__(128, 7)
-        e->use_pipe = getenv("DN_PIPE") != nullptr;
+        e->use_pipe = getenv("DN_PIPE") ? std::max(1, atoi(getenv("DN_PIPE"))) : 0;
     }
     P.targets = e->d_targets; P.segs = e->d_segs; P.block_stats = e->d_block_stats;
 
@@ -806,12 +814,13 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
     // large batches: persistent software-pipelined kernel (>= 2 tiles per resident CTA, single step, no fused obs-RMS)
     const int tiles = (N + dn::kBlock - 1) / dn::kBlock;
     if (env->use_pipe && num_steps == 1 && !env->normalize_obs && tiles >= 2 * env->pipe_ctas) {
-        lc.gridDim = dim3(env->pipe_ctas);
+        const int tpc = env->use_pipe > 1 ? env->use_pipe : 0;       // DN_PIPE=1: persistent grid; DN_PIPE=k>1: k tiles per CTA
+        lc.gridDim = dim3(tpc ? (tiles + tpc - 1) / tpc : env->pipe_ctas);
         switch (phys) {
-            case 0: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<0>, env->P, k, tiles); break;
-            case 1: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<1>, env->P, k, tiles); break;
-            case 2: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<2>, env->P, k, tiles); break;
-            default: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<3>, env->P, k, tiles); break;
+            case 0: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<0>, env->P, k, tiles, tpc); break;
+            case 1: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<1>, env->P, k, tiles, tpc); break;
+            case 2: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<2>, env->P, k, tiles, tpc); break;
+            default: lerr = cudaLaunchKernelEx(&lc, dn::step_kernel_pipe<3>, env->P, k, tiles, tpc); break;
         }
         DN_CUDA(lerr);
         DN_CUDA(cudaGetLastError());
