@@ -449,7 +449,7 @@ def test_pipelined_kernel_matches_single_step_kernel(monkeypatch):
     from oracle.dyn_oracle import make_reference_env
     monkeypatch.setenv("DN_PIPE", "1")
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    N = 2 * sms * 7 * 128 + 12345                       # above the switch-over, not a multiple of 128
+    N = 2 * sms * 1024 + 12345                          # above the switch-over (2 tiles per resident CTA), not a multiple of 128
     M = 4096
     ref = make_reference_env("reaching", pyb_freq=240, ctrl_freq=30)
     mk = lambda n: BatchedDroneEnv(n, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS, pyb_freq=240,
