@@ -95,7 +95,7 @@ __device__ __forceinline__ void flush_stats(const Params& P, const BlockAcc& acc
 }
 
 // MULTI = false: exactly one control step per launch (dn_step): no step loop, no per-thread
-// statistics carried across steps, <= 64 registers (8 CTAs / SM).  MULTI = true: dn_step_many.
+// statistics carried across steps, <= 64 registers (1024 resident threads / SM).  MULTI = true: dn_step_many.
 template <int PHYS, bool NORM, bool MULTI>
 __global__ void __launch_bounds__(kBlock, (MULTI || NORM) ? (kCtasPerSm * 3) / 4 : kCtasPerSm)
 step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int num_steps_arg, int per_step_arg) {
