@@ -165,13 +165,16 @@ class GpuDroneVecEnv(_SB3VecEnv):
                     normed[d_idx] = self._host_normalize(obs[d_idx], d_idx)
                 obs = normed
         if dones.any():
-            epr, epl = self._h_epr.numpy(), self._h_epl.numpy()
+            idx = np.nonzero(dones)[0]
             now = round(time.time() - self._t_start, 6)
-            for i in np.nonzero(dones)[0]:
+            term_rows = term[idx]                                   # one gather (fancy indexing copies): rows are views of it
+            trunc_only = (bits[idx] == L.DN_DONE_TRUNCATED).tolist()
+            ep_r, ep_l = self._h_epr.numpy()[idx].tolist(), self._h_epl.numpy()[idx].tolist()
+            for k, i in enumerate(idx.tolist()):
                 info = infos[i]
-                info["TimeLimit.truncated"] = bool(bits[i] & L.DN_DONE_TRUNCATED) and not bool(bits[i] & L.DN_DONE_TERMINATED)
-                info["terminal_observation"] = term[i].copy()
-                info["episode"] = {"r": round(float(epr[i]), 6), "l": int(epl[i]), "t": now}
+                info["TimeLimit.truncated"] = trunc_only[k]
+                info["terminal_observation"] = term_rows[k]
+                info["episode"] = {"r": round(ep_r[k], 6), "l": ep_l[k], "t": now}
         return obs, rews, dones, infos
 
     def step(self, actions: np.ndarray):
