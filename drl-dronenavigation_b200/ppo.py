@@ -348,7 +348,7 @@ class PPOTrainer:
             self.obs = obs.clone()
         last_values = pol.value(self.obs)
         adv, ret = compute_gae(self.b_rew, self.b_val, self.b_done, last_values, self.cfg.gamma, self.cfg.gae_lambda)
-        self.total_steps += self.T * env.num_envs
+        self.total_steps += self.T * env.num_envs * _world()      # global count: every rank collects its own shard
         return adv, ret
 
     def train_iteration(self) -> Dict[str, float]:

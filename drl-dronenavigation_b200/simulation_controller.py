@@ -11,8 +11,26 @@ from .simulator import PBDroneSimulator
 from .waypoints import Track
 
 
+def _init_distributed():
+    """Under torchrun: one process per GPU, NCCL for the learner's gradient all-reduce (the env shards need none)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return 0, 1
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), world
+
+
 def main(argv=None):
     args = parse_args(argv)
+    rank, world = _init_distributed()
+    args.rank, args.world = rank, world
+    if rank != 0:
+        import builtins
+        builtins.print = lambda *a, **k: None           # rank 0 logs
     print("Initial parsed arguments:")
     print(args)
     random.seed(args.seed); np.random.seed(args.seed); torch.manual_seed(args.seed)
@@ -28,6 +46,12 @@ def main(argv=None):
         sim.test_learning()
     else:
         raise NotImplementedError(f"--run_type {args.run_type}")
+
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -117,7 +117,9 @@ class PBDroneSimulator:
     def run_full_training(self, max_seconds: float = None, log=print):
         args = self.args
         total = int(float(args.total_timesteps))
-        train_env = self.make_device_env(self.num_envs)
+        # under torchrun every rank owns a contiguous shard of global env ids; --num_envs is per GPU
+        rank, world = getattr(args, "rank", 0), getattr(args, "world", 1)
+        train_env = self.make_device_env(self.num_envs, env_id_offset=rank * self.num_envs)
         trainer = self.setup_agent(train_env=train_env)
         if args.run_type == "cont":              # continue from an SB3-format archive (:701-712)
             if not os.path.exists(self.continued_agent):
@@ -134,7 +136,15 @@ class PBDroneSimulator:
         if getattr(args, "tensorboard", None):
             from torch.utils.tensorboard import SummaryWriter
             tb = SummaryWriter(args.tensorboard)
-        while trainer.total_steps < total and (max_seconds is None or time.time() - t0 < max_seconds):
+        def keep_going():
+            go = trainer.total_steps < total and (max_seconds is None or time.time() - t0 < max_seconds)
+            if world > 1:                          # ranks must leave the loop together (the update all-reduces)
+                import torch.distributed as dist
+                flag = torch.tensor([1.0 if go else 0.0], device=trainer.dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                go = bool(flag.item() > 0)
+            return go
+        while keep_going():
             out = trainer.train_iteration()
             it += 1
             if it % 5 == 0 or trainer.total_steps >= total:
