@@ -37,7 +37,7 @@ def main(argv=None):
     track = Track(Waypoints.circle(radius=1, num_points=6, height=1), circle=True)
     sim = PBDroneSimulator(args, track, target_factor=0)
     if args.run_type in ("full", "cont"):
-        sim.run_full_training()
+        sim.run_full_training(log=print if rank == 0 else (lambda *a, **k: None))
     elif args.run_type == "test":
         sim.run_test()
     elif args.run_type == "saved":
