@@ -700,6 +700,29 @@ def run_b200(args):
         line["e2e_vecenv"] = {"value": N * kv / dtv, "unit": UNIT, "us_per_step": 1e6 * dtv / kv,
                               "api": "GpuDroneVecEnv.step (SB3 VecEnv protocol incl. NormalizeObservation, Monitor, info dicts)"}
         venv.close()
+        # BASELINE configs[0], the reference's own CPU-runnable case: num_envs = 12, 240/240 Hz, circle track, per-env
+        # NormalizeObservation + Monitor, through the same SB3 VecEnv protocol the reference's SubprocVecEnv speaks
+        try:
+            import copy
+            a0 = copy.copy(args); a0.substeps, a0.track = 1, "circle"
+            t12, i12, d12, c12 = track_setup("circle")
+            v12 = GpuDroneVecEnv(12, t12, aviary_dim=d12, initial_xyzs=i12, pyb_freq=240, ctrl_freq=240, circle=c12,
+                                 include_distance=True, normalize_actions=True, normalize_obs=True, device=dev)
+            v12.reset()
+            a12 = (np.random.default_rng(0).uniform(-1, 1, size=(64, 12, 4))).astype(np.float32)
+            for k in range(200):
+                v12.step(a12[k % 64])
+            t0 = time.perf_counter()
+            k12 = 3000
+            for k in range(k12):
+                v12.step(a12[k % 64])
+            dt12 = time.perf_counter() - t0
+            line["e2e_vecenv_config1"] = {"value": 12 * k12 / dt12, "unit": UNIT, "us_per_step": 1e6 * dt12 / k12, "num_envs": 12,
+                                          "substeps": 1, "api": "GpuDroneVecEnv.step, README configuration (12 envs, 240/240 Hz)",
+                                          "note": "the reference's 4 h / 1e7 steps anecdote corresponds to ~700 env-steps/s end to end incl. PPO"}
+            v12.close()
+        except Exception as ex:  # noqa: BLE001
+            line["e2e_vecenv_config1"] = {"error": str(ex)[:200]}
 
     # ---- PPO SPS end to end (BASELINE configs[2]): device-resident rollout + update, NCCL gradient all-reduce ----
     if not args.no_ppo:
