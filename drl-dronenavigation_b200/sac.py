@@ -43,6 +43,7 @@ class SACConfig:
     target_entropy: Optional[float] = None   # "auto" -> -|A|
     seed: int = 42
     matmul_precision: str = "tf32"
+    cuda_graph: bool = True        # replay each gradient step from three captured CUDA graphs (CUDA devices only)
 
 
 def _relu_mlp(sizes, out_dim=None):
@@ -63,13 +64,14 @@ class Actor(nn.Module):
         self.mu = nn.Linear(arch[-1], act_dim)
         self.log_std = nn.Linear(arch[-1], act_dim)
 
-    def forward(self, obs, generator=None, deterministic=False):
+    def forward(self, obs, generator=None, deterministic=False, eps=None):
         h = self.latent(obs)
         mu, log_std = self.mu(h), self.log_std(h).clamp(LOG_STD_MIN, LOG_STD_MAX)
         if deterministic:
             return torch.tanh(mu), None
         std = log_std.exp()
-        eps = torch.randn(mu.shape, device=mu.device, dtype=mu.dtype, generator=generator)
+        if eps is None:            # (the graph-replayed update passes pre-drawn noise: no RNG inside a captured graph)
+            eps = torch.randn(mu.shape, device=mu.device, dtype=mu.dtype, generator=generator)
         g = mu + std * eps
         a = torch.tanh(g)
         # Normal(mu, std).log_prob(g).sum - sum log(1 - tanh(g)^2 + eps)   (SquashedDiagGaussianDistribution, epsilon 1e-6)
@@ -167,53 +169,132 @@ class SACLearner:
         self.log_ent_coef = torch.log(torch.ones(1, device=self.device) * cfg.ent_coef_init).requires_grad_(True)
         self.target_entropy = float(-act_dim) if cfg.target_entropy is None else float(cfg.target_entropy)
         lr = cfg.learning_rate
-        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=lr)
-        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=lr)
-        self.ent_opt = torch.optim.Adam([self.log_ent_coef], lr=lr)
+        # (the Polyak decision is baked into the captured graph, so replay is only used with target_update_interval == 1)
+        self.use_graph = bool(cfg.cuda_graph) and self.device.type == "cuda" and cfg.target_update_interval == 1
+        self._graphs = None
+        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=lr, capturable=self.use_graph)
+        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=lr, capturable=self.use_graph)
+        self.ent_opt = torch.optim.Adam([self.log_ent_coef], lr=lr, capturable=self.use_graph)
         # bucket 1: critics + log-alpha (their losses do not depend on each other's step); bucket 2: actor
         self.g_critic = _FlatGrads(list(self.critic.parameters()) + [self.log_ent_coef], self.device)
         self.g_actor = _FlatGrads(self.actor.parameters(), self.device)
         self.n_updates = 0
-        if self.device.type == "cuda" and cfg.matmul_precision == "tf32":
-            torch.backends.cuda.matmul.allow_tf32 = True
+        if self.device.type == "cuda":
+            torch.backends.cuda.matmul.allow_tf32 = (cfg.matmul_precision == "tf32")
 
     @torch.no_grad()
     def act(self, obs, generator=None, deterministic=False):
         return self.actor(obs, generator=generator, deterministic=deterministic)[0]
 
-    def update(self, batch, generator=None) -> Dict[str, torch.Tensor]:
-        """One gradient step of SB3's SAC.train on a sampled batch (obs, act, rew, next_obs, done)."""
-        obs, act, rew, next_obs, done = batch
+    # ---- one gradient step of SB3's SAC.train, in three stages around the two gradient all-reduces -----------------
+    def _stage_critic(self, obs, act, rew, next_obs, done, eps_pi, eps_next, out):
+        """actor forward, entropy-coefficient loss, TD target, critic loss; backward into the critics + log-alpha bucket."""
         cfg = self.cfg
-        actions_pi, log_prob = self.actor(obs, generator=generator)
+        actions_pi, log_prob = self.actor(obs, eps=eps_pi)
         ent_coef = self.log_ent_coef.detach().exp()
         ent_loss = -(self.log_ent_coef * (log_prob + self.target_entropy).detach()).mean()
         with torch.no_grad():
-            next_a, next_logp = self.actor(next_obs, generator=generator)
+            next_a, next_logp = self.actor(next_obs, eps=eps_next)
             next_q = torch.stack(self.critic_target(next_obs, next_a), 0).min(0).values - ent_coef * next_logp
             target_q = rew + (1.0 - done) * cfg.gamma * next_q
         cur_q = self.critic(obs, act)
         critic_loss = 0.5 * sum(torch.nn.functional.mse_loss(q, target_q) for q in cur_q)
         self.g_critic.zero()
         (critic_loss + ent_loss).backward(inputs=self.g_critic.params)
-        self.g_critic.allreduce()
+        out[0].copy_(critic_loss.detach()); out[2].copy_(ent_coef.squeeze(0)); out[3].copy_(ent_loss.detach())
+        return actions_pi, log_prob, ent_coef
+
+    def _stage_actor(self, obs, actions_pi, log_prob, ent_coef, out):
+        """optimiser steps of log-alpha and the critics, then the actor loss against the UPDATED critics (as in SB3)."""
         self.ent_opt.step()
         self.critic_opt.step()
-        # actor: min_i Q_i(s, pi(s)) with the UPDATED critics, as in SB3
         q_pi = torch.stack(self.critic(obs, actions_pi), 0).min(0).values
         actor_loss = (ent_coef * log_prob - q_pi).mean()
         self.g_actor.zero()
         actor_loss.backward(inputs=self.g_actor.params)
-        self.g_actor.allreduce()
+        out[1].copy_(actor_loss.detach())
+
+    def _stage_finish(self):
         self.actor_opt.step()
-        self.n_updates += 1
-        if self.n_updates % cfg.target_update_interval == 0:
+        if (self.n_updates + 1) % self.cfg.target_update_interval == 0:
             with torch.no_grad():                            # polyak_update(critic, critic_target, tau)
                 tp, sp = list(self.critic_target.parameters()), list(self.critic.parameters())
-                torch._foreach_mul_(tp, 1.0 - cfg.tau)
-                torch._foreach_add_(tp, sp, alpha=cfg.tau)
-        return {"critic_loss": critic_loss.detach(), "actor_loss": actor_loss.detach(), "ent_coef": ent_coef.squeeze(0),
-                "ent_coef_loss": ent_loss.detach()}
+                torch._foreach_mul_(tp, 1.0 - self.cfg.tau)
+                torch._foreach_add_(tp, sp, alpha=self.cfg.tau)
+
+    def _capture(self, B, D, A):
+        """Three CUDA graphs per gradient step ([actor fwd + critic losses + backward] | all-reduce | [alpha / critic
+        steps + actor loss + backward] | all-reduce | [actor step + Polyak]): a 1024-sample SAC step is ~300 small
+        kernels, i.e. launch-bound when issued eagerly."""
+        dev = self.device
+        f = dict(dtype=torch.float32, device=dev)
+        st = dict(obs=torch.zeros(B, D, **f), act=torch.zeros(B, A, **f), rew=torch.zeros(B, **f), next_obs=torch.zeros(B, D, **f),
+                  done=torch.zeros(B, **f), eps_pi=torch.zeros(B, A, **f), eps_next=torch.zeros(B, A, **f), out=torch.zeros(4, **f))
+        nets = list(self.actor.parameters()) + list(self.critic.parameters()) + list(self.critic_target.parameters()) + [self.log_ent_coef]
+        saved = [p.detach().clone() for p in nets]
+        snap = [[{k: v.clone() for k, v in o.state[p].items() if torch.is_tensor(v)} if p in o.state else None
+                 for g in o.param_groups for p in g["params"]] for o in (self.actor_opt, self.critic_opt, self.ent_opt)]
+        keep = {}
+
+        def run_all():
+            keep["a"], keep["l"], keep["e"] = self._stage_critic(st["obs"], st["act"], st["rew"], st["next_obs"], st["done"],
+                                                                 st["eps_pi"], st["eps_next"], st["out"])
+            self._stage_actor(st["obs"], keep["a"], keep["l"], keep["e"], st["out"])
+            self._stage_finish()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            st["obs"].normal_(); st["next_obs"].normal_(); st["act"].uniform_(-1, 1); st["eps_pi"].normal_(); st["eps_next"].normal_()
+            for _ in range(3):
+                run_all()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        pool = torch.cuda.graph_pool_handle()                # stage 2 consumes tensors stage 1 produced: one shared pool
+        with torch.cuda.graph(g1, pool=pool):
+            keep["a"], keep["l"], keep["e"] = self._stage_critic(st["obs"], st["act"], st["rew"], st["next_obs"], st["done"],
+                                                                 st["eps_pi"], st["eps_next"], st["out"])
+        with torch.cuda.graph(g2, pool=pool):
+            self._stage_actor(st["obs"], keep["a"], keep["l"], keep["e"], st["out"])
+        with torch.cuda.graph(g3, pool=pool):
+            self._stage_finish()
+        with torch.no_grad():                                # undo the warm-up: parameters, targets, Adam state
+            for p, q in zip(nets, saved):
+                p.copy_(q)
+            for o, sn in zip((self.actor_opt, self.critic_opt, self.ent_opt), snap):
+                ps = [p for g in o.param_groups for p in g["params"]]
+                for p, old in zip(ps, sn):
+                    for k, v in o.state[p].items():
+                        if torch.is_tensor(v):
+                            v.copy_(old[k]) if old is not None else v.zero_()
+        self._graphs = ((B, D, A), g1, g2, g3, st, keep)
+
+    def update(self, batch, generator=None) -> Dict[str, torch.Tensor]:
+        """One gradient step of SB3's SAC.train on a sampled batch (obs, act, rew, next_obs, done)."""
+        obs, act, rew, next_obs, done = batch
+        B, D, A = obs.shape[0], obs.shape[1], act.shape[1]
+        if self.use_graph and obs.is_cuda:
+            if self._graphs is None or self._graphs[0] != (B, D, A):
+                self._capture(B, D, A)
+            _, g1, g2, g3, st, _ = self._graphs
+            st["obs"].copy_(obs); st["act"].copy_(act); st["rew"].copy_(rew); st["next_obs"].copy_(next_obs); st["done"].copy_(done)
+            st["eps_pi"].normal_(generator=generator); st["eps_next"].normal_(generator=generator)
+            g1.replay()
+            self.g_critic.allreduce()
+            g2.replay()
+            self.g_actor.allreduce()
+            g3.replay()
+            out = st["out"].clone()
+        else:
+            out = torch.zeros(4, device=self.device)
+            eps_pi = torch.randn(B, A, device=self.device, generator=generator)
+            eps_next = torch.randn(B, A, device=self.device, generator=generator)
+            actions_pi, log_prob, ent_coef = self._stage_critic(obs, act, rew, next_obs, done, eps_pi, eps_next, out)
+            self.g_critic.allreduce()
+            self._stage_actor(obs, actions_pi, log_prob, ent_coef, out)
+            self.g_actor.allreduce()
+            self._stage_finish()
+        self.n_updates += 1
+        return {"critic_loss": out[0], "actor_loss": out[1], "ent_coef": out[2], "ent_coef_loss": out[3]}
 
     def flat_parameters(self) -> torch.Tensor:
         ps = list(self.actor.parameters()) + list(self.critic.parameters()) + [self.log_ent_coef]

@@ -142,3 +142,31 @@ def test_manager_saved_cont_and_learning_run_types(tmp_path):
     sim2 = PBDroneSimulator(args2, track)
     tr2, _ = sim2.run_full_training(log=lambda *_: None)
     assert tr2.total_steps >= 8192
+
+
+def test_sac_update_cuda_graph_equals_eager():
+    """The three-graph replay of the SAC gradient step is the same computation as the eager path: same batches and
+    noise -> same losses and (up to FP32 reduction-order noise amplified by Adam) the same parameters and targets."""
+    from drl_dronenavigation_b200.sac import SACConfig, SACLearner
+    g = torch.Generator(device="cuda").manual_seed(0)
+    B = 1024
+    batches = [(torch.randn(B, 13, device="cuda", generator=g), torch.rand(B, 4, device="cuda", generator=g) * 2 - 1,
+                torch.randn(B, device="cuda", generator=g), torch.randn(B, 13, device="cuda", generator=g),
+                (torch.rand(B, device="cuda", generator=g) < 0.1).float()) for _ in range(6)]
+    res = {}
+    for graph in (False, True):
+        L = SACLearner(13, 4, SACConfig(cuda_graph=graph, matmul_precision="fp32"), device="cuda")
+        assert L.use_graph == graph
+        p0 = L.flat_parameters().clone()
+        outs = [L.update(b, generator=torch.Generator(device="cuda").manual_seed(10 + k)) for k, b in enumerate(batches)]
+        tgt = torch.cat([p.reshape(-1) for p in L.critic_target.parameters()])
+        res[graph] = (p0, L.flat_parameters().clone(), tgt.clone(), [{k: float(v) for k, v in o.items()} for o in outs])
+    assert torch.equal(res[False][0], res[True][0])                  # capture warm-up left parameters and Adam state untouched
+    for a, b in zip(res[True][3], res[False][3]):
+        for k in ("critic_loss", "actor_loss", "ent_coef", "ent_coef_loss"):
+            assert abs(a[k] - b[k]) <= 1e-3 * max(1.0, abs(b[k])), (k, a[k], b[k])
+    moved = (res[False][1] - res[False][0]).abs().mean()
+    d = (res[True][1] - res[False][1]).abs()
+    print("sac graph-vs-eager: max", float(d.max()), "mean", float(d.mean()), "mean movement", float(moved))
+    assert float(d.mean()) < 0.02 * float(moved) and float(d.max()) < 2e-3
+    torch.testing.assert_close(res[True][2], res[False][2], rtol=1e-3, atol=1e-5)
