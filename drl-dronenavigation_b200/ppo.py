@@ -225,6 +225,9 @@ class PPOLearner:
         opt_state = None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            # the gradient buckets were created on the current stream, the warm-up runs on a side stream: intended
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         with torch.cuda.stream(side):
             st["idx"].copy_(torch.arange(mb, device=dev) % B)
             st["obs"].normal_(); st["act"].uniform_(-1, 1); st["adv"].normal_(); st["ret"].normal_()

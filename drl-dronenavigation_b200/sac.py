@@ -243,6 +243,9 @@ class SACLearner:
             self._stage_finish()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            # the gradient buckets were created on the current stream, the warm-up runs on a side stream: intended
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         with torch.cuda.stream(side):
             st["obs"].normal_(); st["next_obs"].normal_(); st["act"].uniform_(-1, 1); st["eps_pi"].normal_(); st["eps_next"].normal_()
             for _ in range(3):
