@@ -175,10 +175,21 @@ def test_single_step_random_states_all_branches():
     assert total.near_ties <= 8
 
 
-def test_step_many_matches_repeated_step():
-    """dn_step_many (T steps, state in registers) is bit-identical to T dn_step launches."""
-    envA, _ = _make("circle", 1000, 8)
-    envB, _ = _make("circle", 1000, 8)
+@pytest.mark.parametrize("kw", [{}, {"normalize_obs": True, "normalize_reward": True, "clip_reward": 10.0},
+                                {"reward_id": 4, "random_spawn": "midpoint", "seed": 77}, {"reward_id": 5, "random_spawn": "line", "seed": 78},
+                                {"reward_id": 3, "physics": "PYB_GND_DRAG_DW"}],
+                         ids=["default", "wrappers", "reaching_midpoint", "progress_line", "her_drag_gnd"])
+def test_step_many_matches_repeated_step(kw):
+    """dn_step_many (T steps, state in registers) is bit-identical to T dn_step launches -- also with the fused
+    wrappers, the optional planes (aux / spawn / reward statistics) and the physics add-ons in play."""
+    from drl_dronenavigation_b200 import Physics
+    kw = dict(kw)
+    if "physics" in kw:
+        kw["physics"] = getattr(Physics, kw["physics"])
+    norm = kw.pop("normalize_obs", False)
+    track = "reaching" if "random_spawn" in kw else "circle"
+    envA, _ = _make(track, 1000, 8, normalize_obs=norm, **kw)
+    envB, _ = _make(track, 1000, 8, normalize_obs=norm, **kw)
     envA.reset(); envB.reset()
     T = 40
     acts = torch.from_numpy(_actions("saturating", T, 1000, seed=11)).to(envA.device)
