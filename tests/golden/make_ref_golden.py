@@ -63,6 +63,10 @@ CASES = {
     "ref_circle_s1_rw_reaching": ("circle", 1, "saturating", 3, 140, 36, 4096, False, "reaching", False, False),
     "ref_circle_s8_rw_hover": ("circle", 8, "mixed", 2, 40, 37, 4096, False, "hover", False, False),
     "ref_circle_s8_rw_flythrugate": ("circle", 8, "mixed", 2, 40, 38, 4096, False, "flythrugate", False, False),
+    # the other constructor switches of PBDroneEnv: 12-dim observation (include_distance=False) and the physical action
+    # space (normalize_actions=False: actions are per-motor thrusts in newtons, no rescale_action)
+    "ref_circle_s8_obs12_physact": ("circle", 8, "physical", 3, 60, 39, 4096, False, "default", False, False, False, False),
+    "ref_reaching_s1_obs12": ("reaching", 1, "hover_band", 2, 120, 40, 4096, False, "default", False, False, False, True),
 }
 
 
@@ -74,6 +78,8 @@ def actions(mode, T, N, seed):
         return a.astype(np.float32)
     if mode == "hover":
         return np.full((T, N, 4), 0.0922265, np.float32)
+    if mode == "physical":     # per-motor thrust in newtons around the hover thrust 0.06615 N (physical bounds 0.0282 .. 0.1483 N)
+        return (0.06615 + 0.02 * u).astype(np.float32)
     return {"saturating": u, "hover_band": HOVER + 0.002 * u, "mixed": HOVER + 0.006 * u}[mode].astype(np.float32)
 
 
@@ -147,7 +153,8 @@ def _import_reference():
     return variants, normalize, ActionType, Physics, Waypoints, hover_reward is not None
 
 
-def make_env(ref, track, S, max_steps, normalize_obs, reward="default", norm_rew=False, clip_rew=False):
+def make_env(ref, track, S, max_steps, normalize_obs, reward="default", norm_rew=False, clip_rew=False,
+             include_distance=True, normalize_actions=True):
     variants, normalize, ActionType, Physics, Waypoints, _ = ref
     DynEnv = variants[reward]
     if track == "circle":      # simulation_controller.py / PBDroneSimulator.py:111-130
@@ -159,8 +166,8 @@ def make_env(ref, track, S, max_steps, normalize_obs, reward="default", norm_rew
         targets.pop(0)                         # PBDroneSimulator.py:129-130
     env = DynEnv(target_points=targets, threshold=0.3, discount=0.999, max_steps=max_steps, act=ActionType.THRUST,
                  gui=False, initial_xyzs=tr.initial_xyzs, save_folder=None, aviary_dim=tr.aviary_dim,
-                 random_spawn=False, cylinder=True, circle=tr.is_circle, include_distance=True,
-                 normalize_actions=True, collect_rollouts=False, physics=Physics.DYN,
+                 random_spawn=False, cylinder=True, circle=tr.is_circle, include_distance=include_distance,
+                 normalize_actions=normalize_actions, collect_rollouts=False, physics=Physics.DYN,
                  pyb_freq=240, ctrl_freq=240 // S)       # PBDroneSimulator.py:154-172
     env.reset(seed=0)                                    # :173
     raw = env
@@ -188,9 +195,11 @@ class _ClipReward:
         return getattr(self.env, name)
 
 
-def run(ref, track, S, mode, N, T, seed, max_steps, normalize_obs, reward="default", norm_rew=False, clip_rew=False):
+def run(ref, track, S, mode, N, T, seed, max_steps, normalize_obs, reward="default", norm_rew=False, clip_rew=False,
+        include_distance=True, normalize_actions=True):
     with contextlib.redirect_stdout(io.StringIO()):
-        envs = [make_env(ref, track, S, max_steps, normalize_obs, reward, norm_rew, clip_rew) for _ in range(N)]
+        envs = [make_env(ref, track, S, max_steps, normalize_obs, reward, norm_rew, clip_rew, include_distance, normalize_actions)
+                for _ in range(N)]
         a = actions(mode, T, N, seed)
         obs0 = np.stack([np.asarray(e.reset()[0], np.float64) for e, _ in envs])   # VecEnv.reset()
         D = obs0.shape[1]
@@ -221,7 +230,8 @@ def run(ref, track, S, mode, N, T, seed, max_steps, normalize_obs, reward="defau
                     o, _ = e.reset()
                 out["obs"][t, i] = o
     out["meta"] = np.array([track, str(S), mode, str(max_steps), "1" if normalize_obs else "0", reward,
-                            "1" if norm_rew else "0", "1" if clip_rew else "0"])
+                            "1" if norm_rew else "0", "1" if clip_rew else "0", "1" if include_distance else "0",
+                            "1" if normalize_actions else "0"])
     return out
 
 
