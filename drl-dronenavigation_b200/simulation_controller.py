@@ -34,7 +34,10 @@ def main(argv=None):
     print("Initial parsed arguments:")
     print(args)
     random.seed(args.seed); np.random.seed(args.seed); torch.manual_seed(args.seed)
-    track = Track(Waypoints.circle(radius=1, num_points=6, height=1), circle=True)
+    if getattr(args, "track", "circle") == "circle":     # the reference's main() (simulation_controller.py:96-100)
+        track = Track(Waypoints.circle(radius=1, num_points=6, height=1), circle=True)
+    else:                                                # its commented-out alternatives, selectable here
+        track = Track(getattr(Waypoints, args.track)(), circle=False)
     sim = PBDroneSimulator(args, track, target_factor=0)
     if args.run_type in ("full", "cont"):
         sim.run_full_training(log=print if rank == 0 else (lambda *a, **k: None))
