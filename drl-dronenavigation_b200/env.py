@@ -48,6 +48,7 @@ class PBDroneEnv:
         self.INIT_XYZS, self.INIT_RPYS = self._core.INIT_XYZS, self._core.INIT_RPYS
         self._actions = torch.zeros(1, 4, dtype=torch.float32, device=self._core.device)
         self._auto_reset_done = False  # the kernel already reset the env on the last (terminal) step
+        self.last_clipped_action = np.zeros((1, 4))
         self._refresh()
 
     # kinematics the reference's manager pokes (PBDroneSimulator.py:406-407,532-533,775)
@@ -75,6 +76,7 @@ class PBDroneEnv:
         else:
             obs = self._core.reset().cpu().numpy()[0].copy()
         self._auto_reset_done = False
+        self.last_clipped_action = np.zeros((1, 4))
         info = {"found_targets": 0}
         self._refresh()
         return obs, info
@@ -84,6 +86,7 @@ class PBDroneEnv:
         self._actions.copy_(torch.from_numpy(a))
         c = self._core
         c.step(self._actions)
+        self.last_clipped_action = c.action_to_rpm(self._actions).cpu().numpy().astype(np.float64)   # BaseAviary.py:442
         bits = int(c.done.cpu()[0])
         terminated, truncated = bool(bits & 1), bool(bits & 2)
         reward = float(c.reward.cpu()[0])
@@ -93,6 +96,14 @@ class PBDroneEnv:
         self._auto_reset_done = bool(bits)
         self._refresh()
         return obs, reward, terminated, truncated, info
+
+    def _getDroneStateVector(self, nth_drone: int = 0):
+        """BaseAviary._getDroneStateVector (BaseAviary.py:623-643): the 20-vector
+        [pos3, quat4, rpy3, vel3, ang_v3, last_clipped_action4] of the (single) drone; the last four entries are the
+        motor RPMs of the most recent step (zeros after a reset, BaseAviary.py:545)."""
+        if nth_drone != 0:
+            raise IndexError("single-drone environment")
+        return np.hstack([self.pos[0], self.quat[0], self.rpy[0], self.vel[0], self.ang_v[0], self.last_clipped_action[0]]).reshape(20,)
 
     def close(self):
         self._core.close()

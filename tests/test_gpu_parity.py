@@ -513,3 +513,41 @@ def test_vec_env_save_and_load_running_stats(tmp_path):
     assert torch.equal(sa["obs_rms"], sb["obs_rms"]) and torch.equal(sa["rew_rms"], sb["rew_rms"])
     assert float(sa["obs_rms"][:, -1].min()) > 20          # counts advanced
     a.close(); b.close()
+
+
+def test_gymnasium_facade_against_oracle_env():
+    """PBDroneEnv facade (single env, gymnasium 5-tuple): reset / step / terminal step / reset again against the oracle
+    env, including the attributes the manager pokes (pos, rpy, INIT_XYZS, CTRL_FREQ) and _getDroneStateVector."""
+    from drl_dronenavigation_b200.env import PBDroneEnv
+    from oracle.dyn_oracle import make_reference_env
+    ref = make_reference_env("circle", pyb_freq=240, ctrl_freq=30)
+    env = PBDroneEnv(target_points=ref._target_points, threshold=0.3, discount=0.999, max_steps=4096, aviary_dim=ref._aviary_dim,
+                     initial_xyzs=ref.INIT_XYZS, pyb_freq=240, ctrl_freq=30, cylinder=True, circle=True, include_distance=True,
+                     normalize_actions=True)
+    assert env.action_space.shape == (4,) and env.observation_space.shape == (13,) and env.CTRL_FREQ == 30
+    obs, info = env.reset(seed=3)
+    o_ref, _ = ref.reset()
+    np.testing.assert_allclose(obs, o_ref, atol=1e-6)
+    assert info == {"found_targets": 0}
+    acts = _actions("mixed", 80, 1, seed=9)[:, 0]
+    episodes = 0
+    for t in range(80):
+        o, r, term, trunc, info = env.step(acts[t])
+        oo, rr, tt, tr, ii = ref.step(acts[t])
+        assert (term, trunc) == (bool(tt), bool(tr)) and info["found_targets"] == ii["found_targets"]
+        assert PU.obs_error(o, oo, float(np.linalg.norm(ref.ang_v))) < 1e-3 and abs(r - float(rr)) < 1e-2
+        if not (term or trunc):
+            sv = env._getDroneStateVector(0)
+            assert sv.shape == (20,)
+            np.testing.assert_allclose(sv[0:3], ref.pos, atol=1e-4)
+            np.testing.assert_allclose(sv[10:13], ref.vel, atol=1e-3)
+            np.testing.assert_allclose(sv[16:20], np.float64(ref.last_clipped_action), rtol=1e-6)
+            np.testing.assert_allclose(env.rpy[0], ref.rpy, atol=1e-4)
+        else:
+            episodes += 1
+            obs, _ = env.reset()
+            o_ref, _ = ref.reset()
+            np.testing.assert_allclose(obs, o_ref, atol=1e-5)
+            assert np.all(env._getDroneStateVector(0)[16:20] == 0)
+    assert episodes >= 1
+    env.close()
