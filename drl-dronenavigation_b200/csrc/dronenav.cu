@@ -96,7 +96,7 @@ __device__ __forceinline__ void flush_stats(const Params& P, const BlockAcc& acc
 
 // MULTI = false: exactly one control step per launch (dn_step): no step loop, no per-thread
 // statistics carried across steps, <= 64 registers (1024 resident threads / SM).  MULTI = true: dn_step_many.
-template <int PHYS, bool NORM, bool MULTI>
+template <int PHYS, bool NORM, bool MULTI, bool FULL>
 __global__ void __launch_bounds__(kBlock, (MULTI || NORM) ? (kCtasPerSm * 3) / 4 : kCtasPerSm)
 step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int num_steps_arg, int per_step_arg) {
     __shared__ __align__(128) float tile[kBlock * kMaxObs];
@@ -149,7 +149,7 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
         const size_t o = (per_step ? static_cast<size_t>(t) * P.n : 0) + i;      // output element index of this env
         if (active) {
             const float4 act = __ldg(io.actions + static_cast<size_t>(t) * P.n + i);
-            const StepResult r = env_step<PHYS>(P, i, s, act, last_rpm_sum, obs_row,     // obs_row: obs of the step (terminal obs if finished)
+            const StepResult r = env_step<PHYS, FULL>(P, i, s, act, last_rpm_sum, obs_row,   // obs_row: obs of the step (terminal obs if finished)
                                                 MULTI ? nullptr : &aux_stage[tid], kBlock);
             float* term_out = (write_out && r.finished && io.terminal_obs) ? io.terminal_obs + o * D : nullptr;
             if (!MULTI) {
@@ -617,6 +617,7 @@ struct dn_env {
     int64_t launches;
     int pipe_ctas;          // grid of the persistent pipelined kernel: SMs x resident CTAs per SM
     int sms;                // multiprocessor count of the device
+    int full;               // 1: any optional feature is on (random spawn, another reward family, reward wrappers) -> FULL kernels
     int use_pipe;           // DN_PIPE=1 at dn_create: opt into step_kernel_pipe for large batches (experimental)
     float d0;
     // dn_step_host staging (allocated on first use)
@@ -693,6 +694,8 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     std::memset(e, 0, sizeof(*e));
     e->device = device;
     e->normalize_obs = cfg->normalize_obs ? 1 : 0;
+    e->full = (cfg->spawn_mode != DN_SPAWN_FIXED || rw.mode != dn::RW_WAYPOINT || rw.proj_w != 0.0f || cfg->normalize_reward ||
+               cfg->clip_reward > 0.0) ? 1 : 0;
     Params& P = e->P;
     const int N = cfg->num_envs, T = cfg->num_targets;
     std::vector<float4> h_t, h_s;
@@ -833,10 +836,15 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
         env->launches += 1;
         return DN_OK;
     }
-#define DN_LAUNCH(PH, NO)                                                                                          \
-    do {                                                                                                           \
-        if (num_steps == 1) lerr = cudaLaunchKernelEx(&lc, dn::step_kernel<PH, NO, false>, env->P, k, 1, 1);       \
-        else lerr = cudaLaunchKernelEx(&lc, dn::step_kernel<PH, NO, true>, env->P, k, num_steps, per_step);        \
+#define DN_LAUNCH(PH, NO)                                                                                              \
+    do {                                                                                                               \
+        if (env->full) {                                                                                               \
+            if (num_steps == 1) lerr = cudaLaunchKernelEx(&lc, dn::step_kernel<PH, NO, false, true>, env->P, k, 1, 1); \
+            else lerr = cudaLaunchKernelEx(&lc, dn::step_kernel<PH, NO, true, true>, env->P, k, num_steps, per_step);  \
+        } else {                                                                                                       \
+            if (num_steps == 1) lerr = cudaLaunchKernelEx(&lc, dn::step_kernel<PH, NO, false, false>, env->P, k, 1, 1); \
+            else lerr = cudaLaunchKernelEx(&lc, dn::step_kernel<PH, NO, true, false>, env->P, k, num_steps, per_step); \
+        }                                                                                                              \
     } while (0)
     if (env->normalize_obs) {
         switch (phys) { case 0: DN_LAUNCH(0, true); break; case 1: DN_LAUNCH(1, true); break;
