@@ -170,3 +170,26 @@ def test_sac_update_cuda_graph_equals_eager():
     print("sac graph-vs-eager: max", float(d.max()), "mean", float(d.mean()), "mean movement", float(moved))
     assert float(d.mean()) < 0.02 * float(moved) and float(d.max()) < 2e-3
     torch.testing.assert_close(res[True][2], res[False][2], rtol=1e-3, atol=1e-5)
+
+
+def test_fast_linear_matches_nn_linear():
+    """FastLinear (GEMV bias gradient, input width padded to a multiple of 8) against plain nn.Linear in FP32: same
+    outputs and the same gradients for input, weight and bias, for the first-layer (13 -> 512) and a square layer."""
+    from drl_dronenavigation_b200.ppo import FastLinear
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for k, n in ((13, 512), (512, 256), (256, 1)):
+        torch.manual_seed(k)
+        ref = torch.nn.Linear(k, n).cuda()
+        fast = FastLinear(k, n).cuda()
+        fast.load_state_dict(ref.state_dict())
+        x = torch.randn(4096, k, device="cuda")
+        xr, xf = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        g = torch.randn(4096, n, device="cuda")
+        yr, yf = ref(xr), fast(xf)
+        torch.testing.assert_close(yf, yr, rtol=1e-5, atol=1e-5)
+        yr.backward(g); yf.backward(g)
+        torch.testing.assert_close(xf.grad, xr.grad, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(fast.weight.grad, ref.weight.grad, rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(fast.bias.grad, ref.bias.grad, rtol=1e-4, atol=1e-3)
+    with torch.no_grad():
+        assert torch.equal(fast(x), torch.nn.functional.linear(x, fast.weight, fast.bias))      # inference path: plain nn.Linear
