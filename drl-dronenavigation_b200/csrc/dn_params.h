@@ -121,6 +121,7 @@ struct StepIO {
     int32_t*  found_targets;
     float*    episode_return;
     int32_t*  episode_length;
+    int       pdl_prefetch;   // 1: launched as a programmatic dependent grid -> prefetch this thread's lines to L2 while waiting
 };
 
 }  // namespace dn

@@ -109,11 +109,19 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
     // programmatic dependent launch (see launch_step): let the next kernel of the stream be scheduled now, and do not
     // touch global memory before the previous kernel has completed.  Both are no-ops for a normal launch.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const int base = blockIdx.x * kBlock;
     const int i = base + tid;
     const bool active = i < P.n;
+    if (io.pdl_prefetch && active) {
+        // While the previous kernel of the stream is still running: start this thread's lines towards L2.  L2 is the
+        // coherence point, so a line prefetched early is still the one the previous kernel's stores update; for a
+        // handle whose state is cold (another handle ran in between) this overlaps the HBM fetch with that kernel.
+        prefetch_l2(io.actions + i);
+#pragma unroll
+        for (int p = 0; p < kPlanes; ++p) prefetch_l2(&P.s[p][i]);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int D = P.obs_dim;
     float* const obs_row = tile + tid * D;
 
@@ -819,6 +827,7 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
     // CTAs of the next step pile up on the SMs that had free slots, and the step then runs unbalanced (measured:
     // 65 536 envs 7.7 -> 9.8 us, 16 384 envs with drag / ground effect 7.4 -> 9.1 us per replayed step).
     lc.attrs = attr; lc.numAttrs = (use_pdl && static_cast<int>(grid.x) * 2 <= env->sms) ? 1 : 0;
+    k.pdl_prefetch = static_cast<int>(lc.numAttrs);
     cudaError_t lerr = cudaSuccess;
     // large batches: persistent software-pipelined kernel (>= 2 tiles per resident CTA, single step, no fused obs-RMS)
     const int tiles = (N + dn::kBlock - 1) / dn::kBlock;
