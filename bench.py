@@ -548,8 +548,10 @@ def run_b200(args):
     #  harness time against a ~3 us kernel, see `launch_floor`)
     barrier()
     win = {}
-    sec, k_r, m_r, bytes_r, eps_r = time_rotating(args, dev, N, K, W, rank, n_handles=args.rotating_handles,
-                                                  on_timed=lambda start: win.__setitem__("t0" if start else "t1", time.time()))
+    def around_timed(start):          # barrier + synchronize on both sides of the timed region, on every rank
+        barrier()
+        win["t0" if start else "t1"] = time.time()
+    sec, k_r, m_r, bytes_r, eps_r = time_rotating(args, dev, N, K, W, rank, n_handles=args.rotating_handles, on_timed=around_timed)
     assert k_r == K
     barrier()
     sec = max_over_ranks(sec)
