@@ -2,7 +2,7 @@
 # One GPU visit: parity tests, bench, ncu launch list, ncu full captures.  Run under gpurun.
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q -s 2>&1 | tail -25 > gpurun_out/pytest_gpu.txt; tail -25 gpurun_out/pytest_gpu.txt
+python -m pytest tests -m gpu -x -q -rA 2>&1 | grep -v "^$" | tail -400 > gpurun_out/pytest_gpu.txt; tail -5 gpurun_out/pytest_gpu.txt
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/smoke.txt
 ( time python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err ) 2>&1 | tail -3 | tee gpurun_out/bench_default_time.txt
 python bench.py --steps 1000 --warmup 100 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -3 gpurun_out/bench.err

@@ -95,6 +95,9 @@ if os.path.exists(lp):
                 "| kernel | launches | total ns | share |\n|---|---|---|---|\n")
         for k, v in agg.most_common():
             f.write(f"| `{k[:110]}` | {cnt[k]} | {v:.0f} | {100 * v / tot:.1f}% |\n")
+tp = os.path.join(OUT, "pytest_gpu.txt")
+if os.path.exists(tp) and os.path.getsize(tp) > 10:
+    open(os.path.join(dst, f"pytest_gpu_{tag}.txt"), "w").write(open(tp).read())
 bp = os.path.join(OUT, "bench.json")
 if os.path.exists(bp) and os.path.getsize(bp) > 10:
     open(os.path.join(dst, f"bench_{tag}.json"), "w").write(open(bp).read())
