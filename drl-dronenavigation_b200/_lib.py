@@ -12,10 +12,11 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libdronenav.so")
 
-DN_ABI_VERSION = 2
+DN_ABI_VERSION = 3
 
 # enums of include/dronenav.h
-DN_ACT_THRUST, DN_ACT_RPM, DN_ACT_ONE_D_RPM = 0, 1, 2
+DN_ACT_THRUST, DN_ACT_RPM, DN_ACT_ONE_D_RPM, DN_ACT_PID, DN_ACT_VEL, DN_ACT_ONE_D_PID = 0, 1, 2, 3, 4, 5
+DN_MODEL_CF2X, DN_MODEL_CF2P, DN_MODEL_RACE = 0, 1, 2
 DN_PHYS_DYN, DN_PHYS_DRAG, DN_PHYS_GROUND_EFFECT, DN_PHYS_GROUND_CONTACT = 0, 1, 2, 4
 DN_REWARD_DEFAULT, DN_REWARD_DUMMY, DN_REWARD_THRUSTENV, DN_REWARD_HER = 0, 1, 2, 3
 DN_REWARD_REACHING, DN_REWARD_PROGRESS, DN_REWARD_HOVER, DN_REWARD_FLYTHRUGATE = 4, 5, 6, 7
@@ -38,6 +39,7 @@ class dn_config(C.Structure):
         ("num_targets", C.c_int32), ("normalize_reward", C.c_int32),
         ("clip_reward", C.c_double), ("reward_gamma", C.c_double),
         ("targets", C.POINTER(C.c_double)),
+        ("drone_model", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -51,7 +53,7 @@ class dn_step_io(C.Structure):
 
 STATE_FIELDS = ("pos", "quat", "vel", "rpy_rates", "ang_v", "prev_vel", "prev_ang_v", "dist", "prev_dist",
                 "target_idx", "steps", "just_found", "ep_return", "ep_length", "episode_count",
-                "last_rpm_sum", "obs_rms", "aux", "rew_rms", "spawn")
+                "last_rpm_sum", "obs_rms", "aux", "rew_rms", "spawn", "pid")
 
 
 class dn_state_view(C.Structure):

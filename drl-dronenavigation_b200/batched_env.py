@@ -17,7 +17,9 @@ import torch
 from . import _lib as L
 from .enums import ActionType, DroneModel, ObservationType, Physics
 
-_ACT = {ActionType.THRUST: L.DN_ACT_THRUST, ActionType.RPM: L.DN_ACT_RPM, ActionType.ONE_D_RPM: L.DN_ACT_ONE_D_RPM}
+_ACT = {ActionType.THRUST: L.DN_ACT_THRUST, ActionType.RPM: L.DN_ACT_RPM, ActionType.ONE_D_RPM: L.DN_ACT_ONE_D_RPM,
+        ActionType.PID: L.DN_ACT_PID, ActionType.VEL: L.DN_ACT_VEL, ActionType.ONE_D_PID: L.DN_ACT_ONE_D_PID}
+_MODEL = {DroneModel.CF2X: L.DN_MODEL_CF2X, DroneModel.CF2P: L.DN_MODEL_CF2P, DroneModel.RACE: L.DN_MODEL_RACE}
 _PHYS = {
     Physics.DYN: L.DN_PHYS_DYN,
     Physics.PYB: L.DN_PHYS_DYN,          # the reference's default label; the maths integrated is DYN
@@ -33,12 +35,12 @@ _STATE_DTYPES = {
     "target_idx": (torch.int32, 0), "steps": (torch.int32, 0), "just_found": (torch.uint8, 0),
     "ep_return": (torch.float32, 0), "ep_length": (torch.int32, 0), "episode_count": (torch.int32, 0),
     "last_rpm_sum": (torch.float32, 0), "obs_rms": (torch.float32, -1),
-    "aux": (torch.float32, 4), "rew_rms": (torch.float32, 4), "spawn": (torch.float32, 4),
+    "aux": (torch.float32, 4), "rew_rms": (torch.float32, 4), "spawn": (torch.float32, 4), "pid": (torch.float32, 9),
 }
 
 
 class BatchedDroneEnv:
-    """N CF2X waypoint-navigation environments stepped by one fused CUDA kernel."""
+    """N waypoint-navigation environments (CF2X by default) stepped by one fused CUDA kernel."""
 
     def __init__(self, num_envs: int, target_points, threshold=0.3, discount=0.999, max_steps=4096,
                  aviary_dim=(-1, -1, 0, 1, 1, 1), initial_xyzs=None, initial_rpys=None,
@@ -51,12 +53,12 @@ class BatchedDroneEnv:
                  random_spawn=False, device=None, seed: int = 0, env_id_offset: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedDroneEnv needs a CUDA device: there is no CPU fallback")
-        if drone_model != DroneModel.CF2X:
-            raise NotImplementedError(f"{drone_model}: only DroneModel.CF2X is on the CUDA path")
+        if drone_model not in _MODEL:
+            raise ValueError(f"unknown drone model {drone_model}")
         if obs != ObservationType.KIN:
             raise NotImplementedError("only ObservationType.KIN is on the CUDA path")
         if act not in _ACT:
-            raise NotImplementedError(f"{act}: needs the PID controller, which is not on the CUDA path")
+            raise ValueError(f"unknown action type {act}")
         if physics not in _PHYS:
             raise NotImplementedError(f"{physics}: multi-drone downwash is not on the CUDA path")
         lib = L.lib()
@@ -73,6 +75,7 @@ class BatchedDroneEnv:
         c.seed = int(seed)
         c.pyb_freq, c.ctrl_freq = int(pyb_freq), int(ctrl_freq)
         c.act_type = _ACT[act]
+        c.drone_model = _MODEL[drone_model]
         c.normalize_actions = int(bool(normalize_actions))
         c.physics = _PHYS[physics] | (L.DN_PHYS_GROUND_CONTACT if ground_contact else 0)
         c.reward_id = int(reward_id)
@@ -111,7 +114,8 @@ class BatchedDroneEnv:
         self.reward_id = int(reward_id)
         self._optional = {"last_rpm_sum": self.uses_drag, "obs_rms": self.normalize_obs,
                           "aux": self.reward_id == L.DN_REWARD_REACHING, "rew_rms": self.normalize_reward,
-                          "spawn": bool(random_spawn)}
+                          "spawn": bool(random_spawn), "pid": c.act_type >= L.DN_ACT_PID}
+        self.drone_model, self.act_type = drone_model, act
         N, D, dev = self.num_envs, self.obs_dim, self.device
         # the persistent output lines of dn_step, carved out of ONE zero-filled allocation (one fill kernel per handle)
         up = lambda b: (b + 255) & ~255

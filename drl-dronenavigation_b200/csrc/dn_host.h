@@ -11,18 +11,36 @@
 
 namespace dn { namespace host {
 
-// CF2X constants: Sol/resources/safegym/cf2x.urdf:5,11-12,34 ; derived BaseAviary.py:76,163-176
-struct CF2X {
-    static constexpr double M = 0.027, L = 0.0397, T2W = 2.25;
-    static constexpr double IXX = 1.4e-5, IYY = 1.4e-5, IZZ = 2.17e-5;
-    static constexpr double KF = 3.16e-10, KM = 7.94e-12;
+// Airframe constants: Sol/resources/safegym/cf2x.urdf:5,11-12,34,42-78 ; Sol/resources/cf2p.urdf:5,11-12,34,42-78 ;
+// Sol/resources/racer.urdf:5,11-12,28,36-72 ; derived quantities BaseAviary.py:76,163-176.  Only cf2x.urdf carries the
+// pwm attributes (the THRUST action map needs them).
+struct Airframe {
+    double M, L, T2W, IXX, IYY, IZZ, KF, KM, MAX_SPEED_KMH;
+    double PROP_RADIUS;
+    double prop_x[4], prop_y[4];
+    bool plus;          // CF2P torque arms (BaseAviary.py:933-935)
+    bool km_negated;    // RACE: z_torques = -z_torques (BaseAviary.py:927-928)
+    bool has_pwm;       // pwm2rpm_scale / pwm2rpm_const / pwm_min / pwm_max present in the URDF
     static constexpr double COLLISION_H = 0.025;
-    static constexpr double GND_EFF_COEFF = 11.36859, PROP_RADIUS = 2.31348e-2;
+    static constexpr double GND_EFF_COEFF = 11.36859;
     static constexpr double DRAG_XY = 9.1785e-7, DRAG_Z = 10.311e-7;
     static constexpr double PWM2RPM_SCALE = 0.2685, PWM2RPM_CONST = 4070.3, MIN_PWM = 20000.0, MAX_PWM = 65535.0;
     static constexpr double G = 9.8;
 };
-
+inline const Airframe* airframe(int model) {
+    static const Airframe cf2x = {0.027, 0.0397, 2.25, 1.4e-5, 1.4e-5, 2.17e-5, 3.16e-10, 7.94e-12, 30.0, 2.31348e-2,
+                                  {0.028, -0.028, -0.028, 0.028}, {0.028, 0.028, -0.028, -0.028}, false, false, true};
+    static const Airframe cf2p = {0.027, 0.0397, 2.25, 2.3951e-5, 2.3951e-5, 3.2347e-5, 3.16e-10, 7.94e-12, 30.0, 2.31348e-2,
+                                  {0.0397, 0.0, -0.0397, 0.0}, {0.0, 0.0397, 0.0, -0.0397}, true, false, false};
+    static const Airframe race = {0.830, 0.109, 4.17, 3.113e-3, 3.113e-3, 3.113e-3, 8.47e-9, 2.13e-11, 200.0, 12.7e-2,
+                                  {0.085, -0.085, -0.085, 0.085}, {0.0675, 0.0675, -0.0675, -0.0675}, false, true, false};
+    switch (model) {
+        case DN_MODEL_CF2X: return &cf2x;
+        case DN_MODEL_CF2P: return &cf2p;
+        case DN_MODEL_RACE: return &race;
+        default: return nullptr;
+    }
+}
 inline void quat_from_euler(const double rpy[3], double q[4]) {   // p.getQuaternionFromEuler (BaseAviary.py:567)
     const double r = rpy[0] * 0.5, p = rpy[1] * 0.5, y = rpy[2] * 0.5;
     const double cr = std::cos(r), sr = std::sin(r), cp = std::cos(p), sp = std::sin(p), cy = std::cos(y), sy = std::sin(y);
@@ -114,32 +132,41 @@ inline void fill_params(const dn_config& cfg, const RewardParams& rw, Params& P,
         for (int k = 0; k < 12; ++k) P.init_obs[k] = (float)o[k];
     }
     // action map constants: float32 like the reference (PBDroneEnv.py:113-116)
-    const double a_low = CF2X::KF * std::pow(CF2X::PWM2RPM_SCALE * CF2X::MIN_PWM + CF2X::PWM2RPM_CONST, 2);
-    const double a_high = CF2X::KF * std::pow(CF2X::PWM2RPM_SCALE * CF2X::MAX_PWM + CF2X::PWM2RPM_CONST, 2);
+    const Airframe& A = *airframe(cfg.drone_model);
+    const double a_low = A.KF * std::pow(Airframe::PWM2RPM_SCALE * Airframe::MIN_PWM + Airframe::PWM2RPM_CONST, 2);
+    const double a_high = A.KF * std::pow(Airframe::PWM2RPM_SCALE * Airframe::MAX_PWM + Airframe::PWM2RPM_CONST, 2);
     P.a_low = (float)a_low; P.a_high = (float)a_high;
-    P.kf = (float)CF2X::KF; P.km = (float)CF2X::KM;
-    P.pwm_scale = (float)CF2X::PWM2RPM_SCALE; P.pwm_const = (float)CF2X::PWM2RPM_CONST;
-    P.pwm_min = (float)CF2X::MIN_PWM; P.pwm_max = (float)CF2X::MAX_PWM;
+    P.kf = (float)A.KF; P.km = (float)(A.km_negated ? -A.KM : A.KM);   // RACE: -z_torques, exact in every rounding (:927-929)
+    P.pwm_scale = (float)Airframe::PWM2RPM_SCALE; P.pwm_const = (float)Airframe::PWM2RPM_CONST;
+    P.pwm_min = (float)Airframe::MIN_PWM; P.pwm_max = (float)Airframe::MAX_PWM;
     // divisors exactly as numpy forms them in float32, and their correctly rounded float32 reciprocals
     P.a_span = P.a_high - P.a_low;                       // float32 subtraction (PBDroneEnv.py:968)
     P.inv_a_span = (float)(1.0 / (double)P.a_span);
     P.inv_kf = (float)(1.0 / (double)P.kf);
     P.inv_pwm_scale = (float)(1.0 / (double)P.pwm_scale);
-    const double gravity = CF2X::G * CF2X::M;
-    const double hover_rpm = std::sqrt(gravity / (4 * CF2X::KF));
-    const double max_rpm = std::sqrt((CF2X::T2W * gravity) / (4 * CF2X::KF));
-    const double max_thrust = 4 * CF2X::KF * max_rpm * max_rpm;
+    const double gravity = Airframe::G * A.M;
+    const double hover_rpm = std::sqrt(gravity / (4 * A.KF));
+    const double max_rpm = std::sqrt((A.T2W * gravity) / (4 * A.KF));
+    const double max_thrust = 4 * A.KF * max_rpm * max_rpm;
     P.hover_rpm = (float)hover_rpm;
-    P.gravity = (float)gravity; P.inv_m = (float)(1.0 / CF2X::M);
-    P.arm_over_sqrt2 = (float)(CF2X::L / std::sqrt(2.0));
-    P.ixx = (float)CF2X::IXX; P.iyy = (float)CF2X::IYY; P.izz = (float)CF2X::IZZ;
-    P.inv_ixx = (float)(1.0 / CF2X::IXX); P.inv_iyy = (float)(1.0 / CF2X::IYY); P.inv_izz = (float)(1.0 / CF2X::IZZ);
-    P.drag_xy = (float)CF2X::DRAG_XY; P.drag_z = (float)CF2X::DRAG_Z;
-    P.gnd_coeff = (float)CF2X::GND_EFF_COEFF; P.prop_radius = (float)CF2X::PROP_RADIUS;
-    P.gnd_h_clip = (float)(0.25 * CF2X::PROP_RADIUS * std::sqrt((15 * max_rpm * max_rpm * CF2X::KF * CF2X::GND_EFF_COEFF) / max_thrust));
-    P.collision_half_h = (float)(CF2X::COLLISION_H / 2);
-    const double px[4] = {0.028, -0.028, -0.028, 0.028}, py[4] = {0.028, 0.028, -0.028, -0.028};   // safegym/cf2x.urdf:42,54,66,78
-    for (int k = 0; k < 4; ++k) { P.prop_x[k] = (float)px[k]; P.prop_y[k] = (float)py[k]; }
+    P.gravity = (float)gravity; P.inv_m = (float)(1.0 / A.M);
+    P.frame_plus = A.plus ? 1 : 0;
+    P.torque_arm = (float)(A.plus ? A.L : A.L / std::sqrt(2.0));
+    P.ixx = (float)A.IXX; P.iyy = (float)A.IYY; P.izz = (float)A.IZZ;
+    P.inv_ixx = (float)(1.0 / A.IXX); P.inv_iyy = (float)(1.0 / A.IYY); P.inv_izz = (float)(1.0 / A.IZZ);
+    P.drag_xy = (float)Airframe::DRAG_XY; P.drag_z = (float)Airframe::DRAG_Z;
+    P.gnd_coeff = (float)Airframe::GND_EFF_COEFF; P.prop_radius = (float)A.PROP_RADIUS;
+    P.gnd_h_clip = (float)(0.25 * A.PROP_RADIUS * std::sqrt((15 * max_rpm * max_rpm * A.KF * Airframe::GND_EFF_COEFF) / max_thrust));
+    P.collision_half_h = (float)(Airframe::COLLISION_H / 2);
+    for (int k = 0; k < 4; ++k) { P.prop_x[k] = (float)A.prop_x[k]; P.prop_y[k] = (float)A.prop_y[k]; }
+    // DSLPIDControl always reads the cf2x URDF (BaseSingleAgentAviary.py:72-73; BaseControl.py:33-37)
+    {
+        const Airframe& Cx = *airframe(DN_MODEL_CF2X);
+        P.ctrl_dt = (float)(1.0 / cfg.ctrl_freq); P.inv_ctrl_dt = (float)cfg.ctrl_freq;
+        P.speed_limit = (float)(0.03 * A.MAX_SPEED_KMH * (1000.0 / 3600.0));
+        P.pid_gravity = (float)(Airframe::G * Cx.M);
+        P.pid_inv_4kf = (float)(1.0 / (4.0 * Cx.KF));
+    }
     P.rw = rw;
     P.rew_gamma = (float)(cfg.reward_gamma > 0.0 ? cfg.reward_gamma : 0.99);   // gym / normalize.NormalizeReward default
     P.rew_eps = 1e-8f;

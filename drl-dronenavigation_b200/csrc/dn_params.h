@@ -85,7 +85,8 @@ struct Params {
     float a_low, a_high, kf, km, pwm_scale, pwm_const, pwm_min, pwm_max, hover_rpm;
     float a_span, inv_a_span, inv_kf, inv_pwm_scale;   // float32 divisors and their RN reciprocals (div_const_rn)
     // rigid body (BaseAviary.py:899-958)
-    float gravity, inv_m, arm_over_sqrt2, ixx, iyy, izz, inv_ixx, inv_iyy, inv_izz;
+    float gravity, inv_m, torque_arm, ixx, iyy, izz, inv_ixx, inv_iyy, inv_izz;   // torque_arm: L / sqrt(2) (CF2X, RACE), L (CF2P)
+    int   frame_plus;        // 1: DroneModel.CF2P torque mix (BaseAviary.py:933-935); km is negated for RACE (:927-928)
     // add-ons (BaseAviary.py:798-865)
     float drag_xy, drag_z, gnd_coeff, prop_radius, gnd_h_clip, collision_half_h;
     float prop_x[4], prop_y[4];
@@ -108,6 +109,12 @@ struct Params {
     float4* rew_rms;         // [N] {returns, mean, var, count} of normalize.NormalizeReward (normalize.py:100-147); normalize_reward only
     float rew_gamma, rew_eps, rew_clip;   // NormalizeReward gamma / epsilon; TransformReward clip bound (<= 0: off), PBDroneSimulator.py:190-193
     float ep_time_scale;     // S / (PYB_FREQ * EPISODE_LEN_SEC): step_counter / PYB_FREQ / EPISODE_LEN_SEC = ep_len * this
+    // DSLPIDControl (Sol/PyBullet/DSLPIDControl.py:20-80) for DN_ACT_PID / VEL / ONE_D_PID; its constants are the CF2X ones
+    // whatever the airframe (BaseSingleAgentAviary.py:72-73), gains are compile-time constants in dn_device.cuh
+    float ctrl_dt, inv_ctrl_dt;   // CTRL_TIMESTEP = 1 / ctrl_freq and its reciprocal
+    float speed_limit;            // 0.03 * MAX_SPEED_KMH * 1000 / 3600 (BaseSingleAgentAviary.py:91)
+    float pid_gravity, pid_inv_4kf;   // BaseControl.GRAVITY = g * m, 1 / (4 KF) of the controller's URDF (cf2x)
+    float4* pid[3];               // [N] integral_pos_e | integral_rpy_e | last_rpy (w unused); PID action types only
     BlockStats* block_stats; // [ceil(N / CTA)] Monitor statistics slots
     int prefetch_ctas;       // software-prefetch distance in CTAs (= CTAs resident on the whole GPU)
 };

@@ -449,6 +449,7 @@ __global__ void init_kernel(const __grid_constant__ Params P, float d0) {
     if (P.spawn) P.spawn[i] = make_float4(P.init_pos[0], P.init_pos[1], P.init_pos[2], 0.f);
     if (P.aux) P.aux[i] = make_float4(P.init_pos[0], P.init_pos[1], P.init_pos[2], 0.f);   // _last_position = _current_position = INIT_XYZS[0]
     if (P.rew_rms) P.rew_rms[i] = make_float4(0.f, 0.f, 1.f, 1e-4f);                       // returns 0; RunningMeanStd(): mean 0, var 1, count 1e-4
+    if (P.pid[0]) { P.pid[0][i] = P.pid[1][i] = P.pid[2][i] = make_float4(0.f, 0.f, 0.f, 0.f); }   // DSLPIDControl.reset (DSLPIDControl.py:66-80)
     if (P.obs_rms) {
         const size_t N = P.n; const int D = P.obs_dim;
         for (int k = 0; k < D; ++k) { P.obs_rms[k * N + i] = 0.f; P.obs_rms[(D + k) * N + i] = 1.f; }
@@ -539,7 +540,7 @@ __global__ void gae_kernel(const float* __restrict__ rew, const float* __restric
 struct StateView {   // device mirror of dn_state_view
     float *pos, *quat, *vel, *rpy_rates, *ang_v, *prev_vel, *prev_ang_v, *dist, *prev_dist;
     int32_t *target_idx, *steps; uint8_t* just_found; float* ep_return; int32_t* ep_length;
-    uint32_t* episode_count; float* last_rpm_sum; float* obs_rms; float* aux; float* rew_rms; float* spawn;
+    uint32_t* episode_count; float* last_rpm_sum; float* obs_rms; float* aux; float* rew_rms; float* spawn; float* pid;
 };
 
 template <bool SET>
@@ -583,6 +584,13 @@ __global__ void state_xfer_kernel(const __grid_constant__ Params P, const __grid
     if (V.spawn && P.spawn) {
         float4* g = reinterpret_cast<float4*>(V.spawn);
         if (SET) P.spawn[i] = g[i]; else g[i] = P.spawn[i];
+    }
+    if (V.pid && P.pid[0]) {                                  // [N,9] integral_pos_e | integral_rpy_e | last_rpy
+        float* g = V.pid + 9 * static_cast<size_t>(i);
+        for (int k = 0; k < 3; ++k) {
+            if (SET) P.pid[k][i] = make_float4(g[3 * k], g[3 * k + 1], g[3 * k + 2], 0.f);
+            else { const float4 v = P.pid[k][i]; g[3 * k] = v.x; g[3 * k + 1] = v.y; g[3 * k + 2] = v.z; }
+        }
     }
     if (V.rew_rms && P.rew_rms) {
         float4* g = reinterpret_cast<float4*>(V.rew_rms);
@@ -682,7 +690,13 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
         return fail(DN_EINVAL, "dn_create: pyb_freq is not divisible by ctrl_freq");   // BaseAviary.py:81-82
     if (cfg->num_targets <= 0 || cfg->num_targets >= 2047 || !cfg->targets)
         return fail(DN_EINVAL, "dn_create: need 1..2046 targets");
-    if (cfg->act_type < 0 || cfg->act_type > DN_ACT_ONE_D_RPM) return fail(DN_EINVAL, "dn_create: unsupported act_type");
+    if (cfg->act_type < 0 || cfg->act_type > DN_ACT_ONE_D_PID) return fail(DN_EINVAL, "dn_create: unsupported act_type");
+    const dn::host::Airframe* frame = dn::host::airframe(cfg->drone_model);
+    if (!frame) return fail(DN_EINVAL, "dn_create: unknown drone_model");
+    if (cfg->act_type == DN_ACT_THRUST && !frame->has_pwm)     // BaseAviary._parse_urdf_parameters, BaseAviary.py:1157-1160
+        return fail(DN_EINVAL, "dn_create: the THRUST action map needs the pwm2rpm attributes, which only cf2x.urdf has");
+    if (cfg->act_type >= DN_ACT_PID && cfg->drone_model == DN_MODEL_RACE)   // BaseSingleAgentAviary.py:72-75
+        return fail(DN_EINVAL, "dn_create: no controller is available for DroneModel.RACE");
     if (cfg->physics & ~7) return fail(DN_EINVAL, "dn_create: unknown physics flags");
     if (cfg->spawn_mode < DN_SPAWN_FIXED || cfg->spawn_mode > DN_SPAWN_MIDPOINT) return fail(DN_EINVAL, "dn_create: unknown spawn_mode");
     if (cfg->spawn_mode != DN_SPAWN_FIXED && cfg->num_targets < 2) return fail(DN_EINVAL, "dn_create: random spawn needs >= 2 targets");
@@ -703,7 +717,7 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     e->device = device;
     e->normalize_obs = cfg->normalize_obs ? 1 : 0;
     e->full = (cfg->spawn_mode != DN_SPAWN_FIXED || rw.mode != dn::RW_WAYPOINT || rw.proj_w != 0.0f || cfg->normalize_reward ||
-               cfg->clip_reward > 0.0) ? 1 : 0;
+               cfg->clip_reward > 0.0 || cfg->act_type >= DN_ACT_PID) ? 1 : 0;
     Params& P = e->P;
     const int N = cfg->num_envs, T = cfg->num_targets;
     std::vector<float4> h_t, h_s;
@@ -727,7 +741,8 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     const size_t rms_floats = e->normalize_obs ? static_cast<size_t>(2 * P.obs_dim + 1) * N : 0;
     bytes += ((rms_floats * sizeof(float) + 255) / 256) * 256;
     const bool need_aux = (rw.mode == dn::RW_REACHING), need_rew_rms = (cfg->normalize_reward != 0);
-    const bool need_spawn = (cfg->spawn_mode != DN_SPAWN_FIXED);
+    const bool need_spawn = (cfg->spawn_mode != DN_SPAWN_FIXED), need_pid = (cfg->act_type >= DN_ACT_PID);
+    if (need_pid) bytes += 3 * plane;
     if (need_aux) bytes += plane;
     if (need_rew_rms) bytes += plane;
     if (need_spawn) bytes += plane;
@@ -740,6 +755,7 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     if (need_aux) { P.aux = reinterpret_cast<float4*>(p); p += plane; }
     if (need_rew_rms) { P.rew_rms = reinterpret_cast<float4*>(p); p += plane; }
     if (need_spawn) { P.spawn = reinterpret_cast<float4*>(p); p += plane; }
+    if (need_pid) { for (int k = 0; k < 3; ++k) { P.pid[k] = reinterpret_cast<float4*>(p); p += plane; } }
     if ((ce = cudaMalloc(&e->d_targets, T * sizeof(float4))) != cudaSuccess ||
         (ce = cudaMalloc(&e->d_segs, 2 * T * sizeof(float4))) != cudaSuccess ||
         (ce = cudaMalloc(&e->d_stats, sizeof(dn::Stats))) != cudaSuccess ||
@@ -944,6 +960,8 @@ int dn_step_host(dn_env* env, const dn_step_io* h) {
 
 int dn_action_to_rpm(dn_env* env, const float* actions, float* rpm_out, int64_t n, void* stream) {
     if (!env || !actions || !rpm_out || n < 0) return fail(DN_EINVAL, "dn_action_to_rpm: bad argument");
+    if (env->P.act_type >= DN_ACT_PID)
+        return fail(DN_EINVAL, "dn_action_to_rpm: the PID action types are not elementwise maps (the RPMs depend on the drone and controller state)");
     if (n == 0) return DN_OK;
     DeviceGuard guard(env->device);
     dn::action_map_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(env->P, actions, rpm_out, n);
@@ -971,7 +989,7 @@ static int state_xfer(dn_env* env, const dn_state_view* v, bool set, void* strea
     V.prev_vel = v->prev_vel; V.prev_ang_v = v->prev_ang_v; V.dist = v->dist; V.prev_dist = v->prev_dist;
     V.target_idx = v->target_idx; V.steps = v->steps; V.just_found = v->just_found; V.ep_return = v->ep_return;
     V.ep_length = v->ep_length; V.episode_count = v->episode_count; V.last_rpm_sum = v->last_rpm_sum; V.obs_rms = v->obs_rms;
-    V.aux = v->aux; V.rew_rms = v->rew_rms; V.spawn = v->spawn;
+    V.aux = v->aux; V.rew_rms = v->rew_rms; V.spawn = v->spawn; V.pid = v->pid;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int N = env->P.n;
     if (set) dn::state_xfer_kernel<true><<<(N + 255) / 256, 256, 0, st>>>(env->P, V);

@@ -8,9 +8,9 @@ from enum import Enum
 
 
 class DroneModel(Enum):
-    CF2X = "cf2x"    # ON PATH
-    CF2P = "cf2p"
-    RACE = "racer"
+    CF2X = "cf2x"    # ON PATH (the only model the reference itself can construct)
+    CF2P = "cf2p"    # ON PATH: BaseAviary._dynamics' + frame branch (RPM and PID action types)
+    RACE = "racer"   # ON PATH: X frame with reversed propeller spin (RPM action types)
 
 
 class Physics(Enum):
@@ -31,10 +31,10 @@ class ImageType(Enum):
 
 class ActionType(Enum):
     RPM = "rpm"                # ON PATH
-    PID = "pid"
-    VEL = "vel"
+    PID = "pid"                # ON PATH (DSLPIDControl fused into the step kernel)
+    VEL = "vel"                # ON PATH
     ONE_D_RPM = "one_d_rpm"    # ON PATH
-    ONE_D_PID = "one_d_pid"
+    ONE_D_PID = "one_d_pid"    # ON PATH
     THRUST = "thrust"          # ON PATH (what PBDroneSimulator.make_env selects)
 
 

@@ -86,7 +86,11 @@ class PBDroneEnv:
         self._actions.copy_(torch.from_numpy(a))
         c = self._core
         c.step(self._actions)
-        self.last_clipped_action = c.action_to_rpm(self._actions).cpu().numpy().astype(np.float64)   # BaseAviary.py:442
+        if self.ACT_TYPE in (ActionType.PID, ActionType.VEL, ActionType.ONE_D_PID):
+            # the RPMs of the PID family depend on the controller state inside the kernel; not exported per step
+            self.last_clipped_action = np.full((1, 4), np.nan)
+        else:
+            self.last_clipped_action = c.action_to_rpm(self._actions).cpu().numpy().astype(np.float64)   # BaseAviary.py:442
         bits = int(c.done.cpu()[0])
         terminated, truncated = bool(bits & 1), bool(bits & 2)
         reward = float(c.reward.cpu()[0])

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 2
+#define DN_ABI_VERSION 3
 
 /* error codes */
 #define DN_OK        0
@@ -49,10 +49,24 @@ extern "C" {
 #define DN_ECUDA    -2   /* CUDA runtime error (message has the cudaError string) */
 #define DN_ENOMEM   -3
 
-/* ActionType (Sol/PyBullet/enums.py:36-43) -- only the RPM-producing types are on the path */
+/* ActionType (Sol/PyBullet/enums.py:36-43).  THRUST is what PBDroneEnv runs; the others are the
+ * BaseSingleAgentAviary._preprocessAction branches (BaseSingleAgentAviary.py:153-225) that PBDroneEnv overrides. */
 #define DN_ACT_THRUST     0   /* PBDroneEnv._preprocessAction, PBDroneEnv.py:872-895 */
 #define DN_ACT_RPM        1   /* BaseSingleAgentAviary.py:176-179 */
 #define DN_ACT_ONE_D_RPM  2   /* BaseSingleAgentAviary.py:211-212 (uses action[:,0]) */
+#define DN_ACT_PID        3   /* :180-194: action[:,0:3] = destination; _calculateNextStep (BaseAviary.py:1255-1297)
+                                 + DSLPIDControl.computeControl (Sol/PyBullet/DSLPIDControl.py:82-261) fused into the step */
+#define DN_ACT_VEL        4   /* :195-210: action = (direction xyz, speed fraction); PID velocity tracking, current yaw held */
+#define DN_ACT_ONE_D_PID  5   /* :213-223: target = current position + 0.1 * (0, 0, action[:,0]) */
+
+/* DroneModel (Sol/PyBullet/enums.py:3-8): airframe constants of Sol/resources/{safegym/cf2x,cf2p,racer}.urdf and the
+ * torque-mix branch of BaseAviary._dynamics (BaseAviary.py:927-935).  The reference itself can only construct CF2X
+ * (BaseAviary.py:99 opens Sol/resources/safegym/<model>.urdf and the other two URDFs lack the pwm attributes its
+ * parser reads, :1157-1160), so THRUST actions need CF2X; CF2P / RACE take the RPM types, CF2P also the PID types
+ * (with the CF2X mixer, as BaseSingleAgentAviary.py:72-73 constructs it). */
+#define DN_MODEL_CF2X     0
+#define DN_MODEL_CF2P     1
+#define DN_MODEL_RACE     2
 
 /* physics flags.  0 == Physics.DYN (BaseAviary.py:899-973).  The add-ons restate the
  * PYB_* formulas inside the DYN integrator (documented extension). */
@@ -118,11 +132,13 @@ typedef struct dn_config {
     double   clip_reward;        /* > 0: clip the reward to +-this before normalisation (args.clip_rew, PBDroneSimulator.py:191-192: 10) */
     double   reward_gamma;       /* NormalizeReward gamma; 0 = its default 0.99 */
     const double* targets;       /* HOST pointer, [T,3] row-major (copied by dn_create) */
+    int32_t  drone_model;        /* DN_MODEL_* (BaseAviary.__init__ drone_model, BaseAviary.py:30,76) */
+    int32_t  reserved0;          /* = 0 */
 } dn_config;
 
 /* Buffers of one dn_step call.  Device pointers, caller-owned.  Nullable where noted. */
 typedef struct dn_step_io {
-    const float* actions;        /* [N,4] f32 (ONE_D_RPM reads column 0)                       */
+    const float* actions;        /* [N,4] f32 (ONE_D_RPM / ONE_D_PID read column 0, PID columns 0..2) */
     float*       obs;            /* [N,obs_dim] f32 : obs of the step, or the reset obs if done */
     float*       reward;         /* [N] f32                                                     */
     uint8_t*     done;           /* [N] u8 : DN_DONE_TERMINATED | DN_DONE_TRUNCATED             */
@@ -155,6 +171,9 @@ typedef struct dn_state_view {
     float*    aux;            /* [N,4] _current_position.xyz | last travel; only with DN_REWARD_REACHING */
     float*    rew_rms;        /* [N,4] returns | mean | var | count (normalize.py:100-147); only if normalize_reward */
     float*    spawn;          /* [N,4] INIT_XYZS[0] of the current episode | target roll; only with a random spawn mode */
+    float*    pid;            /* [N,9] DSLPIDControl.integral_pos_e | integral_rpy_e | last_rpy (DSLPIDControl.py:66-80);
+                                 only with the PID action types.  Like the reference's controller object it survives
+                                 episode resets (BaseSingleAgentAviary never calls ctrl.reset()) */
 } dn_state_view;
 
 /* Aggregated Monitor statistics since the last clear (SB3 Monitor / ep_info_buffer). */
@@ -207,7 +226,8 @@ int dn_step_host(dn_env* env, const dn_step_io* host_io);
 /* The action map alone, elementwise over `n` action components (device pointers):
  * PBDroneEnv._preprocessAction(rescale_action(a)) (PBDroneEnv.py:872-895,949-971) or the RPM map
  * (BaseSingleAgentAviary.py:176-179), whichever the handle was created with.  Bit-identical to
- * the reference's float32 numpy arithmetic; used by the parity tests and by callers that log RPMs. */
+ * the reference's float32 numpy arithmetic; used by the parity tests and by callers that log RPMs.
+ * DN_EINVAL for the PID action types (their RPMs depend on the drone and controller state). */
 int dn_action_to_rpm(dn_env* env, const float* actions, float* rpm_out, int64_t n, void* stream);
 
 int dn_get_state(dn_env* env, const dn_state_view* view, void* stream);

@@ -31,6 +31,13 @@ What each piece follows (all paths relative to ``/root/reference``):
 * action map (THRUST)       ``Sol/Model/Environments/PBDroneEnv.py:872-895,949-971``;
                             ``Sol/Model/env_utils.py:8-59``
 * action map (RPM)          ``Sol/PyBullet/BaseSingleAgentAviary.py:176-179,211-212``
+* action map (PID family)   ``Sol/PyBullet/BaseSingleAgentAviary.py:72-75,91,180-223``; ``Sol/PyBullet/BaseAviary.py:1255-1297``;
+                            ``Sol/PyBullet/DSLPIDControl.py:20-261``; ``Sol/PyBullet/BaseControl.py:20-52``.  scipy's
+                            ``Rotation.from_matrix(..).as_euler('XYZ')`` / ``from_euler('XYZ', ..)`` (third party, present in
+                            this image but kept out of the oracle) are restated in numpy; the fixtures
+                            ``tests/golden/ref_*_{pid,vel,one_d_pid}*.npz`` were minted with the real scipy
+* airframes                 ``Sol/resources/cf2p.urdf:5,11-12,34,42-78``; ``Sol/resources/racer.urdf:5,11-12,28,36-72``;
+                            torque-mix branches ``Sol/PyBullet/BaseAviary.py:927-935``
 * substep loop / ordering   ``Sol/PyBullet/BaseAviary.py:407-453``
 * rigid body                ``Sol/PyBullet/BaseAviary.py:899-973``
 * drag / ground effect      ``Sol/PyBullet/BaseAviary.py:838-865,798-834`` (formulas only;
@@ -127,6 +134,15 @@ class CF2XConstants:
 
 
 CF2X = CF2XConstants()
+# The other two airframes of Sol/PyBullet/enums.py:3-8.  Their URDFs carry no pwm attributes (the values below are the
+# class defaults, only ever used by DSLPIDControl, which hard-codes the same numbers: DSLPIDControl.py:43-46).
+CF2P = CF2XConstants(IXX=2.3951e-5, IYY=2.3951e-5, IZZ=3.2347e-5,
+                     PROP_XY=((0.0397, 0.0), (0.0, 0.0397), (-0.0397, 0.0), (0.0, -0.0397)))
+RACE = CF2XConstants(M=0.830, L=0.109, THRUST2WEIGHT_RATIO=4.17, IXX=3.113e-3, IYY=3.113e-3, IZZ=3.113e-3,
+                     KF=8.47e-9, KM=2.13e-11, MAX_SPEED_KMH=200.0, PROP_RADIUS=12.7e-2,
+                     PROP_XY=((0.085, 0.0675), (-0.085, 0.0675), (-0.085, -0.0675), (0.085, -0.0675)))
+MODEL_CF2X, MODEL_CF2P, MODEL_RACE = "cf2x", "cf2p", "racer"
+AIRFRAMES = {MODEL_CF2X: CF2X, MODEL_CF2P: CF2P, MODEL_RACE: RACE}
 
 
 # --------------------------------------------------------------------------
@@ -250,7 +266,107 @@ def rpm_action_to_rpm(action, c: CF2XConstants = CF2X, numpy_legacy_cast: bool =
     if numpy_legacy_cast and a.dtype == np.float32:
         one_plus = np.float32(1) + np.float32(0.05) * a
         return np.float32(c.HOVER_RPM) * one_plus
-    return np.array(c.HOVER_RPM * (1 + 0.05 * a))
+    # numpy >= 2 (NEP 50): the float32 array (1 + 0.05 a) times the np.float64 SCALAR HOVER_RPM (BaseAviary.py:164) is float64
+    return np.array(np.float64(c.HOVER_RPM) * (1 + 0.05 * a), dtype=np.float64)
+
+
+# --------------------------------------------------------------------------
+# DSLPIDControl (Sol/PyBullet/DSLPIDControl.py:20-261 over BaseControl.py:20-52)
+# --------------------------------------------------------------------------
+
+
+def euler_XYZ_from_matrix(R):
+    """scipy ``Rotation.from_matrix(R).as_euler('XYZ')`` (intrinsic x-y'-z''), DSLPIDControl.py:193:
+    R = Rx(a) Ry(b) Rz(c) -> b = asin(R02), a = atan2(-R12, R22), c = atan2(-R01, R00) (away from gimbal lock)."""
+    return np.array([math.atan2(-R[1, 2], R[2, 2]), math.asin(min(1.0, max(-1.0, R[0, 2]))), math.atan2(-R[0, 1], R[0, 0])])
+
+
+def matrix_from_euler_XYZ(e):
+    """scipy ``Rotation.from_euler('XYZ', e)`` -> ``as_quat`` -> ``from_quat`` -> ``as_matrix`` (DSLPIDControl.py:233-235;
+    the ``w,x,y,z = target_quat`` / ``from_quat([w, x, y, z])`` pair re-assembles the same array, a no-op)."""
+    ca, sa, cb, sb, cc, sc = math.cos(e[0]), math.sin(e[0]), math.cos(e[1]), math.sin(e[1]), math.cos(e[2]), math.sin(e[2])
+    return np.array([[cb * cc, -cb * sc, sb],
+                     [ca * sc + sa * sb * cc, ca * cc - sa * sb * sc, -sa * cb],
+                     [sa * sc - ca * sb * cc, sa * cc + ca * sb * sc, ca * cb]])
+
+
+class OracleDSLPID:
+    """DSLPIDControl(drone_model=DroneModel.CF2X): BaseSingleAgentAviary.py:72-73 constructs the CF2X controller for CF2X
+    and CF2P airframes alike, and never resets it (no ``ctrl.reset()`` in any env reset)."""
+
+    def __init__(self, g=9.8, c: CF2XConstants = CF2X):
+        self.GRAVITY = g * c.M                      # BaseControl.py:33 (URDF of the controller's model: cf2x)
+        self.KF = c.KF
+        self.P_COEFF_FOR = np.array([.4, .4, 1.25])
+        self.I_COEFF_FOR = np.array([.05, .05, .05])
+        self.D_COEFF_FOR = np.array([.2, .2, .5])
+        self.P_COEFF_TOR = np.array([70000., 70000., 60000.])
+        self.I_COEFF_TOR = np.array([.0, .0, 500.])
+        self.D_COEFF_TOR = np.array([20000., 20000., 12000.])
+        self.PWM2RPM_SCALE, self.PWM2RPM_CONST, self.MIN_PWM, self.MAX_PWM = 0.2685, 4070.3, 20000, 65535
+        self.MIXER_MATRIX = np.array([[-.5, -.5, -1], [-.5, .5, 1], [.5, .5, -1], [.5, -.5, 1]])
+        self.reset()
+
+    def reset(self):                                # DSLPIDControl.py:66-80
+        self.control_counter = 0
+        self.last_rpy = np.zeros(3)
+        self.integral_pos_e = np.zeros(3)
+        self.integral_rpy_e = np.zeros(3)
+
+    def computeControl(self, control_timestep, cur_pos, cur_quat, cur_vel, cur_ang_vel, target_pos,
+                       target_rpy=np.zeros(3), target_vel=np.zeros(3), target_rpy_rates=np.zeros(3)):
+        self.control_counter += 1
+        thrust, computed_target_rpy, pos_e = self._dslPIDPositionControl(
+            control_timestep, cur_pos, cur_quat, cur_vel, target_pos, target_rpy, target_vel)
+        rpm = self._dslPIDAttitudeControl(control_timestep, thrust, cur_quat, computed_target_rpy, target_rpy_rates)
+        cur_rpy = bullet_euler_from_quaternion(cur_quat)
+        return rpm, pos_e, computed_target_rpy[2] - cur_rpy[2]
+
+    def _dslPIDPositionControl(self, control_timestep, cur_pos, cur_quat, cur_vel, target_pos, target_rpy, target_vel):
+        cur_rotation = bullet_matrix_from_quaternion(cur_quat)                                # :163
+        pos_e = target_pos - cur_pos
+        vel_e = target_vel - cur_vel
+        self.integral_pos_e = self.integral_pos_e + pos_e * control_timestep
+        self.integral_pos_e = np.clip(self.integral_pos_e, -2., 2.)
+        self.integral_pos_e[2] = np.clip(self.integral_pos_e[2], -0.15, .15)
+        target_thrust = (np.multiply(self.P_COEFF_FOR, pos_e) + np.multiply(self.I_COEFF_FOR, self.integral_pos_e)
+                         + np.multiply(self.D_COEFF_FOR, vel_e) + np.array([0, 0, self.GRAVITY]))
+        scalar_thrust = max(0., np.dot(target_thrust, cur_rotation[:, 2]))
+        thrust = (math.sqrt(scalar_thrust / (4 * self.KF)) - self.PWM2RPM_CONST) / self.PWM2RPM_SCALE
+        target_z_ax = target_thrust / np.linalg.norm(target_thrust)
+        target_x_c = np.array([math.cos(target_rpy[2]), math.sin(target_rpy[2]), 0])
+        target_y_ax = np.cross(target_z_ax, target_x_c) / np.linalg.norm(np.cross(target_z_ax, target_x_c))
+        target_x_ax = np.cross(target_y_ax, target_z_ax)
+        target_rotation = (np.vstack([target_x_ax, target_y_ax, target_z_ax])).transpose()
+        target_euler = euler_XYZ_from_matrix(target_rotation)                                 # :193
+        return thrust, target_euler, pos_e
+
+    def _dslPIDAttitudeControl(self, control_timestep, thrust, cur_quat, target_euler, target_rpy_rates):
+        cur_rotation = bullet_matrix_from_quaternion(cur_quat)
+        cur_rpy = np.array(bullet_euler_from_quaternion(cur_quat))
+        target_rotation = matrix_from_euler_XYZ(target_euler)                                 # :233-235
+        rot_matrix_e = np.dot(target_rotation.transpose(), cur_rotation) - np.dot(cur_rotation.transpose(), target_rotation)
+        rot_e = np.array([rot_matrix_e[2, 1], rot_matrix_e[0, 2], rot_matrix_e[1, 0]])
+        rpy_rates_e = target_rpy_rates - (cur_rpy - self.last_rpy) / control_timestep
+        self.last_rpy = cur_rpy
+        self.integral_rpy_e = self.integral_rpy_e - rot_e * control_timestep
+        self.integral_rpy_e = np.clip(self.integral_rpy_e, -1500., 1500.)
+        self.integral_rpy_e[0:2] = np.clip(self.integral_rpy_e[0:2], -1., 1.)
+        target_torques = (- np.multiply(self.P_COEFF_TOR, rot_e) + np.multiply(self.D_COEFF_TOR, rpy_rates_e)
+                          + np.multiply(self.I_COEFF_TOR, self.integral_rpy_e))
+        target_torques = np.clip(target_torques, -3200, 3200)
+        pwm = thrust + np.dot(self.MIXER_MATRIX, target_torques)
+        pwm = np.clip(pwm, self.MIN_PWM, self.MAX_PWM)
+        return self.PWM2RPM_SCALE * pwm + self.PWM2RPM_CONST
+
+
+def calculate_next_step(current_position, destination, step_size=1):
+    """BaseAviary._calculateNextStep, BaseAviary.py:1255-1297."""
+    direction = destination - current_position
+    distance = np.linalg.norm(direction)
+    if distance <= step_size:
+        return destination
+    return current_position + direction / distance * step_size
 
 
 # --------------------------------------------------------------------------
@@ -328,6 +444,9 @@ def spawn_midpoint(targets, seed, global_env_id, counter):
 ACT_THRUST = "thrust"
 ACT_RPM = "rpm"
 ACT_ONE_D_RPM = "one_d_rpm"
+ACT_PID = "pid"
+ACT_VEL = "vel"
+ACT_ONE_D_PID = "one_d_pid"
 
 
 class OracleDroneEnv:
@@ -339,8 +458,18 @@ class OracleDroneEnv:
                  pyb_freq=240, ctrl_freq=240, act=ACT_THRUST, cylinder=True,
                  circle=False, include_distance=False, normalize_actions=False,
                  ground_contact=False, reward_id="default", random_spawn=False, seed=0, global_env_id=0,
-                 consts: CF2XConstants = CF2X):
+                 consts: CF2XConstants = None, drone_model=MODEL_CF2X):
+        self.DRONE_MODEL = drone_model
+        # RPM action types: float32 arithmetic as under the reference's pinned numpy 1.26 (see rpm_action_to_rpm); set to
+        # False to reproduce fixtures minted under numpy >= 2 (float64 promotion)
+        self.numpy_legacy_cast = True
+        consts = AIRFRAMES[drone_model] if consts is None else consts
         self.C = consts
+        if act in (ACT_PID, ACT_VEL, ACT_ONE_D_PID):           # BaseSingleAgentAviary.py:70-75,90-91
+            if drone_model not in (MODEL_CF2X, MODEL_CF2P):
+                raise ValueError("no controller is available for the specified drone_model")
+            self.ctrl = OracleDSLPID()
+            self.SPEED_LIMIT = 0.03 * consts.MAX_SPEED_KMH * (1000 / 3600)
         self.random_spawn, self.seed, self.global_env_id, self._reset_counter = random_spawn, seed, global_env_id, 0
         self.reward_id = reward_id        # which reference reward function runs inside the PBDroneEnv step machine
         self.EPISODE_LEN_SEC = 1          # PBDroneEnv.py:68 says 5, but _clipAndNormalizeState overwrites it with 1 on every
@@ -475,9 +604,29 @@ class OracleDroneEnv:
         if self.ACT_TYPE == ACT_THRUST:
             return thrust_to_rpm(action, self.physical_action_bounds, self.C)
         if self.ACT_TYPE == ACT_RPM:
-            return rpm_action_to_rpm(action, self.C)
+            return rpm_action_to_rpm(action, self.C, self.numpy_legacy_cast)
         if self.ACT_TYPE == ACT_ONE_D_RPM:
-            return np.repeat(rpm_action_to_rpm(np.asarray(action).reshape(-1)[:1], self.C), 4)
+            return np.repeat(rpm_action_to_rpm(np.asarray(action).reshape(-1)[:1], self.C, self.numpy_legacy_cast), 4)
+        # ---- BaseSingleAgentAviary.py:180-223: the PID family; the controller sees the state vector of step entry
+        state = self._getDroneStateVector()
+        action = np.asarray(action).reshape(-1)     # dtype kept: VEL's unit vector / target velocity stay float32 for float32 actions
+        kw = dict(control_timestep=self.CTRL_TIMESTEP, cur_pos=state[0:3], cur_quat=state[3:7],
+                  cur_vel=state[10:13], cur_ang_vel=state[13:16])
+        if self.ACT_TYPE == ACT_PID:
+            next_pos = calculate_next_step(current_position=state[0:3], destination=action[0:3], step_size=1)
+            rpm, _, _ = self.ctrl.computeControl(target_pos=next_pos, **kw)
+            return rpm
+        if self.ACT_TYPE == ACT_VEL:
+            if np.linalg.norm(action[0:3]) != 0:
+                v_unit_vector = action[0:3] / np.linalg.norm(action[0:3])
+            else:
+                v_unit_vector = np.zeros(3)
+            rpm, _, _ = self.ctrl.computeControl(target_pos=state[0:3], target_rpy=np.array([0, 0, state[9]]),
+                                                 target_vel=self.SPEED_LIMIT * np.abs(action[3]) * v_unit_vector, **kw)
+            return rpm
+        if self.ACT_TYPE == ACT_ONE_D_PID:
+            rpm, _, _ = self.ctrl.computeControl(target_pos=state[0:3] + 0.1 * np.array([0, 0, action[0]]), **kw)
+            return rpm
         raise ValueError(self.ACT_TYPE)
 
     # ---- BaseAviary._dynamics (BaseAviary.py:899-958) ----------------------
@@ -495,9 +644,15 @@ class OracleDroneEnv:
         if self.PHYSICS in (PHYSICS_DYN_DRAG, PHYSICS_DYN_GND_DRAG):
             force_world_frame = force_world_frame + self._drag(rotation)  # extension (a7)
         z_torques = np.array(rpm ** 2) * c.KM
+        if self.DRONE_MODEL == MODEL_RACE:                          # :927-928
+            z_torques = -z_torques
         z_torque = (-z_torques[0] + z_torques[1] - z_torques[2] + z_torques[3])
-        x_torque = (forces[0] + forces[1] - forces[2] - forces[3]) * (c.L / np.sqrt(2))
-        y_torque = (-forces[0] + forces[1] + forces[2] - forces[3]) * (c.L / np.sqrt(2))
+        if self.DRONE_MODEL in (MODEL_CF2X, MODEL_RACE):            # :930-932
+            x_torque = (forces[0] + forces[1] - forces[2] - forces[3]) * (c.L / np.sqrt(2))
+            y_torque = (-forces[0] + forces[1] + forces[2] - forces[3]) * (c.L / np.sqrt(2))
+        else:                                                       # DroneModel.CF2P, :933-935
+            x_torque = (forces[1] - forces[3]) * c.L
+            y_torque = (-forces[0] + forces[2]) * c.L
         torques = np.array([x_torque, y_torque, z_torque], dtype=np.float64)
         torques = torques - np.cross(rpy_rates, np.dot(self.J, rpy_rates))
         rpy_rates_deriv = np.dot(self.J_INV, torques)

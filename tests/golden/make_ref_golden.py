@@ -23,6 +23,11 @@ The three things that are NOT the reference (each unavoidable, each documented i
    a subclass; the assignment at :418 becomes a no-op), i.e. the loop runs as written minus that line;
 3. ``BaseAviary.py:944`` reads the undefined ``self.TIMESTEP``; the subclass defines it as ``PYB_TIMESTEP``.
 
+For the ``*_act_*`` / ``*_cf2p_*`` / ``*_race_*`` cases (action types and airframes PBDroneEnv itself never selects) three more,
+all in ``make_env`` / ``_BsaAct`` below: the action type and its controller are attached after construction (PBDroneEnv drops
+the ``act`` keyword), ``_saveLastAction`` stores 3- and 1-element actions as given (``BaseAviary.py:1013`` would raise), and
+the CF2P / RACE constants are read from the reference's own URDFs and assigned to a CF2X-constructed env.
+
 The SubprocVecEnv worker's auto-reset and the Monitor accumulators are SB3 code (absent); the loop in ``run``
 restates that contract (reset on done, returned obs = reset obs, terminal obs kept aside).
 """
@@ -67,10 +72,22 @@ CASES = {
     # space (normalize_actions=False: actions are per-motor thrusts in newtons, no rescale_action)
     "ref_circle_s8_obs12_physact": ("circle", 8, "physical", 3, 60, 39, 4096, False, "default", False, False, False, False),
     "ref_reaching_s1_obs12": ("reaching", 1, "hover_band", 2, 120, 40, 4096, False, "default", False, False, False, True),
+    # BaseSingleAgentAviary._preprocessAction (the branches PBDroneEnv overrides) bound onto the same step machine:
+    # RPM / ONE_D_RPM maps, and the PID family through the reference's DSLPIDControl (with the real scipy Rotation)
+    "ref_circle_s8_act_rpm": ("circle", 8, "rpm", 3, 60, 41, 4096, False, "default", False, False, True, False, "rpm", "cf2x"),
+    "ref_reaching_s1_act_one_d_rpm": ("reaching", 1, "rpm", 2, 150, 42, 4096, False, "default", False, False, True, False, "one_d_rpm", "cf2x"),
+    "ref_circle_s8_act_pid": ("circle", 8, "pid", 3, 80, 43, 4096, False, "default", False, False, True, False, "pid", "cf2x"),
+    "ref_reaching_s1_act_pid": ("reaching", 1, "pid", 3, 200, 44, 4096, False, "default", False, False, True, False, "pid", "cf2x"),
+    "ref_circle_s8_act_vel": ("circle", 8, "vel", 3, 80, 45, 4096, False, "default", False, False, True, False, "vel", "cf2x"),
+    "ref_circle_s8_act_one_d_pid": ("circle", 8, "one_d", 3, 120, 46, 4096, False, "default", False, False, True, False, "one_d_pid", "cf2x"),
+    # the other airframes of BaseAviary._dynamics (:927-935), constants parsed from the reference's own URDFs
+    "ref_circle_s8_cf2p_rpm": ("circle", 8, "rpm", 3, 60, 47, 4096, False, "default", False, False, True, False, "rpm", "cf2p"),
+    "ref_reaching_s8_race_rpm": ("reaching", 8, "rpm", 3, 60, 48, 4096, False, "default", False, False, True, False, "rpm", "racer"),
+    "ref_circle_s8_cf2p_pid": ("circle", 8, "pid", 3, 80, 49, 4096, False, "default", False, False, True, False, "pid", "cf2p"),
 }
 
 
-def actions(mode, T, N, seed):
+def actions(mode, T, N, seed, track="circle"):
     u = np.random.default_rng(seed).uniform(-1, 1, size=(T, N, 4))
     if mode == "scripted":     # SURVEY 8c scenarios: hover band, max thrust, min thrust
         a = np.zeros((T, N, 4))
@@ -78,6 +95,14 @@ def actions(mode, T, N, seed):
         return a.astype(np.float32)
     if mode == "hover":
         return np.full((T, N, 4), 0.0922265, np.float32)
+    if mode == "rpm":          # BaseSingleAgentAviary RPM map: rpm = HOVER_RPM (1 + 0.05 a)
+        return (0.6 * u).astype(np.float32)
+    if mode in ("pid", "vel", "one_d"):   # piecewise-constant commands, held for 10 control steps
+        h = np.repeat(np.random.default_rng(seed + 1000).uniform(-1, 1, size=((T + 9) // 10, N, 4)), 10, axis=0)[:T]
+        if mode == "pid":      # destinations within ~0.5 m of the spawn point
+            base = np.array([1.0, 0.0, 1.0, 0.0]) if track == "circle" else np.array([-0.5, 0.9, 1.2, 0.0])
+            return (base + 0.5 * h).astype(np.float32)
+        return h.astype(np.float32)
     if mode == "physical":     # per-motor thrust in newtons around the hover thrust 0.06615 N (physical bounds 0.0282 .. 0.1483 N)
         return (0.06615 + 0.02 * u).astype(np.float32)
     return {"saturating": u, "hover_band": HOVER + 0.002 * u, "mixed": HOVER + 0.006 * u}[mode].astype(np.float32)
@@ -148,15 +173,41 @@ def _import_reference():
     class _FlyThru(_DynEnv):
         _computeReward = FlyThruGateAviary._computeReward
 
+    with contextlib.redirect_stdout(io.StringIO()):
+        from Sol.PyBullet.BaseSingleAgentAviary import BaseSingleAgentAviary
+        from Sol.PyBullet.DSLPIDControl import DSLPIDControl
+        from Sol.PyBullet.enums import DroneModel
+
+    class _BsaAct(_DynEnv):
+        """PBDroneEnv with BaseSingleAgentAviary's own action pre-processing (BaseSingleAgentAviary.py:153-225)."""
+        _preprocessAction = BaseSingleAgentAviary._preprocessAction
+
+        def _saveLastAction(self, action):
+            # BaseAviary.py:1013 reshapes every action to (NUM_DRONES, 4) for the GUI's benefit, which raises for the
+            # 3-element PID and 1-element ONE_D_* actions (upstream sizes it by the action space); stored as given
+            self.last_action = np.array(action)
+
+    _import_reference.extras = dict(BsaAct=_BsaAct, DSLPIDControl=DSLPIDControl, DroneModel=DroneModel)
     variants = {"default": _DynEnv, "dummy": _Dummy, "thrustenv": _Thrust, "her": _Her, "reaching": _Reaching,
                 "hover": _Hover, "flythrugate": _FlyThru}
     return variants, normalize, ActionType, Physics, Waypoints, hover_reward is not None
 
 
+def _urdf_constants(path):
+    """The attributes BaseAviary._parse_urdf_parameters (BaseAviary.py:1123-1163) reads, minus the pwm ones that
+    cf2p.urdf / racer.urdf do not have."""
+    import xml.etree.ElementTree as etxml
+    t = etxml.parse(path).getroot()
+    a = t[0].attrib
+    return dict(M=float(t[1][0][1].attrib["value"]), L=float(a["arm"]), T2W=float(a["thrust2weight"]),
+                J=np.diag([float(t[1][0][2].attrib[k]) for k in ("ixx", "iyy", "izz")]), KF=float(a["kf"]), KM=float(a["km"]),
+                MAX_SPEED_KMH=float(a["max_speed_kmh"]))
+
+
 def make_env(ref, track, S, max_steps, normalize_obs, reward="default", norm_rew=False, clip_rew=False,
-             include_distance=True, normalize_actions=True):
+             include_distance=True, normalize_actions=True, act="thrust", model="cf2x"):
     variants, normalize, ActionType, Physics, Waypoints, _ = ref
-    DynEnv = variants[reward]
+    DynEnv = variants[reward] if act == "thrust" else _import_reference.extras["BsaAct"]
     if track == "circle":      # simulation_controller.py / PBDroneSimulator.py:111-130
         tr = Waypoints.Track(Waypoints.circle(radius=1, num_points=6, height=1), circle=True)
     else:
@@ -169,6 +220,27 @@ def make_env(ref, track, S, max_steps, normalize_obs, reward="default", norm_rew
                  random_spawn=False, cylinder=True, circle=tr.is_circle, include_distance=include_distance,
                  normalize_actions=normalize_actions, collect_rollouts=False, physics=Physics.DYN,
                  pyb_freq=240, ctrl_freq=240 // S)       # PBDroneSimulator.py:154-172
+    if model != "cf2x":
+        # The reference cannot construct the other airframes itself (BaseAviary.py:99 looks for
+        # Sol/resources/safegym/<model>.urdf, and cf2p.urdf / racer.urdf lack the pwm attributes its parser reads):
+        # built as CF2X, then given the constants of ITS OWN URDF for that model, derived as BaseAviary.py:163-176 does
+        k = _urdf_constants(os.path.join(REF, "Sol/resources", model + ".urdf"))
+        env.DRONE_MODEL = _import_reference.extras["DroneModel"](model)
+        env.M, env.L, env.THRUST2WEIGHT_RATIO, env.J, env.KF, env.KM = k["M"], k["L"], k["T2W"], k["J"], k["KF"], k["KM"]
+        env.J_INV = np.linalg.inv(env.J)
+        env.MAX_SPEED_KMH = k["MAX_SPEED_KMH"]
+        env.GRAVITY = env.G * env.M
+        env.HOVER_RPM = np.sqrt(env.GRAVITY / (4 * env.KF))
+        env.MAX_RPM = np.sqrt((env.THRUST2WEIGHT_RATIO * env.GRAVITY) / (4 * env.KF))
+        env.MAX_THRUST = (4 * env.KF * env.MAX_RPM ** 2)
+    if act != "thrust":
+        # PBDroneEnv.__init__ drops the `act` keyword on its way to BaseSingleAgentAviary.__init__ (PBDroneEnv.py:98-111),
+        # so what BaseSingleAgentAviary.__init__ would have done for this action type (:67-75,:90-91) is done here
+        env.ACT_TYPE = ActionType(act)
+        if act in ("pid", "vel", "one_d_pid"):
+            with contextlib.redirect_stdout(io.StringIO()):
+                env.ctrl = _import_reference.extras["DSLPIDControl"](drone_model=_import_reference.extras["DroneModel"].CF2X)
+            env.SPEED_LIMIT = 0.03 * env.MAX_SPEED_KMH * (1000 / 3600)
     env.reset(seed=0)                                    # :173
     raw = env
     if normalize_obs:
@@ -196,11 +268,11 @@ class _ClipReward:
 
 
 def run(ref, track, S, mode, N, T, seed, max_steps, normalize_obs, reward="default", norm_rew=False, clip_rew=False,
-        include_distance=True, normalize_actions=True):
+        include_distance=True, normalize_actions=True, act="thrust", model="cf2x"):
     with contextlib.redirect_stdout(io.StringIO()):
-        envs = [make_env(ref, track, S, max_steps, normalize_obs, reward, norm_rew, clip_rew, include_distance, normalize_actions)
-                for _ in range(N)]
-        a = actions(mode, T, N, seed)
+        envs = [make_env(ref, track, S, max_steps, normalize_obs, reward, norm_rew, clip_rew, include_distance, normalize_actions,
+                         act, model) for _ in range(N)]
+        a = actions(mode, T, N, seed, track)
         obs0 = np.stack([np.asarray(e.reset()[0], np.float64) for e, _ in envs])   # VecEnv.reset()
         D = obs0.shape[1]
         out = dict(actions=a, obs0=obs0, obs=np.zeros((T, N, D)), terminal_obs=np.full((T, N, D), np.nan),
@@ -209,10 +281,14 @@ def run(ref, track, S, mode, N, T, seed, max_steps, normalize_obs, reward="defau
                    pos=np.zeros((T, N, 3)), quat=np.zeros((T, N, 4)), vel=np.zeros((T, N, 3)),
                    rpy_rates=np.zeros((T, N, 3)), ang_v=np.zeros((T, N, 3)), dist=np.zeros((T, N)),
                    rpm=np.zeros((T, N, 4)))
+        if act in ("pid", "vel", "one_d_pid"):
+            out["pid"] = np.zeros((T, N, 9))     # DSLPIDControl.integral_pos_e | integral_rpy_e | last_rpy after the step
         ep_ret, ep_len = np.zeros(N), np.zeros(N, np.int64)
         for t in range(T):
             for i, (e, raw) in enumerate(envs):
-                o, r, term, trunc, info = e.step(a[t, i])
+                o, r, term, trunc, info = e.step(a[t, i, :{"pid": 3, "one_d_rpm": 1, "one_d_pid": 1}.get(act, 4)])
+                if "pid" in out:
+                    out["pid"][t, i] = np.concatenate([raw.ctrl.integral_pos_e, raw.ctrl.integral_rpy_e, raw.ctrl.last_rpy])
                 ep_ret[i] += float(r)
                 ep_len[i] += 1
                 out["reward"][t, i] = float(r)
@@ -231,7 +307,7 @@ def run(ref, track, S, mode, N, T, seed, max_steps, normalize_obs, reward="defau
                 out["obs"][t, i] = o
     out["meta"] = np.array([track, str(S), mode, str(max_steps), "1" if normalize_obs else "0", reward,
                             "1" if norm_rew else "0", "1" if clip_rew else "0", "1" if include_distance else "0",
-                            "1" if normalize_actions else "0"])
+                            "1" if normalize_actions else "0", act, model])
     return out
 
 

@@ -21,6 +21,8 @@ What is shimmed and how faithfully:
     - ``getContactPoints`` -> ()  (DYN never calls stepSimulation, so Bullet has no contacts to report)
   Every other attribute is a no-op returning 0 (GUI, cameras, debug items, gravity, time step ...).
 * ``gymnasium`` / ``gym`` -- ``Env``, ``Wrapper``/``core.Wrapper``, ``spaces.Box`` with just the attributes used.
+* ``gymnasium.envs.registration.register`` -- no-op (the vendored upstream package registers env ids when
+  ``BaseControl._getURDFParameter`` imports it through ``pkg_resources`` to find ``assets/cf2x.urdf``).
 * ``stable_baselines3.common.running_mean_std`` -- imported by PBDroneEnv.py:21 but unused on the path.
 * ``matplotlib``, ``mpl_toolkits``, ``torchviz``, ``graphviz``, ``hiddenlayer``, ``pybullet_data`` -- inert.
 """
@@ -266,6 +268,17 @@ def install(reference_root="/root/reference"):
     for name in ("gymnasium", "gym"):
         if name not in sys.modules:
             sys.modules[name] = _gym_module(name)
+        if name + ".envs.registration" not in sys.modules:
+            # the vendored gym_pybullet_drones/__init__.py registers its env ids on import (BaseControl._getURDFParameter
+            # imports that package through pkg_resources to locate assets/cf2x.urdf): registration is a no-op here
+            g = sys.modules[name]
+            if not hasattr(g, "__path__"):
+                g.__path__ = []
+            envs, reg = types.ModuleType(name + ".envs"), types.ModuleType(name + ".envs.registration")
+            envs.__path__ = []
+            reg.register = lambda *a, **k: None
+            g.envs, envs.registration = envs, reg
+            sys.modules[name + ".envs"], sys.modules[name + ".envs.registration"] = envs, reg
     for name in ("pybullet_data", "matplotlib", "matplotlib.pyplot", "matplotlib.collections", "matplotlib.animation",
                  "mpl_toolkits", "mpl_toolkits.mplot3d", "torchviz", "graphviz", "hiddenlayer"):
         if name not in sys.modules:

@@ -29,20 +29,22 @@ class HostEmuEnv:
                  aviary_dim=(-1, -1, 0, 1, 1, 1), initial_xyzs=None, pyb_freq=240, ctrl_freq=240,
                  act_type=0, cylinder=True, circle=False, include_distance=False, normalize_actions=False,
                  physics=0, reward_id=0, normalize_reward=False, clip_reward=0.0, reward_gamma=0.99,
-                 random_spawn=False, seed=0, env_id_offset=0):
+                 random_spawn=False, seed=0, env_id_offset=0, drone_model=0):
         from drl_dronenavigation_b200 import _lib as L
         self.lib = C.CDLL(build())
         self.lib.emu_create.restype = C.c_void_p
         self.lib.emu_create.argtypes = [C.POINTER(L.dn_config)]
         self.lib.emu_action_to_rpm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
         self.lib.emu_action_to_rpm.restype = None
-        for name, n in (("emu_step", 7), ("emu_get_planes", 2), ("emu_set_planes", 2), ("emu_set_last_rpm_sum", 2), ("emu_destroy", 1)):
+        for name, n in (("emu_step", 7), ("emu_get_planes", 2), ("emu_set_planes", 2), ("emu_set_last_rpm_sum", 2), ("emu_destroy", 1),
+                        ("emu_get_pid", 2), ("emu_set_pid", 2)):
             getattr(self.lib, name).argtypes = [C.c_void_p] * n
             getattr(self.lib, name).restype = None
         targets = np.ascontiguousarray(np.array(target_points, dtype=np.float64).reshape(-1, 3))
         c = L.dn_config()
         c.abi_version, c.num_envs = L.DN_ABI_VERSION, num_envs
         c.pyb_freq, c.ctrl_freq, c.act_type = pyb_freq, ctrl_freq, act_type
+        c.drone_model = drone_model
         c.normalize_actions, c.physics, c.reward_id = int(normalize_actions), physics, reward_id
         c.include_distance, c.cylinder, c.circle, c.max_steps = int(include_distance), int(cylinder), int(circle), max_steps
         c.threshold, c.discount = threshold, discount
@@ -93,7 +95,12 @@ class HostEmuEnv:
                     ang_v=pl[4, :, :3].copy(), steps=(bits & _KSTEPS).astype(np.int32),
                     just_found=((bits & _KJF) != 0).astype(np.uint8), target_idx=(bits >> _KIDX).astype(np.int32),
                     prev_vel=pl[5, :, :3].copy(), ep_length=pl[5, :, 3].view(np.int32).copy(),
-                    prev_ang_v=pl[6, :, :3].copy(), episode_count=pl[6, :, 3].view(np.int32).copy())
+                    prev_ang_v=pl[6, :, :3].copy(), episode_count=pl[6, :, 3].view(np.int32).copy(), pid=self.get_pid())
+
+    def get_pid(self):
+        out = np.zeros((self.num_envs, 9), np.float32)
+        self.lib.emu_get_pid(self.h, self._p(out))
+        return out
 
     def set_state(self, st):
         pl = self._planes()
@@ -110,6 +117,8 @@ class HostEmuEnv:
         if "ep_length" in st:
             pl[5, :, 3] = np.asarray(st["ep_length"], np.int32).view(np.float32)
         self.lib.emu_set_planes(self.h, self._p(np.ascontiguousarray(pl)))
+        if "pid" in st:
+            self.lib.emu_set_pid(self.h, self._p(np.ascontiguousarray(st["pid"], dtype=np.float32)))
         if self.uses_drag and "last_rpm_sum" in st:
             self.lib.emu_set_last_rpm_sum(self.h, self._p(np.ascontiguousarray(st["last_rpm_sum"], dtype=np.float32)))
 

@@ -13,7 +13,7 @@ struct Emu {
     std::vector<float4> planes[dn::kPlanes];
     std::vector<float4> targets, segs;
     std::vector<float> last_rpm_sum, obs_rms;
-    std::vector<float4> aux, rew_rms, spawn;
+    std::vector<float4> aux, rew_rms, spawn, pid[3];
     int normalize_obs;
     float d0;
 };
@@ -43,6 +43,7 @@ extern "C" {
 Emu* emu_create(const dn_config* cfg) {
     dn::RewardParams rw;
     if (!dn::host::reward_table(cfg->reward_id, cfg->discount, rw)) return nullptr;
+    if (!dn::host::airframe(cfg->drone_model)) return nullptr;
     Emu* e = new Emu();
     memset(&e->P, 0, sizeof(e->P));
     dn::host::fill_params(*cfg, rw, e->P, e->targets, e->segs, e->d0);
@@ -56,6 +57,9 @@ Emu* emu_create(const dn_config* cfg) {
     }
     if (cfg->spawn_mode != DN_SPAWN_FIXED) {
         e->spawn.assign(N, make_float4(e->P.init_pos[0], e->P.init_pos[1], e->P.init_pos[2], 0.f)); e->P.spawn = e->spawn.data();
+    }
+    if (cfg->act_type >= DN_ACT_PID) {
+        for (int k = 0; k < 3; ++k) { e->pid[k].assign(N, float4{0, 0, 0, 0}); e->P.pid[k] = e->pid[k].data(); }
     }
     if (cfg->normalize_reward) { e->rew_rms.assign(N, make_float4(0.f, 0.f, 1.f, 1e-4f)); e->P.rew_rms = e->rew_rms.data(); }
     for (int i = 0; i < N; ++i) {
@@ -89,6 +93,17 @@ void emu_get_planes(Emu* e, float* out) {
 }
 void emu_set_planes(Emu* e, const float* in) {
     for (int k = 0; k < dn::kPlanes; ++k) memcpy(e->planes[k].data(), in + (size_t)k * e->P.n * 4, (size_t)e->P.n * 16);
+}
+void emu_get_pid(Emu* e, float* out) {     // [N,9]
+    if (!e->P.pid[0]) return;
+    for (int i = 0; i < e->P.n; ++i) for (int k = 0; k < 3; ++k) {
+        const float4 v = e->pid[k][i]; out[9 * i + 3 * k] = v.x; out[9 * i + 3 * k + 1] = v.y; out[9 * i + 3 * k + 2] = v.z;
+    }
+}
+void emu_set_pid(Emu* e, const float* in) {
+    if (!e->P.pid[0]) return;
+    for (int i = 0; i < e->P.n; ++i) for (int k = 0; k < 3; ++k)
+        e->pid[k][i] = make_float4(in[9 * i + 3 * k], in[9 * i + 3 * k + 1], in[9 * i + 3 * k + 2], 0.f);
 }
 void emu_set_last_rpm_sum(Emu* e, const float* in) { if (e->P.last_rpm_sum) memcpy(e->P.last_rpm_sum, in, (size_t)e->P.n * 4); }
 

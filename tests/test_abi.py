@@ -33,9 +33,9 @@ def test_struct_layouts_match_header(built_lib):
     from drl_dronenavigation_b200 import _lib
     # sizes implied by include/dronenav.h on LP64
     assert C.sizeof(_lib.dn_step_io) == 8 * 8
-    assert C.sizeof(_lib.dn_state_view) == 20 * 8
+    assert C.sizeof(_lib.dn_state_view) == 21 * 8
     assert C.sizeof(_lib.dn_stats) == 7 * 8
-    assert C.sizeof(_lib.dn_config) == 4 + 4 + 8 + 8 + 12 * 4 + 2 * 8 + 12 * 8 + 4 + 4 + 2 * 8 + 8
+    assert C.sizeof(_lib.dn_config) == 4 + 4 + 8 + 8 + 12 * 4 + 2 * 8 + 12 * 8 + 4 + 4 + 2 * 8 + 8 + 4 + 4
 
 
 def test_bad_config_is_rejected_without_a_gpu(built_lib):
@@ -77,10 +77,19 @@ def test_config_validation_messages(built_lib):
     h = C.c_void_p()
     for kw, msg in ((dict(num_envs=0), b"num_envs"), (dict(num_targets=0), b"targets"), (dict(act_type=7), b"act_type"),
                     (dict(physics=64), b"physics"), (dict(spawn_mode=9), b"spawn_mode"), (dict(reward_id=99), b"reward_id"),
-                    (dict(max_steps=1 << 21), b"max_steps"), (dict(spawn_mode=1, num_targets=1), b"random spawn")):
+                    (dict(max_steps=1 << 21), b"max_steps"), (dict(spawn_mode=1, num_targets=1), b"random spawn"),
+                    (dict(drone_model=3), b"drone_model"),
+                    # only cf2x.urdf has the pwm attributes of the THRUST map; the reference builds a controller for CF2X / CF2P only
+                    (dict(drone_model=_lib.DN_MODEL_CF2P, act_type=_lib.DN_ACT_THRUST), b"pwm2rpm"),
+                    (dict(drone_model=_lib.DN_MODEL_RACE, act_type=_lib.DN_ACT_PID), b"no controller")):
         assert built_lib.dn_create(C.byref(cfg(**kw)), 0, C.byref(h)) == -1, kw
         assert msg in built_lib.dn_last_error(), (kw, built_lib.dn_last_error())
     # a valid configuration passes validation and then fails on the missing device (no CPU fallback) -- or succeeds on a GPU box
+    for ok in (dict(), dict(drone_model=_lib.DN_MODEL_RACE, act_type=_lib.DN_ACT_RPM), dict(drone_model=_lib.DN_MODEL_CF2P, act_type=_lib.DN_ACT_VEL)):
+        rc = built_lib.dn_create(C.byref(cfg(**ok)), 0, C.byref(h))
+        assert rc in (0, -2), (ok, built_lib.dn_last_error())
+        if rc == 0:
+            built_lib.dn_destroy(h)
     rc = built_lib.dn_create(C.byref(cfg()), 0, C.byref(h))
     assert rc in (0, -2)
     if rc == 0:
