@@ -60,6 +60,7 @@ class HostEmuEnv:
         assert self.h
         self.num_envs, self.obs_dim = num_envs, 13 if include_distance else 12
         self.uses_drag = bool(physics & 1)
+        self._optional = {"pid": act_type >= 3}
         N, D = num_envs, self.obs_dim
         self.obs = np.zeros((N, D), np.float32)
         self.reward = np.zeros(N, np.float32)

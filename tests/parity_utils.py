@@ -39,6 +39,9 @@ def upload_oracle_state(gpu_env, workers):
     st = oracle_state_arrays([w.env for w in workers])
     st["ep_return"] = np.array([w.ep_return for w in workers], np.float32)
     st["ep_length"] = np.array([w.ep_len for w in workers], np.int32)
+    if getattr(gpu_env, "_optional", {}).get("pid"):   # DSLPIDControl state (PID action types)
+        st["pid"] = np.stack([np.concatenate([w.env.ctrl.integral_pos_e, w.env.ctrl.integral_rpy_e, w.env.ctrl.last_rpy])
+                              for w in workers]).astype(np.float32)
     if gpu_env.uses_drag:
         st["last_rpm_sum"] = np.array([float(np.sum(w.env.last_clipped_action)) for w in workers], np.float32)
     gpu_env.set_state(st)
@@ -148,3 +151,42 @@ def run_lockstep(gpu_env, workers, actions, resync_every, report=None, check_sta
                 np.testing.assert_array_equal(st["just_found"], ref["just_found"])
             upload_oracle_state(gpu_env, workers)
     return rep
+
+
+# (model, action type, track, S, control steps, re-synchronisation period)
+CONTROLLER_CASES = [
+    ("cf2p", "rpm", "circle", 8, 90, 30), ("racer", "rpm", "reaching", 8, 90, 30), ("racer", "one_d_rpm", "circle", 1, 240, 240),
+    ("cf2x", "one_d_pid", "circle", 8, 120, 30), ("cf2x", "vel", "circle", 8, 90, 1), ("cf2p", "pid", "reaching", 1, 240, 1),
+]
+
+
+def controller_lockstep_case(make_env, N, model, act, track, S, T, resync, get_pid):
+    """Airframes other than CF2X and BaseSingleAgentAviary's action types, FP32 implementation against the oracle in
+    lock-step.  PID and VEL close a loop whose roll axis is a POSITIVE feedback under the reference's DYN torque signs
+    (BaseAviary.py:931 vs the DSLPIDControl mixer, DSLPIDControl.py:47-53), so those two are
+    re-synchronised every step -- one-step errors are what is compared; the vertical ONE_D_PID loop is stable and runs
+    whole horizons.  The oracle's RPM map runs with the float32 semantics of the reference's pinned numpy 1.26."""
+    from oracle.dyn_oracle import OracleWorker, circle_track, make_reference_env, reaching_track
+    targets, init, dim = circle_track() if track == "circle" else reaching_track()
+    env = make_env(N, targets, init, dim)
+    workers = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S, act=act, drone_model=model,
+                                               normalize_actions=False), normalize_obs=False) for _ in range(N)]
+    obs = _np(env.reset())
+    for i, w in enumerate(workers):
+        o, _ = w.reset()
+        if obs.any():      # (the host emulator has no reset kernel and returns zeros)
+            np.testing.assert_allclose(obs[i], o, atol=1e-6)
+    rng = np.random.default_rng(1234 + S + len(act))
+    if act in ("rpm", "one_d_rpm"):
+        a = rng.uniform(-1, 1, size=(T, N, 4))
+    else:
+        a = np.repeat(rng.uniform(-1, 1, size=((T + 9) // 10, N, 4)), 10, axis=0)[:T]
+        if act == "pid":
+            a = np.concatenate([init[0] + 0.5 * a[..., :3], a[..., 3:]], axis=-1)
+    rep = run_lockstep(env, workers, a.astype(np.float32), resync_every=resync)
+    print(f"\n[{model} {act} {track} S={S}] {rep}")
+    assert rep.near_ties <= 2 and rep.env_steps == T * N
+    if act in ("pid", "vel", "one_d_pid"):
+        want = np.stack([np.concatenate([w.env.ctrl.integral_pos_e, w.env.ctrl.integral_rpy_e, w.env.ctrl.last_rpy]) for w in workers])
+        np.testing.assert_allclose(get_pid(env), want, atol=1e-5)
+    return env, workers

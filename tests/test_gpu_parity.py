@@ -177,15 +177,21 @@ def test_single_step_random_states_all_branches():
 
 @pytest.mark.parametrize("kw", [{}, {"normalize_obs": True, "normalize_reward": True, "clip_reward": 10.0},
                                 {"reward_id": 4, "random_spawn": "midpoint", "seed": 77}, {"reward_id": 5, "random_spawn": "line", "seed": 78},
-                                {"reward_id": 3, "physics": "PYB_GND_DRAG_DW"}],
-                         ids=["default", "wrappers", "reaching_midpoint", "progress_line", "her_drag_gnd"])
+                                {"reward_id": 3, "physics": "PYB_GND_DRAG_DW"},
+                                {"act": "VEL"}, {"act": "PID", "drone_model": "CF2P", "physics": "PYB_GND"}, {"act": "RPM", "drone_model": "RACE"}],
+                         ids=["default", "wrappers", "reaching_midpoint", "progress_line", "her_drag_gnd", "vel", "cf2p_pid_gnd", "race_rpm"])
 def test_step_many_matches_repeated_step(kw):
     """dn_step_many (T steps, state in registers) is bit-identical to T dn_step launches -- also with the fused
     wrappers, the optional planes (aux / spawn / reward statistics) and the physics add-ons in play."""
     from drl_dronenavigation_b200 import Physics
+    from drl_dronenavigation_b200.enums import ActionType, DroneModel
     kw = dict(kw)
     if "physics" in kw:
         kw["physics"] = getattr(Physics, kw["physics"])
+    if "act" in kw:
+        kw["act"] = getattr(ActionType, kw["act"])
+    if "drone_model" in kw:
+        kw["drone_model"] = getattr(DroneModel, kw["drone_model"])
     norm = kw.pop("normalize_obs", False)
     track = "reaching" if "random_spawn" in kw else "circle"
     envA, _ = _make(track, 1000, 8, normalize_obs=norm, **kw)
@@ -550,4 +556,24 @@ def test_gymnasium_facade_against_oracle_env():
             np.testing.assert_allclose(obs, o_ref, atol=1e-5)
             assert np.all(env._getDroneStateVector(0)[16:20] == 0)
     assert episodes >= 1
+    env.close()
+
+
+
+@pytest.mark.parametrize("model,act,track,S,T,resync", PU.CONTROLLER_CASES)
+def test_airframes_and_controller_action_types_lockstep(model, act, track, S, T, resync):
+    """DroneModel.CF2P / RACE (BaseAviary.py:927-935) and BaseSingleAgentAviary's action types incl. the fused
+    DSLPIDControl: the CUDA path against the oracle in lock-step over 24 envs (see parity_utils.controller_lockstep_case)."""
+    from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
+    from drl_dronenavigation_b200.enums import ActionType, DroneModel
+
+    def make(N, targets, init, dim):
+        return BatchedDroneEnv(N, targets, threshold=0.3, discount=0.999, max_steps=4096, aviary_dim=dim, initial_xyzs=init,
+                               pyb_freq=240, ctrl_freq=240 // S, cylinder=True, circle=(track == "circle"), include_distance=True,
+                               act=ActionType(act), drone_model=DroneModel(model))
+    env, workers = PU.controller_lockstep_case(make, 24, model, act, track, S, T, resync,
+                                               get_pid=lambda e: e.get_state()["pid"].cpu().numpy())
+    if act in ("pid", "vel", "one_d_pid"):
+        with pytest.raises(Exception, match="not elementwise"):
+            env.action_to_rpm(torch.zeros(4, device=env.device))
     env.close()

@@ -186,3 +186,17 @@ def test_device_logic_midpoint_spawn_captures_on_a_tight_track():
     rolls = {int(np.argmin(np.linalg.norm(targets - w.env._target_points[0], axis=1))) for w in workers}
     assert len(rolls) >= 3                                        # several different rolled orders were in play
     env.close()
+
+
+
+@pytest.mark.parametrize("model,act,track,S,T,resync", PU.CONTROLLER_CASES)
+def test_device_logic_airframes_and_controller_action_types(model, act, track, S, T, resync):
+    """CF2P / RACE torque mixes and the fused DSLPIDControl of csrc/dn_device.cuh (host build) against the oracle."""
+    from tests.host_emu import HostEmuEnv
+    from tests.test_ref_golden import ACT_IDS, MODEL_IDS
+
+    def make(N, targets, init, dim):
+        return HostEmuEnv(N, targets, aviary_dim=dim, initial_xyzs=init, pyb_freq=240, ctrl_freq=240 // S,
+                          circle=(track == "circle"), include_distance=True, act_type=ACT_IDS[act], drone_model=MODEL_IDS[model])
+    env, _ = PU.controller_lockstep_case(make, 6, model, act, track, S, T, resync, get_pid=lambda e: e.get_pid())
+    env.close()
