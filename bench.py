@@ -18,6 +18,8 @@ Printed JSON line (rank 0): see the task contract.  Extra keys:
   e2e              the same metric through the C-ABI host-buffer call (dn_step_host): pinned host
                    actions -> H2D -> kernel -> D2H obs/reward/done/found every step
   cpu_baseline     the CPU oracle (numpy port of the reference step) on the host cores, bounded sample
+  cpu_baseline_batched  best-case CPU: the same algorithm as array operations over all envs at once
+                   (oracle/batched_oracle.py), one process per host core -- not how the reference runs
 `--impl reference` times that CPU path as its own arm (the reference is pure Python; pybullet / SB3 are
 not installable here).
 """
@@ -138,6 +140,33 @@ def cpu_baseline(track, S, budget_s=12.0):
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"numpy oracle (FP64 port of PBDroneEnv.step + BaseAviary._dynamics), {cores} processes x 4 envs x {steps} "
                       f"control steps, S={S}, {track} track, saturating actions, {dt:.1f} s"}
+
+
+def _cpu_batched_worker(args):
+    track, S, n_envs, n_steps, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle.batched_oracle import BatchedOracle
+    B = BatchedOracle(n_envs, track, pyb_freq=240, ctrl_freq=240 // S)
+    acts = np.random.default_rng(seed).uniform(-1, 1, size=(n_steps + 1, n_envs, 4)).astype(np.float32)
+    B.step(acts[0])
+    t0 = time.perf_counter()
+    for t in range(n_steps):
+        B.step(acts[t + 1])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_batched(track, S, envs, budget_s=10.0):
+    """Best-case CPU figure: the batched numpy oracle, one replica of the workload's batch per host core
+    (splitting the batch over the cores instead leaves each process dominated by the interpreter: 3.6e5 vs 1e6 here)."""
+    cores = os.cpu_count() or 1
+    per = max(1, envs)
+    with mp.get_context("fork").Pool(cores) as pool:
+        t1 = max(pool.map(_cpu_batched_worker, [(track, S, per, 2, 50 + p) for p in range(cores)])) / 2      # calibration
+        steps = int(max(3, min(200, budget_s / max(t1, 1e-6))))
+        times = pool.map(_cpu_batched_worker, [(track, S, per, steps, 100 + p) for p in range(cores)])
+    return {"value": cores * per * steps / max(times), "unit": UNIT, "cores": cores, "kind": "port (batched numpy)",
+            "sample": f"oracle/batched_oracle.py, {cores} processes x {per} envs x {steps} control steps, S={S}, {track} track, "
+                      f"saturating actions, {max(times):.1f} s; the reference itself steps one Python env per worker process"}
 
 
 def run_reference(args):
@@ -741,6 +770,10 @@ def run_b200(args):
 
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.track, args.substeps, budget_s=args.cpu_budget)
+        try:
+            line["cpu_baseline_batched"] = cpu_baseline_batched(args.track, args.substeps, args.envs)
+        except Exception as ex:  # noqa: BLE001
+            line["cpu_baseline_batched"] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
     elif world > 1:
         line["cpu_baseline"] = None
     env.close()

@@ -190,3 +190,56 @@ def controller_lockstep_case(make_env, N, model, act, track, S, T, resync, get_p
         want = np.stack([np.concatenate([w.env.ctrl.integral_pos_e, w.env.ctrl.integral_rpy_e, w.env.ctrl.last_rpy]) for w in workers])
         np.testing.assert_allclose(get_pid(env), want, atol=1e-5)
     return env, workers
+
+
+def run_lockstep_batched(env, B, actions, resync_every, obs_tol=OBS_TOL, rew_tol=REW_TOL):
+    """FULL-SIZE lock-step: the FP32 implementation `env` (CUDA BatchedDroneEnv, or the host emulator) against the batched
+    FP64 oracle `B` (oracle/batched_oracle.py) on `actions` [T, N, 4], every environment compared at every step.  Same
+    rules as run_lockstep: continuous quantities within the stated horizon tolerances, the oracle state uploaded again every
+    `resync_every` control steps (one stated horizon), discrete outputs exact unless the oracle's own margin to the
+    threshold involved is below MARGIN_TOL (near-tie: counted, environment re-synchronised)."""
+    rep = ParityReport()
+    T, N = actions.shape[:2]
+    on_gpu = hasattr(env, "device")
+    if on_gpu:
+        import torch
+        a_dev = torch.from_numpy(actions).to(env.device)
+    for t in range(T):
+        o, r, d, f = [_np(x).copy() for x in env.step(a_dev[t] if on_gpu else actions[t])]
+        term = _np(env.terminal_obs).copy()
+        oo, rr, bits, found, tt, ep_r, ep_l = B.step(actions[t])
+        rep.env_steps += N
+        tie = B.margin < MARGIN_TOL
+        bad = (d != bits) | (f != found)
+        assert not (bad & ~tie).any(), (f"discrete mismatch at t={t}, envs {np.nonzero(bad & ~tie)[0][:8]}: "
+                                        f"done {d[bad & ~tie][:8]} vs {bits[bad & ~tie][:8]}, margins {B.margin[bad & ~tie][:8]}")
+        rep.near_ties += int(bad.sum())
+        ok = ~bad
+        rew_err = np.abs(r.astype(np.float64) - np.float32(rr).astype(np.float64))
+        soft = tie | (B.rew_margin < MARGIN_TOL)            # a reward-only threshold (orientation, smoothness) near its tie
+        assert (rew_err[ok & ~soft] <= rew_tol).all(), f"reward mismatch at t={t}: {rew_err[ok & ~soft].max():.3e}"
+        rep.near_ties += int((ok & soft & (rew_err > rew_tol)).sum())
+        rep.max_rew = max(rep.max_rew, float(rew_err[ok & ~soft].max(initial=0.0)))
+        done = bits != 0
+        for got, want, sel in ((np.where(done[:, None], term, o), tt, ok), (o, oo, ok & done)):     # step obs; reset obs where done
+            e = np.abs(got.astype(np.float64) - want.astype(np.float64))
+            e[:, 3:6] = np.minimum(e[:, 3:6], np.abs(2.0 - e[:, 3:6]))
+            e[:, 9:12] = np.maximum(e[:, 9:12] - ANGV_ABS_TOL / np.maximum(B.last_ang_v_norm, 1e-30)[:, None], 0.0)
+            if sel.any():
+                m = float(e[sel].max())
+                rep.max_obs = max(rep.max_obs, m)
+                assert m <= obs_tol, f"obs drift {m:.3e} at t={t} env {int(np.argmax(e.max(axis=1) * sel))}"
+        rep.dones += int(done.sum())
+        if (t + 1) % resync_every == 0 or bad.any() or t == T - 1:
+            st = {k: _np(v) for k, v in env.get_state().items()}
+            ref = B.state()
+            sel = ok
+            rep.max_pos = max(rep.max_pos, float(np.abs(st["pos"] - ref["pos"])[sel].max()))
+            rep.max_vel = max(rep.max_vel, float(np.abs(st["vel"] - ref["vel"])[sel].max()))
+            qd = np.minimum(np.abs(st["quat"] - ref["quat"]).max(axis=1), np.abs(st["quat"] + ref["quat"]).max(axis=1))
+            rep.max_quat = max(rep.max_quat, float(qd[sel].max()))
+            assert rep.max_pos <= POS_TOL and rep.max_vel <= VEL_TOL and rep.max_quat <= QUAT_TOL, str(rep)
+            for k in ("target_idx", "steps", "just_found"):
+                np.testing.assert_array_equal(np.asarray(st[k])[sel], np.asarray(ref[k])[sel])
+            env.set_state({k: v for k, v in ref.items() if k not in ("ep_return", "ep_length") or on_gpu})
+    return rep

@@ -577,3 +577,30 @@ def test_airframes_and_controller_action_types_lockstep(model, act, track, S, T,
         with pytest.raises(Exception, match="not elementwise"):
             env.action_to_rpm(torch.zeros(4, device=env.device))
     env.close()
+
+
+@pytest.mark.parametrize("track,S,mode,N,T,kw", [
+    ("circle", 8, "saturating", 4096, 240, {}),          # BASELINE config 2 at its full size, 8 s of flight per environment
+    ("circle", 8, "hover_band", 4096, 120, {}),
+    ("reaching", 8, "mixed", 65536, 45, {}),             # BASELINE config 3's per-GPU shard (segment tube)
+    ("circle", 1, "saturating", 4096, 480, {"reward_id": "dummy"}),
+    ("reaching", 8, "saturating", 16384, 60, {"reward_id": "thrustenv"}),
+], ids=["config2_saturating", "config2_hover_band", "config3_65536", "circle_s1_dummy", "reaching_thrustenv"])
+def test_full_size_lockstep_against_batched_oracle(track, S, mode, N, T, kw):
+    """EVERY environment of the BASELINE shapes compared with the FP64 oracle at EVERY step (oracle/batched_oracle.py,
+    itself checked against the per-environment oracle and the reference fixtures in tests/test_batched_oracle.py)."""
+    from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
+    from oracle.batched_oracle import BatchedOracle
+    from oracle.dyn_oracle import circle_track, reaching_track
+    rid = {"default": 0, "dummy": 1, "thrustenv": 2}[kw.get("reward_id", "default")]
+    targets, init, dim = circle_track() if track == "circle" else reaching_track()
+    env = BatchedDroneEnv(N, targets, threshold=0.3, discount=0.999, max_steps=4096, aviary_dim=dim, initial_xyzs=init,
+                          pyb_freq=240, ctrl_freq=240 // S, cylinder=True, circle=(track == "circle"), include_distance=True,
+                          normalize_actions=True, reward_id=rid)
+    B = BatchedOracle(N, track, pyb_freq=240, ctrl_freq=240 // S, **kw)
+    np.testing.assert_allclose(env.reset().cpu().numpy(), B.reset_obs(), atol=1e-6)
+    rep = PU.run_lockstep_batched(env, B, _actions(mode, T, N, seed=N % 97 + S), resync_every=240 // S)
+    print(f"\n[full size {track} S={S} {mode} N={N} T={T}] {rep}")
+    assert rep.env_steps == N * T and rep.near_ties <= max(2, rep.env_steps // 20000), str(rep)
+    assert rep.dones > 0 or mode == "hover_band"
+    env.close()

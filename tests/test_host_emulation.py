@@ -200,3 +200,21 @@ def test_device_logic_airframes_and_controller_action_types(model, act, track, S
                           circle=(track == "circle"), include_distance=True, act_type=ACT_IDS[act], drone_model=MODEL_IDS[model])
     env, _ = PU.controller_lockstep_case(make, 6, model, act, track, S, T, resync, get_pid=lambda e: e.get_pid())
     env.close()
+
+
+
+@pytest.mark.parametrize("track,S,mode,N,T", [("circle", 8, "saturating", 512, 90), ("reaching", 8, "mixed", 512, 60), ("circle", 1, "saturating", 256, 240)])
+def test_device_logic_lockstep_against_batched_oracle(track, S, mode, N, T):
+    """Hundreds of environments per step against oracle/batched_oracle.py (the -m gpu suite runs the same helper at the
+    BASELINE sizes: 4096 and 65 536 environments)."""
+    from oracle.batched_oracle import BatchedOracle
+    from oracle.dyn_oracle import circle_track, reaching_track
+    from tests.host_emu import HostEmuEnv
+    targets, init, dim = circle_track() if track == "circle" else reaching_track()
+    env = HostEmuEnv(N, targets, aviary_dim=dim, initial_xyzs=init, pyb_freq=240, ctrl_freq=240 // S, circle=(track == "circle"),
+                     include_distance=True, normalize_actions=True)
+    B = BatchedOracle(N, track, pyb_freq=240, ctrl_freq=240 // S)
+    rep = PU.run_lockstep_batched(env, B, _actions(mode, T, N, seed=5 + S), resync_every=240 // S)
+    print(f"\n[emu batched {track} S={S} {mode} N={N}] {rep}")
+    assert rep.near_ties <= max(2, rep.env_steps // 5000) and rep.dones > 0
+    env.close()
