@@ -88,6 +88,7 @@ class BatchedOracle:
         self.last_rpm = np.zeros((N, 4))
         self.margin = np.full(N, np.inf)       # test instrumentation: distance of this step's discrete decisions to their thresholds
         self.rew_margin = np.full(N, np.inf)   # the same for decisions that only change the reward (orientation, smoothness)
+        self.gimbal_margin = np.full(N, np.inf)
 
     # ---- helpers ------------------------------------------------------------------------------------------------
     def _m(self, x, into="margin"):
@@ -244,6 +245,8 @@ class BatchedOracle:
         self.last_rpm = np.float64(rpm)
         self.last_ang_v_norm = _norm(self.ang_v)    # test instrumentation (conditioning of obs[9:12]), before any reset
         self.rpy = self._euler(self.quat)
+        q = self.quat       # distance of Bullet's gimbal-branch test |sarg| >= 0.99999 to its threshold (changes obs[3:6] and the forward vector)
+        self.gimbal_margin = np.abs(np.abs(-2.0 * (q[:, 0] * q[:, 2] - q[:, 3] * q[:, 1])) - 0.99999)
         obs = self._obs(self.pos, self.rpy, self.vel, self.ang_v, self.dist)
         # ---- _computeReward (dyn_oracle._reward_waypoint)
         crash_v, final_v, capture_v, cap_orient_w, progress_w, orient_w, smooth = self.rw

@@ -18,6 +18,13 @@ POS_TOL, VEL_TOL, QUAT_TOL, OBS_TOL, REW_TOL = 1e-4, 1e-3, 1e-4, 1e-4, 1e-3
 # three entries are compared as  |d| <= OBS_TOL + ANGV_ABS_TOL / |ang_v_oracle|, i.e. an absolute
 # angular-velocity tolerance of 1e-4 rad/s over the horizon (rates reach ~50 rad/s: 6e-8 * 50 * sqrt(240))
 ANGV_ABS_TOL = 1e-4
+# Roll and yaw (obs[3], obs[5]) are ill-conditioned near gimbal lock: d(roll, yaw) ~ d(quat) / cos(pitch).  Among 65 536 tumbling
+# environments some always sit within a degree of |pitch| = 90 deg (cos ~ 5e-3), so in the full-size tests those two entries
+# are compared as  |d| <= OBS_TOL + EULER_COND_TOL / cos(pitch_oracle)  (in units of pi; the quaternion itself has its own bound)
+EULER_COND_TOL = 5e-6
+# FP32 orientation error grows with the rotation traversed (relative error ~2e-6 of the angle): an environment tumbling at
+# 200 rad/s turns 30 revolutions within one horizon.  Beyond EULER_RATE_REF the Euler-angle tolerance scales with |omega|.
+EULER_RATE_REF = 60.0
 MARGIN_TOL = 2e-5          # oracle margin below which an FP32/FP64 discrete disagreement is a near-tie
 HORIZON_SUBSTEPS = 240
 
@@ -216,7 +223,9 @@ def run_lockstep_batched(env, B, actions, resync_every, obs_tol=OBS_TOL, rew_tol
         rep.near_ties += int(bad.sum())
         ok = ~bad
         rew_err = np.abs(r.astype(np.float64) - np.float32(rr).astype(np.float64))
-        soft = tie | (B.rew_margin < MARGIN_TOL)            # a reward-only threshold (orientation, smoothness) near its tie
+        gimbal = B.gimbal_margin < MARGIN_TOL               # Bullet's |sarg| >= 0.99999 Euler branch near its tie: obs[3:6] and the
+        rep.near_ties += int(gimbal.sum())                  # forward vector of the orientation reward jump, the state does not
+        soft = tie | gimbal | (B.rew_margin < MARGIN_TOL)   # a reward-only threshold (orientation, smoothness) near its tie
         assert (rew_err[ok & ~soft] <= rew_tol).all(), f"reward mismatch at t={t}: {rew_err[ok & ~soft].max():.3e}"
         rep.near_ties += int((ok & soft & (rew_err > rew_tol)).sum())
         rep.max_rew = max(rep.max_rew, float(rew_err[ok & ~soft].max(initial=0.0)))
@@ -225,6 +234,10 @@ def run_lockstep_batched(env, B, actions, resync_every, obs_tol=OBS_TOL, rew_tol
             e = np.abs(got.astype(np.float64) - want.astype(np.float64))
             e[:, 3:6] = np.minimum(e[:, 3:6], np.abs(2.0 - e[:, 3:6]))
             e[:, 9:12] = np.maximum(e[:, 9:12] - ANGV_ABS_TOL / np.maximum(B.last_ang_v_norm, 1e-30)[:, None], 0.0)
+            cond = EULER_COND_TOL / np.maximum(np.cos(np.pi * want[:, 4].astype(np.float64)), 1e-5)
+            e[:, 3], e[:, 5] = np.maximum(e[:, 3] - cond, 0.0), np.maximum(e[:, 5] - cond, 0.0)
+            e[gimbal, 3:6] = 0.0
+            e[:, 3:6] /= np.maximum(1.0, B.last_ang_v_norm / EULER_RATE_REF)[:, None]
             if sel.any():
                 m = float(e[sel].max())
                 rep.max_obs = max(rep.max_obs, m)
