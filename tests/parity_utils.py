@@ -214,7 +214,9 @@ def run_lockstep_batched(env, B, actions, resync_every, obs_tol=OBS_TOL, rew_tol
     for t in range(T):
         o, r, d, f = [_np(x).copy() for x in env.step(a_dev[t] if on_gpu else actions[t])]
         term = _np(env.terminal_obs).copy()
+        prev_idx = B.idx.copy()
         oo, rr, bits, found, tt, ep_r, ep_l = B.step(actions[t])
+        rep.captures += int((found > prev_idx).sum())
         rep.env_steps += N
         tie = B.margin < MARGIN_TOL
         bad = (d != bits) | (f != found)
