@@ -234,7 +234,7 @@ def baseline_configs(args, dev, K):
         (4, "16384 envs, 240/30 Hz, circle, drag + ground effect", 16384, 8, "circle", dict(physics=Physics.PYB_GND_DRAG_DW)),
     ] + [(5, f"131072 envs per GPU (1 Mi / 8), 240/30 Hz, circle, reward_id={rid}", 131072, 8, "circle", dict(reward_id=rid))
          for rid in (L.DN_REWARD_DEFAULT, L.DN_REWARD_DUMMY, L.DN_REWARD_THRUSTENV, L.DN_REWARD_HER, L.DN_REWARD_REACHING, L.DN_REWARD_PROGRESS,
-                     L.DN_REWARD_HOVER, L.DN_REWARD_FLYTHRUGATE)]
+                     L.DN_REWARD_HOVER, L.DN_REWARD_FLYTHRUGATE, L.DN_REWARD_BOOTSTRAPPED, L.DN_REWARD_CHAMP)]
     out = []
     for cid, name, n, S, track, kw in specs:
         try:

@@ -20,6 +20,7 @@ DN_MODEL_CF2X, DN_MODEL_CF2P, DN_MODEL_RACE = 0, 1, 2
 DN_PHYS_DYN, DN_PHYS_DRAG, DN_PHYS_GROUND_EFFECT, DN_PHYS_GROUND_CONTACT = 0, 1, 2, 4
 DN_REWARD_DEFAULT, DN_REWARD_DUMMY, DN_REWARD_THRUSTENV, DN_REWARD_HER = 0, 1, 2, 3
 DN_REWARD_REACHING, DN_REWARD_PROGRESS, DN_REWARD_HOVER, DN_REWARD_FLYTHRUGATE = 4, 5, 6, 7
+DN_REWARD_BOOTSTRAPPED, DN_REWARD_CHAMP = 8, 9
 DN_SPAWN_FIXED, DN_SPAWN_LINE, DN_SPAWN_MIDPOINT = 0, 1, 2
 DN_DONE_TERMINATED, DN_DONE_TRUNCATED = 1, 2
 

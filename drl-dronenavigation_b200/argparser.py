@@ -55,7 +55,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--pyb_freq", type=int, default=240)
     p.add_argument("--ctrl_freq", type=int, default=240)
     p.add_argument("--reward_id", type=int, default=0, help="DN_REWARD_* (include/dronenav.h): 0 PBDroneEnv, 1 dummy_env, "
-                   "2 ThrustEnv, 3 HER, 4 reaching-progress, 6 hover, 7 fly-thru-gate")
+                   "2 ThrustEnv, 3 HER, 4 reaching-progress (2310.10943), 5 projection progress (2103.08624), 6 hover, 7 fly-thru-gate, "
+                   "8 bootstrapped vision racing (2403.12203), 9 champion-level racing (Nature 2023)")
     p.add_argument("--track", type=str, default="circle", help="circle (the reference's main) or another Waypoints track function, e.g. reaching")
     p.add_argument("--model_path", type=str, default=None, help="SB3-format archive for --run_type cont / saved")
     p.add_argument("--max_seconds", type=float, default=None, help="wall-clock cap of run_full_training")

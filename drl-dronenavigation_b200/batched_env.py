@@ -113,7 +113,7 @@ class BatchedDroneEnv:
         self.normalize_reward = bool(normalize_reward)
         self.reward_id = int(reward_id)
         self._optional = {"last_rpm_sum": self.uses_drag, "obs_rms": self.normalize_obs,
-                          "aux": self.reward_id == L.DN_REWARD_REACHING, "rew_rms": self.normalize_reward,
+                          "aux": self.reward_id in (L.DN_REWARD_REACHING, L.DN_REWARD_BOOTSTRAPPED, L.DN_REWARD_CHAMP), "rew_rms": self.normalize_reward,
                           "spawn": bool(random_spawn), "pid": c.act_type >= L.DN_ACT_PID}
         self.drone_model, self.act_type = drone_model, act
         N, D, dev = self.num_envs, self.obs_dim, self.device

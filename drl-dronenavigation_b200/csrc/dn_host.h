@@ -88,6 +88,12 @@ inline bool reward_table(int id, double discount, dn::RewardParams& w) {
         case DN_REWARD_PROGRESS:   // PBDroneEnv._computeReward with the progress term of Rewarder.py:43-62, weight 2000 (ThrustEnv.py:416-421)
             w = {-10.f, 200.f, 75.f, 5.f, 3.f, 2.f, 3000.f, 3.f, 0.7f, 0.3f, 1.f, 25.f, 0.04f};
             w.proj_w = 2000.f; return true;
+        case DN_REWARD_BOOTSTRAPPED:   // Rewarder.py:66-104: lambda1..4 = 0.5, 0.025, 2e-4, 5e-4; c1 = 10, c2 = 4
+            w.mode = dn::RW_LITERATURE; w.lit_prog = 0.5f; w.lit_perc_poly = (float)(0.025 * 2e-4); w.lit_da1 = -2e-4f; w.lit_w1 = -5e-4f;
+            w.lit_pass = 10.f; w.lit_crash = 4.f; w.crash = -4.f; return true;
+        case DN_REWARD_CHAMP:          // Rewarder.py:107-150: lambda1..5 = 1, 0.02, -10, -2e-4, -1e-4; c1 = 5 (also when p_z < 0)
+            w.mode = dn::RW_LITERATURE; w.lit_prog = 1.f; w.lit_perc_exp_w = 0.02f; w.lit_perc_exp_k = -10.f; w.lit_w2 = -2e-4f; w.lit_da2 = -1e-4f;
+            w.lit_crash = 5.f; w.lit_pz = 1; w.crash = -5.f; return true;
         default: return false;
     }
 }

@@ -32,9 +32,14 @@ struct RewardParams {
     int   mode;              // RW_* below
     float decay_log2;        // HER: log2(discount) / 10, capture bonus * discount^(steps/10) (HerPBDroneEnv.py:371)
     float proj_w;            // DN_REWARD_PROGRESS: weight of the projection progress that replaces (prev_d - d) * progress_w; 0 = off
+    // LITERATURE: Rewarder.BootstrappedImiVisionRewardCalculator / ChampRewardCalculator (Rewarder.py:66-150) as one formula:
+    // prog (prev_d - d) + perc_poly dc^4 + perc_exp_w exp(perc_exp_k dc^4) + da1 |da| + da2 |da|^2 + w1 |w| + w2 |w|^2
+    // + pass [passed] - crash [crashed (or p_z < 0 if lit_pz)]
+    float lit_prog, lit_perc_poly, lit_perc_exp_w, lit_perc_exp_k, lit_da1, lit_da2, lit_w1, lit_w2, lit_pass, lit_crash;
+    int   lit_pz;
     float pt_x, pt_y_rate, pt_z, pt_w;   // POINT: -pt_w * |(pt_x, pt_y_rate * t_norm, pt_z) - pos|^2 (HoverAviary.py:65-76, FlyThruGateAviary.py:100-112)
 };
-enum { RW_WAYPOINT = 0, RW_HER = 1, RW_REACHING = 2, RW_POINT = 3 };
+enum { RW_WAYPOINT = 0, RW_HER = 1, RW_REACHING = 2, RW_POINT = 3, RW_LITERATURE = 4 };
 
 struct Stats {               // device mirror of dn_stats
     double             return_sum;
@@ -105,7 +110,8 @@ struct Params {
     float* last_rpm_sum;     // [N], drag only
     float* obs_rms;          // [(2*obs_dim+1)][N] mean planes | var planes | count, normalize_obs only
     float4* spawn;           // [N] {spawn point of the current episode, 0}; DN_SPAWN_LINE only (segment 0 of the tube starts there)
-    float4* aux;             // [N] {_current_position.xyz (stale across resets), |_current_position - _last_position|}; RW_REACHING only
+    float4* aux;             // [N] {_current_position.xyz (stale across resets), |_current_position - _last_position|} (RW_REACHING);
+                             //     PBDroneEnv._last_action (RW_LITERATURE)
     float4* rew_rms;         // [N] {returns, mean, var, count} of normalize.NormalizeReward (normalize.py:100-147); normalize_reward only
     float rew_gamma, rew_eps, rew_clip;   // NormalizeReward gamma / epsilon; TransformReward clip bound (<= 0: off), PBDroneSimulator.py:190-193
     float ep_time_scale;     // S / (PYB_FREQ * EPISODE_LEN_SEC): step_counter / PYB_FREQ / EPISODE_LEN_SEC = ep_len * this

@@ -447,7 +447,8 @@ __global__ void init_kernel(const __grid_constant__ Params P, float d0) {
     store_state(P, i, s);
     if (P.last_rpm_sum) P.last_rpm_sum[i] = 0.f;
     if (P.spawn) P.spawn[i] = make_float4(P.init_pos[0], P.init_pos[1], P.init_pos[2], 0.f);
-    if (P.aux) P.aux[i] = make_float4(P.init_pos[0], P.init_pos[1], P.init_pos[2], 0.f);   // _last_position = _current_position = INIT_XYZS[0]
+    if (P.aux) P.aux[i] = (P.rw.mode == RW_LITERATURE) ? make_float4(0.f, 0.f, 0.f, 0.f)      // _last_action = 0 (PBDroneEnv.py:131)
+                                                        : make_float4(P.init_pos[0], P.init_pos[1], P.init_pos[2], 0.f);   // _last_position = _current_position = INIT_XYZS[0]
     if (P.rew_rms) P.rew_rms[i] = make_float4(0.f, 0.f, 1.f, 1e-4f);                       // returns 0; RunningMeanStd(): mean 0, var 1, count 1e-4
     if (P.pid[0]) { P.pid[0][i] = P.pid[1][i] = P.pid[2][i] = make_float4(0.f, 0.f, 0.f, 0.f); }   // DSLPIDControl.reset (DSLPIDControl.py:66-80)
     if (P.obs_rms) {
@@ -480,7 +481,7 @@ __global__ void reset_kernel(const __grid_constant__ Params P, const uint8_t* ma
         if (P.spawn_mode == DN_SPAWN_LINE) spawn_line(P, i, s.ep_count, s.px, s.py, s.pz);
         else spawn_midpoint(P, i, s.ep_count, s.px, s.py, s.pz, roll);
         P.spawn[i] = make_float4(s.px, s.py, s.pz, static_cast<float>(roll));
-        if (P.aux) { float4 ax = P.aux[i]; ax.x = s.px; ax.y = s.py; ax.z = s.pz; P.aux[i] = ax; }
+        if (P.aux && P.rw.mode == RW_REACHING) { float4 ax = P.aux[i]; ax.x = s.px; ax.y = s.py; ax.z = s.pz; P.aux[i] = ax; }
         const float4 t0 = target_at(P, roll);
         const float dx = s.px - t0.x, dy = s.py - t0.y, dz = s.pz - t0.z;
         D0 = sqrtf(dx * dx + dy * dy + dz * dz);
@@ -740,7 +741,7 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     if (drag) bytes += fplane;
     const size_t rms_floats = e->normalize_obs ? static_cast<size_t>(2 * P.obs_dim + 1) * N : 0;
     bytes += ((rms_floats * sizeof(float) + 255) / 256) * 256;
-    const bool need_aux = (rw.mode == dn::RW_REACHING), need_rew_rms = (cfg->normalize_reward != 0);
+    const bool need_aux = (rw.mode == dn::RW_REACHING || rw.mode == dn::RW_LITERATURE), need_rew_rms = (cfg->normalize_reward != 0);
     const bool need_spawn = (cfg->spawn_mode != DN_SPAWN_FIXED), need_pid = (cfg->act_type >= DN_ACT_PID);
     if (need_pid) bytes += 3 * plane;
     if (need_aux) bytes += plane;

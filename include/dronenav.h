@@ -86,7 +86,13 @@ extern "C" {
                                    code, ThrustEnv.py:416-421; p_t / p_t-1 = position after / before the step) */
 #define DN_REWARD_HOVER     6   /* upstream HoverAviary.py:65-76 */
 #define DN_REWARD_FLYTHRUGATE 7 /* FlyThruGateAviary.py:100-112 */
-#define DN_NUM_REWARDS      8
+#define DN_REWARD_BOOTSTRAPPED 8 /* Rewarder.BootstrappedImiVisionRewardCalculator (Rewarder.py:66-104, arXiv 2403.12203) */
+#define DN_REWARD_CHAMP     9   /* Rewarder.ChampRewardCalculator (Rewarder.py:107-150, Nature 2023).  Both are formula classes the
+                                   reference never calls ("yet unused"); here they are fed from PBDroneEnv's waypoint machine:
+                                   (prev_dis, dis) = the stale distance pair of the default reward, delta_cam = angle between the
+                                   forward vector and the direction to the current target, a_t / a_t-1 = this step's action /
+                                   _last_action, omega_t = rpy_rates, passed = target captured this step, crashed = collision */
+#define DN_NUM_REWARDS      10
 
 /* spawn modes for (auto-)reset.  0 is the reference behaviour (PBDroneEnv.py:609-665). */
 #define DN_SPAWN_FIXED      0   /* INIT_XYZS / INIT_RPYS, deterministic */
@@ -168,7 +174,8 @@ typedef struct dn_state_view {
     uint32_t* episode_count;  /* [N]    episodes finished so far (Philox counter)        */
     float*    last_rpm_sum;   /* [N]    sum(last_clipped_action) (drag only, BaseAviary.py:429,442) */
     float*    obs_rms;        /* [N,2*obs_dim+1] mean | var | count (normalize.py:10-47); only if normalize_obs */
-    float*    aux;            /* [N,4] _current_position.xyz | last travel; only with DN_REWARD_REACHING */
+    float*    aux;            /* [N,4] _current_position.xyz | last travel with DN_REWARD_REACHING; PBDroneEnv._last_action with
+                                 DN_REWARD_BOOTSTRAPPED / DN_REWARD_CHAMP; absent otherwise */
     float*    rew_rms;        /* [N,4] returns | mean | var | count (normalize.py:100-147); only if normalize_reward */
     float*    spawn;          /* [N,4] INIT_XYZS[0] of the current episode | target roll; only with a random spawn mode */
     float*    pid;            /* [N,9] DSLPIDControl.integral_pos_e | integral_rpy_e | last_rpy (DSLPIDControl.py:66-80);

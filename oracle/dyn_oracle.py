@@ -527,6 +527,7 @@ class OracleDroneEnv:
         self._is_done = False
         self._steps = 0
         self._last_position = self._current_position.copy()   # dummy_env.py:125 (reaching-progress reward only)
+        self._last_action = np.zeros(4, dtype=np.float32)      # PBDroneEnv.py:131; never reset (:655 is commented out)
         # test instrumentation: signed distances of this step's threshold comparisons to their
         # thresholds (so FP32-vs-FP64 near-ties can be recognised); never read by the step itself
         self.margins = []
@@ -577,6 +578,7 @@ class OracleDroneEnv:
     def step(self, action):
         action = np.asarray(action)
         self.margins = []
+        self._cur_action = action            # the raw policy action of this step (literature rewards: a_t)
         self._pos_at_entry = self.pos.copy()
         a = self.rescale_action(action) if self.normalize_actions else action
         rpm = np.reshape(self._preprocessAction(a), 4)
@@ -819,12 +821,50 @@ class OracleDroneEnv:
             return self._reward_her()
         if rid == "reaching":
             return self._reward_reaching()
+        if rid in ("bootstrapped", "champ"):
+            return self._reward_literature(rid)
         if rid == "hover":          # HoverAviary.py:65-76
             return -1 * np.linalg.norm(np.array([0, 0, 1]) - self.pos) ** 2
         if rid == "flythrugate":    # FlyThruGateAviary.py:100-112
             norm_ep_time = (self.step_counter / self.PYB_FREQ) / self.EPISODE_LEN_SEC
             return -10 * np.linalg.norm(np.array([0, -2 * norm_ep_time, 0.75]) - self.pos) ** 2
         raise ValueError(rid)
+
+    def _reward_literature(self, rid):
+        """Rewarder.BootstrappedImiVisionRewardCalculator.calculate_reward (Rewarder.py:66-104, arXiv 2403.12203) and
+        Rewarder.ChampRewardCalculator.calculate_reward (Rewarder.py:107-150, Nature 2023).  The reference never calls
+        these classes ("yet unused"); the wiring into PBDroneEnv's waypoint machine is ours and is the one the fixture
+        generator uses around the reference's own calculator objects (tests/golden/make_ref_golden.py::_Literature):
+        (prev_dis, dis) = the stale distance pair of the default reward, delta_cam = angle between the forward vector and
+        the direction to the current target (0 on the target), a_t / a_t-1 = this step's action / _last_action,
+        omega_t = rpy_rates, passed = target captured this step, crashed = collision before any capture."""
+        crashed = bool(self._computeTerminated() and not self._is_done)
+        passed = False
+        if not crashed:
+            self.margins.append(self._distance_to_target - self._threshold)
+            if self._distance_to_target <= self._threshold:
+                self._current_target_index += 1
+                passed = True
+                if self._current_target_index == len(self._target_points):
+                    self._is_done = True
+        target = self._target_points[min(self._current_target_index, len(self._target_points) - 1)]
+        v = np.array(target, dtype=np.float64) - np.array(self.pos)
+        n = np.linalg.norm(v)
+        delta_cam = float(np.arccos(np.clip(np.dot(self.get_forward_vector(), v / n), -1.0, 1.0))) if n > 0 else 0.0
+        a_t, a_tm1, omega = np.asarray(self._cur_action, np.float64), np.asarray(self._last_action, np.float64), self.rpy_rates
+        prev_dis, dis = self._prev_distance_to_target, self._distance_to_target
+        if rid == "bootstrapped":
+            l1, l2, l3, l4, c1, c2 = 0.5, 0.025, 2e-4, 5e-4, 10, 4
+            r = (l1 * (prev_dis - dis) + l2 * (l3 * (delta_cam ** 4)) - l3 * np.linalg.norm(a_t - a_tm1)
+                 - l4 * np.linalg.norm(omega) + (c1 if passed else 0) + (-c2 if crashed else 0))
+        else:
+            l1, l2, l3, l4, l5, c1 = 1.0, 0.02, -10.0, -2e-4, -1e-4, 5.0
+            r = (l1 * (prev_dis - dis) + l2 * np.exp(l3 * (delta_cam ** 4))
+                 + (l4 * np.linalg.norm(omega) ** 2 + l5 * np.linalg.norm(a_t - a_tm1) ** 2)
+                 - (c1 if self.pos[2] < 0 or crashed else 0))
+        if not crashed:
+            self._prev_distance_to_target = self._distance_to_target
+        return r
 
     def _reward_her(self):
         """HerPBDroneEnv._computeReward (HerPBDroneEnv.py:314-398), first element of the returned tuple."""
@@ -932,6 +972,7 @@ class OracleDroneEnv:
     # ---- post-step (PBDroneEnv.py:201-223) ----------------------------------
     def _update_state_post_step(self, action):
         self._steps += 1
+        self._last_action = action                              # PBDroneEnv.py:205
         self._last_position = self._current_position.copy()     # dummy_env.py:196 (reaching-progress reward only)
         self._current_position = self.pos.copy()
         self.prev_vel, self.prev_ang_v = self.current_vel.copy(), self.current_ang_v.copy()

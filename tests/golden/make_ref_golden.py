@@ -72,6 +72,11 @@ CASES = {
     # space (normalize_actions=False: actions are per-motor thrusts in newtons, no rescale_action)
     "ref_circle_s8_obs12_physact": ("circle", 8, "physical", 3, 60, 39, 4096, False, "default", False, False, False, False),
     "ref_reaching_s1_obs12": ("reaching", 1, "hover_band", 2, 120, 40, 4096, False, "default", False, False, False, True),
+    # the two literature reward calculators of Rewarder.py ("yet unused" in the reference): the reference's own calculator objects
+    # fed from PBDroneEnv's waypoint machine (_Literature below)
+    "ref_reaching_s8_rw_bootstrapped": ("reaching", 8, "mixed", 3, 50, 50, 4096, False, "bootstrapped", False, False),
+    "ref_circle_s8_rw_champ": ("circle", 8, "mixed", 3, 50, 51, 4096, False, "champ", False, False),
+    "ref_reaching_s1_rw_champ": ("reaching", 1, "hover_band", 2, 150, 52, 4096, False, "champ", False, False),
     # BaseSingleAgentAviary._preprocessAction (the branches PBDroneEnv overrides) bound onto the same step machine:
     # RPM / ONE_D_RPM maps, and the PID family through the reference's DSLPIDControl (with the real scipy Rotation)
     "ref_circle_s8_act_rpm": ("circle", 8, "rpm", 3, 60, 41, 4096, False, "default", False, False, True, False, "rpm", "cf2x"),
@@ -174,6 +179,47 @@ def _import_reference():
         _computeReward = FlyThruGateAviary._computeReward
 
     with contextlib.redirect_stdout(io.StringIO()):
+        from Sol.Model.Environments import Rewarder
+
+    class _Literature(_DynEnv):
+        """Rewarder.py's calculator classes, called with quantities of PBDroneEnv's waypoint machine (the wiring is ours: the
+        reference never calls them; it is restated in oracle/dyn_oracle.py::_reward_literature and in the kernel)."""
+        calculator = None
+
+        def step(self, action):
+            self._cur_action = np.array(action)
+            return super().step(action)
+
+        def _computeReward(self):
+            crashed = bool(self._computeTerminated() and not self._is_done)
+            passed = False
+            if not crashed and self._distance_to_target <= self._threshold:
+                self._current_target_index += 1
+                passed = True
+                if self._current_target_index == len(self._target_points):
+                    self._is_done = True
+            target = self._target_points[min(self._current_target_index, len(self._target_points) - 1)]
+            v = np.array(target, dtype=np.float64) - np.array(self.pos[0])
+            n = np.linalg.norm(v)
+            delta_cam = float(np.arccos(np.clip(np.dot(self.get_forward_vector(), v / n), -1.0, 1.0))) if n > 0 else 0.0
+            a_t, a_tm1 = np.asarray(self._cur_action, np.float64), np.asarray(self._last_action, np.float64)
+            if isinstance(self.calculator, Rewarder.ChampRewardCalculator):
+                r = self.calculator.calculate_reward(self._prev_distance_to_target, self._distance_to_target, delta_cam, a_t, a_tm1,
+                                                     self.rpy_rates[0], self.pos[0][2], crashed)
+            else:
+                r = self.calculator.calculate_reward(self._prev_distance_to_target, self._distance_to_target, delta_cam, a_t, a_tm1,
+                                                     self.rpy_rates[0], passed, crashed)
+            if not crashed:
+                self._prev_distance_to_target = self._distance_to_target
+            return r
+
+    class _Bootstrapped(_Literature):
+        calculator = Rewarder.BootstrappedImiVisionRewardCalculator()
+
+    class _Champ(_Literature):
+        calculator = Rewarder.ChampRewardCalculator()
+
+    with contextlib.redirect_stdout(io.StringIO()):
         from Sol.PyBullet.BaseSingleAgentAviary import BaseSingleAgentAviary
         from Sol.PyBullet.DSLPIDControl import DSLPIDControl
         from Sol.PyBullet.enums import DroneModel
@@ -189,7 +235,7 @@ def _import_reference():
 
     _import_reference.extras = dict(BsaAct=_BsaAct, DSLPIDControl=DSLPIDControl, DroneModel=DroneModel)
     variants = {"default": _DynEnv, "dummy": _Dummy, "thrustenv": _Thrust, "her": _Her, "reaching": _Reaching,
-                "hover": _Hover, "flythrugate": _FlyThru}
+                "hover": _Hover, "flythrugate": _FlyThru, "bootstrapped": _Bootstrapped, "champ": _Champ}
     return variants, normalize, ActionType, Physics, Waypoints, hover_reward is not None
 
 

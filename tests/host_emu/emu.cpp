@@ -55,6 +55,7 @@ Emu* emu_create(const dn_config* cfg) {
     if (rw.mode == dn::RW_REACHING) {
         e->aux.assign(N, make_float4(e->P.init_pos[0], e->P.init_pos[1], e->P.init_pos[2], 0.f)); e->P.aux = e->aux.data();
     }
+    if (rw.mode == dn::RW_LITERATURE) { e->aux.assign(N, make_float4(0.f, 0.f, 0.f, 0.f)); e->P.aux = e->aux.data(); }
     if (cfg->spawn_mode != DN_SPAWN_FIXED) {
         e->spawn.assign(N, make_float4(e->P.init_pos[0], e->P.init_pos[1], e->P.init_pos[2], 0.f)); e->P.spawn = e->spawn.data();
     }

@@ -178,8 +178,10 @@ def test_single_step_random_states_all_branches():
 @pytest.mark.parametrize("kw", [{}, {"normalize_obs": True, "normalize_reward": True, "clip_reward": 10.0},
                                 {"reward_id": 4, "random_spawn": "midpoint", "seed": 77}, {"reward_id": 5, "random_spawn": "line", "seed": 78},
                                 {"reward_id": 3, "physics": "PYB_GND_DRAG_DW"},
-                                {"act": "VEL"}, {"act": "PID", "drone_model": "CF2P", "physics": "PYB_GND"}, {"act": "RPM", "drone_model": "RACE"}],
-                         ids=["default", "wrappers", "reaching_midpoint", "progress_line", "her_drag_gnd", "vel", "cf2p_pid_gnd", "race_rpm"])
+                                {"act": "VEL"}, {"act": "PID", "drone_model": "CF2P", "physics": "PYB_GND"}, {"act": "RPM", "drone_model": "RACE"},
+                                {"reward_id": 8, "random_spawn": "line", "seed": 79}, {"reward_id": 9, "normalize_reward": True}],
+                         ids=["default", "wrappers", "reaching_midpoint", "progress_line", "her_drag_gnd", "vel", "cf2p_pid_gnd", "race_rpm",
+                              "bootstrapped_line", "champ_normrew"])
 def test_step_many_matches_repeated_step(kw):
     """dn_step_many (T steps, state in registers) is bit-identical to T dn_step launches -- also with the fused
     wrappers, the optional planes (aux / spawn / reward statistics) and the physics add-ons in play."""
@@ -317,6 +319,8 @@ FULL_SIZE = [
     ("cfg5_131072_reward_progress", 131072, "circle", {"reward_id": 5}),
     ("cfg5_131072_reward_reaching", 131072, "circle", {"reward_id": 4}),
     ("cfg5_131072_reward_flythru_normrew", 131072, "circle", {"reward_id": 7, "normalize_reward": True, "clip_reward": 10.0}),
+    ("cfg5_131072_reward_bootstrapped", 131072, "circle", {"reward_id": 8}),
+    ("cfg5_131072_reward_champ", 131072, "circle", {"reward_id": 9}),
 ]
 
 
@@ -333,7 +337,7 @@ def test_full_size_properties(name, N, track, kw):
     if "physics" in kw:
         kw["physics"] = getattr(Physics, kw["physics"])
         okw["physics"] = "dyn_gnd_drag"
-    rid = {0: "default", 3: "her", 4: "reaching", 5: "progress", 7: "flythrugate"}[kw.get("reward_id", 0)]
+    rid = {0: "default", 3: "her", 4: "reaching", 5: "progress", 7: "flythrugate", 8: "bootstrapped", 9: "champ"}[kw.get("reward_id", 0)]
     ref = make_reference_env(track, pyb_freq=240, ctrl_freq=30)
     env = BatchedDroneEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS,
                           pyb_freq=240, ctrl_freq=30, circle=(track == "circle"), include_distance=True, normalize_actions=True, **kw)

@@ -218,3 +218,22 @@ def test_device_logic_lockstep_against_batched_oracle(track, S, mode, N, T):
     print(f"\n[emu batched {track} S={S} {mode} N={N}] {rep}")
     assert rep.near_ties <= max(2, rep.env_steps // 5000) and rep.dones > 0
     env.close()
+
+
+@pytest.mark.parametrize("rid,name,track,S,mode", [(8, "bootstrapped", "circle", 8, "mixed"), (8, "bootstrapped", "reaching", 1, "hover_band"),
+                                                   (9, "champ", "reaching", 8, "saturating"), (9, "champ", "circle", 1, "saturating")])
+def test_device_logic_literature_rewards(rid, name, track, S, mode):
+    """DN_REWARD_BOOTSTRAPPED / DN_REWARD_CHAMP (Rewarder.py:66-150 fed from the waypoint machine) against the oracle."""
+    from oracle.dyn_oracle import OracleWorker, make_reference_env
+    from tests.host_emu import HostEmuEnv
+    N, T = 8, 60 if S == 8 else 240
+    ref = make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S)
+    env = HostEmuEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS, pyb_freq=240,
+                     ctrl_freq=240 // S, circle=(track == "circle"), include_distance=True, normalize_actions=True, reward_id=rid)
+    workers = [OracleWorker(make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S, reward_id=name), normalize_obs=False) for _ in range(N)]
+    for w in workers:
+        w.reset()
+    rep = PU.run_lockstep(env, workers, _actions(mode, T, N, seed=rid * 10 + S), resync_every=240 // S, check_state=False)
+    print(f"\n[emu {name} {track} S={S}] {rep}")
+    assert rep.near_ties <= 2 and (rep.dones > 0 or mode == "hover_band")
+    env.close()

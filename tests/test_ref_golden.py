@@ -20,7 +20,8 @@ IDS = [os.path.basename(p)[:-4] for p in GOLD]
 HAVE_REF = os.path.isdir("/root/reference/Sol")
 
 
-REWARD_IDS = {"default": 0, "dummy": 1, "thrustenv": 2, "her": 3, "reaching": 4, "progress": 5, "hover": 6, "flythrugate": 7}
+REWARD_IDS = {"default": 0, "dummy": 1, "thrustenv": 2, "her": 3, "reaching": 4, "progress": 5, "hover": 6, "flythrugate": 7,
+              "bootstrapped": 8, "champ": 9}
 
 
 def _meta(g):
