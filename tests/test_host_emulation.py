@@ -237,3 +237,18 @@ def test_device_logic_literature_rewards(rid, name, track, S, mode):
     print(f"\n[emu {name} {track} S={S}] {rep}")
     assert rep.near_ties <= 2 and (rep.dones > 0 or mode == "hover_band")
     env.close()
+
+
+def test_smoke_comparison_logic_on_the_host_build():
+    """__graft_entry__.smoke() compares the CUDA path with the batched oracle; the same comparison on the host build."""
+    import __graft_entry__ as G
+    from oracle.dyn_oracle import circle_track
+    from tests.host_emu import HostEmuEnv
+    N, T = 64, 60
+    targets, init, dim = circle_track()
+    env = HostEmuEnv(N, targets, aviary_dim=dim, initial_xyzs=init, pyb_freq=240, ctrl_freq=30, circle=True, include_distance=True,
+                     normalize_actions=True)
+    from oracle.batched_oracle import BatchedOracle
+    worst, worst_r, dones = G._smoke_compare(env.step, BatchedOracle(N, "circle", 240, 30).reset_obs(), N, T)
+    assert dones > 0
+    env.close()
