@@ -214,3 +214,87 @@ def test_normalize_observation_running_stats():
     assert w.obs_rms.count == pytest.approx(1.0001)
     assert w.obs_rms.mean[0] == pytest.approx(0.5 / 1.0001)
     assert o.shape == (13,)
+
+
+# ---- airframes, controller and literature rewards: analytic pins of the restatements added for SURVEY f3 / a19 -----------
+def test_airframe_constants_and_torque_mix_signs():
+    """Sol/resources/cf2p.urdf / racer.urdf constants and the torque-mix branches of BaseAviary._dynamics (:927-935)."""
+    from oracle.dyn_oracle import CF2P, RACE, ACT_RPM, MODEL_CF2P, MODEL_RACE
+    assert (CF2P.IXX, CF2P.IZZ, CF2P.L, CF2P.M) == (2.3951e-5, 3.2347e-5, 0.0397, 0.027)
+    assert (RACE.M, RACE.L, RACE.KF, RACE.KM, RACE.THRUST2WEIGHT_RATIO) == (0.830, 0.109, 8.47e-9, 2.13e-11, 4.17)
+    assert RACE.HOVER_RPM == pytest.approx(math.sqrt(9.8 * 0.830 / (4 * 8.47e-9)))
+    # one substep from rest with a single motor sped up: sign and size of the body-rate change per airframe
+    for model, c in ((MODEL_CF2P, CF2P), (MODEL_RACE, RACE)):
+        for motor in range(4):
+            e = make_reference_env("circle", act=ACT_RPM, drone_model=model, normalize_actions=False)
+            e.reset()
+            rpm = np.full(4, c.HOVER_RPM)
+            rpm[motor] *= 1.1
+            e._dynamics(rpm)
+            df = c.KF * (rpm[motor] ** 2 - c.HOVER_RPM ** 2)
+            dz = c.KM * (rpm[motor] ** 2 - c.HOVER_RPM ** 2) * (1 if motor in (1, 3) else -1) * (-1 if model == MODEL_RACE else 1)
+            if model == MODEL_CF2P:       # + frame: motor 1 / 3 on the +-y arm roll, motor 0 / 2 on the +-x arm pitch (:933-935)
+                tx = {1: df, 3: -df}.get(motor, 0.0) * c.L
+                ty = {0: -df, 2: df}.get(motor, 0.0) * c.L
+            else:                         # x frame (:930-932)
+                tx = (df if motor in (0, 1) else -df) * c.L / math.sqrt(2)
+                ty = (df if motor in (1, 2) else -df) * c.L / math.sqrt(2)
+            want = np.array([tx / c.IXX, ty / c.IYY, dz / c.IZZ]) / 240
+            np.testing.assert_allclose(e.rpy_rates, want, rtol=1e-9, atol=1e-12)
+
+
+def test_dslpid_hover_fixed_point_and_mixer():
+    """DSLPIDControl at rest on its target with zero integrals commands exactly the hover RPM on all four motors
+    (thrust = M g along body z; DSLPIDControl.py:164-195,225-261); a pure yaw error moves the motor pairs as the CF2X
+    mixer's third column says (:47-53)."""
+    from oracle.dyn_oracle import OracleDSLPID
+    c = OracleDSLPID()
+    q0 = np.array([0.0, 0.0, 0.0, 1.0])
+    rpm, pos_e, yaw_e = c.computeControl(1 / 30, np.array([1.0, 0, 1]), q0, np.zeros(3), np.zeros(3), np.array([1.0, 0, 1]))
+    np.testing.assert_allclose(rpm, CF2X.HOVER_RPM, rtol=1e-12)
+    assert np.all(pos_e == 0) and yaw_e == 0
+    assert np.all(c.integral_pos_e == 0) and np.all(c.integral_rpy_e == 0)
+    # 0.1 rad of yaw: rot_e = (0, 0, 2 sin(0.1)); torque_z = -60000 rot_e_z + 12000 * (-(0.1 - 0) / ct) + 500 * integral
+    c = OracleDSLPID()
+    qy = np.array([0.0, 0.0, math.sin(0.05), math.cos(0.05)])
+    rpm, _, yaw_e = c.computeControl(1 / 30, np.zeros(3), qy, np.zeros(3), np.zeros(3), np.zeros(3))
+    assert yaw_e == pytest.approx(-0.1)
+    e2 = 2 * math.sin(0.1)
+    tz = max(-3200.0, -60000 * e2 + 12000 * (-0.1 * 30) + 500 * (-e2 / 30))
+    base = (math.sqrt(CF2X.GRAVITY / (4 * CF2X.KF)) - 4070.3) / 0.2685
+    want = 0.2685 * np.clip(base + np.array([-1, 1, -1, 1]) * tz, 20000, 65535) + 4070.3
+    np.testing.assert_allclose(rpm, want, rtol=1e-12)
+    np.testing.assert_allclose(c.last_rpy, [0, 0, 0.1], atol=1e-15)
+
+
+def test_one_d_pid_holds_altitude_and_pid_family_never_resets_the_controller():
+    from oracle.dyn_oracle import ACT_ONE_D_PID
+    e = make_reference_env("circle", pyb_freq=240, ctrl_freq=30, act=ACT_ONE_D_PID, normalize_actions=False)
+    e.reset()
+    for _ in range(120):
+        e.step(np.zeros(4, np.float32))           # target = current position: hover in place
+    assert abs(e.pos[2] - 1.0) < 1e-9 and np.abs(e.vel).max() < 1e-9
+    e.step(np.array([1.0, 0, 0, 0], np.float32))  # 0.1 m up: integral_pos_e[2] = 0.1 / 30
+    assert e.ctrl.integral_pos_e[2] == pytest.approx(0.1 / 30)
+    kept = e.ctrl.integral_pos_e.copy()
+    e.reset()
+    np.testing.assert_array_equal(e.ctrl.integral_pos_e, kept)      # BaseSingleAgentAviary never calls ctrl.reset()
+
+
+def test_literature_reward_first_step_values():
+    """Rewarder.py:66-150 by hand for the first step from the spawn point of the circle track: prev_dis = dis = 1 (stale pair),
+    a_t-1 = 0, no capture, no crash; delta_cam = angle between (1, 0, 0) and the direction to target 0 = (0.5, 0.866, 1) - pos."""
+    a = np.full(4, HOVER_ACTION, np.float32)
+    for rid in ("bootstrapped", "champ"):
+        e = make_reference_env("circle", reward_id=rid)
+        e.reset()
+        _, r, term, _, _ = e.step(a)
+        v = e._target_points[0] - e.pos
+        dc = math.acos(np.clip(np.dot(e.get_forward_vector(), v / np.linalg.norm(v)), -1, 1))
+        da, w = np.linalg.norm(np.float64(a)), np.linalg.norm(e.rpy_rates)
+        if rid == "bootstrapped":
+            want = 0.5 * 0.0 + 0.025 * (2e-4 * dc ** 4) - 2e-4 * da - 5e-4 * w
+        else:
+            want = 1.0 * 0.0 + 0.02 * math.exp(-10 * dc ** 4) - 2e-4 * w ** 2 - 1e-4 * da ** 2
+        assert not term and float(r) == pytest.approx(want, rel=1e-12, abs=1e-15)
+        assert dc == pytest.approx(math.acos(-0.5 / 1.0), abs=2e-3)     # target 0 of the circle sits 120 degrees off the nose
