@@ -17,7 +17,8 @@ Coverage (what the full-size parity tests need): CF2X / CF2P / RACE; THRUST (+ `
 ONE_D_RPM action maps; ``Physics.DYN``; 12 / 13-dim observation; the PBDroneEnv reward family (``default``, ``dummy``,
 ``thrustenv``); circle and segment-tube termination; truncation; deterministic reset with the stale-distance quirks.
 Not covered here (per-environment oracle only): drag / ground effect, the other reward families, random spawns, the
-PID action types, NormalizeObservation / NormalizeReward.
+PID action types.  The wrappers of ``make_env`` (NormalizeObservation, reward clip, NormalizeReward; ``normalize.py:10-147``)
+are included, per environment like the reference's worker processes.
 
 Line citations (all under ``/root/reference``) are the ones of ``dyn_oracle.py``; each method names its counterpart.
 """
@@ -43,7 +44,8 @@ class BatchedOracle:
 
     def __init__(self, num_envs, track="circle", pyb_freq=240, ctrl_freq=240, max_steps=4096, act=O.ACT_THRUST,
                  normalize_actions=True, include_distance=True, reward_id="default", threshold=0.3, cylinder=True,
-                 drone_model=O.MODEL_CF2X, numpy_legacy_cast=True):
+                 drone_model=O.MODEL_CF2X, numpy_legacy_cast=True, normalize_obs=False, normalize_reward=False, clip_reward=0.0,
+                 reward_gamma=0.99):
         if reward_id not in _REWARDS:
             raise ValueError(f"reward {reward_id!r} is only in the per-environment oracle")
         if act not in (O.ACT_THRUST, O.ACT_RPM, O.ACT_ONE_D_RPM):
@@ -86,11 +88,40 @@ class BatchedOracle:
         self.just_found = np.zeros(N, bool)
         self.ep_return, self.ep_len = np.zeros(N), np.zeros(N, np.int64)
         self.last_rpm = np.zeros((N, 4))
+        # the wrappers of PBDroneSimulator.make_env (:181-195), per environment as each worker process has its own:
+        # NormalizeObservation / NormalizeReward (normalize.py:50-147) with RunningMeanStd batches of one, TransformReward clip
+        self.normalize_obs, self.normalize_reward, self.clip_reward, self.reward_gamma = normalize_obs, normalize_reward, clip_reward, reward_gamma
+        D = self.obs_dim
+        self.obs_mean, self.obs_var, self.obs_count = np.zeros((N, D)), np.ones((N, D)), np.full(N, 1e-4)
+        self.ret_mean, self.ret_var, self.ret_count, self.returns = np.zeros(N), np.ones(N), np.full(N, 1e-4), np.zeros(N)
         self.margin = np.full(N, np.inf)       # test instrumentation: distance of this step's discrete decisions to their thresholds
         self.rew_margin = np.full(N, np.inf)   # the same for decisions that only change the reward (orientation, smoothness)
         self.gimbal_margin = np.full(N, np.inf)
 
     # ---- helpers ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _rms_update(x, mean, var, count, sel):
+        """normalize.RunningMeanStd.update with a batch of one (normalize.py:19-47) for the rows `sel`; in place."""
+        lead = (slice(None),) + (None,) * (x.ndim - 1)
+        cnt = count[lead]
+        batch_mean, batch_var, batch_count = x, 0.0, 1             # np.mean / np.var of a batch of one
+        delta = batch_mean - mean
+        tot = cnt + batch_count
+        new_mean = mean + delta * batch_count / tot
+        M2 = var * cnt + batch_var * batch_count + np.square(delta) * cnt * batch_count / tot
+        new_var = M2 / tot
+        s_ = sel[lead]
+        mean[...] = np.where(s_, new_mean, mean)
+        var[...] = np.where(s_, new_var, var)
+        tot = count + batch_count
+        count[...] = np.where(sel, tot, count)
+
+    def _normalize_obs(self, obs, sel):
+        """NormalizeObservation.normalize (normalize.py:94-97): update, then (obs - mean) / sqrt(var + 1e-8); rows `sel`."""
+        x = obs.astype(np.float64)
+        self._rms_update(x, self.obs_mean, self.obs_var, self.obs_count, sel)
+        return np.where(sel[:, None], (x - self.obs_mean) / np.sqrt(self.obs_var + 1e-8), x)
+
     def _m(self, x, into="margin"):
         with np.errstate(invalid="ignore"):
             a = np.abs(x)
@@ -306,7 +337,18 @@ class BatchedOracle:
         self.current_ang_v = np.where(nt[:, None], self.ang_v, self.current_ang_v)
         new_dist = _norm(self.targets[np.minimum(self.idx, T - 1)] - self.cur_pos)
         self.dist = np.where(nt, new_dist, self.dist)
-        # ---- Monitor + worker auto-reset (dyn_oracle.OracleWorker.step)
+        # ---- wrappers between the env and Monitor (dyn_oracle.OracleWorker.step): observation statistics, reward clip and normalisation
+        all_envs = np.ones(N, bool)
+        if self.normalize_obs:
+            obs = self._normalize_obs(obs, all_envs)
+        if self.clip_reward > 0:
+            reward = np.clip(reward, -self.clip_reward, self.clip_reward)
+        if self.normalize_reward:
+            self.returns = self.returns * self.reward_gamma + reward
+            self._rms_update(self.returns, self.ret_mean, self.ret_var, self.ret_count, all_envs)
+            reward = reward / np.sqrt(self.ret_var + 1e-8)
+            self.returns = np.where(terminated | truncated, 0.0, self.returns)
+        # ---- Monitor + worker auto-reset
         self.ep_return = self.ep_return + reward
         self.ep_len = self.ep_len + 1
         done = terminated | truncated
@@ -319,6 +361,8 @@ class BatchedOracle:
             self.pos[d], self.quat[d], self.rpy[d] = self.INIT_XYZ, self.q0, O.bullet_euler_from_quaternion(self.q0)
             self.vel[d], self.ang_v[d], self.rpy_rates[d] = 0.0, 0.0, 0.0
             reset_obs = self._obs(self.pos, self.rpy, self.vel, self.ang_v, self.dist)
+            if self.normalize_obs:                                   # NormalizeObservation.reset normalises (and counts) the reset obs too
+                reset_obs = self._normalize_obs(reset_obs, d)
             obs = np.where(d[:, None], reset_obs, obs)
             dnew = _norm(self.cur_pos - self.targets[0])               # stale _current_position
             self.dist = np.where(d, dnew, self.dist)
@@ -331,8 +375,9 @@ class BatchedOracle:
         return obs, reward, bits, found, terminal_obs, ep_r, ep_l
 
     def reset_obs(self):
-        """VecEnv.reset() right after construction."""
-        return self._obs(self.pos, self.rpy, self.vel, self.ang_v, self.dist)
+        """VecEnv.reset() right after construction (call once: with normalize_obs it updates the statistics like a reset does)."""
+        o = self._obs(self.pos, self.rpy, self.vel, self.ang_v, self.dist)
+        return self._normalize_obs(o, np.ones(self.N, bool)) if self.normalize_obs else o
 
     def state(self):
         """The row-major arrays ``dn_set_state`` takes."""

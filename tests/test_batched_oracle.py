@@ -26,13 +26,20 @@ def _actions(mode, T, N, seed):
     ("circle", 8, "rpm", {"act": O.ACT_RPM, "drone_model": O.MODEL_CF2P, "normalize_actions": False}),
     ("reaching", 8, "rpm", {"act": O.ACT_ONE_D_RPM, "drone_model": O.MODEL_RACE, "normalize_actions": False}),
     ("circle", 1, "hover_band", {"max_steps": 25}),
+    ("circle", 8, "mixed", {"normalize_obs": True}),
+    ("reaching", 8, "saturating", {"normalize_obs": True, "normalize_reward": True, "clip_reward": 10.0}),
+    ("circle", 1, "saturating", {"normalize_reward": True, "max_steps": 40}),
 ])
 def test_batched_oracle_equals_per_environment_oracle(track, S, mode, kw):
     N, T = 12, 240 if S == 1 else 80
     B = BatchedOracle(N, track, pyb_freq=240, ctrl_freq=240 // S, **kw)
-    ws = [O.OracleWorker(O.make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S, **kw), normalize_obs=False) for _ in range(N)]
+    kw = dict(kw)
+    wrap = dict(normalize_obs=kw.pop("normalize_obs", False), normalize_reward=kw.pop("normalize_reward", False),
+                clip_reward=kw.pop("clip_reward", 0.0))
+    ws = [O.OracleWorker(O.make_reference_env(track, pyb_freq=240, ctrl_freq=240 // S, **kw), **wrap) for _ in range(N)]
     obs0 = np.stack([w.reset()[0] for w in ws])
-    np.testing.assert_array_equal(B.reset_obs(), obs0)
+    np.testing.assert_allclose(B.reset_obs(), obs0, rtol=0, atol=1e-12 if wrap["normalize_obs"] else 0)
+    otol = 1e-9 if wrap["normalize_obs"] else 2e-7
     acts = _actions(mode, T, N, seed=S + len(mode) + len(kw))
     dones = captures = 0
     for t in range(T):
@@ -42,11 +49,11 @@ def test_batched_oracle_equals_per_environment_oracle(track, S, mode, kw):
             o, r, d, info = w.step(acts[t, i])
             want = (1 if w.last_terminated else 0) | (2 if w.last_truncated else 0)
             assert bits[i] == want and found[i] == info["found_targets"], (t, i)
-            np.testing.assert_allclose(obs[i], o, rtol=0, atol=2e-7)
-            assert abs(rew[i] - float(r)) <= 1e-11 * max(1.0, abs(float(r))), (t, i, rew[i], r)
+            np.testing.assert_allclose(obs[i], o, rtol=0, atol=otol)
+            assert abs(rew[i] - float(r)) <= (1e-9 if wrap["normalize_reward"] else 1e-11) * max(1.0, abs(float(r))), (t, i, rew[i], r)
             if d:
                 dones += 1
-                np.testing.assert_allclose(term[i], info["terminal_observation"], rtol=0, atol=2e-7)
+                np.testing.assert_allclose(term[i], info["terminal_observation"], rtol=0, atol=otol)
                 assert ep_l[i] == info["episode"]["l"] and abs(ep_r[i] - info["episode"]["r"]) <= 1e-5 + 1e-9 * abs(ep_r[i])
             captures += int(info["found_targets"] > prev_idx[i])
             mm = min(B.margin[i], B.rew_margin[i])           # the per-environment oracle keeps one list for both kinds

@@ -252,3 +252,31 @@ def test_smoke_comparison_logic_on_the_host_build():
     worst, worst_r, dones = G._smoke_compare(env.step, BatchedOracle(N, "circle", 240, 30).reset_obs(), N, T)
     assert dones > 0
     env.close()
+
+
+def test_device_logic_reward_wrappers_against_batched_oracle():
+    """Reward clip + NormalizeReward (PBDroneSimulator.py:190-195, normalize.py:100-147) fused into the step, 512 envs against the
+    batched oracle; the normalised reward divides by sqrt(var) of a running variance that starts near 0, hence the relative bound."""
+    from oracle.batched_oracle import BatchedOracle
+    from oracle.dyn_oracle import reaching_track
+    from tests.host_emu import HostEmuEnv
+    N, T, S = 512, 60, 8
+    targets, init, dim = reaching_track()
+    env = HostEmuEnv(N, targets, aviary_dim=dim, initial_xyzs=init, pyb_freq=240, ctrl_freq=240 // S, circle=False, include_distance=True,
+                     normalize_actions=True, normalize_reward=True, clip_reward=10.0)
+    B = BatchedOracle(N, "reaching", pyb_freq=240, ctrl_freq=240 // S, normalize_reward=True, clip_reward=10.0)
+    acts = _actions("saturating", T, N, seed=99)
+    dones = 0
+    alive = np.ones(N, bool)                         # envs still in lock-step (open loop: an FP32 / FP64 near-tie parts the two runs)
+    for t in range(T):
+        o, r, d, f = env.step(acts[t])
+        oo, rr, bits, found, *_ = B.step(acts[t])
+        alive &= B.margin > PU.MARGIN_TOL
+        np.testing.assert_array_equal(d[alive], bits[alive])
+        np.testing.assert_array_equal(f[alive], found[alive])
+        soft = alive & (B.rew_margin > PU.MARGIN_TOL) & (B.gimbal_margin > PU.MARGIN_TOL)
+        np.testing.assert_allclose(r[soft], rr[soft], rtol=5e-3, atol=2e-2)
+        alive &= (B.rew_margin > PU.MARGIN_TOL) & (B.gimbal_margin > PU.MARGIN_TOL)     # a flipped reward term shifts the return statistics
+        dones += int((bits != 0).sum())
+    assert alive.sum() >= N - 8 and dones > 100
+    env.close()
