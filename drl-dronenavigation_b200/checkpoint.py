@@ -1,4 +1,4 @@
-"""SB3-format checkpoint I/O for the PPO policy.
+"""SB3-format checkpoint I/O for the PPO and SAC learners.
 
 The reference saves and reloads Stable-Baselines3 archives -- ``best_model.zip`` / ``success_model.zip`` written by
 ``EvalCallback`` / ``model.save`` (Sol/Model/PBDroneSimulator.py:719-746) and read back by ``PPO.load`` in
@@ -26,6 +26,21 @@ Key map for ``net_arch=dict(pi=[512, 512, 256], vf=[512, 512, 256])``, ``share_f
     mlp_extractor.value_net.{0,2,4}.{weight,bias}   <->  vf.{0,2,4}.{weight,bias}
     value_net.{weight,bias}                         <->  vf.6.{weight,bias}
     log_std                                         <->  log_std
+
+SAC (``SAC.load(self.continued_agent)`` / ``model.save``, PBDroneSimulator.py:355-362,741-746; hyper-parameters :290-331).  An SB3
+SAC archive holds ``policy.pth`` (SACPolicy: actor, critic, critic_target), ``actor.optimizer.pth``, ``critic.optimizer.pth``,
+``ent_coef_optimizer.pth`` and ``pytorch_variables.pth`` = ``{"log_ent_coef": tensor}``.  Key map for
+``net_arch=dict(pi=[256, 256], qf=[256, 256, 128])``:
+
+    actor.latent_pi.{0,2}.{weight,bias}             <->  actor.latent.{0,2}.{weight,bias}
+    actor.mu / actor.log_std .{weight,bias}         <->  actor.mu / actor.log_std
+    critic.qf{i}.{0,2,4,6}.{weight,bias}            <->  critic.qs.{i}.{0,2,4,6}.{weight,bias}
+    critic_target.qf{i}.{0,2,4,6}.{weight,bias}     <->  critic_target.qs.{i}.{0,2,4,6}.{weight,bias}
+
+The replay buffer the reference's ``SaveReplayBufferCallback`` writes (``Sol/Utilities/Callbacks.py:13-39``:
+``model.save_replay_buffer(".../replay_buffer.pkl")``) is SB3's pickled ``ReplayBuffer`` object; without SB3 in this image the
+file written here is a pickled dict with that object's attribute names (``observations``, ``next_observations``, ``actions``,
+``rewards``, ``dones``, ``pos``, ``full``, ``buffer_size``, ``n_envs``) and the loader accepts either (see ``sac.ReplayBuffer``).
 """
 from __future__ import annotations
 
@@ -89,7 +104,10 @@ def _save_tensor_member(zf: zipfile.ZipFile, name: str, obj) -> None:
 
 
 def save_sb3_zip(path: str, learner, extra: Optional[dict] = None) -> str:
-    """Writes an SB3-layout archive of a ``PPOLearner`` (policy + Adam state + hyper-parameters)."""
+    """Writes an SB3-layout archive of a ``PPOLearner`` (policy + Adam state + hyper-parameters); a ``SACLearner`` goes to
+    :func:`save_sb3_sac_zip`."""
+    if hasattr(learner, "actor") and hasattr(learner, "critic_target"):
+        return save_sb3_sac_zip(path, learner, extra)
     cfg = learner.cfg
     sd = policy_to_sb3_state_dict(learner.policy)
     km = _key_map(len(cfg.pi_arch), len(cfg.vf_arch))
@@ -125,7 +143,9 @@ def save_sb3_zip(path: str, learner, extra: Optional[dict] = None) -> str:
 
 def load_sb3_zip(path: str, learner, load_optimizer: bool = False, strict: bool = True) -> dict:
     """Loads ``policy.pth`` of an SB3 archive (the reference's ``best_model.zip``) into ``learner.policy``.
-    Returns the parsed ``data`` member (or {} when it is not plain JSON-decodable)."""
+    Returns the parsed ``data`` member (or {} when it is not plain JSON-decodable).  A ``SACLearner`` goes to :func:`load_sb3_sac_zip`."""
+    if hasattr(learner, "actor") and hasattr(learner, "critic_target"):
+        return load_sb3_sac_zip(path, learner, load_optimizer=load_optimizer, strict=strict)
     with zipfile.ZipFile(path) as zf:
         names = set(zf.namelist())
         if "policy.pth" not in names:
@@ -148,6 +168,117 @@ def load_sb3_zip(path: str, learner, load_optimizer: bool = False, strict: bool 
                     # load_state_dict re-creates the state tensors: captured CUDA graphs (if any) must be rebuilt
                     if hasattr(learner, "_graphs"):
                         learner._graphs = None
+        data = {}
+        if "data" in names:
+            try:
+                data = json.loads(zf.read("data").decode())
+            except Exception:  # noqa: BLE001
+                data = {}
+    return data
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SAC
+# ---------------------------------------------------------------------------------------------------------------------
+def _sac_key(ours: str) -> str:
+    """name in SACLearner's modules ("actor.latent.0.weight", "critic.qs.1.4.bias") -> SB3 SACPolicy key."""
+    parts = ours.split(".")
+    if parts[0] == "actor" and parts[1] == "latent":
+        parts[1] = "latent_pi"
+    elif parts[0] in ("critic", "critic_target") and parts[1] == "qs":
+        parts[1:3] = [f"qf{parts[2]}"]
+    return ".".join(parts)
+
+
+def _sac_modules(learner):
+    return (("actor", learner.actor), ("critic", learner.critic), ("critic_target", learner.critic_target))
+
+
+def sac_to_sb3_state_dict(learner) -> Dict[str, torch.Tensor]:
+    return {_sac_key(f"{pre}.{k}"): v.detach().cpu().clone() for pre, mod in _sac_modules(learner) for k, v in mod.state_dict().items()}
+
+
+def sb3_state_dict_to_sac(learner, sb3_sd: Dict[str, torch.Tensor], strict: bool = True) -> None:
+    used = set()
+    for pre, mod in _sac_modules(learner):
+        own = mod.state_dict()
+        new = {}
+        for k, v in own.items():
+            theirs = _sac_key(f"{pre}.{k}")
+            if theirs not in sb3_sd:
+                if strict:
+                    raise KeyError(f"{theirs} missing from the SB3 SAC policy state_dict (has: {sorted(sb3_sd)[:6]} ...)")
+                continue
+            t = sb3_sd[theirs]
+            if tuple(t.shape) != tuple(v.shape):
+                raise ValueError(f"{theirs}: shape {tuple(t.shape)} does not match this learner's {tuple(v.shape)} "
+                                 "(net_arch differs from PBDroneSimulator.py:296-300?)")
+            new[k] = t.to(v.device, v.dtype)
+            used.add(theirs)
+        mod.load_state_dict(new, strict=strict)
+    extra = [k for k in sb3_sd if k not in used and "features_extractor" not in k]
+    if strict and extra:
+        raise KeyError(f"unexpected keys in the SB3 SAC policy state_dict: {extra[:6]}")
+
+
+def _opt_cpu(opt) -> dict:
+    sd = opt.state_dict()
+    return {"state": {i: {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in st.items()} for i, st in sd["state"].items()},
+            "param_groups": sd["param_groups"]}
+
+
+def save_sb3_sac_zip(path: str, learner, extra: Optional[dict] = None) -> str:
+    """Writes an SB3-layout archive of a ``SACLearner``: SB3's member names, SACPolicy's key names, parameter order of the
+    optimisers = ``actor.parameters()`` / ``critic.parameters()`` as in SB3 (latent layers, then mu, then log_std; qf0, then qf1)."""
+    cfg = learner.cfg
+    data = {"policy_class": "stable_baselines3.sac.policies.SACPolicy", "algo": "SAC", "batch_size": cfg.batch_size,
+            "buffer_size": cfg.buffer_size, "learning_starts": cfg.learning_starts, "train_freq": cfg.train_freq,
+            "gradient_steps": cfg.gradient_steps, "tau": cfg.tau, "gamma": cfg.gamma, "learning_rate": cfg.learning_rate,
+            "target_update_interval": cfg.target_update_interval, "ent_coef": "auto", "target_entropy": learner.target_entropy,
+            "policy_kwargs": {"activation_fn": "torch.nn.ReLU", "net_arch": {"pi": list(cfg.pi_arch), "qf": list(cfg.qf_arch)},
+                              "n_critics": cfg.n_critics, "share_features_extractor": False},
+            "observation_space": {"type": "Box", "shape": [learner.actor.latent[0].in_features], "dtype": "float32"},
+            "action_space": {"type": "Box", "low": -1.0, "high": 1.0, "shape": [learner.actor.mu.out_features], "dtype": "float32"},
+            "n_updates": learner.n_updates, "seed": cfg.seed, "written_by": "drl_dronenavigation_b200"}
+    if extra:
+        data.update(extra)
+    if not path.endswith(".zip"):
+        path += ".zip"
+    with zipfile.ZipFile(path, "w", zipfile.ZIP_DEFLATED) as zf:
+        zf.writestr("data", json.dumps(data, indent=2))
+        _save_tensor_member(zf, "policy.pth", sac_to_sb3_state_dict(learner))
+        _save_tensor_member(zf, "actor.optimizer.pth", _opt_cpu(learner.actor_opt))
+        _save_tensor_member(zf, "critic.optimizer.pth", _opt_cpu(learner.critic_opt))
+        _save_tensor_member(zf, "ent_coef_optimizer.pth", _opt_cpu(learner.ent_opt))
+        _save_tensor_member(zf, "pytorch_variables.pth", {"log_ent_coef": learner.log_ent_coef.detach().cpu().clone()})
+        zf.writestr("_stable_baselines3_version", SB3_VERSION_TAG)
+        zf.writestr("system_info.txt", f"torch {torch.__version__}\n")
+    return path
+
+
+def load_sb3_sac_zip(path: str, learner, load_optimizer: bool = False, strict: bool = True) -> dict:
+    """Loads an SB3 SAC archive (``SAC.load`` of the reference's ``--run_type cont``, PBDroneSimulator.py:355-357) into a ``SACLearner``."""
+    with zipfile.ZipFile(path) as zf:
+        names = set(zf.namelist())
+        if "policy.pth" not in names:
+            raise KeyError(f"{path}: no policy.pth member (members: {sorted(names)})")
+        sb3_state_dict_to_sac(learner, torch.load(io.BytesIO(zf.read("policy.pth")), map_location="cpu", weights_only=True), strict=strict)
+        if "pytorch_variables.pth" in names:
+            pv = torch.load(io.BytesIO(zf.read("pytorch_variables.pth")), map_location="cpu", weights_only=False)
+            if isinstance(pv, dict) and pv.get("log_ent_coef") is not None:
+                with torch.no_grad():
+                    learner.log_ent_coef.copy_(pv["log_ent_coef"].reshape(learner.log_ent_coef.shape).to(learner.log_ent_coef.device))
+        if load_optimizer:
+            for member, opt in (("actor.optimizer.pth", learner.actor_opt), ("critic.optimizer.pth", learner.critic_opt),
+                                ("ent_coef_optimizer.pth", learner.ent_opt)):
+                if member in names:
+                    st = torch.load(io.BytesIO(zf.read(member)), map_location="cpu", weights_only=False)
+                    own = opt.state_dict()
+                    if len(st.get("state", {})) in (0, len(own["param_groups"][0]["params"])):
+                        own["state"] = st.get("state", {})
+                        opt.load_state_dict(own)
+            if hasattr(learner, "_graphs"):
+                learner._graphs = None            # optimiser state tensors were re-created: captured CUDA graphs must be rebuilt
         data = {}
         if "data" in names:
             try:

@@ -410,13 +410,14 @@ class PPOTrainer:
 
     def train_iteration(self) -> Dict[str, float]:
         t0 = time.perf_counter()
+        sync = (lambda: torch.cuda.synchronize(self.dev)) if torch.device(self.dev).type == "cuda" else (lambda: None)
         adv, ret = self.collect_rollouts()
-        torch.cuda.synchronize(self.dev)
+        sync()
         t1 = time.perf_counter()
         N, D = self.env.num_envs, self.env.obs_dim
         out = self.learner.update(self.b_obs.reshape(-1, D), self.b_act.reshape(-1, 4), self.b_logp.reshape(-1),
                                   self.b_val.reshape(-1), adv.reshape(-1), ret.reshape(-1), generator=self.gen)
-        torch.cuda.synchronize(self.dev)
+        sync()
         t2 = time.perf_counter()
         out.update(rollout_s=t1 - t0, update_s=t2 - t1, samples=self.T * N * _world(),
                    sps=self.T * N * _world() / (t2 - t0))

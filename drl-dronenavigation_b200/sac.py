@@ -147,6 +147,50 @@ class ReplayBuffer:
     def __len__(self):
         return (self.cap if self.full else self.pos) * self.N
 
+    # ---- SaveReplayBufferCallback / load_replay_buffer (Sol/Utilities/Callbacks.py:13-39; PBDroneSimulator.py:357,998-1017) ----
+    def save(self, path: str) -> str:
+        """``model.save_replay_buffer(path)``: SB3 pickles its ReplayBuffer object; here a dict with that object's attribute
+        names and array layouts ([buffer_size, n_envs, ...]) is pickled, which :meth:`load` -- and anything that reads the
+        attributes of an SB3 buffer -- understands."""
+        import pickle
+        n = self.cap if self.full else self.pos
+        arr = lambda t: t[:n].detach().cpu().numpy() if not self.full else t.detach().cpu().numpy()
+        with open(path, "wb") as f:
+            pickle.dump({"observations": arr(self.obs), "next_observations": arr(self.next_obs), "actions": arr(self.act),
+                         "rewards": arr(self.rew), "dones": arr(self.done), "pos": self.pos, "full": self.full,
+                         "buffer_size": self.cap, "n_envs": self.N, "written_by": "drl_dronenavigation_b200"}, f, protocol=4)
+        return path
+
+    def load(self, path: str) -> int:
+        """``model.load_replay_buffer(path)``: accepts the dict written by :meth:`save` or a pickled SB3 ``ReplayBuffer`` (when
+        SB3 is importable); returns the number of transitions restored.  n_envs must match; a larger saved buffer is truncated
+        to the most recent ``capacity`` steps."""
+        import pickle
+        with open(path, "rb") as f:
+            obj = pickle.load(f)
+        get = (lambda k: obj[k]) if isinstance(obj, dict) else (lambda k: getattr(obj, k))
+        n_envs, pos, full = int(get("n_envs")), int(get("pos")), bool(get("full"))
+        if n_envs != self.N:
+            raise ValueError(f"replay buffer was saved with n_envs={n_envs}, this trainer has {self.N}")
+        def ordered(a):                      # oldest -> newest
+            a = torch.as_tensor(a, dtype=torch.float32)
+            if full and a.shape[0] > pos:
+                a = torch.cat([a[pos:], a[:pos]])
+            elif not full:
+                a = a[:pos]
+            return a[-self.cap:]
+        fields = {"obs": "observations", "next_obs": "next_observations", "act": "actions", "rew": "rewards", "done": "dones"}
+        n = 0
+        for ours, theirs in fields.items():
+            a = ordered(get(theirs))
+            dst = getattr(self, ours)
+            a = a.reshape((a.shape[0],) + tuple(dst.shape[1:]))
+            n = a.shape[0]
+            dst[:n].copy_(a.to(dst.device))
+        self.full = n == self.cap
+        self.pos = 0 if self.full else n
+        return n * self.N
+
     def sample(self, batch_size: int, generator=None):
         n = len(self)
         idx = torch.randint(0, n, (batch_size,), device=self.obs.device, generator=generator)

@@ -100,9 +100,13 @@ class PBDroneSimulator:
         env = self.make_device_env(n_envs, device=trainer.dev)
         obs = env.reset()
         gen = torch.Generator(device=trainer.dev).manual_seed(123)
+        sac = not hasattr(trainer.learner, "policy")
         with torch.no_grad():
             for k in range(max_steps):
-                a, _, _ = trainer.learner.policy.act(obs, generator=gen)
+                if sac:
+                    a = trainer.learner.act(obs, generator=gen)
+                else:
+                    a, _, _ = trainer.learner.policy.act(obs, generator=gen)
                 obs, _, _, _ = env.step(a.clamp(-1, 1).contiguous())
                 # statistics are read (one host sync) every 64 steps; run at least one full time-limit horizon so that
                 # long (successful / truncated) episodes are not under-represented against quick crashes
@@ -125,11 +129,16 @@ class PBDroneSimulator:
             if not os.path.exists(self.continued_agent):
                 raise FileNotFoundError(f"--run_type cont: {self.continued_agent} not found (pass --model_path)")
             load_sb3_zip(self.continued_agent, trainer.learner, load_optimizer=True)
+            if args.agent == "SAC":              # model.load_replay_buffer(load_most_recent_replay_buffer(chkpt_path)), :357
+                rb = load_most_recent_replay_buffer(os.path.dirname(self.continued_agent))
+                if rb:
+                    log(f"replay buffer {rb}: {trainer.buffer.load(rb)} transitions")
         chk = None
-        if args.savemodel:
+        if args.savemodel and rank == 0:           # one writer per job
             chk = os.path.join("Sol", "model_chkpts", f"{args.agent}_save_{datetime.now().strftime('%m.%d.%Y_%H.%M.%S')}")
             os.makedirs(chk, exist_ok=True)
         t0, it, best = time.time(), 0, -np.inf
+        rb_saves = 0                               # SaveReplayBufferCallback(save_freq=100_000 env.step calls), :706-710
         max_seconds = max_seconds if max_seconds is not None else getattr(args, "max_seconds", None)
         # TensorBoard scalars under SB3's tag names (what Sol/Utilities/TensorboardManager.py reads back), SURVEY f.4
         tb = None
@@ -161,17 +170,27 @@ class PBDroneSimulator:
                                          ("value_loss", "train/value_loss"), ("std", "train/std")):
                         if k_src in out:
                             tb.add_scalar(k_dst, out[k_src], step)
+                    for k_src, k_dst in (("critic_loss", "train/critic_loss"), ("actor_loss", "train/actor_loss"),
+                                         ("ent_coef", "train/ent_coef"), ("ent_coef_loss", "train/ent_coef_loss")):      # SB3 SAC.train's tags
+                        if k_src in out:
+                            tb.add_scalar(k_dst, out[k_src], step)
+                tail = (f"kl {out['approx_kl']:.4f}  std {out['std']:.3f}" if "approx_kl" in out else
+                        f"critic_loss {out.get('critic_loss', float('nan')):.4g}  ent_coef {out.get('ent_coef', float('nan')):.4g}")
                 log(f"[{time.time() - t0:7.1f}s] steps {trainer.total_steps:>12d}  sps {out['sps']:.3g}  ep_rew {st['return_sum'] / e:8.3f}  "
-                    f"ep_len {st['length_sum'] / e:7.1f}  found {st['found_targets'] / e:5.2f}  success {st['successes'] / e:5.3f}  "
-                    f"kl {out['approx_kl']:.4f}  std {out['std']:.3f}")
-                if chk and st["return_sum"] / e > best and hasattr(trainer.learner, "policy"):
+                    f"ep_len {st['length_sum'] / e:7.1f}  found {st['found_targets'] / e:5.2f}  success {st['successes'] / e:5.3f}  {tail}")
+                if chk and st["return_sum"] / e > best:
                     best = st["return_sum"] / e
                     save_sb3_zip(os.path.join(chk, "best_model.zip"), trainer.learner)     # EvalCallback(best_model_save_path), :719-729
-        if chk and hasattr(trainer.learner, "policy"):
+            if chk and args.agent == "SAC" and (trainer.total_steps // max(self.num_envs * world, 1)) // 100_000 > rb_saves:
+                rb_saves = (trainer.total_steps // max(self.num_envs * world, 1)) // 100_000
+                trainer.buffer.save(os.path.join(chk, "replay_buffer.pkl"))
+        if chk:
             save_sb3_zip(os.path.join(chk, "success_model.zip"), trainer.learner)          # model.save(...), :741-746
+            if args.agent == "SAC":
+                trainer.buffer.save(os.path.join(chk, "replay_buffer.pkl"))
         if tb is not None:
             tb.close()
-        ev = self.evaluate(trainer, n_eval_episodes=1000, n_envs=256) if hasattr(trainer.learner, "policy") else {}
+        ev = self.evaluate(trainer, n_eval_episodes=1000, n_envs=256)
         log(f"final evaluation: {ev}")
         train_env.close()
         return trainer, ev
@@ -224,3 +243,20 @@ class PBDroneSimulator:
         out = self.evaluate(trainer, n_eval_episodes=episodes)
         env.close()
         return out
+
+
+def load_most_recent_replay_buffer(directory: str):
+    """PBDroneSimulator.load_most_recent_replay_buffer (PBDroneSimulator.py:998-1017): the ``replay_buffer_<n>.pkl`` with the
+    largest n in `directory`; the reference's own callback writes ``replay_buffer.pkl`` (Callbacks.py:30), which its loader's
+    pattern does not match -- accepted here as the fallback.  Returns None when there is none."""
+    import re
+    if not directory or not os.path.isdir(directory):
+        return None
+    best, best_n = None, -1
+    for f in os.listdir(directory):
+        m = re.match(r"replay_buffer_(\d+)\.pkl$", f)
+        if m and int(m.group(1)) > best_n:
+            best, best_n = f, int(m.group(1))
+    if best is None and os.path.exists(os.path.join(directory, "replay_buffer.pkl")):
+        best = "replay_buffer.pkl"
+    return os.path.join(directory, best) if best else None

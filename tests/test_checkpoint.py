@@ -91,3 +91,102 @@ def test_wrong_architecture_is_rejected(tmp_path):
     with pytest.raises(ValueError, match="shape"):
         load_sb3_zip(path, L)
     assert sorted(policy_to_sb3_state_dict(L.policy)) == sorted(SB3_KEYS)
+
+
+# ---- SAC archives and the replay buffer (PBDroneSimulator.py:355-362,704-710; Sol/Utilities/Callbacks.py:13-39) -----------------
+SAC_SB3_KEYS = ([f"actor.latent_pi.{i}.{leaf}" for i in (0, 2) for leaf in ("weight", "bias")]
+                + [f"actor.{h}.{leaf}" for h in ("mu", "log_std") for leaf in ("weight", "bias")]
+                + [f"{c}.qf{q}.{i}.{leaf}" for c in ("critic", "critic_target") for q in (0, 1) for i in (0, 2, 4, 6) for leaf in ("weight", "bias")])
+
+
+def test_sac_archive_has_sb3_members_and_keys_and_round_trips(tmp_path):
+    from drl_dronenavigation_b200.sac import SACConfig, SACLearner
+    cfg = SACConfig(cuda_graph=False)
+    A = SACLearner(13, 4, cfg)
+    obs, act = torch.randn(32, 13), torch.rand(32, 4) * 2 - 1
+    for _ in range(2):      # two updates so the optimisers and log_ent_coef carry state
+        A.update((obs, act, torch.randn(32), torch.randn(32, 13), torch.zeros(32)))
+    p = save_sb3_zip(str(tmp_path / "success_model"), A)
+    with zipfile.ZipFile(p) as zf:
+        assert {"data", "policy.pth", "actor.optimizer.pth", "critic.optimizer.pth", "ent_coef_optimizer.pth", "pytorch_variables.pth",
+                "_stable_baselines3_version"} <= set(zf.namelist())
+        sd = torch.load(io.BytesIO(zf.read("policy.pth")), weights_only=True)
+        data = json.loads(zf.read("data"))
+    assert sorted(sd) == sorted(SAC_SB3_KEYS)
+    assert sd["actor.latent_pi.0.weight"].shape == (256, 13) and sd["critic.qf1.0.weight"].shape == (256, 17) and sd["critic.qf0.6.weight"].shape == (1, 128)
+    assert data["policy_kwargs"]["net_arch"] == {"pi": [256, 256], "qf": [256, 256, 128]} and data["algo"] == "SAC"
+    B = SACLearner(13, 4, SACConfig(cuda_graph=False, seed=99))
+    load_sb3_zip(p, B, load_optimizer=True)
+    with torch.no_grad():
+        assert torch.equal(A.actor(obs, deterministic=True)[0], B.actor(obs, deterministic=True)[0])
+        for qa, qb in zip(A.critic(obs, act), B.critic(obs, act)):
+            assert torch.equal(qa, qb)
+        for qa, qb in zip(A.critic_target(obs, act), B.critic_target(obs, act)):
+            assert torch.equal(qa, qb)
+    assert torch.equal(A.log_ent_coef, B.log_ent_coef)
+    # same optimiser state -> the next update moves both learners identically
+    batch = (obs, act, torch.randn(32), torch.randn(32, 13), torch.zeros(32))
+    ga, gb = torch.Generator().manual_seed(1), torch.Generator().manual_seed(1)
+    A.update(batch, generator=ga); B.update(batch, generator=gb)
+    assert torch.allclose(A.flat_parameters(), B.flat_parameters(), atol=1e-7)
+
+
+def test_sb3_style_sac_archive_loads(tmp_path):
+    from drl_dronenavigation_b200.sac import SACConfig, SACLearner
+    L = SACLearner(13, 4, SACConfig(cuda_graph=False))
+    g = torch.Generator().manual_seed(3)
+    own = {k: v for pre, mod in (("actor", L.actor), ("critic", L.critic), ("critic_target", L.critic_target)) for k, v in
+           ((f"{pre}.{k}", v) for k, v in mod.state_dict().items())}
+    from drl_dronenavigation_b200.checkpoint import _sac_key
+    sd = {_sac_key(k): torch.randn(v.shape, generator=g) * 0.1 for k, v in own.items()}
+    assert sorted(sd) == sorted(SAC_SB3_KEYS)
+    path = str(tmp_path / "best_model.zip")
+    with zipfile.ZipFile(path, "w") as zf:
+        buf = io.BytesIO(); torch.save(sd, buf); zf.writestr("policy.pth", buf.getvalue())
+        buf = io.BytesIO(); torch.save({"log_ent_coef": torch.tensor([-1.25])}, buf); zf.writestr("pytorch_variables.pth", buf.getvalue())
+    load_sb3_zip(path, L)
+    obs = torch.randn(5, 13)
+    h = torch.relu(torch.relu(obs @ sd["actor.latent_pi.0.weight"].T + sd["actor.latent_pi.0.bias"]) @ sd["actor.latent_pi.2.weight"].T
+                   + sd["actor.latent_pi.2.bias"])
+    want = torch.tanh(h @ sd["actor.mu.weight"].T + sd["actor.mu.bias"])
+    with torch.no_grad():
+        assert torch.allclose(L.actor(obs, deterministic=True)[0], want, atol=1e-6)
+    assert float(L.log_ent_coef) == pytest.approx(-1.25)
+    bad = dict(sd); bad["actor.mu.weight"] = torch.zeros(4, 128)
+    with zipfile.ZipFile(path, "w") as zf:
+        buf = io.BytesIO(); torch.save(bad, buf); zf.writestr("policy.pth", buf.getvalue())
+    with pytest.raises(ValueError, match="net_arch"):
+        load_sb3_zip(path, L)
+
+
+def test_replay_buffer_save_and_load(tmp_path):
+    from drl_dronenavigation_b200.sac import ReplayBuffer
+    N, D = 4, 13
+    A = ReplayBuffer(6 * N, N, D, 4, "cpu")           # 6 steps of capacity
+    g = torch.Generator().manual_seed(0)
+    rows = []
+    for t in range(9):                                # wraps around: steps 3..8 survive
+        o, o2, a = torch.randn(N, D, generator=g), torch.randn(N, D, generator=g), torch.rand(N, 4, generator=g)
+        r = torch.randn(N, generator=g)
+        done = torch.tensor([0, 1, 2, 3], dtype=torch.uint8) if t % 4 == 0 else torch.zeros(N, dtype=torch.uint8)
+        term = torch.randn(N, D, generator=g)
+        A.add(o, o2, a, r, done, term)
+        rows.append((o, torch.where((done != 0).unsqueeze(-1), term, o2), a, r, ((done & 1) != 0).float()))
+    path = A.save(str(tmp_path / "replay_buffer.pkl"))
+    import pickle
+    d = pickle.load(open(path, "rb"))
+    assert d["observations"].shape == (6, N, D) and d["full"] and d["pos"] == 3 and d["n_envs"] == N
+    B = ReplayBuffer(6 * N, N, D, 4, "cpu")
+    assert B.load(path) == 6 * N and len(B) == 6 * N and B.full
+    for k, (o, o2, a, r, dn) in enumerate(rows[3:]):   # oldest -> newest after the reload
+        assert torch.equal(B.obs[k], o) and torch.equal(B.next_obs[k], o2) and torch.equal(B.act[k], a)
+        assert torch.equal(B.rew[k], r) and torch.equal(B.done[k], dn)
+    C = ReplayBuffer(4 * N, N, D, 4, "cpu")            # smaller buffer keeps the most recent steps
+    assert C.load(path) == 4 * N and torch.equal(C.obs[0], rows[5][0]) and torch.equal(C.obs[3], rows[8][0])
+    P = ReplayBuffer(8 * N, N, D, 4, "cpu")            # partially filled buffers round-trip too
+    P.add(*[rows[0][0], rows[0][1], rows[0][2], rows[0][3]], torch.zeros(N, dtype=torch.uint8), rows[0][1])
+    P.save(path)
+    Q = ReplayBuffer(8 * N, N, D, 4, "cpu")
+    assert Q.load(path) == N and Q.pos == 1 and not Q.full and torch.equal(Q.obs[0], rows[0][0])
+    with pytest.raises(ValueError, match="n_envs"):
+        ReplayBuffer(8, 2, D, 4, "cpu").load(path)

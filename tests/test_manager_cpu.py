@@ -1,0 +1,89 @@
+"""PBDroneSimulator (the reference's experiment manager, Sol/Model/PBDroneSimulator.py) driven end to end on the CPU: the
+device step logic comes from its host build (tests/emu_torch_env.py), the learners run on torch CPU tensors.  Covers the
+paths the reference's command line reaches: --agent PPO / SAC, --run_type full / cont, --savemodel (SB3-layout archives,
+SAC replay buffer), --tensorboard."""
+import argparse
+import glob
+import os
+import zipfile
+
+import pytest
+import torch
+
+from drl_dronenavigation_b200 import waypoints as W
+from drl_dronenavigation_b200.simulator import PBDroneSimulator, load_most_recent_replay_buffer
+from tests.emu_torch_env import EmuTorchEnv
+
+
+def _args(**kw):
+    a = dict(agent="PPO", run_type="full", num_envs=32, max_env_steps=200, total_timesteps=32 * 16 * 3, savemodel=True, pyb_freq=240,
+             ctrl_freq=30, rollout_steps=16, minibatch=128, n_epochs=2, clip_rew=False, norm_rew=False, reward_id=0, tensorboard=None,
+             model_path=None, max_seconds=None, rank=0, world=1)
+    a.update(kw)
+    return argparse.Namespace(**a)
+
+
+@pytest.fixture
+def manager(monkeypatch, tmp_path):
+    monkeypatch.chdir(tmp_path)
+
+    def make(**kw):
+        track = W.Track(W.circle(radius=1, num_points=6, height=1), circle=True)
+        sim = PBDroneSimulator(_args(**kw), track)
+
+        def make_device_env(num_envs, normalize_obs=False, device=None, env_id_offset=0):
+            return EmuTorchEnv(num_envs, sim.targets, **sim._env_kwargs(None, sim.aviary_dim, True, True))
+        sim.make_device_env = make_device_env
+        return sim
+    return make
+
+
+def test_ppo_full_run_saves_sb3_archives_and_continues(manager, tmp_path):
+    lines = []
+    sim = manager(tensorboard=str(tmp_path / "tb"))
+    trainer, ev = sim.run_full_training(log=lines.append)
+    assert trainer.total_steps >= 32 * 16 * 3 and ev["episodes"] >= 1000 and 0.0 <= ev["success_rate"] <= 1.0
+    assert any(l.startswith("final evaluation") for l in lines)
+    zips = sorted(glob.glob(str(tmp_path / "Sol" / "model_chkpts" / "PPO_save_*" / "*.zip")))
+    assert any(z.endswith("success_model.zip") for z in zips)
+    assert glob.glob(str(tmp_path / "tb" / "events.out.tfevents.*"))
+    cont = manager(run_type="cont", model_path=[z for z in zips if z.endswith("success_model.zip")][0], savemodel=False,
+                   total_timesteps=32 * 16)
+    t2, _ = cont.run_full_training(log=lines.append)
+    # the continued learner starts from the saved parameters (then trains one iteration on top)
+    assert t2.learner.n_updates > 0
+
+
+def test_sac_full_run_saves_archive_and_replay_buffer_and_continues(manager, tmp_path):
+    from drl_dronenavigation_b200 import sac as S
+    lines = []
+    sim = manager(agent="SAC", total_timesteps=32 * 3 * 12)
+    orig = S.SACConfig
+    try:
+        # the reference's SAC hyper-parameters with a small buffer / early learning start so that updates happen within the test
+        S.SACConfig = lambda: orig(learning_starts=32 * 3 * 4, batch_size=64, buffer_size=32 * 64, cuda_graph=False)
+        trainer, ev = sim.run_full_training(log=lines.append)
+        assert trainer.learner.n_updates > 0 and len(trainer.buffer) > 0 and ev["episodes"] >= 1000
+        assert any("critic_loss" in l for l in lines)
+        chk = glob.glob(str(tmp_path / "Sol" / "model_chkpts" / "SAC_save_*"))[0]
+        with zipfile.ZipFile(os.path.join(chk, "success_model.zip")) as zf:
+            assert {"policy.pth", "actor.optimizer.pth", "critic.optimizer.pth", "ent_coef_optimizer.pth", "pytorch_variables.pth"} <= set(zf.namelist())
+        assert load_most_recent_replay_buffer(chk) == os.path.join(chk, "replay_buffer.pkl")
+        saved = trainer.learner.flat_parameters().clone()
+        filled = len(trainer.buffer)
+        cont = manager(agent="SAC", run_type="cont", model_path=os.path.join(chk, "success_model.zip"), savemodel=False, total_timesteps=0)
+        t2, _ = cont.run_full_training(log=lines.append)
+        assert torch.equal(t2.learner.flat_parameters(), saved)          # SAC.load(...) restored actor, critics and log_ent_coef
+        assert len(t2.buffer) == filled                                  # model.load_replay_buffer(...)
+        assert any(l.startswith("replay buffer") for l in lines)
+    finally:
+        S.SACConfig = orig
+
+
+def test_most_recent_replay_buffer_pattern(tmp_path):
+    assert load_most_recent_replay_buffer(str(tmp_path)) is None
+    (tmp_path / "replay_buffer.pkl").write_bytes(b"")
+    assert load_most_recent_replay_buffer(str(tmp_path)).endswith("replay_buffer.pkl")
+    for n in (3, 12, 7):
+        (tmp_path / f"replay_buffer_{n}.pkl").write_bytes(b"")
+    assert load_most_recent_replay_buffer(str(tmp_path)).endswith("replay_buffer_12.pkl")      # PBDroneSimulator.py:998-1017
