@@ -87,3 +87,21 @@ def test_most_recent_replay_buffer_pattern(tmp_path):
     for n in (3, 12, 7):
         (tmp_path / f"replay_buffer_{n}.pkl").write_bytes(b"")
     assert load_most_recent_replay_buffer(str(tmp_path)).endswith("replay_buffer_12.pkl")      # PBDroneSimulator.py:998-1017
+
+
+def test_learning_and_saved_run_types(manager, tmp_path):
+    """--run_type learning (PBDroneSimulator.py:574-612) and --run_type saved (:438-572)."""
+    sim = manager(num_envs=1, max_env_steps=64, batch_size=32, savemodel=False)
+    trainer, out = sim.test_learning(total_timesteps=128, log=lambda *_: None)
+    assert trainer.total_steps >= 128 and "approx_kl" in out
+    assert [m.out_features for m in trainer.learner.policy.pi if hasattr(m, "out_features")] == [512, 512, 256, 128, 4]
+    # a saved PPO archive and a saved SAC archive are both rolled out by test_saved
+    from drl_dronenavigation_b200.checkpoint import save_sb3_zip
+    from drl_dronenavigation_b200.ppo import PPOConfig, PPOLearner
+    from drl_dronenavigation_b200.sac import SACConfig, SACLearner
+    p_ppo = save_sb3_zip(str(tmp_path / "ppo_best_model"), PPOLearner(13, 4, PPOConfig()))
+    p_sac = save_sb3_zip(str(tmp_path / "sac_best_model"), SACLearner(13, 4, SACConfig(cuda_graph=False)))
+    ev = manager(savemodel=False).test_saved(p_ppo, episodes=20)
+    assert ev["episodes"] >= 20 and ev["mean_ep_length"] > 0
+    ev = manager(agent="SAC", savemodel=False).test_saved(p_sac, episodes=20)
+    assert ev["episodes"] >= 20 and ev["mean_found_targets"] >= 0
