@@ -105,3 +105,49 @@ def test_learning_and_saved_run_types(manager, tmp_path):
     assert ev["episodes"] >= 20 and ev["mean_ep_length"] > 0
     ev = manager(agent="SAC", savemodel=False).test_saved(p_sac, episodes=20)
     assert ev["episodes"] >= 20 and ev["mean_found_targets"] >= 0
+
+
+# ---- N > 1: the manager's data-parallel path (one process per shard, gradients all-reduced) on gloo, world_size 2 --------------
+def _dp_worker(rank, world, port, tmp, agent):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.chdir(tmp)
+    torch.set_num_threads(2)                      # two ranks share the host's cores
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from drl_dronenavigation_b200 import sac as S
+        track = W.Track(W.circle(radius=1, num_points=6, height=1), circle=True)
+        # rank 1 would stop one iteration later on its own (a later wall-clock cap would do the same): ranks must leave together
+        sim = PBDroneSimulator(_args(agent=agent, rank=rank, world=world, savemodel=(rank == 0), num_envs=16,
+                                     total_timesteps=(16 * 2 * 16 * 3 if agent == "PPO" else 16 * 2 * 3 * 10)), track)
+        offsets = []
+
+        def make_device_env(num_envs, normalize_obs=False, device=None, env_id_offset=0):
+            offsets.append(env_id_offset)
+            return EmuTorchEnv(num_envs, sim.targets, **sim._env_kwargs(None, sim.aviary_dim, True, True))
+        sim.make_device_env = make_device_env
+        orig = S.SACConfig
+        S.SACConfig = lambda: orig(learning_starts=16 * 2 * 3 * 3, batch_size=64, buffer_size=16 * 64, cuda_graph=False)
+        try:
+            trainer, ev = sim.run_full_training(log=lambda *_: None)
+        finally:
+            S.SACConfig = orig
+        torch.save({"p": trainer.learner.flat_parameters(), "steps": trainer.total_steps, "offset": offsets[0],
+                    "n_updates": trainer.learner.n_updates}, os.path.join(tmp, f"dp_{agent}_{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("agent", ["PPO", "SAC"])
+def test_two_rank_gloo_manager_run(agent, tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path), agent), nprocs=2, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"dp_{agent}_{k}.pt"), weights_only=False) for k in range(2)]
+    assert torch.equal(r[0]["p"], r[1]["p"])                          # parameters stay bit-identical across ranks
+    assert r[0]["steps"] == r[1]["steps"] and r[0]["n_updates"] == r[1]["n_updates"] > 0
+    assert (r[0]["offset"], r[1]["offset"]) == (0, 16)                # contiguous global env-id shards
+    assert len(glob.glob(str(tmp_path / "Sol" / "model_chkpts" / f"{agent}_save_*"))) == 1      # one writer per job
