@@ -40,7 +40,13 @@ def main(argv=None):
         track = Track(getattr(Waypoints, args.track)(), circle=False)
     sim = PBDroneSimulator(args, track, target_factor=0)
     if args.run_type in ("full", "cont"):
-        sim.run_full_training(log=print if rank == 0 else (lambda *a, **k: None))
+        log = print if rank == 0 else (lambda *a, **k: None)
+        if getattr(args, "profile", False):              # simulation_controller.py:111-117
+            from .profiler import Profiler
+            with Profiler(print_fn=log):
+                sim.run_full_training(log=log)
+        else:
+            sim.run_full_training(log=log)
     elif args.run_type == "test":
         sim.run_test()
     elif args.run_type == "saved":
@@ -49,7 +55,6 @@ def main(argv=None):
         sim.test_learning()
     else:
         raise NotImplementedError(f"--run_type {args.run_type}")
-
 
     if world > 1:
         import torch.distributed as dist

@@ -151,3 +151,19 @@ def test_two_rank_gloo_manager_run(agent, tmp_path):
     assert r[0]["steps"] == r[1]["steps"] and r[0]["n_updates"] == r[1]["n_updates"] > 0
     assert (r[0]["offset"], r[1]["offset"]) == (0, 16)                # contiguous global env-id shards
     assert len(glob.glob(str(tmp_path / "Sol" / "model_chkpts" / f"{agent}_save_*"))) == 1      # one writer per job
+
+
+def test_profile_flag_wraps_the_training_run(monkeypatch, tmp_path, capsys):
+    """--profile t (Sol/Model/simulation_controller.py:111-117): cProfile around run_full_training, cumtime-sorted report."""
+    from drl_dronenavigation_b200 import simulation_controller as SC
+    monkeypatch.chdir(tmp_path)
+    real = PBDroneSimulator.make_device_env
+
+    def make_device_env(self, num_envs, normalize_obs=False, device=None, env_id_offset=0):
+        return EmuTorchEnv(num_envs, self.targets, **self._env_kwargs(None, self.aviary_dim, True, True))
+    monkeypatch.setattr(PBDroneSimulator, "make_device_env", make_device_env)
+    SC.main(["--agent", "PPO", "--run_type", "full", "--num_envs", "16", "--total_timesteps", "512", "--rollout_steps", "16", "--minibatch", "64",
+             "--n_epochs", "1", "--max_env_steps", "100", "--savemodel", "f", "--profile", "t", "--ctrl_freq", "30"])
+    out = capsys.readouterr().out
+    assert "cumulative" in out and "train_iteration" in out and "final evaluation" in out
+    assert real is not None
