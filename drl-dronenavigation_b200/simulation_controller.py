@@ -24,8 +24,23 @@ def _init_distributed():
     return dist.get_rank(), world
 
 
+def _reject_out_of_scope(args):
+    """Flags of the reference's parser that select subsystems outside the env-step path: accepted by the parser
+    so that the reference's command lines parse, but selecting one fails loudly instead of silently running something else."""
+    if getattr(args, "lib", "sb3") != "sb3":
+        raise NotImplementedError(f"--lib {args.lib}: the Ray / TF-Agents / CleanRL launchers are out of scope; the torch-native learners replace --lib sb3")
+    for flag, why in (("wandb", "wandb logging is out of scope (no network); use --tensorboard DIR"),
+                      ("capture_video", "video capture needs the PyBullet renderer"), ("gui", "the PyBullet GUI is outside the CUDA hot path"),
+                      ("vec_normalize", "the reference wraps a single gym env in VecNormalize here, which raises (PBDroneSimulator.py:186-189); "
+                                        "NormalizeObservation is always fused, --norm_rew / --clip_rew select the reward wrappers"),
+                      ("vec_check_nan", "the reference wraps a single gym env in VecCheckNan here, which raises (PBDroneSimulator.py:186-189)")):
+        if getattr(args, flag, False):
+            raise NotImplementedError(f"--{flag}: {why}")
+
+
 def main(argv=None):
     args = parse_args(argv)
+    _reject_out_of_scope(args)
     rank, world = _init_distributed()
     args.rank, args.world = rank, world
     if rank != 0:

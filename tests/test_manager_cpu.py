@@ -167,3 +167,12 @@ def test_profile_flag_wraps_the_training_run(monkeypatch, tmp_path, capsys):
     out = capsys.readouterr().out
     assert "cumulative" in out and "train_iteration" in out and "final evaluation" in out
     assert real is not None
+
+
+@pytest.mark.parametrize("flags,msg", [(["--lib", "ray"], "out of scope"), (["--wandb", "t"], "tensorboard"), (["--gui", "t"], "GUI"),
+                                       (["--capture-video", "t"], "renderer"), (["--vec_normalize", "t"], "VecNormalize"),
+                                       (["--vec_check_nan", "t"], "VecCheckNan")])
+def test_out_of_scope_flags_fail_loudly(flags, msg):
+    from drl_dronenavigation_b200 import simulation_controller as SC
+    with pytest.raises(NotImplementedError, match=msg):
+        SC.main(flags)
