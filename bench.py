@@ -169,6 +169,19 @@ def cpu_baseline_batched(track, S, envs, budget_s=10.0):
                       f"saturating actions, {max(times):.1f} s; the reference itself steps one Python env per worker process"}
 
 
+def pybullet_cpu():
+    """the reference's real PyBullet path can only be timed if its third-party stack imports."""
+    missing = []
+    for mod in ("pybullet", "gymnasium", "stable_baselines3"):
+        try:
+            __import__(mod)
+        except Exception:  # noqa: BLE001
+            missing.append(mod)
+    if missing:
+        return "n/a (not installable: " + ", ".join(missing) + " missing on this box, no network, no wheel)"
+    return "n/a (modules import, but /root/reference is not present on the GPU box)"
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python on
     PyBullet; neither pybullet nor gymnasium nor SB3 is installable here, and its own DYN branch is dead
@@ -195,11 +208,19 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * max(times) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "envs_in_sample": n_envs, "substeps": S, "track": track},
+            "config": bench_config(args, int(os.environ.get("WORLD_SIZE", "1"))), "envs_in_sample": n_envs,
+            "pybullet_cpu": pybullet_cpu(),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
     print(json.dumps(line), flush=True)
+
+
+def bench_config(args, world):
+    """The `config` object of BOTH arms (the reference arm runs "on your arm's config"): identical keys and values."""
+    return {"workload": workload_name(args), "envs_per_gpu": args.envs, "substeps": args.substeps, "track": args.track,
+            "actions": args.actions, "l2": "inputs larger than L2 (rotating handles, no flush kernel)",
+            "parallelism": f"env-shard x{world} (no data-path collective)"}
 
 
 def workload_name(args):
@@ -285,14 +306,18 @@ def time_flushed(env, acts, K, W, flush_buf):
     return float(per.sum()) * 1e-3, per
 
 
-def time_rotating(args, dev, N, K, W, rank, n_handles=None, on_timed=None):
+def time_rotating(args, dev, N, K, W, rank, n_handles=None, on_timed=None, min_timed_s=0.02):
     """`inputs larger than L2`: M independent N-env handles (state + actions + outputs of all of them > 126 MB L2) are
-    stepped round-robin, one launch per handle, replayed from CUDA graphs on one stream; one event pair around
-    EXACTLY K launches.  Every launch therefore finds its state, its actions and its output lines in HBM, not in
-    L2, without a flush kernel between launches and without per-launch event records in the timed region."""
+    stepped round-robin, one launch per handle, replayed from CUDA graphs on one stream.  The unit that is timed is a
+    block of EXACTLY K launches; when K launches are shorter than `min_timed_s` the block is repeated R times inside the
+    one CUDA-event pair (successive blocks continue the rotation, so every launch still finds its state, its actions and
+    its output lines in HBM, not in L2) and the mean over the R blocks is reported.  Every graph that is replayed inside
+    the timed region has been replayed once before it (a first replay pays the graph upload)."""
     import torch
     per_handle = N * (BYTES_PER_ENV_STEP - 112)          # state planes once + actions + outputs, bytes resident per handle
     M = n_handles or max(8, int(np.ceil(160e6 / per_handle)))
+    if not n_handles and K < M:
+        M = K * -(-M // K)                               # whole number of K-launch blocks per rotation
     envs = [make_env(N, args, dev, env_id_offset=rank * N) for _ in range(M)]
     for e in envs:
         e.reset()
@@ -305,36 +330,45 @@ def time_rotating(args, dev, N, K, W, rank, n_handles=None, on_timed=None):
                 e.step(acts[m])
     torch.cuda.current_stream(dev).wait_stream(s)
     torch.cuda.synchronize()
-    full, rem = divmod(K, M)
-    g_full, g_rem = torch.cuda.CUDAGraph(), (torch.cuda.CUDAGraph() if rem else None)
-    with torch.cuda.graph(g_full, stream=s):
-        for m, e in enumerate(envs):
-            e.step(acts[m])
-    if rem:
-        with torch.cuda.graph(g_rem, stream=s):
-            for m, e in enumerate(envs[:rem]):
-                e.step(acts[m])
-    g_full.replay()                                      # one more untimed rotation through the graph path
+    # the K launches of block b are handles (b*K + j) % M, j < K.  Graphs: one per distinct starting handle; the list of
+    # starting handles is periodic with period M / gcd(K, M), capped so that capture stays cheap (the cap only shortens
+    # the rotation: with >= 160 MB in flight per period it stays larger than L2 whenever n_period * K >= M)
+    period = M // int(np.gcd(K, M))
+    n_graphs = max(1, M // K) if K < M else min(period, 4)   # K < M: whole blocks of one rotation (>= 126 MB before any reuse)
+    graphs = []
+    for b in range(n_graphs):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for j in range(K):
+                m = (b * K + j) % M
+                envs[m].step(acts[m])
+        graphs.append(g)
+    for g in graphs:                                     # first replay of every graph outside the timed region
+        g.replay()
     torch.cuda.synchronize()
-    if on_timed:
-        on_timed(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(full):
-        g_full.replay()
-    if rem:
-        g_rem.replay()
+    graphs[0].replay()
+    e1.record()
+    torch.cuda.synchronize()
+    est = max(e0.elapsed_time(e1) * 1e-3, 1e-6)          # one block, to size R
+    R = int(max(1, min(100000, np.ceil(min_timed_s / est))))
+    if on_timed:
+        on_timed(True)
+    e0.record()
+    for r in range(R):
+        graphs[r % n_graphs].replay()
     e1.record()
     torch.cuda.synchronize()
     if on_timed:
         on_timed(False)
-    sec = e0.elapsed_time(e1) * 1e-3
+    total = e0.elapsed_time(e1) * 1e-3
     eps = sum(int(e.episode_stats()["episodes"]) for e in envs[:4])
     for e in envs:
         e.close()
-    del envs, acts
+    del envs, acts, graphs
     torch.cuda.empty_cache()
-    return sec, full * M + rem, M, per_handle * M, eps
+    return total / R, K, M, per_handle * M, eps, R, total, n_graphs
 
 
 def time_launch_floor(env, K, flush_buf):
@@ -383,7 +417,7 @@ def time_launch_floor(env, K, flush_buf):
             "kernel": "dn::action_map_kernel over 4 floats (empty-kernel stand-in)"}
 
 
-def time_graph(env, acts, K, W, group=None):
+def time_graph(env, acts, K, W, group=None, min_timed_s=0.02):
     """K launches replayed from CUDA graphs of `group` steps each, back to back, one event pair around all."""
     import torch
     A = acts.shape[0]
@@ -409,7 +443,14 @@ def time_graph(env, acts, K, W, group=None):
         g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e-3, group
+    est = max(e0.elapsed_time(e1) * 1e-3, 1e-6)
+    R = int(max(1, min(100000, np.ceil(min_timed_s / est))))   # K launches repeated R times inside one event pair
+    e0.record()
+    for _ in range(R * (K // group)):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / R, group
 
 
 def time_plain(env, acts, K, W):
@@ -580,12 +621,13 @@ def run_b200(args):
     def around_timed(start):          # barrier + synchronize on both sides of the timed region, on every rank
         barrier()
         win["t0" if start else "t1"] = time.time()
-    sec, k_r, m_r, bytes_r, eps_r = time_rotating(args, dev, N, K, W, rank, n_handles=args.rotating_handles, on_timed=around_timed)
+    sec, k_r, m_r, bytes_r, eps_r, reps, timed_s, n_graphs = time_rotating(args, dev, N, K, W, rank, n_handles=args.rotating_handles,
+                                                                           on_timed=around_timed)
     assert k_r == K
     barrier()
     sec = max_over_ranks(sec)
     value = world * N * K / sec
-    launches = K
+    launches = K * reps
     l2_note = ("PROFILING RUN with a reduced number of handles (L2-resident): " if args.rotating_handles else "") + \
               (f"inputs larger than L2: {m_r} independent {N}-env handles = {bytes_r / 1e6:.0f} MB of state + actions + outputs "
                "(> 126 MB L2) stepped round-robin from CUDA graphs on one stream, so every launch reads its inputs from HBM; "
@@ -613,9 +655,12 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * sec / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "envs_per_gpu": N, "substeps": args.substeps, "track": args.track,
-                       "actions": args.actions, "l2": l2_note, "handles": m_r,
-                       "parallelism": f"env-shard x{world} (no data-path collective)"},
+            "config": bench_config(args, world),
+            "reps": reps, "timed_region_s": timed_s,
+            "timing": {"l2": l2_note, "handles": m_r, "graphs": n_graphs, "launches_per_graph": K, "reps": reps,
+                       "timed_region_s": timed_s, "launches_in_timed_region": K * reps,
+                       "note": "ms_per_step = timed_region_s / (reps * steps): the K-launch block is repeated `reps` times inside ONE "
+                               "CUDA-event pair because K launches alone are shorter than 20 ms; every replayed graph is warmed first"},
             "physics_steps_per_s": value * args.substeps,
             "clocks": clocks, "gpu_launches": int(launches), "l2_resident": resident, "flushed_event_bracket": flushed,
             "episodes_finished_sample": eps_r}
@@ -770,6 +815,7 @@ def run_b200(args):
 
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.track, args.substeps, budget_s=args.cpu_budget)
+        line["pybullet_cpu"] = pybullet_cpu()
         try:
             line["cpu_baseline_batched"] = cpu_baseline_batched(args.track, args.substeps, args.envs)
         except Exception as ex:  # noqa: BLE001
