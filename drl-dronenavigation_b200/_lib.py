@@ -88,6 +88,9 @@ SYMBOLS = {
     "dn_get_state": (C.c_int, [C.c_void_p, C.POINTER(dn_state_view), C.c_void_p]),
     "dn_set_state": (C.c_int, [C.c_void_p, C.POINTER(dn_state_view), C.c_void_p]),
     "dn_episode_stats": (C.c_int, [C.c_void_p, C.POINTER(dn_stats), C.c_int, C.c_void_p]),
+    # include/dnppo.h
+    "dn_mlp_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,387 @@
+// dn_umma.cuh -- hand-written sm_100a GEMM building blocks for the PPO minibatch update:
+// TMA (cp.async.bulk.tensor) operand loads into 128B-swizzled shared memory, tcgen05.mma (kind::f16, BF16 inputs,
+// FP32 accumulation in TMEM) issued by one thread, tcgen05.ld epilogues fused with the elementwise work of the layer.
+//
+// One persistent, warp-specialised kernel template `umma_gemm<KIND, BN>` serves the three contractions of an MLP layer
+//   FWD    Y  = tanh(X W^T + b)            A = X  [M,K]   K-major, B = W  [N,K]    K-major
+//   DGRAD  dX = (dY W) * (1 - H^2)         A = dY [M,N]   K-major, B = W  [N,K]    MN-major (reduction over W's rows)
+//   WGRAD  dW = dY^T X  (split over rows)  A = dY [m,N]   MN-major, B = X [m,K]    MN-major (reduction over the batch rows)
+// so that no transposed copy of an activation, a gradient or a weight is ever written.
+//
+// FP32-faithful arithmetic on BF16 tensor cores: every FP32 matrix is stored as two BF16 planes, hi = bf16(x) and
+// lo = bf16(x - hi) (plane 1 follows plane 0 in the same allocation), and a product is accumulated as
+//   A B ~= A_hi B_hi + A_hi B_lo + A_lo B_hi          (3 passes over K into the same TMEM accumulator; the dropped
+// lo*lo term and the rounding of lo are ~2^-16 relative to |a||b| per product, 7e-6 on the network's gradients).
+// `passes = 1` is plain BF16 (hi planes only), offered as a labelled option.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dnmma {
+
+constexpr int BM = 128;            // UMMA M (rows of the accumulator = TMEM lanes)
+constexpr int BK = 64;             // BF16 elements per k-block = one 128-byte swizzle row
+constexpr int UK = 16;             // K of one tcgen05.mma.kind::f16
+constexpr int NUM_THREADS = 384;   // warp 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 spare, 4..11 epilogue
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;
+constexpr uint32_t SMEM_BUDGET = 196608;   // operand ring; barriers and the TMEM pointer live after it
+
+enum Kind { K_FWD = 0, K_DGRAD = 1, K_WGRAD = 2 };
+
+struct GemmArgs {
+    int m_tiles, n_tiles, slices;   // tile grid: accumulator rows / BM, accumulator columns / BN, split of the reduction
+    int k_blocks;                   // 64-wide k-blocks per pass per tile
+    int passes;                     // 1 (BF16) or 3 (hi*hi + hi*lo + lo*hi)
+    int a_lo_row, b_lo_row;         // row of the lo plane inside the A / B tensor maps (rows of plane 0)
+    int act;                        // FWD: 1 = tanh, 0 = identity
+    int write_lo;                   // FWD / DGRAD: also write the lo plane of the result
+    const float* bias;              // FWD: [N]
+    __nv_bfloat16* out_hi;          // FWD / DGRAD: result [M, ld_out], hi plane
+    __nv_bfloat16* out_lo;          //              lo plane (write_lo)
+    int ld_out;
+    const __nv_bfloat16* h_hi;      // DGRAD: tanh output H [M, ld_out] whose derivative 1 - H^2 multiplies the product
+    const __nv_bfloat16* h_lo;      //        (nullptr: hi plane only)
+    float* partial;                 // WGRAD: [slices][rows][ld_partial] FP32 partial products
+    int ld_partial;
+    long long slice_stride;         // elements between slices of `partial`
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol error becomes a trap (an error the host sees) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 28)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2-D tiled load: box lands densely in shared memory with the map's 128-byte swizzle, bytes counted on `bar`.
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], BF16 inputs, FP32 accumulate.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once every MMA issued so far by this thread has completed (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive FP32 columns of the accumulator -> 32 registers per thread (thread = accumulator row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp of the CUTLASS tree vendored in this image)
+// ------------------------------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, 128-byte swizzle; offsets in bytes
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);              // [0,14)  start address >> 4
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;    // [16,30) leading-dimension byte offset >> 4
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;    // [32,46) stride-dimension byte offset >> 4
+    d |= static_cast<uint64_t>(1) << 46;                            // [46,48) descriptor version 1 (Blackwell)
+    d |= static_cast<uint64_t>(2) << 61;                            // [61,64) layout type 2 = SWIZZLE_128B
+    return d;
+}
+// K-major operand tile: rows x 64 BF16, each row one swizzled 128-byte line; 8-row groups 1024 bytes apart;
+// the k-th UMMA_K slice starts 32 bytes further inside the line
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int k) { return smem_desc(tile + k * (UK * 2), 16, 1024); }
+// MN-major operand tile: TMA boxes of 64 k-rows x 64 contiguous MN elements (8192 bytes per box, boxes side by side
+// along MN); 8-k-row groups 1024 bytes apart (SBO), 64-element MN chunks one box apart (LBO); the k-th UMMA_K slice
+// starts 16 k-rows = 2048 bytes further
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int k) { return smem_desc(tile + k * (UK * 128), 8192, 1024); }
+
+// instruction descriptor: D = F32, A = B = BF16, M = 128, N = n
+__host__ __device__ constexpr uint32_t instr_desc(int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4)                                  // [4,6)   D format F32
+           | (1u << 7)                                // [7,10)  A format BF16
+           | (1u << 10)                               // [10,13) B format BF16
+           | (static_cast<uint32_t>(a_mn_major) << 15)  // [15]    A major (0 = K, 1 = MN)
+           | (static_cast<uint32_t>(b_mn_major) << 16)  // [16]    B major
+           | (static_cast<uint32_t>(n >> 3) << 17)      // [17,23) N >> 3
+           | (static_cast<uint32_t>(BM >> 4) << 24);    // [24,29) M >> 4
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// helpers of the epilogues
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+__device__ __forceinline__ float bf16lo_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// x -> (hi, lo) BF16 planes, 32 values = 4 x 16-byte stores per plane
+__device__ __forceinline__ void store_split32(const float (&y)[32], __nv_bfloat16* hi_row, __nv_bfloat16* lo_row, bool write_lo) {
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * j]), h1 = __float2bfloat16_rn(y[2 * j + 1]);
+        h[j] = pack_bf16(h0, h1);
+        l[j] = pack_bf16(__float2bfloat16_rn(y[2 * j] - __bfloat162float(h0)), __float2bfloat16_rn(y[2 * j + 1] - __bfloat162float(h1)));
+    }
+    uint4* ph = reinterpret_cast<uint4*>(hi_row);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ph[q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    if (write_lo) {
+        uint4* pl = reinterpret_cast<uint4*>(lo_row);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pl[q] = make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
+    }
+}
+
+template <int BN>
+struct Cfg {
+    static constexpr uint32_t A_BYTES = BM * BK * 2;                 // 16 KB
+    static constexpr uint32_t B_BYTES = BN * BK * 2;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+    static constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES;
+    static constexpr uint32_t SMEM_BYTES = RING_BYTES + 1024 /* alignment slack */ + 256 /* barriers + TMEM pointer */;
+    static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------------
+template <int KIND, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+    using C = Cfg<BN>;
+    static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
+    constexpr int STAGES = C::STAGES;
+    constexpr uint32_t IDESC = instr_desc(BN, KIND == K_WGRAD, KIND != K_FWD);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;       // [2] accumulator stage ready for the epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator stage drained
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = g.m_tiles * g.n_tiles * g.slices;
+    const int kb_total = g.k_blocks * g.passes;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], EPI_WARPS);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int nt = t % g.n_tiles, mt = (t / g.n_tiles) % g.m_tiles, sl = t / (g.n_tiles * g.m_tiles);
+                for (int p = 0; p < g.passes; ++p) {
+                    const int a_row = (p == 2) ? g.a_lo_row : 0;       // passes: (hi,hi) (hi,lo) (lo,hi)
+                    const int b_row = (p == 1) ? g.b_lo_row : 0;
+                    for (int kb = 0; kb < g.k_blocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                        uint8_t* sb = sa + C::A_BYTES;
+                        mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                        if constexpr (KIND == K_FWD) {
+                            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, a_row + mt * BM);                 // X rows, K slice
+                            tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, b_row + nt * BN);                 // W rows, K slice
+                        } else if constexpr (KIND == K_DGRAD) {
+                            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, a_row + mt * BM);                 // dY rows, N slice
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)                                                   // W rows = reduction
+                                tma_load_2d(&tmB, &full_bar[stage], sb + j * 8192, nt * BN + j * 64, b_row + kb * BK);
+                        } else {
+                            const int r0 = (sl * g.k_blocks + kb) * BK;                                         // batch rows = reduction
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j)
+                                tma_load_2d(&tmA, &full_bar[stage], sa + j * 8192, mt * BM + j * 64, a_row + r0);
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_2d(&tmB, &full_bar[stage], sb + j * 8192, nt * BN + j * 64, b_row + r0);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES), sb = sa + C::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) {
+                        const uint64_t da = (KIND == K_WGRAD) ? desc_mnmajor(sa, k) : desc_kmajor(sa, k);
+                        const uint64_t db = (KIND == K_FWD) ? desc_kmajor(sb, k) : desc_mnmajor(sb, k);
+                        umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);                // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================================== epilogue ==========================================
+        const int q = warp & 3;                              // TMEM lane quadrant this warp may read
+        const int half = (warp - EPI_WARP0) >> 2;            // which half of the BN columns
+        const int row_in_tile = q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int nt = t % g.n_tiles, mt = (t / g.n_tiles) % g.m_tiles, sl = t / (g.n_tiles * g.m_tiles);
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+            const long long row = static_cast<long long>(mt) * BM + row_in_tile;
+#pragma unroll 1
+            for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+                float v[32];
+                tmem_ld32(t_row + c, v);
+                const int col = nt * BN + c;
+                if constexpr (KIND == K_FWD) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float z = v[j] + __ldg(g.bias + col + j);
+                        v[j] = g.act ? tanhf(z) : z;
+                    }
+                    store_split32(v, g.out_hi + row * g.ld_out + col, g.out_lo + row * g.ld_out + col, g.write_lo != 0);
+                } else if constexpr (KIND == K_DGRAD) {
+                    const uint4* hh = reinterpret_cast<const uint4*>(g.h_hi + row * g.ld_out + col);
+                    uint32_t hw[16], lw[16];
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const uint4 u = __ldg(hh + qd);
+                        hw[4 * qd] = u.x; hw[4 * qd + 1] = u.y; hw[4 * qd + 2] = u.z; hw[4 * qd + 3] = u.w;
+                    }
+                    if (g.h_lo != nullptr) {
+                        const uint4* hl = reinterpret_cast<const uint4*>(g.h_lo + row * g.ld_out + col);
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) {
+                            const uint4 u = __ldg(hl + qd);
+                            lw[4 * qd] = u.x; lw[4 * qd + 1] = u.y; lw[4 * qd + 2] = u.z; lw[4 * qd + 3] = u.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) lw[j] = 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float h0 = bf16lo_f(hw[j]) + bf16lo_f(lw[j]), h1 = bf16hi_f(hw[j]) + bf16hi_f(lw[j]);
+                        v[2 * j] *= fmaf(-h0, h0, 1.0f);
+                        v[2 * j + 1] *= fmaf(-h1, h1, 1.0f);
+                    }
+                    store_split32(v, g.out_hi + row * g.ld_out + col, g.out_lo + row * g.ld_out + col, g.write_lo != 0);
+                } else {
+                    float4* dst = reinterpret_cast<float4*>(g.partial + sl * g.slice_stride + row * g.ld_partial + col);
+#pragma unroll
+                    for (int qd = 0; qd < 8; ++qd) dst[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+}  // namespace dnmma

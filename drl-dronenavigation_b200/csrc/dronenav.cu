@@ -648,6 +648,7 @@ struct dn_env {
 static thread_local std::string g_err;
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int dn_internal_fail(int code, const std::string& msg) { return fail(code, msg); }   // other translation units (ppo_update.cu)
 
 #define DN_CUDA(expr)                                                                    \
     do {                                                                                 \
