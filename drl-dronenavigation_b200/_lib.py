@@ -69,6 +69,37 @@ class dn_stats(C.Structure):
     ]
 
 
+# ---- include/dnppo.h ------------------------------------------------------------------------------------------
+DN_MLP_BF16X3, DN_MLP_BF16 = 0, 1
+DN_PPO_MAX_LAYERS = 4
+
+
+class dn_ppo_config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("max_rows", C.c_int32),
+        ("n_pi", C.c_int32), ("n_vf", C.c_int32),
+        ("pi_hidden", C.c_int32 * DN_PPO_MAX_LAYERS), ("vf_hidden", C.c_int32 * DN_PPO_MAX_LAYERS),
+        ("precision", C.c_int32), ("normalize_advantage", C.c_int32), ("world_size", C.c_int32), ("reserved0", C.c_int32),
+        ("clip_range", C.c_float), ("clip_range_vf", C.c_float), ("ent_coef", C.c_float), ("vf_coef", C.c_float),
+        ("max_grad_norm", C.c_float), ("target_kl", C.c_float),
+        ("learning_rate", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+        ("pi_w_off", C.c_int64 * (DN_PPO_MAX_LAYERS + 1)), ("pi_b_off", C.c_int64 * (DN_PPO_MAX_LAYERS + 1)),
+        ("vf_w_off", C.c_int64 * (DN_PPO_MAX_LAYERS + 1)), ("vf_b_off", C.c_int64 * (DN_PPO_MAX_LAYERS + 1)),
+        ("log_std_off", C.c_int64), ("n_params", C.c_int64),
+    ]
+
+
+class dn_ppo_rollout(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("actions", C.c_void_p), ("old_log_prob", C.c_void_p), ("old_values", C.c_void_p),
+                ("advantages", C.c_void_p), ("returns", C.c_void_p)]
+
+
+class dn_ppo_stats(C.Structure):
+    _fields_ = [("policy_gradient_loss", C.c_double), ("value_loss", C.c_double), ("approx_kl", C.c_double),
+                ("clip_fraction", C.c_double), ("minibatches", C.c_int32), ("optimizer_steps", C.c_int32),
+                ("early_stop", C.c_int32), ("last_approx_kl", C.c_float), ("last_grad_norm", C.c_float)]
+
+
 # every symbol include/dronenav.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "dn_abi_version": (C.c_int, []),
@@ -91,6 +122,17 @@ SYMBOLS = {
     # include/dnppo.h
     "dn_mlp_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dn_ppo_create": (C.c_int, [C.POINTER(dn_ppo_config), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.POINTER(C.c_void_p)]),
+    "dn_ppo_destroy": (C.c_int, [C.c_void_p]),
+    "dn_ppo_sync_weights": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dn_ppo_begin_update": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dn_ppo_minibatch_grad": (C.c_int, [C.c_void_p, C.POINTER(dn_ppo_rollout), C.c_void_p, C.c_int32, C.c_void_p]),
+    "dn_ppo_minibatch_apply": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dn_ppo_get_stats": (C.c_int, [C.c_void_p, C.POINTER(dn_ppo_stats), C.c_void_p]),
+    "dn_ppo_poll": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "dn_ppo_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dn_ppo_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
 }
 
 _lib = None

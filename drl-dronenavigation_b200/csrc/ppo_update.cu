@@ -14,6 +14,7 @@
 #include "../../include/dnppo.h"
 #include "../../include/dronenav.h"
 #include "dn_umma.cuh"
+#include "ppo_kernels.cuh"
 
 int dn_internal_fail(int code, const std::string& msg);   // dronenav.cu: sets the thread-local dn_last_error message
 
@@ -148,6 +149,255 @@ int plan_wgrad(GemmPlan* p, int passes, int Mo, int No, int rows, int slices, co
     return DN_OK;
 }
 
+
+// ====================================================================================================================
+// the update handle
+// ====================================================================================================================
+using namespace dnppo;
+
+struct Net {                      // one MLP (pi or vf)
+    int L = 0;                    // hidden layers
+    int n[MAX_LAYERS + 1] = {};   // n[0] = XPAD (padded observation), n[l] = width of hidden layer l
+    long long w_off[MAX_LAYERS + 1] = {}, b_off[MAX_LAYERS + 1] = {};   // flat offsets; index L = head
+    __nv_bfloat16* h[MAX_LAYERS + 1] = {};     // activation planes [2][max_rows][n[l]] (h[0] = shared observation planes)
+    __nv_bfloat16* dz[MAX_LAYERS + 1] = {};    // pre-activation gradient planes
+    __nv_bfloat16* w[MAX_LAYERS + 1] = {};     // weight planes [2][n[l]][n[l-1]]
+    float* wpart[MAX_LAYERS + 1] = {};         // split-K partials of the weight gradient [slices][n[l]][n[l-1]]
+    float* bpart[MAX_LAYERS + 1] = {};         // column-sum partials of the bias gradient [COLSUM_CHUNKS][n[l]]
+    int slices_max[MAX_LAYERS + 1] = {};
+    GemmPlan fwd[MAX_LAYERS + 1], dgrad[MAX_LAYERS + 1], wgrad[MAX_LAYERS + 1];
+};
+
+}  // namespace
+
+struct dn_ppo {
+    dn_ppo_config cfg;
+    int device = 0, passes = 3, sms = 148;
+    int max_rows = 0;
+    float *params = nullptr, *grads = nullptr, *exp_avg = nullptr, *exp_avg_sq = nullptr, *step = nullptr;
+    Net pi, vf;
+    __nv_bfloat16* x = nullptr;
+    float *m_act = nullptr, *m_logp = nullptr, *m_val = nullptr, *m_adv = nullptr, *m_ret = nullptr;
+    double *adv_partial = nullptr, *norm_partial = nullptr;
+    float* head_partial = nullptr;
+    int head_blocks_max = 0, head_psize = 0;
+    size_t head_smem = 0;
+    Ctrl* ctrl = nullptr;
+    int* mirror = nullptr;          // pinned + mapped
+    int* mirror_dev = nullptr;
+    Seg* segs_dev = nullptr; int* seg_of_block_dev = nullptr; int n_segs = 0, reduce_blocks = 0;
+    std::vector<Seg> segs_host;
+    PlaneSeg* psegs_dev = nullptr; int* pseg_of_block_dev = nullptr; int plane_blocks = 0;
+    int cur_rows = -1;
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+int wgrad_slices(int rows, int tiles, int sms) {
+    const int target = std::max(1, sms / std::max(tiles, 1));
+    int s = 1;
+    while (s * 2 <= target && rows % (64 * s * 2) == 0 && rows / (s * 2) >= 256) s *= 2;
+    return s;
+}
+
+template <typename T>
+int dev_alloc(dn_ppo* h, T** p, size_t count) {
+    void* q = nullptr;
+    PPO_CUDA(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    PPO_CUDA(cudaMemset(q, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    h->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return DN_OK;
+}
+
+int setup_net(dn_ppo* h, Net& net, int L, const int32_t* hidden, const int64_t* w_off, const int64_t* b_off) {
+    net.L = L;
+    net.n[0] = XPAD;
+    const long long R = h->max_rows;
+    int rc;
+    for (int l = 1; l <= L; ++l) net.n[l] = hidden[l - 1];
+    for (int l = 0; l <= L; ++l) { net.w_off[l] = w_off[l]; net.b_off[l] = b_off[l]; }
+    net.h[0] = h->x;
+    for (int l = 1; l <= L; ++l) {
+        const int N = net.n[l], K = net.n[l - 1];
+        if ((rc = dev_alloc(h, &net.h[l], 2 * R * N)) || (rc = dev_alloc(h, &net.dz[l], 2 * R * N)) ||
+            (rc = dev_alloc(h, &net.w[l], 2LL * N * K)))
+            return rc;
+        const int tiles = (N / BM) * (K / pick_bn(K));
+        net.slices_max[l] = wgrad_slices(h->max_rows, tiles, h->sms);
+        if ((rc = dev_alloc(h, &net.wpart[l], static_cast<size_t>(net.slices_max[l]) * N * K)) ||
+            (rc = dev_alloc(h, &net.bpart[l], static_cast<size_t>(COLSUM_CHUNKS) * N)))
+            return rc;
+        // plans: tensor maps over the full workspaces (lo plane max_rows rows after the hi plane), tile counts set per call
+        const float* bias = h->params + net.b_off[l - 1];
+        if ((rc = plan_fwd(&net.fwd[l], h->passes, h->max_rows, N, K, net.h[l - 1], net.w[l], bias, 1, net.h[l]))) return rc;
+        if (l > 1 && (rc = plan_dgrad(&net.dgrad[l], h->passes, h->max_rows, K, N, net.dz[l], net.w[l], net.h[l - 1], net.dz[l - 1]))) return rc;
+        if ((rc = plan_wgrad(&net.wgrad[l], h->passes, N, K, h->max_rows, 1, net.dz[l], net.h[l - 1], net.wpart[l]))) return rc;
+    }
+    return DN_OK;
+}
+
+void set_rows(dn_ppo* h, Net& net, int rows) {
+    for (int l = 1; l <= net.L; ++l) {
+        GemmPlan& f = net.fwd[l];
+        f.args.m_tiles = rows / BM;
+        f.grid = std::min(f.args.m_tiles * f.args.n_tiles, h->sms);
+        if (l > 1) {
+            GemmPlan& d = net.dgrad[l];
+            d.args.m_tiles = rows / BM;
+            d.grid = std::min(d.args.m_tiles * d.args.n_tiles, h->sms);
+        }
+        GemmPlan& w = net.wgrad[l];
+        const int tiles = w.args.m_tiles * w.args.n_tiles;
+        w.args.slices = wgrad_slices(rows, tiles, h->sms);
+        w.args.k_blocks = rows / w.args.slices / BK;
+        w.grid = std::min(tiles * w.args.slices, h->sms);
+    }
+}
+
+// reduction table: every parameter tensor <- its partials
+void add_seg(std::vector<Seg>& v, const float* src, long long stride, int n_slices, int rows, int cols, int ld, long long dst) {
+    Seg s;
+    s.src = src; s.slice_stride = stride; s.dst_off = dst; s.n_slices = n_slices; s.rows = rows; s.cols = cols; s.ld = ld;
+    s.first_block = 0; s.n_blocks = 0;
+    v.push_back(s);
+}
+
+int build_reduce_table(dn_ppo* h, int rows) {
+    std::vector<Seg>& v = h->segs_host;
+    v.clear();
+    const int A = h->cfg.act_dim, npi = h->pi.n[h->pi.L], nvf = h->vf.n[h->vf.L];
+    const int head_blocks = std::min(std::max(rows / HEAD_WARPS, 1), h->head_blocks_max);
+    Net* nets[2] = {&h->pi, &h->vf};
+    for (Net* net : nets) {
+        for (int l = 1; l <= net->L; ++l) {
+            const int N = net->n[l], K = net->n[l - 1];
+            const int cols = (l == 1) ? h->cfg.obs_dim : K;                         // the first layer's padding columns are dropped
+            add_seg(v, net->wpart[l], static_cast<long long>(N) * K, net->wgrad[l].args.slices, N, cols, K, net->w_off[l - 1]);
+            add_seg(v, net->bpart[l], N, COLSUM_CHUNKS, 1, N, N, net->b_off[l - 1]);
+        }
+    }
+    const long long P = h->head_psize;
+    const float* hp = h->head_partial;
+    add_seg(v, hp, P, head_blocks, A, npi, npi, h->pi.w_off[h->pi.L]);
+    add_seg(v, hp + A * npi, P, head_blocks, 1, A, A, h->pi.b_off[h->pi.L]);
+    add_seg(v, hp + A * npi + A, P, head_blocks, 1, nvf, nvf, h->vf.w_off[h->vf.L]);
+    add_seg(v, hp + A * npi + A + nvf, P, head_blocks, 1, 1, 1, h->vf.b_off[h->vf.L]);
+    add_seg(v, hp + A * npi + A + nvf + 1, P, head_blocks, 1, A, A, h->cfg.log_std_off);
+    std::vector<int> sob;
+    for (size_t i = 0; i < v.size(); ++i) {
+        const long long count = static_cast<long long>(v[i].rows) * v[i].cols;
+        v[i].first_block = static_cast<int>(sob.size());
+        v[i].n_blocks = static_cast<int>((count + REDUCE_PER_BLOCK - 1) / REDUCE_PER_BLOCK);
+        for (int b = 0; b < v[i].n_blocks; ++b) sob.push_back(static_cast<int>(i));
+    }
+    if (static_cast<int>(v.size()) > h->n_segs || static_cast<int>(sob.size()) > h->reduce_blocks) {
+        if (h->segs_dev) { cudaFree(h->segs_dev); cudaFree(h->seg_of_block_dev); }
+        PPO_CUDA(cudaMalloc(&h->segs_dev, v.size() * sizeof(Seg)));
+        PPO_CUDA(cudaMalloc(&h->seg_of_block_dev, sob.size() * sizeof(int)));
+    }
+    h->n_segs = static_cast<int>(v.size());
+    h->reduce_blocks = static_cast<int>(sob.size());
+    // synchronous copies: this runs only when the minibatch size changes (never inside a captured graph)
+    PPO_CUDA(cudaMemcpy(h->segs_dev, v.data(), v.size() * sizeof(Seg), cudaMemcpyHostToDevice));
+    PPO_CUDA(cudaMemcpy(h->seg_of_block_dev, sob.data(), sob.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return DN_OK;
+}
+
+int build_plane_table(dn_ppo* h) {
+    std::vector<PlaneSeg> v;
+    std::vector<int> sob;
+    Net* nets[2] = {&h->pi, &h->vf};
+    for (Net* net : nets)
+        for (int l = 1; l <= net->L; ++l) {
+            PlaneSeg s;
+            s.param_off = net->w_off[l - 1]; s.rows = net->n[l]; s.ld = net->n[l - 1];
+            s.cols = (l == 1) ? h->cfg.obs_dim : net->n[l - 1];
+            s.planes = net->w[l];
+            const long long count = static_cast<long long>(s.rows) * s.ld / 2;
+            s.first_block = static_cast<int>(sob.size());
+            s.n_blocks = static_cast<int>((count + 255) / 256);
+            for (int b = 0; b < s.n_blocks; ++b) sob.push_back(static_cast<int>(v.size()));
+            v.push_back(s);
+        }
+    PPO_CUDA(cudaMalloc(&h->psegs_dev, v.size() * sizeof(PlaneSeg)));
+    PPO_CUDA(cudaMalloc(&h->pseg_of_block_dev, sob.size() * sizeof(int)));
+    PPO_CUDA(cudaMemcpy(h->psegs_dev, v.data(), v.size() * sizeof(PlaneSeg), cudaMemcpyHostToDevice));
+    PPO_CUDA(cudaMemcpy(h->pseg_of_block_dev, sob.data(), sob.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->plane_blocks = static_cast<int>(sob.size());
+    return DN_OK;
+}
+
+int ensure_rows(dn_ppo* h, int rows) {
+    if (rows == h->cur_rows) return DN_OK;
+    set_rows(h, h->pi, rows);
+    set_rows(h, h->vf, rows);
+    int rc = build_reduce_table(h, rows);
+    if (rc) return rc;
+    h->cur_rows = rows;
+    return DN_OK;
+}
+
+template <int ACT>
+int launch_head(dn_ppo* h, const HeadArgs& a, int blocks, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        PPO_CUDA(cudaFuncSetAttribute(head_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    head_kernel<ACT><<<blocks, HEAD_WARPS * 32, h->head_smem, st>>>(a);
+    PPO_CUDA(cudaGetLastError());
+    return DN_OK;
+}
+
+int run_head(dn_ppo* h, HeadArgs& a, int blocks, cudaStream_t st) {
+    switch (h->cfg.act_dim) {
+        case 1: return launch_head<1>(h, a, blocks, st);
+        case 3: return launch_head<3>(h, a, blocks, st);
+        case 4: return launch_head<4>(h, a, blocks, st);
+        default: return dn_internal_fail(DN_EINVAL, "dn_ppo: act_dim must be 1, 3 or 4");
+    }
+}
+
+int run_gather(dn_ppo* h, const float* obs, const dn_ppo_rollout* r, const long long* idx, int rows, bool train, cudaStream_t st) {
+    GatherArgs g;
+    memset(&g, 0, sizeof(g));
+    g.obs = obs; g.idx = idx; g.rows = rows; g.obs_dim = h->cfg.obs_dim; g.act_dim = h->cfg.act_dim;
+    g.x_hi = h->x; g.x_lo = (h->passes > 1) ? h->x + static_cast<long long>(h->max_rows) * XPAD : nullptr;
+    if (train) {
+        g.act = r->actions; g.logp = r->old_log_prob; g.val = r->old_values; g.adv = r->advantages; g.ret = r->returns;
+        g.m_act = h->m_act; g.m_logp = h->m_logp; g.m_val = h->m_val; g.m_adv = h->m_adv; g.m_ret = h->m_ret;
+        g.adv_partial = h->adv_partial;
+    }
+    const int blocks = (rows * 8 + 255) / 256;
+    gather_kernel<<<blocks, 256, 0, st>>>(g);
+    PPO_CUDA(cudaGetLastError());
+    return DN_OK;
+}
+
+int run_forward_chain(dn_ppo* h, cudaStream_t st) {
+    int rc;
+    Net* nets[2] = {&h->pi, &h->vf};
+    for (Net* net : nets)
+        for (int l = 1; l <= net->L; ++l)
+            if ((rc = launch_gemm(net->fwd[l], st))) return rc;
+    return DN_OK;
+}
+
+void fill_head_common(dn_ppo* h, HeadArgs& a, int rows) {
+    memset(&a, 0, sizeof(a));
+    const long long R = h->max_rows;
+    const int npi = h->pi.n[h->pi.L], nvf = h->vf.n[h->vf.L];
+    a.rows = rows; a.act_dim = h->cfg.act_dim; a.n_pi = npi; a.n_vf = nvf;
+    a.hp_hi = h->pi.h[h->pi.L]; a.hp_lo = (h->passes > 1) ? a.hp_hi + R * npi : nullptr;
+    a.hv_hi = h->vf.h[h->vf.L]; a.hv_lo = (h->passes > 1) ? a.hv_hi + R * nvf : nullptr;
+    a.w_pi = h->params + h->pi.w_off[h->pi.L]; a.b_pi = h->params + h->pi.b_off[h->pi.L];
+    a.w_vf = h->params + h->vf.w_off[h->vf.L]; a.b_vf = h->params + h->vf.b_off[h->vf.L];
+    a.log_std = h->params + h->cfg.log_std_off;
+    a.partial_size = h->head_psize;
+}
+
 }  // namespace
 
 extern "C" {
@@ -172,6 +422,234 @@ int dn_mlp_gemm(int kind, int passes, int M, int N, int K, int slices, const voi
     }
     if (rc) return rc;
     return launch_gemm(p, static_cast<cudaStream_t>(stream));
+}
+
+
+int dn_ppo_create(const dn_ppo_config* cfg, int device, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* step,
+                  dn_ppo** out) {
+    if (!cfg || !out || !params || !grads || !exp_avg || !exp_avg_sq || !step) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != DN_ABI_VERSION) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: abi_version mismatch");
+    if (cfg->obs_dim < 1 || cfg->obs_dim > XPAD) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: obs_dim must be 1..64");
+    if (cfg->act_dim != 1 && cfg->act_dim != 3 && cfg->act_dim != 4) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: act_dim must be 1, 3 or 4");
+    if (cfg->max_rows < BM || cfg->max_rows % BM) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: max_rows must be a positive multiple of 128");
+    if (cfg->n_pi < 1 || cfg->n_pi > MAX_LAYERS || cfg->n_vf < 1 || cfg->n_vf > MAX_LAYERS)
+        return dn_internal_fail(DN_EINVAL, "dn_ppo_create: 1..4 hidden layers per network");
+    for (int l = 0; l < cfg->n_pi; ++l)
+        if (cfg->pi_hidden[l] < 128 || cfg->pi_hidden[l] % 128) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: hidden widths must be multiples of 128");
+    for (int l = 0; l < cfg->n_vf; ++l)
+        if (cfg->vf_hidden[l] < 128 || cfg->vf_hidden[l] % 128) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: hidden widths must be multiples of 128");
+    if (cfg->pi_hidden[cfg->n_pi - 1] > MAX_HEAD_COLS || cfg->vf_hidden[cfg->n_vf - 1] > MAX_HEAD_COLS)
+        return dn_internal_fail(DN_EINVAL, "dn_ppo_create: the last hidden layer may be at most 512 wide");
+    if (cfg->precision != DN_MLP_BF16X3 && cfg->precision != DN_MLP_BF16) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: unknown precision");
+    if (cfg->world_size < 1) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: world_size must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return dn_internal_fail(DN_ECUDA, "dn_ppo_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: bad device index");
+    PPO_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PPO_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return dn_internal_fail(DN_ECUDA, "dn_ppo_create: the update kernels are sm_100a only (tcgen05 / TMEM / TMA)");
+
+    dn_ppo* h = new dn_ppo();
+    h->cfg = *cfg;
+    h->device = device;
+    h->passes = (cfg->precision == DN_MLP_BF16X3) ? 3 : 1;
+    h->sms = prop.multiProcessorCount;
+    g_num_sms = h->sms;
+    h->max_rows = cfg->max_rows;
+    h->params = params; h->grads = grads; h->exp_avg = exp_avg; h->exp_avg_sq = exp_avg_sq; h->step = step;
+    const long long R = h->max_rows;
+    const int A = cfg->act_dim;
+    int rc = DN_OK;
+    auto bail = [&](int code) { dn_ppo_destroy(h); return code; };
+    if ((rc = dev_alloc(h, &h->x, 2 * R * XPAD))) return bail(rc);
+    if ((rc = setup_net(h, h->pi, cfg->n_pi, cfg->pi_hidden, cfg->pi_w_off, cfg->pi_b_off))) return bail(rc);
+    if ((rc = setup_net(h, h->vf, cfg->n_vf, cfg->vf_hidden, cfg->vf_w_off, cfg->vf_b_off))) return bail(rc);
+    if ((rc = dev_alloc(h, &h->m_act, R * A)) || (rc = dev_alloc(h, &h->m_logp, R)) || (rc = dev_alloc(h, &h->m_val, R)) ||
+        (rc = dev_alloc(h, &h->m_adv, R)) || (rc = dev_alloc(h, &h->m_ret, R)))
+        return bail(rc);
+    if ((rc = dev_alloc(h, &h->adv_partial, 2 * ((R * 8 + 255) / 256))) || (rc = dev_alloc(h, &h->norm_partial, NORM_BLOCKS))) return bail(rc);
+    const int npi = h->pi.n[h->pi.L], nvf = h->vf.n[h->vf.L];
+    h->head_psize = head_partial_size(A, npi, nvf);
+    h->head_blocks_max = 2 * h->sms;
+    h->head_smem = static_cast<size_t>(A * npi + nvf + HEAD_WARPS * h->head_psize) * sizeof(float);
+    if (h->head_smem > 200 * 1024) return bail(dn_internal_fail(DN_EINVAL, "dn_ppo_create: head kernel shared memory exceeds 200 KB"));
+    if ((rc = dev_alloc(h, &h->head_partial, static_cast<size_t>(h->head_blocks_max) * h->head_psize))) return bail(rc);
+    if ((rc = dev_alloc(h, &h->ctrl, 1))) return bail(rc);
+    {
+        void* m = nullptr;
+        cudaError_t e = cudaHostAlloc(&m, 4 * sizeof(int), cudaHostAllocMapped);
+        if (e != cudaSuccess) return bail(dn_internal_fail(DN_ECUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)));
+        h->mirror = static_cast<int*>(m);
+        memset(h->mirror, 0, 4 * sizeof(int));
+        void* d = nullptr;
+        e = cudaHostGetDevicePointer(&d, m, 0);
+        if (e != cudaSuccess) return bail(dn_internal_fail(DN_ECUDA, std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e)));
+        h->mirror_dev = static_cast<int*>(d);
+    }
+    if ((rc = build_plane_table(h))) return bail(rc);
+    if ((rc = ensure_rows(h, h->max_rows))) return bail(rc);
+    if ((rc = dn_ppo_sync_weights(h, nullptr))) return bail(rc);
+    PPO_CUDA(cudaStreamSynchronize(nullptr));
+    *out = h;
+    return DN_OK;
+}
+
+int dn_ppo_destroy(dn_ppo* h) {
+    if (!h) return DN_OK;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->mirror) cudaFreeHost(h->mirror);
+    if (h->segs_dev) cudaFree(h->segs_dev);
+    if (h->seg_of_block_dev) cudaFree(h->seg_of_block_dev);
+    if (h->psegs_dev) cudaFree(h->psegs_dev);
+    if (h->pseg_of_block_dev) cudaFree(h->pseg_of_block_dev);
+    delete h;
+    return DN_OK;
+}
+
+int dn_ppo_sync_weights(dn_ppo* h, void* stream) {
+    if (!h) return dn_internal_fail(DN_EINVAL, "dn_ppo_sync_weights: null handle");
+    planes_kernel<<<h->plane_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->psegs_dev, h->pseg_of_block_dev, h->params, h->passes > 1);
+    PPO_CUDA(cudaGetLastError());
+    return DN_OK;
+}
+
+int dn_ppo_begin_update(dn_ppo* h, void* stream) {
+    if (!h) return dn_internal_fail(DN_EINVAL, "dn_ppo_begin_update: null handle");
+    PPO_CUDA(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), static_cast<cudaStream_t>(stream)));
+    h->mirror[0] = h->mirror[1] = h->mirror[2] = 0;
+    return DN_OK;
+}
+
+int dn_ppo_minibatch_grad(dn_ppo* h, const dn_ppo_rollout* r, const int64_t* idx, int32_t rows, void* stream) {
+    if (!h || !r || !idx) return dn_internal_fail(DN_EINVAL, "dn_ppo_minibatch_grad: null argument");
+    if (rows < BM || rows % BM || rows > h->max_rows) return dn_internal_fail(DN_EINVAL, "dn_ppo_minibatch_grad: rows must be a multiple of 128 within max_rows");
+    if (!r->obs || !r->actions || !r->old_log_prob || !r->old_values || !r->advantages || !r->returns)
+        return dn_internal_fail(DN_EINVAL, "dn_ppo_minibatch_grad: null rollout array");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if ((rc = ensure_rows(h, rows))) return rc;
+    if ((rc = run_gather(h, r->obs, r, reinterpret_cast<const long long*>(idx), rows, true, st))) return rc;
+    if ((rc = run_forward_chain(h, st))) return rc;
+    // heads, losses, gradients w.r.t. the last hidden pre-activations
+    const long long R = h->max_rows;
+    const int npi = h->pi.n[h->pi.L], nvf = h->vf.n[h->vf.L];
+    const int head_blocks = std::min(std::max(rows / HEAD_WARPS, 1), h->head_blocks_max);
+    HeadArgs a;
+    fill_head_common(h, a, rows);
+    a.train = 1;
+    a.m_act = h->m_act; a.m_logp = h->m_logp; a.m_val = h->m_val; a.m_adv = h->m_adv; a.m_ret = h->m_ret;
+    a.adv_partial = h->adv_partial; a.adv_blocks = (rows * 8 + 255) / 256;
+    a.normalize_adv = h->cfg.normalize_advantage && rows > 1;
+    a.clip_range = h->cfg.clip_range; a.clip_range_vf = h->cfg.clip_range_vf; a.vf_coef = h->cfg.vf_coef;
+    a.dzp_hi = h->pi.dz[h->pi.L]; a.dzp_lo = (h->passes > 1) ? a.dzp_hi + R * npi : nullptr;
+    a.dzv_hi = h->vf.dz[h->vf.L]; a.dzv_lo = (h->passes > 1) ? a.dzv_hi + R * nvf : nullptr;
+    a.partial = h->head_partial;
+    if ((rc = run_head(h, a, head_blocks, st))) return rc;
+    // backward through the hidden layers
+    Net* nets[2] = {&h->pi, &h->vf};
+    for (Net* net : nets)
+        for (int l = net->L; l >= 1; --l) {
+            if ((rc = launch_gemm(net->wgrad[l], st))) return rc;
+            const __nv_bfloat16* dz = net->dz[l];
+            colsum_kernel<<<dim3(net->n[l] / 64, COLSUM_CHUNKS), 256, 0, st>>>(dz, (h->passes > 1) ? dz + R * net->n[l] : nullptr, rows, net->n[l],
+                                                                              net->bpart[l]);
+            PPO_CUDA(cudaGetLastError());
+            if (l > 1 && (rc = launch_gemm(net->dgrad[l], st))) return rc;
+        }
+    // every partial -> the flat bucket; statistics; early-stop vote
+    ReduceArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.segs = h->segs_dev; ra.n_segs = h->n_segs; ra.seg_of_block = h->seg_of_block_dev;
+    ra.grads = h->grads; ra.n_params = h->cfg.n_params;
+    ra.head_partial = h->head_partial; ra.head_blocks = head_blocks; ra.head_psize = h->head_psize;
+    ra.head_stats_off = h->head_psize - 4;
+    ra.ent_coef = h->cfg.ent_coef; ra.act_dim = h->cfg.act_dim; ra.log_std_off = h->cfg.log_std_off;
+    ra.kl_limit = (h->cfg.target_kl >= 0.0f) ? 1.5f * h->cfg.target_kl : -1.0f;
+    ra.rows = rows; ra.ctrl = h->ctrl;
+    reduce_kernel<<<h->reduce_blocks + 1, 256, 0, st>>>(ra);
+    PPO_CUDA(cudaGetLastError());
+    return DN_OK;
+}
+
+int dn_ppo_minibatch_apply(dn_ppo* h, void* stream) {
+    if (!h) return dn_internal_fail(DN_EINVAL, "dn_ppo_minibatch_apply: null handle");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n = h->cfg.n_params;
+    norm_kernel<<<NORM_BLOCKS, 256, 0, st>>>(h->grads, n, h->norm_partial);
+    PPO_CUDA(cudaGetLastError());
+    AdamArgs a;
+    a.params = h->params; a.grads = h->grads; a.exp_avg = h->exp_avg; a.exp_avg_sq = h->exp_avg_sq; a.step = h->step; a.n = n;
+    a.norm_partial = h->norm_partial;
+    a.lr = h->cfg.learning_rate; a.beta1 = h->cfg.beta1; a.beta2 = h->cfg.beta2; a.eps = h->cfg.adam_eps;
+    a.max_grad_norm = h->cfg.max_grad_norm; a.inv_world = 1.0f / static_cast<float>(h->cfg.world_size);
+    a.ctrl = h->ctrl;
+    adam_kernel<<<std::min<long long>((n + 255) / 256, 4 * h->sms), 256, 0, st>>>(a);
+    PPO_CUDA(cudaGetLastError());
+    // the planes are refreshed unconditionally (a stopped step leaves the parameters, hence the planes, unchanged)
+    planes_kernel<<<h->plane_blocks, 256, 0, st>>>(h->psegs_dev, h->pseg_of_block_dev, h->params, h->passes > 1);
+    PPO_CUDA(cudaGetLastError());
+    ctrl_commit_kernel<<<1, 32, 0, st>>>(h->ctrl, h->grads, n, h->step, h->norm_partial, a.inv_world, h->mirror_dev);
+    PPO_CUDA(cudaGetLastError());
+    return DN_OK;
+}
+
+int dn_ppo_get_stats(dn_ppo* h, dn_ppo_stats* out, void* stream) {
+    if (!h || !out) return dn_internal_fail(DN_EINVAL, "dn_ppo_get_stats: null argument");
+    Ctrl c;
+    PPO_CUDA(cudaMemcpyAsync(&c, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    PPO_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    const double inv = 1.0 / std::max(c.n_done, 1);
+    out->policy_gradient_loss = c.stats[0] * inv; out->value_loss = c.stats[1] * inv;
+    out->approx_kl = c.stats[2] * inv; out->clip_fraction = c.stats[3] * inv;
+    out->minibatches = c.n_done; out->optimizer_steps = c.n_applied; out->early_stop = c.stopped;
+    out->last_approx_kl = c.last_kl; out->last_grad_norm = c.last_norm;
+    return DN_OK;
+}
+
+int dn_ppo_poll(dn_ppo* h, int32_t* early_stop, int32_t* minibatches, int32_t* optimizer_steps) {
+    if (!h) return dn_internal_fail(DN_EINVAL, "dn_ppo_poll: null handle");
+    volatile int* m = h->mirror;
+    if (early_stop) *early_stop = m[0];
+    if (minibatches) *minibatches = m[1];
+    if (optimizer_steps) *optimizer_steps = m[2];
+    return DN_OK;
+}
+
+int dn_ppo_forward(dn_ppo* h, const float* obs, int32_t rows, float* mean, float* value, void* stream) {
+    if (!h || !obs || !mean || !value) return dn_internal_fail(DN_EINVAL, "dn_ppo_forward: null argument");
+    if (rows < 1 || rows > h->max_rows) return dn_internal_fail(DN_EINVAL, "dn_ppo_forward: rows must be within max_rows");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rows_pad = (rows + BM - 1) / BM * BM;
+    int rc;
+    if ((rc = ensure_rows(h, rows_pad))) return rc;
+    if ((rc = run_gather(h, obs, nullptr, nullptr, rows, false, st))) return rc;
+    if ((rc = run_forward_chain(h, st))) return rc;
+    HeadArgs a;
+    fill_head_common(h, a, rows);
+    a.train = 0; a.out_mean = mean; a.out_value = value;
+    const int head_blocks = std::min(std::max((rows + HEAD_WARPS - 1) / HEAD_WARPS, 1), h->head_blocks_max);
+    return run_head(h, a, head_blocks, st);
+}
+
+int dn_ppo_buffer(dn_ppo* h, const char* name, void** ptr, int64_t* elems) {
+    if (!h || !name || !ptr || !elems) return dn_internal_fail(DN_EINVAL, "dn_ppo_buffer: null argument");
+    const long long R = h->max_rows;
+    std::string s(name);
+    if (s == "x") { *ptr = h->x; *elems = 2 * R * XPAD; return DN_OK; }
+    if (s.size() >= 5 && (s.compare(0, 3, "pi.") == 0 || s.compare(0, 3, "vf.") == 0)) {
+        Net& net = (s[0] == 'p') ? h->pi : h->vf;
+        const int l = s.back() - '0';
+        const std::string kind = s.substr(3, s.size() - 4);
+        if (l >= 1 && l <= net.L) {
+            if (kind == "h") { *ptr = net.h[l]; *elems = 2 * R * net.n[l]; return DN_OK; }
+            if (kind == "dz") { *ptr = net.dz[l]; *elems = 2 * R * net.n[l]; return DN_OK; }
+            if (kind == "w") { *ptr = net.w[l]; *elems = 2LL * net.n[l] * net.n[l - 1]; return DN_OK; }
+        }
+    }
+    return dn_internal_fail(DN_EINVAL, "dn_ppo_buffer: unknown buffer name");
 }
 
 }  // extern "C"

@@ -45,8 +45,11 @@ class PPOConfig:
     log_std_init: float = 0.0
     adam_eps: float = 1e-5
     seed: int = 42                      # model.set_random_seed(42), PBDroneSimulator.py:690
-    matmul_precision: str = "tf32"      # "fp32" | "tf32": precision of the MLP GEMMs (cuBLAS)
-    cuda_graph: bool = True             # replay each minibatch step from two captured CUDA graphs (CUDA devices only)
+    matmul_precision: str = "tf32"      # "fp32" | "tf32": precision of the MLP GEMMs of the torch path (cuBLAS)
+    cuda_graph: bool = True             # torch path: replay each minibatch step from two captured CUDA graphs (CUDA devices only)
+    update_impl: str = "auto"           # "fused": hand-written sm_100a kernels (include/dnppo.h); "torch": eager PyTorch;
+                                        # "auto": fused on a compute-capability-10 device when the shapes allow it
+    mlp_precision: str = "bf16x3"       # fused path: "bf16x3" (FP32-faithful hi/lo split, default) | "bf16" (labelled option)
 
 
 _ONES: Dict[tuple, torch.Tensor] = {}
@@ -184,6 +187,149 @@ def _world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+class FusedUpdate:
+    """ctypes face of the dn_ppo handle (include/dnppo.h): the body of PPO.train's minibatch loop and the policy forward
+    as hand-written sm_100a kernels on ONE flat FP32 parameter vector.  The torch ``Parameter`` s of the policy, their
+    ``.grad`` s and the Adam moments are views into the flat buffers this object hands to the library, so checkpoints,
+    the eager torch path and the kernels all see the same memory."""
+
+    @staticmethod
+    def supported(cfg: "PPOConfig", obs_dim: int, act_dim: int, device) -> bool:
+        dev = torch.device(device)
+        if dev.type != "cuda" or torch.cuda.get_device_capability(dev)[0] != 10:
+            return False
+        ok_w = all(w % 128 == 0 and w >= 128 for w in tuple(cfg.pi_arch) + tuple(cfg.vf_arch))
+        return (ok_w and 1 <= len(cfg.pi_arch) <= 4 and 1 <= len(cfg.vf_arch) <= 4 and cfg.pi_arch[-1] <= 512 and cfg.vf_arch[-1] <= 512
+                and obs_dim <= 64 and act_dim in (1, 3, 4))
+
+    def __init__(self, learner: "PPOLearner", max_rows: int):
+        from . import _lib as L
+        self.L, self.lib = L, L.lib()
+        self.learner = learner
+        cfg, dev = learner.cfg, learner.device
+        pol = learner.policy
+        self.device = dev
+        self.max_rows = int(-(-max_rows // 128) * 128)
+        n = learner.n_params
+        f = dict(dtype=torch.float32, device=dev)
+        self.params = torch.empty(n, **f)
+        self.exp_avg, self.exp_avg_sq = torch.zeros(n, **f), torch.zeros(n, **f)
+        self.step = torch.zeros((), **f)
+        # re-seat parameters (and the Adam state) as views of the flat vectors
+        offs = {}
+        off = 0
+        with torch.no_grad():
+            for name, p in pol.named_parameters():
+                k = p.numel()
+                self.params[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.params[off:off + k].view_as(p)
+                old = learner.opt.state.get(p)
+                if old:                                  # keep the moments of an optimiser that has already stepped / was loaded
+                    self.exp_avg[off:off + k].copy_(old["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[off:off + k].copy_(old["exp_avg_sq"].reshape(-1))
+                    self.step.copy_(torch.as_tensor(old["step"], dtype=torch.float32).reshape(()))
+                learner.opt.state[p] = {"step": self.step, "exp_avg": self.exp_avg[off:off + k].view_as(p),
+                                        "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(p)}
+                offs[name] = off
+                off += k
+        c = L.dn_ppo_config()
+        c.abi_version = L.DN_ABI_VERSION
+        c.obs_dim, c.act_dim, c.max_rows = pol.pi[0].in_features, pol.log_std.numel(), self.max_rows
+        c.n_pi, c.n_vf = len(cfg.pi_arch), len(cfg.vf_arch)
+        for i, w in enumerate(cfg.pi_arch):
+            c.pi_hidden[i] = w
+        for i, w in enumerate(cfg.vf_arch):
+            c.vf_hidden[i] = w
+        c.precision = {"bf16x3": L.DN_MLP_BF16X3, "bf16": L.DN_MLP_BF16}[cfg.mlp_precision]
+        c.normalize_advantage = int(cfg.normalize_advantage)
+        c.world_size = _world()
+        c.clip_range = cfg.clip_range
+        c.clip_range_vf = -1.0 if cfg.clip_range_vf is None else cfg.clip_range_vf
+        c.ent_coef, c.vf_coef, c.max_grad_norm = cfg.ent_coef, cfg.vf_coef, cfg.max_grad_norm
+        c.target_kl = -1.0 if cfg.target_kl is None else cfg.target_kl
+        c.learning_rate, c.beta1, c.beta2, c.adam_eps = cfg.learning_rate, 0.9, 0.999, cfg.adam_eps
+        for l in range(c.n_pi + 1):          # nn.Sequential indices: Linear at 0, 2, 4, ... (Tanh in between)
+            c.pi_w_off[l], c.pi_b_off[l] = offs[f"pi.{2 * l}.weight"], offs[f"pi.{2 * l}.bias"]
+        for l in range(c.n_vf + 1):
+            c.vf_w_off[l], c.vf_b_off[l] = offs[f"vf.{2 * l}.weight"], offs[f"vf.{2 * l}.bias"]
+        c.log_std_off, c.n_params = offs["log_std"], n
+        self.cfg_c = c
+        self.handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            torch.cuda.synchronize(dev)
+            L.check(self.lib.dn_ppo_create(C.byref(c), dev.index or 0, self.params.data_ptr(), learner._flat.data_ptr(), self.exp_avg.data_ptr(),
+                                           self.exp_avg_sq.data_ptr(), self.step.data_ptr(), C.byref(self.handle)), "dn_ppo_create")
+        self.launches = 0
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.dn_ppo_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def sync_weights(self):
+        with torch.cuda.device(self.device):
+            self.L.check(self.lib.dn_ppo_sync_weights(self.handle, self._stream()), "dn_ppo_sync_weights")
+
+    def forward(self, obs: torch.Tensor):
+        """(mean [n, act_dim], value [n]) with the kernels and arithmetic of the update."""
+        obs = obs.contiguous().float()
+        n = obs.shape[0]
+        mean = torch.empty(n, self.cfg_c.act_dim, dtype=torch.float32, device=self.device)
+        value = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.L.check(self.lib.dn_ppo_sync_weights(self.handle, self._stream()), "dn_ppo_sync_weights")
+            self.L.check(self.lib.dn_ppo_forward(self.handle, obs.data_ptr(), n, mean.data_ptr(), value.data_ptr(), self._stream()), "dn_ppo_forward")
+        return mean, value
+
+    def begin_update(self):
+        with torch.cuda.device(self.device):
+            self.L.check(self.lib.dn_ppo_sync_weights(self.handle, self._stream()), "dn_ppo_sync_weights")
+            self.L.check(self.lib.dn_ppo_begin_update(self.handle, self._stream()), "dn_ppo_begin_update")
+
+    def minibatch_grad(self, ro, idx: torch.Tensor):
+        with torch.cuda.device(self.device):
+            self.L.check(self.lib.dn_ppo_minibatch_grad(self.handle, C.byref(ro), idx.data_ptr(), idx.numel(), self._stream()), "dn_ppo_minibatch_grad")
+
+    def minibatch_apply(self):
+        with torch.cuda.device(self.device):
+            self.L.check(self.lib.dn_ppo_minibatch_apply(self.handle, self._stream()), "dn_ppo_minibatch_apply")
+
+    def poll(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self.lib.dn_ppo_poll(self.handle, C.byref(a), C.byref(b), C.byref(c))
+        return bool(a.value), b.value, c.value
+
+    def stats(self):
+        st = self.L.dn_ppo_stats()
+        with torch.cuda.device(self.device):
+            self.L.check(self.lib.dn_ppo_get_stats(self.handle, C.byref(st), self._stream()), "dn_ppo_get_stats")
+        return st
+
+    def buffer(self, name: str, rows: int, cols: int):
+        """Test hook: FP32 reconstruction (hi + lo) of the first `rows` rows of an internal BF16 plane pair."""
+        ptr, elems = C.c_void_p(), C.c_int64()
+        self.L.check(self.lib.dn_ppo_buffer(self.handle, name.encode(), C.byref(ptr), C.byref(elems)), "dn_ppo_buffer")
+        n = elems.value
+
+        class _Arr:      # __cuda_array_interface__ view of the library's allocation
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i2", "data": (ptr.value, False), "version": 2}
+        raw = torch.as_tensor(a, device=self.device).view(torch.bfloat16)
+        full_rows = n // 2 // cols
+        planes = raw.view(2, full_rows, cols)[:, :rows]
+        return planes[0].float() + (planes[1].float() if self.learner.cfg.mlp_precision == "bf16x3" else 0.0)
+
+
 class PPOLearner:
     """Policy + optimiser + the PPO update; independent of the environment (works on any device, which
     is what the world_size-2 gloo tests use)."""
@@ -200,16 +346,112 @@ class PPOLearner:
         self.n_params = sum(p.numel() for p in self.params)
         # the one gradient bucket: every parameter's .grad is a view into it, so backward() writes the
         # bucket in place and the all-reduce / norm clip are single operations on one contiguous tensor
-        self._flat = torch.zeros(self.n_params, device=self.device)
+        # (one extra element: the fused update carries this rank's KL early-stop vote through the same all-reduce)
+        self._bucket = torch.zeros(self.n_params + 1, device=self.device)
+        self._flat = self._bucket[:self.n_params]
         off = 0
         for p in self.params:
             p.grad = self._flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.n_updates = 0
         self.allreduce_calls = 0
+        self.obs_dim, self.act_dim = obs_dim, act_dim
+        impl = cfg.update_impl
+        if impl not in ("auto", "fused", "torch"):
+            raise ValueError(f"update_impl={impl!r}")
+        can = FusedUpdate.supported(cfg, obs_dim, act_dim, self.device)
+        if impl == "fused" and not can:
+            raise RuntimeError("update_impl='fused' needs a compute-capability-10 CUDA device, hidden widths that are multiples of "
+                               "128 (last <= 512), at most 4 hidden layers, obs_dim <= 64 and act_dim in (1, 3, 4)")
+        self.want_fused = can and impl in ("auto", "fused")
+        self.fused: Optional[FusedUpdate] = None
         if self.device.type == "cuda":                  # process-wide switches: set both ways so "fp32" means FP32
             torch.backends.cuda.matmul.allow_tf32 = (cfg.matmul_precision == "tf32")
             torch.backends.cudnn.allow_tf32 = (cfg.matmul_precision == "tf32")
+
+    # ---- fused path (include/dnppo.h) ------------------------------------------------------------------------
+    def ensure_fused(self, rows: int) -> Optional[FusedUpdate]:
+        """The fused handle with workspaces for at least `rows` rows (re-created when a larger batch shows up)."""
+        if not self.want_fused:
+            return None
+        if self.fused is None or rows > self.fused.max_rows:
+            if self.fused is not None:
+                torch.cuda.synchronize(self.device)
+                self.fused.close()
+            self.fused = FusedUpdate(self, rows)
+            self._graphs = None            # parameters were re-seated: graphs of the torch path are stale
+        return self.fused
+
+    def forward(self, obs):
+        """(mean, value) of the policy: fused kernels when available, else the torch modules."""
+        fu = self.ensure_fused(obs.shape[0])
+        if fu is not None:
+            return fu.forward(obs)
+        return self.policy.pi(obs), self.policy.value(obs)
+
+    @torch.no_grad()
+    def act(self, obs, generator=None, deterministic=False):
+        """ActorCriticPolicy.forward: (action, log_prob, value)."""
+        if not self.want_fused:
+            return self.policy.act(obs, generator=generator, deterministic=deterministic)
+        mean, value = self.forward(obs)
+        if deterministic:
+            action = mean
+        else:
+            noise = torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
+            action = mean + noise * self.policy.log_std.exp()
+        return action, self.policy._log_prob(mean, action), value
+
+    @torch.no_grad()
+    def value(self, obs):
+        if not self.want_fused:
+            return self.policy.value(obs)
+        return self.forward(obs)[1]
+
+    def _update_fused(self, obs, actions, old_logp, old_values, advantages, returns, generator) -> Dict[str, float]:
+        """PPO.train (sb3_ppo.py:190-316) with the minibatch body in the library: per minibatch ONE gradient half
+        (gather .. backward), the flat-bucket all-reduce when there are several ranks, ONE apply half (clip, Adam).  The KL
+        early stop (:283-287) is decided on the device (each rank's vote rides in the bucket's extra element, so ranks stop
+        together without a second collective or a host synchronisation); the host learns about it from a pinned mirror and
+        stops launching -- minibatches launched in between are no-ops on the device."""
+        cfg = self.cfg
+        B = obs.shape[0]
+        mb = min(cfg.batch_size, B)
+        if mb % 128 or B % mb:
+            raise ValueError(f"fused PPO update: minibatch {mb} must be a multiple of 128 and divide the rollout ({B} samples); "
+                             "use update_impl='torch' for ragged batches")
+        n_mb = B // mb
+        fu = self.ensure_fused(mb)
+        ro = fu.L.dn_ppo_rollout()
+        keep = [t.contiguous().float() for t in (obs, actions, old_logp, old_values, advantages, returns)]
+        ro.obs, ro.actions, ro.old_log_prob, ro.old_values, ro.advantages, ro.returns = [t.data_ptr() for t in keep]
+        fu.begin_update()
+        world = _world()
+        launched = 0
+        stop = False
+        for epoch in range(cfg.n_epochs):
+            perm = torch.randperm(B, device=self.device, generator=generator)
+            keep.append(perm)
+            for k in range(n_mb):
+                fu.minibatch_grad(ro, perm[k * mb:(k + 1) * mb])
+                if world > 1:
+                    dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM)
+                    self.allreduce_calls += 1
+                fu.minibatch_apply()
+                launched += 1
+                stop = fu.poll()[0]
+                if stop:
+                    break
+            if stop:
+                break
+        st = fu.stats()                       # synchronises the stream
+        epochs_run = -(-st.minibatches // n_mb) if st.minibatches else 0
+        self.n_updates += epochs_run
+        return {"policy_gradient_loss": st.policy_gradient_loss, "value_loss": st.value_loss,
+                "entropy_loss": float(-(0.5 + 0.5 * math.log(2 * math.pi) + self.policy.log_std.detach()).sum()),
+                "approx_kl": st.approx_kl, "clip_fraction": st.clip_fraction, "epochs": epochs_run, "minibatches": st.minibatches,
+                "optimizer_steps": st.optimizer_steps, "early_stop": bool(st.early_stop), "launched_minibatches": launched,
+                "grad_norm": st.last_grad_norm, "std": float(self.policy.log_std.detach().exp().mean()), "impl": "fused/" + cfg.mlp_precision}
 
     # ---- the only collective: one flat bucket per optimiser step (between backward and clip, sb3_ppo.py:291-293)
     def _allreduce_grads(self):
@@ -255,6 +497,7 @@ class PPOLearner:
         return approx_kl
 
     def _clip_and_step(self):
+        assert self.fused is None, "the torch optimiser step must not run once the fused update owns the Adam state"
         # th.nn.utils.clip_grad_norm_(parameters, max_grad_norm) on the flat bucket, then Adam
         norm = torch.linalg.vector_norm(self._flat)
         self._flat.mul_(torch.clamp(self.cfg.max_grad_norm / (norm + 1e-6), max=1.0))
@@ -320,6 +563,14 @@ class PPOLearner:
         cfg = self.cfg
         B = obs.shape[0]
         mb = min(cfg.batch_size, B)
+        if self.want_fused and obs.is_cuda and (mb % 128 or B % mb) and self.fused is None and cfg.update_impl == "auto":
+            self.want_fused = False          # ragged / tiny minibatches: this learner stays on the torch path
+        if self.want_fused and obs.is_cuda:
+            return self._update_fused(obs, actions, old_logp, old_values, advantages, returns, generator)
+        if B % mb:
+            # SB3's RolloutBuffer.get yields the trailing partial minibatch; neither the graph replay nor the fixed-shape
+            # buffers here can, so refuse instead of silently dropping up to mb - 1 samples per epoch
+            raise ValueError(f"rollout of {B} samples is not a multiple of the minibatch size {mb}")
         n_mb = B // mb
         graphed = self.use_graph and obs.is_cuda
         if graphed:
@@ -378,6 +629,10 @@ class PPOTrainer:
         self.dev = env.device
         self.T = int(rollout_steps or cfg.n_steps)
         self.learner = PPOLearner(env.obs_dim, 4, cfg, device=self.dev)
+        B, mb = self.T * env.num_envs, min(cfg.batch_size, self.T * env.num_envs)
+        if cfg.update_impl == "auto" and (mb % 128 or B % mb):
+            self.learner.want_fused = False  # the fused kernels need minibatches that are multiples of 128 and divide the rollout
+        self.learner.ensure_fused(max(env.num_envs, mb))
         rank = dist.get_rank() if _world() > 1 else 0
         self.gen = torch.Generator(device=self.dev).manual_seed(cfg.seed + 1000 * (rank + 1))   # exploration noise differs per shard
         N, D, T = env.num_envs, env.obs_dim, self.T
@@ -391,7 +646,7 @@ class PPOTrainer:
 
     @torch.no_grad()
     def collect_rollouts(self):
-        env, pol = self.env, self.learner.policy
+        env, pol = self.env, self.learner
         for t in range(self.T):
             action, logp, value = pol.act(self.obs, generator=self.gen)
             self.b_obs[t], self.b_act[t], self.b_logp[t], self.b_val[t] = self.obs, action, logp, value

@@ -106,7 +106,7 @@ class PBDroneSimulator:
                 if sac:
                     a = trainer.learner.act(obs, generator=gen)
                 else:
-                    a, _, _ = trainer.learner.policy.act(obs, generator=gen)
+                    a, _, _ = trainer.learner.act(obs, generator=gen)
                 obs, _, _, _ = env.step(a.clamp(-1, 1).contiguous())
                 # statistics are read (one host sync) every 64 steps; run at least one full time-limit horizon so that
                 # long (successful / truncated) episodes are not under-represented against quick crashes

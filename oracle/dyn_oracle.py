@@ -691,9 +691,13 @@ class OracleDroneEnv:
         """BaseAviary.py:838-865: force R.(-DRAG_COEFF * v_world * sum(2 pi rpm_prev/60)),
         applied to link 4 in LINK_FRAME, i.e. Bullet rotates the vector by R once
         more -- reproduced literally."""
+        return np.dot(rotation, self._drag_link(rotation))
+
+    def _drag_link(self, rotation):
+        """The forceObj BaseAviary._drag hands to p.applyExternalForce(..., flags=p.LINK_FRAME) (BaseAviary.py:855-865);
+        pinned against the reference's own function by tests/golden/ref_forces.npz."""
         drag_factors = -1 * self.DRAG_COEFF * np.sum(np.array(2 * np.pi * self.last_clipped_action / 60))
-        drag_link = np.dot(rotation, drag_factors * np.array(self.vel))
-        return np.dot(rotation, drag_link)
+        return np.dot(rotation, drag_factors * np.array(self.vel))
 
     def _ground_effect(self, rpm, rotation):
         """BaseAviary.py:798-834: per-prop extra thrust along body z."""

@@ -136,12 +136,31 @@ def _import_reference():
         spec = importlib.util.spec_from_file_location(
             "_ref_hover", os.path.join(REF, "Sol/PyBullet/GymPybulletDronesMain/gym_pybullet_drones/envs/single_agent_rl/HoverAviary.py"))
     try:
+        # HoverAviary.py:3-4 imports `gym_pybullet_drones.utils.enums` (fine) and
+        # `gym_pybullet_drones.envs.single_agent_rl.BaseSingleAgentAviary`, whose vendored copy cannot be imported by anyone:
+        # its line 8 reads `sys.path.append(....gym_pybullet_drones)` (attribute access on Ellipsis -> AttributeError), and the
+        # package __init__ files import it.  The base-class module (and the two package levels above it) are therefore stubbed
+        # with the reference's OWN working copy of the same class, Sol/PyBullet/BaseSingleAgentAviary.py; HoverAviary.py itself
+        # is then executed unmodified and its `_computeReward` function object is what the fixture binds.
+        import types
         sys.path.insert(1, os.path.join(REF, "Sol/PyBullet/GymPybulletDronesMain"))   # the vendored upstream package tree
+        with contextlib.redirect_stdout(io.StringIO()):
+            import gym_pybullet_drones.utils.enums  # noqa: F401  (the real vendored module)
+            from Sol.PyBullet import BaseSingleAgentAviary as sol_bsa
+        for pkg in ("gym_pybullet_drones.envs", "gym_pybullet_drones.envs.single_agent_rl"):
+            if pkg not in sys.modules:
+                m = types.ModuleType(pkg)
+                m.__path__ = []
+                sys.modules[pkg] = m
+        stub = types.ModuleType("gym_pybullet_drones.envs.single_agent_rl.BaseSingleAgentAviary")
+        stub.ActionType, stub.ObservationType, stub.BaseSingleAgentAviary = sol_bsa.ActionType, sol_bsa.ObservationType, sol_bsa.BaseSingleAgentAviary
+        sys.modules[stub.__name__] = stub
         hover_mod = importlib.util.module_from_spec(spec)
         with contextlib.redirect_stdout(io.StringIO()):
             spec.loader.exec_module(hover_mod)
         hover_reward = hover_mod.HoverAviary._computeReward
-    except Exception:          # the vendored upstream package imports its own (absent) module tree
+    except Exception as ex:    # noqa: BLE001
+        print("HoverAviary import failed:", repr(ex), file=sys.stderr)
         hover_reward = None
 
     class _Dummy(_DynEnv):
@@ -357,8 +376,73 @@ def run(ref, track, S, mode, N, T, seed, max_steps, normalize_obs, reward="defau
     return out
 
 
+def _urdf_link_offsets(path):
+    """xyz of the fixed joints' child links prop0..prop3 and center_of_mass, in link-index order (cf2x.urdf)."""
+    import xml.etree.ElementTree as etxml
+    root = etxml.parse(path).getroot()
+    links = {l.attrib["name"]: l for l in root.findall("link")}
+    out = []
+    for name in ("prop0_link", "prop1_link", "prop2_link", "prop3_link", "center_of_mass_link"):
+        origin = links[name].find("inertial").find("origin")
+        out.append(tuple(float(v) for v in origin.attrib["xyz"].split()))
+    return out
+
+
+def mint_forces(ref, n_rollout=40, seed=77):
+    """ref_forces.npz: the reference's OWN BaseAviary._drag (BaseAviary.py:838-865) and BaseAviary._groundEffect (:798-834)
+    evaluated on states of a DYN rollout plus hand-placed edge states; what is stored is the argument each of them hands
+    to p.applyExternalForce (recorded by the pybullet shim), next to the state it was computed from.  These two functions
+    only run under Physics.PYB_* in the reference (which needs Bullet's integrator); the oracle / the kernel apply the same
+    forces inside DYN as a documented extension, and this fixture pins the FORMULAS against the reference's code.
+    Restated, not reference: the propeller link heights (Bullet forward kinematics over the fixed joints of the reference's
+    cf2x.urdf, ref_shims.getLinkStates)."""
+    import pybullet as p                                   # the shim
+    p.link_offsets = _urdf_link_offsets(os.path.join(REF, "Sol/resources/safegym/cf2x.urdf"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        env, raw = make_env(ref, "circle", 8, 4096, False)
+    rng = np.random.default_rng(seed)
+    acts = (HOVER + 0.006 * rng.uniform(-1, 1, size=(n_rollout, 4))).astype(np.float32)
+    recs = []
+
+    def record(rpm_now):
+        st = dict(pos=np.array(raw.pos[0]), quat=np.array(raw.quat[0]), rpy=np.array(raw.rpy[0]), vel=np.array(raw.vel[0]),
+                  last_rpm=np.array(raw.last_clipped_action[0], dtype=np.float64), rpm=np.array(rpm_now, dtype=np.float64))
+        p.force_log = []
+        raw._drag(raw.last_clipped_action[0, :], 0)        # BaseAviary.py:431,443: the PREVIOUS step's clipped action
+        raw._groundEffect(np.array(rpm_now), 0)            # BaseAviary.py:425,437: this step's clipped action
+        log, p.force_log = p.force_log, None
+        drag = [e for e in log if e[2] == 4]
+        gnd = sorted((e for e in log if e[2] < 4), key=lambda e: e[2])
+        assert len(drag) == 1 and drag[0][5] == p.LINK_FRAME and len(gnd) in (0, 4)
+        st["drag_force_link"] = np.array(drag[0][3])
+        st["gnd_force_z"] = np.array([e[3][2] for e in gnd]) if gnd else np.zeros(4)
+        st["gnd_applied"] = np.array(1 if gnd else 0)
+        recs.append(st)
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        for t in range(n_rollout):
+            env.step(acts[t])
+            record(raw.last_clipped_action[0] * rng.uniform(0.8, 1.1, size=4))
+        # edge states: near the ground (height clip GND_EFF_H_CLIP), upside down (no ground effect), fast and tilted
+        for pos, rpy, vel in (((0.3, -0.2, 0.012), (0.05, -0.1, 0.4), (0.4, 0.1, -0.3)),
+                              ((0.0, 0.0, 0.05), (0.6, 0.4, -2.0), (1.5, -2.0, 0.5)),
+                              ((0.1, 0.1, 0.2), (2.0, 0.1, 0.3), (0.2, 0.2, 0.2)),
+                              ((0.1, 0.1, 0.2), (0.1, -1.7, 0.3), (-1.0, 0.7, 0.1)),
+                              ((-0.5, 0.8, 1.6), (-0.9, 1.2, 3.0), (2.5, 2.5, -1.0))):
+            quat = np.array(p.getQuaternionFromEuler(rpy))
+            raw.pos[0], raw.quat[0], raw.rpy[0], raw.vel[0] = np.array(pos), quat, np.array(rpy), np.array(vel)
+            p.resetBasePositionAndOrientation(raw.DRONE_IDS[0], pos, quat, physicsClientId=raw.CLIENT)
+            raw.last_clipped_action[0] = rng.uniform(9000, 21000, size=4)
+            record(rng.uniform(9000, 21000, size=4))
+    out = {k: np.stack([r[k] for r in recs]) for k in recs[0]}
+    out["constants"] = np.array([raw.KF, raw.GND_EFF_COEFF, raw.PROP_RADIUS, raw.GND_EFF_H_CLIP, *np.ravel(raw.DRAG_COEFF)], dtype=np.float64)
+    out["link_offsets"] = np.array(p.link_offsets)
+    return out
+
+
 if __name__ == "__main__":
     ref = _import_reference()
+    np.savez_compressed(os.path.join(HERE, "ref_forces.npz"), **mint_forces(ref))
     print("HoverAviary imported from the reference:", ref[-1], file=sys.stderr)
     for name, cfg in CASES.items():
         out = run(ref, *cfg)

@@ -188,6 +188,36 @@ class _PyBullet(types.ModuleType):
         b = self._body(uid, k)
         return b["lin"], b["ang"]
 
+    # ---- external forces: recorded, never integrated (the PYB_* force models of BaseAviary.py:798-895 hand their result
+    #      to Bullet; the recorder lets a fixture pin the numbers the reference computes) ----------------------------------
+    force_log = None            # list while recording: (kind, body uid, link index, vector, posObj, flags)
+
+    def applyExternalForce(self, objectUniqueId, linkIndex, forceObj, posObj, flags, *a, **k):
+        if self.force_log is not None:
+            self.force_log.append(("force", int(objectUniqueId), int(linkIndex), tuple(float(v) for v in forceObj),
+                                   tuple(float(v) for v in posObj), int(flags)))
+        return 0
+
+    def applyExternalTorque(self, objectUniqueId, linkIndex, torqueObj, flags, *a, **k):
+        if self.force_log is not None:
+            self.force_log.append(("torque", int(objectUniqueId), int(linkIndex), tuple(float(v) for v in torqueObj), (), int(flags)))
+        return 0
+
+    # propeller links 0..3 and the centre-of-mass link 4 of cf2x.urdf are fixed joints: world position = base position +
+    # R(base quaternion) . joint origin (Bullet forward kinematics for fixed joints; joint origins read from the reference's URDF
+    # by the caller into `link_offsets`)
+    link_offsets = None
+
+    def getLinkStates(self, bodyUniqueId, linkIndices, *a, **k):
+        b = self._body(bodyUniqueId, k)
+        m = _bt_matrix_from_quat(b["quat"])
+        out = []
+        for li in linkIndices:
+            off = self.link_offsets[int(li)]
+            world = tuple(b["pos"][r] + sum(m[r][c] * off[c] for c in range(3)) for r in range(3))
+            out.append((world, b["quat"], (0.0, 0.0, 0.0), (0.0, 0.0, 0.0, 1.0), world, b["quat"], b["lin"], b["ang"]))
+        return tuple(out)
+
 
 # --------------------------------------------------------------------------------------------
 # gymnasium / gym

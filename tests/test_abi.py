@@ -8,9 +8,12 @@ from tests.conftest import ROOT
 
 
 def _declared_functions():
-    text = open(os.path.join(ROOT, "include", "dronenav.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(dn_[a-z_]+)\s*\(", text)))
+    names = set()
+    for header in ("dronenav.h", "dnppo.h"):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(dn_[a-z_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_header_declares_expected_entry_points():
@@ -36,6 +39,28 @@ def test_struct_layouts_match_header(built_lib):
     assert C.sizeof(_lib.dn_state_view) == 21 * 8
     assert C.sizeof(_lib.dn_stats) == 7 * 8
     assert C.sizeof(_lib.dn_config) == 4 + 4 + 8 + 8 + 12 * 4 + 2 * 8 + 12 * 8 + 4 + 4 + 2 * 8 + 8 + 4 + 4
+    # include/dnppo.h
+    assert C.sizeof(_lib.dn_ppo_config) == 6 * 4 + 8 * 4 + 4 * 4 + 10 * 4 + 20 * 8 + 2 * 8
+    assert C.sizeof(_lib.dn_ppo_rollout) == 6 * 8
+    assert C.sizeof(_lib.dn_ppo_stats) == 4 * 8 + 3 * 4 + 2 * 4 + 4      # + tail padding to 8
+
+
+def test_ppo_update_rejects_bad_config_without_a_gpu(built_lib):
+    from drl_dronenavigation_b200 import _lib
+    h = C.c_void_p()
+    cfg = _lib.dn_ppo_config()
+    buf = (C.c_float * 8)()
+    args = (C.byref(cfg), 0, buf, buf, buf, buf, buf, C.byref(h))
+    cfg.abi_version = 999
+    assert built_lib.dn_ppo_create(*args) == -1 and b"abi_version" in built_lib.dn_last_error()
+    cfg.abi_version = _lib.DN_ABI_VERSION
+    cfg.obs_dim, cfg.act_dim, cfg.max_rows, cfg.n_pi, cfg.n_vf = 13, 4, 100, 3, 3
+    assert built_lib.dn_ppo_create(*args) == -1 and b"128" in built_lib.dn_last_error()
+    cfg.max_rows = 256
+    for i, w in enumerate((512, 500, 256)):
+        cfg.pi_hidden[i] = cfg.vf_hidden[i] = w
+    assert built_lib.dn_ppo_create(*args) == -1 and b"multiples of 128" in built_lib.dn_last_error()
+    assert built_lib.dn_mlp_gemm(5, 3, 128, 64, 64, 1, buf, buf, buf, 1, None, buf, None, None) == -1
 
 
 def test_bad_config_is_rejected_without_a_gpu(built_lib):

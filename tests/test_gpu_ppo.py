@@ -92,7 +92,7 @@ def test_ppo_update_cuda_graph_equals_eager():
     adv, ret = torch.randn(B, device="cuda", generator=g), torch.randn(B, device="cuda", generator=g)
     outs = {}
     for graph in (False, True):
-        L = PPOLearner(13, 4, PPOConfig(batch_size=1024, n_epochs=3, target_kl=None, cuda_graph=graph, matmul_precision="fp32"), device="cuda")
+        L = PPOLearner(13, 4, PPOConfig(batch_size=1024, n_epochs=3, target_kl=None, cuda_graph=graph, matmul_precision="fp32", update_impl="torch"), device="cuda")
         assert L.use_graph == graph
         with torch.no_grad():
             v, logp, _ = L.policy.evaluate(obs, act)
@@ -111,7 +111,7 @@ def test_ppo_update_cuda_graph_equals_eager():
         assert abs(outs[True][2][k] - outs[False][2][k]) < 1e-4 and abs(outs[True][3][k] - outs[False][3][k]) < 1e-3
     assert outs[True][2]["minibatches"] == outs[False][2]["minibatches"] == 24
     # early stop path under replay
-    L = PPOLearner(13, 4, PPOConfig(batch_size=1024, n_epochs=30, target_kl=1e-4, learning_rate=1e-2, cuda_graph=True), device="cuda")
+    L = PPOLearner(13, 4, PPOConfig(batch_size=1024, n_epochs=30, target_kl=1e-4, learning_rate=1e-2, cuda_graph=True, update_impl="torch"), device="cuda")
     with torch.no_grad():
         v, logp, _ = L.policy.evaluate(obs, act)
     out = L.update(obs, act, logp, v, adv, ret, generator=torch.Generator(device="cuda").manual_seed(1))
