@@ -66,6 +66,17 @@ def _key_map(n_hidden_pi: int, n_hidden_vf: int) -> Dict[str, str]:
     return m
 
 
+def _sb3_param_order(n_hidden_pi: int, n_hidden_vf: int):
+    """SB3 names in the order of ``ActorCriticPolicy.parameters()`` -- the positional index of ``policy.optimizer.pth``:
+    log_std, mlp_extractor.policy_net.*, mlp_extractor.value_net.*, action_net.*, value_net.* (checked against the archive SB3
+    itself wrote, Sol/pyfly/ppo_quadx_waypoints.zip)."""
+    names = ["log_std"]
+    for net, n in (("policy_net", n_hidden_pi), ("value_net", n_hidden_vf)):
+        for layer in range(n):
+            names += [f"mlp_extractor.{net}.{2 * layer}.weight", f"mlp_extractor.{net}.{2 * layer}.bias"]
+    return names + ["action_net.weight", "action_net.bias", "value_net.weight", "value_net.bias"]
+
+
 def policy_to_sb3_state_dict(policy) -> Dict[str, torch.Tensor]:
     sd = policy.state_dict()
     n_pi = sum(1 for k in sd if k.startswith("pi.") and k.endswith(".weight")) - 1
@@ -111,12 +122,20 @@ def save_sb3_zip(path: str, learner, extra: Optional[dict] = None) -> str:
     cfg = learner.cfg
     sd = policy_to_sb3_state_dict(learner.policy)
     km = _key_map(len(cfg.pi_arch), len(cfg.vf_arch))
-    # SB3's optimiser state_dict indexes parameters by position in policy.parameters(); keep ours and record the names
+    # SB3's optimiser state_dict indexes parameters by position in ITS policy.parameters() (log_std first, then the two
+    # extractor nets, then the heads): re-index ours (pi.*, vf.*, log_std) into that order so that SB3's
+    # optimizer.load_state_dict attaches every Adam moment to the parameter it belongs to; the names are recorded as well
     opt_sd = learner.opt.state_dict()
-    opt_state = {"state": {i: {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in st.items()}
-                           for i, st in opt_sd["state"].items()},
-                 "param_groups": opt_sd["param_groups"],
-                 "param_names": [km[n] for n, _ in learner.policy.named_parameters()]}
+    ours_names = [km[n] for n, _ in learner.policy.named_parameters()]
+    sb3_order = _sb3_param_order(len(cfg.pi_arch), len(cfg.vf_arch))
+    pos_ours = {nm: i for i, nm in enumerate(ours_names)}
+    groups = [dict(g) for g in opt_sd["param_groups"]]
+    for g in groups:
+        g["params"] = list(range(len(sb3_order)))
+    opt_state = {"state": {j: {k: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for k, v in opt_sd["state"][pos_ours[nm]].items()}
+                           for j, nm in enumerate(sb3_order) if pos_ours[nm] in opt_sd["state"]},
+                 "param_groups": groups,
+                 "param_names": sb3_order}
     data = {"policy_class": "stable_baselines3.common.policies.ActorCriticPolicy", "algo": "PPO",
             "n_steps": cfg.n_steps, "batch_size": cfg.batch_size, "n_epochs": cfg.n_epochs, "gamma": cfg.gamma,
             "gae_lambda": cfg.gae_lambda, "ent_coef": cfg.ent_coef, "vf_coef": cfg.vf_coef, "clip_range": cfg.clip_range,
@@ -154,20 +173,28 @@ def load_sb3_zip(path: str, learner, load_optimizer: bool = False, strict: bool 
         sb3_state_dict_to_policy(learner.policy, sb3_sd, strict=strict)
         if load_optimizer and "policy.optimizer.pth" in names:
             opt = torch.load(io.BytesIO(zf.read("policy.optimizer.pth")), map_location="cpu", weights_only=False)
-            own = learner.opt.state_dict()
-            if len(opt.get("state", {})) == len(list(learner.policy.parameters())):
-                # SB3 orders parameters as policy.parameters() does: log_std, policy_net, value_net, action_net, value_net head;
-                # ours: pi..., vf..., log_std -- re-index by name when the names were recorded, else by shape-compatible order
-                names_theirs = opt.get("param_names")
-                if names_theirs is not None:
-                    km = _key_map(len(learner.cfg.pi_arch), len(learner.cfg.vf_arch))
-                    order = {km[n]: i for i, (n, _) in enumerate(learner.policy.named_parameters())}
-                    state = {order[nm]: opt["state"][j] for j, nm in enumerate(names_theirs) if j in opt["state"]}
-                    own["state"] = state
-                    learner.opt.load_state_dict(own)
-                    # load_state_dict re-creates the state tensors: captured CUDA graphs (if any) must be rebuilt
-                    if hasattr(learner, "_graphs"):
-                        learner._graphs = None
+            # SB3 orders parameters as ITS policy.parameters() does (log_std, policy_net, value_net, action_net, value_net head);
+            # ours: pi..., vf..., log_std.  Re-index by name: the recorded names when this repo wrote the archive, SB3's known
+            # order otherwise (every genuine SB3 archive); a state that does not fit is dropped LOUDLY, never silently
+            import warnings
+            params = list(learner.policy.named_parameters())
+            names_theirs = opt.get("param_names") or _sb3_param_order(len(learner.cfg.pi_arch), len(learner.cfg.vf_arch))
+            km = _key_map(len(learner.cfg.pi_arch), len(learner.cfg.vf_arch))
+            order = {km[n]: i for i, (n, _) in enumerate(params)}
+            state, ok = {}, len(names_theirs) == len(params) and set(names_theirs) == set(order)
+            if ok:
+                for j, nm in enumerate(names_theirs):
+                    if j in opt.get("state", {}):
+                        st = opt["state"][j]
+                        if tuple(st["exp_avg"].shape) != tuple(params[order[nm]][1].shape):
+                            ok = False
+                            break
+                        state[order[nm]] = st
+            if ok and state:
+                learner.load_optimizer_state(state)
+            else:
+                warnings.warn(f"{path}: the optimiser state does not match this policy's parameters and was NOT loaded "
+                              "(Adam restarts from zero moments)", RuntimeWarning)
         data = {}
         if "data" in names:
             try:

@@ -47,7 +47,11 @@ struct GemmArgs {
     float* partial;                 // WGRAD: [slices][rows][ld_partial] FP32 partial products
     int ld_partial;
     long long slice_stride;         // elements between slices of `partial`
+    float* colsum;                  // DGRAD, optional: [gridDim.x][ld_out] column sums of the FP32 result over this CTA's tiles
+                                    // (= this CTA's share of the bias gradient of the layer below)
 };
+
+constexpr int MAX_COLSUM_COLS = 1024;   // widest DGRAD result whose column sums fit the shared-memory accumulator
 
 // ------------------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -178,6 +182,18 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 __device__ __forceinline__ float bf16lo_f(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
+// tanh(x) = 1 - 2 / (1 + e^(2x)) with the two MUFU approximations (ex2, rcp): absolute error <= 3e-7 over the whole
+// range (|tanh| <= 1, so this is the FP32-level accuracy the planes can carry anyway), saturates to +-1 without special
+// cases, 5 instructions instead of libm's ~30 -- the forward epilogue would otherwise take as long as the tile's MMAs
+__device__ __forceinline__ float tanh_fast(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return fmaf(-2.0f, r, 1.0f);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // x -> (hi, lo) BF16 planes, 32 values = 4 x 16-byte stores per plane
 __device__ __forceinline__ void store_split32(const float (&y)[32], __nv_bfloat16* hi_row, __nv_bfloat16* lo_row, bool write_lo) {
     uint32_t h[16], l[16];
@@ -204,7 +220,8 @@ struct Cfg {
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
     static constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES;
-    static constexpr uint32_t SMEM_BYTES = RING_BYTES + 1024 /* alignment slack */ + 256 /* barriers + TMEM pointer */;
+    static constexpr uint32_t COLSUM_BYTES = 4 * MAX_COLSUM_COLS * 4;   // [TMEM lane quadrant][column] FP32
+    static constexpr uint32_t SMEM_BYTES = RING_BYTES + 1024 /* alignment slack */ + 256 /* barriers + TMEM pointer */ + COLSUM_BYTES;
     static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -226,6 +243,7 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint64_t* tfull_bar = empty_bar + STAGES;       // [2] accumulator stage ready for the epilogue
     uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator stage drained
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* colsum_s = reinterpret_cast<float*>(smem + C::RING_BYTES + 256);      // [4][ld_out] (DGRAD with g.colsum)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = g.m_tiles * g.n_tiles * g.slices;
@@ -248,6 +266,10 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         fence_proxy_async();
     }
     if (warp == 2) tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    if constexpr (KIND == K_DGRAD) {
+        if (g.colsum != nullptr)
+            for (int i = threadIdx.x; i < 4 * g.ld_out; i += NUM_THREADS) colsum_s[i] = 0.0f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -325,10 +347,22 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int nt = t % g.n_tiles, mt = (t / g.n_tiles) % g.m_tiles, sl = t / (g.n_tiles * g.m_tiles);
+            const long long row = static_cast<long long>(mt) * BM + row_in_tile;
+            if constexpr (KIND == K_DGRAD) {
+                // this thread's slice of H (BN bytes per plane) is needed right after the accumulator: pull it into L2
+                // while the tile's MMAs run (it was written a whole forward + backward pass ago)
+                const char* ph = reinterpret_cast<const char*>(g.h_hi + row * g.ld_out + nt * BN + half * (BN / 2));
+#pragma unroll
+                for (int o = 0; o < BN; o += 128) prefetch_l2(ph + o);
+                if (g.h_lo != nullptr) {
+                    const char* pl = reinterpret_cast<const char*>(g.h_lo + row * g.ld_out + nt * BN + half * (BN / 2));
+#pragma unroll
+                    for (int o = 0; o < BN; o += 128) prefetch_l2(pl + o);
+                }
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-            const long long row = static_cast<long long>(mt) * BM + row_in_tile;
 #pragma unroll 1
             for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
                 float v[32];
@@ -338,7 +372,7 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float z = v[j] + __ldg(g.bias + col + j);
-                        v[j] = g.act ? tanhf(z) : z;
+                        v[j] = g.act ? tanh_fast(z) : z;
                     }
                     store_split32(v, g.out_hi + row * g.ld_out + col, g.out_lo + row * g.ld_out + col, g.write_lo != 0);
                 } else if constexpr (KIND == K_DGRAD) {
@@ -367,6 +401,21 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         v[2 * j + 1] *= fmaf(-h1, h1, 1.0f);
                     }
                     store_split32(v, g.out_hi + row * g.ld_out + col, g.out_lo + row * g.ld_out + col, g.write_lo != 0);
+                    if (g.colsum != nullptr) {
+                        // column sums over the warp's 32 rows by a transposing butterfly (31 shuffles): afterwards lane j
+                        // holds the sum of column col + j.  This warp is the only writer of (quadrant q, these columns).
+#pragma unroll
+                        for (int s = 16; s >= 1; s >>= 1) {
+                            const bool up = (lane & s) != 0;
+#pragma unroll
+                            for (int j = 0; j < s; ++j) {
+                                const float send = up ? v[j] : v[j + s];
+                                const float keep = up ? v[j + s] : v[j];
+                                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                            }
+                        }
+                        colsum_s[q * g.ld_out + col + lane] += v[0];
+                    }
                 } else {
                     float4* dst = reinterpret_cast<float4*>(g.partial + sl * g.slice_stride + row * g.ld_partial + col);
 #pragma unroll
@@ -377,6 +426,14 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if constexpr (KIND == K_DGRAD) {
+            if (g.colsum != nullptr) {
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");       // epilogue warps only
+                for (int c = threadIdx.x - EPI_WARP0 * 32; c < g.ld_out; c += EPI_WARPS * 32)
+                    g.colsum[static_cast<long long>(blockIdx.x) * g.ld_out + c] =
+                        ((colsum_s[c] + colsum_s[g.ld_out + c]) + colsum_s[2 * g.ld_out + c]) + colsum_s[3 * g.ld_out + c];
+            }
         }
     }
     tc_fence_before();

@@ -113,8 +113,11 @@ struct HeadArgs {
     int partial_size;
 };
 // layout of one block's partial: dW_pi [act_dim * n_pi] | db_pi [act_dim] | dW_vf [n_vf] | db_vf [1] | dlog_std [act_dim]
+//                                | dbh_pi [n_pi] | dbh_vf [n_vf]  (bias gradients of the LAST HIDDEN layers = column sums of dz)
 //                                | stats [4] (pg loss, value loss, approx_kl, clip fraction; sums over the block's samples)
-__host__ __device__ inline int head_partial_size(int act_dim, int n_pi, int n_vf) { return act_dim * n_pi + act_dim + n_vf + 1 + act_dim + 4; }
+__host__ __device__ inline int head_partial_size(int act_dim, int n_pi, int n_vf) {
+    return act_dim * n_pi + act_dim + n_vf + 1 + act_dim + n_pi + n_vf + 4;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -136,10 +139,18 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
     const int ip = g.n_pi / 64, iv = g.n_vf / 64;         // column pairs per lane
     float adv_mean = 0.0f, adv_rstd = 1.0f;
     if (g.train && g.normalize_adv) {
+        // advantage moments: the gather blocks' (sum, sum of squares) pairs, added in a fixed order by the whole block
+        __shared__ double s_adv[2][HEAD_WARPS * 32];
         double a = 0.0, b = 0.0;
-        for (int i = 0; i < g.adv_blocks; ++i) { a += g.adv_partial[2 * i]; b += g.adv_partial[2 * i + 1]; }
-        const double n = g.rows, mean = a / n;
-        double var = (b - n * mean * mean) / (n - 1.0);   // torch.std: unbiased
+        for (int i = threadIdx.x; i < g.adv_blocks; i += HEAD_WARPS * 32) { a += g.adv_partial[2 * i]; b += g.adv_partial[2 * i + 1]; }
+        s_adv[0][threadIdx.x] = a; s_adv[1][threadIdx.x] = b;
+        __syncthreads();
+        for (int o = HEAD_WARPS * 16; o > 0; o >>= 1) {
+            if (threadIdx.x < o) { s_adv[0][threadIdx.x] += s_adv[0][threadIdx.x + o]; s_adv[1][threadIdx.x] += s_adv[1][threadIdx.x + o]; }
+            __syncthreads();
+        }
+        const double n = g.rows, mean = s_adv[0][0] / n;
+        double var = (s_adv[1][0] - n * mean * mean) / (n - 1.0);   // torch.std: unbiased
         if (var < 0.0) var = 0.0;
         adv_mean = static_cast<float>(mean);
         adv_rstd = 1.0f / (static_cast<float>(sqrt(var)) + 1e-8f);
@@ -151,7 +162,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
     const float inv_rows = 1.0f / static_cast<float>(g.rows);
 
     // per-lane accumulators of the head weight gradients (training)
-    float gw_pi[ACT][MAX_HEAD_COLS / 32], gw_vf[MAX_HEAD_COLS / 32];
+    float gw_pi[ACT][MAX_HEAD_COLS / 32], gw_vf[MAX_HEAD_COLS / 32], gbh_pi[MAX_HEAD_COLS / 32], gbh_vf[MAX_HEAD_COLS / 32];
     float gb_pi[ACT], gls[ACT], gb_vf = 0.0f, st_pg = 0.0f, st_v = 0.0f, st_kl = 0.0f, st_cf = 0.0f;
 #pragma unroll
     for (int a = 0; a < ACT; ++a) {
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
         for (int i = 0; i < MAX_HEAD_COLS / 32; ++i) gw_pi[a][i] = 0.0f;
     }
 #pragma unroll
-    for (int i = 0; i < MAX_HEAD_COLS / 32; ++i) gw_vf[i] = 0.0f;
+    for (int i = 0; i < MAX_HEAD_COLS / 32; ++i) { gw_vf[i] = 0.0f; gbh_pi[i] = 0.0f; gbh_vf[i] = 0.0f; }
 
     for (int row = blockIdx.x * HEAD_WARPS + warp; row < g.rows; row += gridDim.x * HEAD_WARPS) {
         // ---- load the two activation rows (hi + lo) ----
@@ -270,6 +281,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
                 }
                 d0 *= fmaf(-hp[2 * i], hp[2 * i], 1.0f);
                 d1 *= fmaf(-hp[2 * i + 1], hp[2 * i + 1], 1.0f);
+                gbh_pi[2 * i] += d0; gbh_pi[2 * i + 1] += d1;
                 const __nv_bfloat16 h0 = __float2bfloat16_rn(d0), h1 = __float2bfloat16_rn(d1);
                 reinterpret_cast<uint32_t*>(g.dzp_hi + op)[lane + 32 * i] = dnmma::pack_bf16(h0, h1);
                 if (g.dzp_lo)
@@ -283,6 +295,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
                 gw_vf[2 * i + 1] = fmaf(dvalue, hv[2 * i + 1], gw_vf[2 * i + 1]);
                 d0 *= fmaf(-hv[2 * i], hv[2 * i], 1.0f);
                 d1 *= fmaf(-hv[2 * i + 1], hv[2 * i + 1], 1.0f);
+                gbh_vf[2 * i] += d0; gbh_vf[2 * i + 1] += d1;
                 const __nv_bfloat16 h0 = __float2bfloat16_rn(d0), h1 = __float2bfloat16_rn(d1);
                 reinterpret_cast<uint32_t*>(g.dzv_hi + ov)[lane + 32 * i] = dnmma::pack_bf16(h0, h1);
                 if (g.dzv_lo)
@@ -295,7 +308,8 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
     // ---- block reduction in warp order (deterministic), one partial vector per block ----
     const int P = g.partial_size;
     float* mine = s_red + warp * P;
-    const int o_bpi = ACT * g.n_pi, o_wvf = o_bpi + ACT, o_bvf = o_wvf + g.n_vf, o_ls = o_bvf + 1, o_st = o_ls + ACT;
+    const int o_bpi = ACT * g.n_pi, o_wvf = o_bpi + ACT, o_bvf = o_wvf + g.n_vf, o_ls = o_bvf + 1, o_bhp = o_ls + ACT, o_bhv = o_bhp + g.n_pi,
+              o_st = o_bhv + g.n_vf;
 #pragma unroll
     for (int i = 0; i < MAX_HEAD_COLS / 64; ++i) {
         if (i < ip) {
@@ -304,10 +318,14 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
                 mine[a * g.n_pi + 2 * lane + 64 * i] = gw_pi[a][2 * i];
                 mine[a * g.n_pi + 2 * lane + 64 * i + 1] = gw_pi[a][2 * i + 1];
             }
+            mine[o_bhp + 2 * lane + 64 * i] = gbh_pi[2 * i];
+            mine[o_bhp + 2 * lane + 64 * i + 1] = gbh_pi[2 * i + 1];
         }
         if (i < iv) {
             mine[o_wvf + 2 * lane + 64 * i] = gw_vf[2 * i];
             mine[o_wvf + 2 * lane + 64 * i + 1] = gw_vf[2 * i + 1];
+            mine[o_bhv + 2 * lane + 64 * i] = gbh_vf[2 * i];
+            mine[o_bhv + 2 * lane + 64 * i + 1] = gbh_vf[2 * i + 1];
         }
     }
     if (lane == 0) {
@@ -412,7 +430,15 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs g) {
             const int r = static_cast<int>(i / s.cols), c = static_cast<int>(i % s.cols);
             const float* p = s.src + static_cast<long long>(r) * s.ld + c;
             float acc = 0.0f;
-            for (int sl = 0; sl < s.n_slices; ++sl) acc += p[sl * s.slice_stride];
+            int sl = 0;
+            for (; sl + 8 <= s.n_slices; sl += 8) {          // 8 loads in flight, added in slice order (deterministic)
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (sl + u) * s.slice_stride);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += v[u];
+            }
+            for (; sl < s.n_slices; ++sl) acc += __ldg(p + sl * s.slice_stride);
             // entropy bonus: ent_loss = -sum_a(0.5 + 0.5 log 2 pi + log_std_a) -> d/dlog_std_a = -ent_coef
             if (s.dst_off == g.log_std_off) acc -= g.ent_coef;
             g.grads[s.dst_off + i] = acc;

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -59,7 +60,15 @@ int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, i
     return DN_OK;
 }
 
-int pick_bn(int n) { return (n % 256 == 0) ? 256 : (n % 128 == 0) ? 128 : 64; }
+int pick_bn(int n) {
+    static int forced = -1;        // DN_MLP_BN=64|128|256: tile-width experiments
+    if (forced < 0) {
+        const char* e = getenv("DN_MLP_BN");
+        forced = e ? atoi(e) : 0;
+    }
+    if ((forced == 64 || forced == 128 || forced == 256) && n % forced == 0) return forced;
+    return (n % 256 == 0) ? 256 : (n % 128 == 0) ? 128 : 64;
+}
 
 struct GemmPlan {       // one contraction, ready to launch
     int kind = 0, bn = 0, grid = 0;
@@ -227,12 +236,15 @@ int setup_net(dn_ppo* h, Net& net, int L, const int32_t* hidden, const int64_t* 
         const int tiles = (N / BM) * (K / pick_bn(K));
         net.slices_max[l] = wgrad_slices(h->max_rows, tiles, h->sms);
         if ((rc = dev_alloc(h, &net.wpart[l], static_cast<size_t>(net.slices_max[l]) * N * K)) ||
-            (rc = dev_alloc(h, &net.bpart[l], static_cast<size_t>(COLSUM_CHUNKS) * N)))
+            (rc = dev_alloc(h, &net.bpart[l], static_cast<size_t>(std::max(h->sms, COLSUM_CHUNKS)) * N)))
             return rc;
         // plans: tensor maps over the full workspaces (lo plane max_rows rows after the hi plane), tile counts set per call
         const float* bias = h->params + net.b_off[l - 1];
         if ((rc = plan_fwd(&net.fwd[l], h->passes, h->max_rows, N, K, net.h[l - 1], net.w[l], bias, 1, net.h[l]))) return rc;
-        if (l > 1 && (rc = plan_dgrad(&net.dgrad[l], h->passes, h->max_rows, K, N, net.dz[l], net.w[l], net.h[l - 1], net.dz[l - 1]))) return rc;
+        if (l > 1) {
+            if ((rc = plan_dgrad(&net.dgrad[l], h->passes, h->max_rows, K, N, net.dz[l], net.w[l], net.h[l - 1], net.dz[l - 1]))) return rc;
+            net.dgrad[l].args.colsum = net.bpart[l - 1];      // bias gradient of layer l-1 = column sums of dz[l-1], per CTA
+        }
         if ((rc = plan_wgrad(&net.wgrad[l], h->passes, N, K, h->max_rows, 1, net.dz[l], net.h[l - 1], net.wpart[l]))) return rc;
     }
     return DN_OK;
@@ -275,7 +287,8 @@ int build_reduce_table(dn_ppo* h, int rows) {
             const int N = net->n[l], K = net->n[l - 1];
             const int cols = (l == 1) ? h->cfg.obs_dim : K;                         // the first layer's padding columns are dropped
             add_seg(v, net->wpart[l], static_cast<long long>(N) * K, net->wgrad[l].args.slices, N, cols, K, net->w_off[l - 1]);
-            add_seg(v, net->bpart[l], N, COLSUM_CHUNKS, 1, N, N, net->b_off[l - 1]);
+            if (l < net->L)      // per-CTA column sums written by the dgrad launch that produced dz[l]; layer L: head kernel, below
+                add_seg(v, net->bpart[l], N, net->dgrad[l + 1].grid, 1, N, N, net->b_off[l - 1]);
         }
     }
     const long long P = h->head_psize;
@@ -285,6 +298,8 @@ int build_reduce_table(dn_ppo* h, int rows) {
     add_seg(v, hp + A * npi + A, P, head_blocks, 1, nvf, nvf, h->vf.w_off[h->vf.L]);
     add_seg(v, hp + A * npi + A + nvf, P, head_blocks, 1, 1, 1, h->vf.b_off[h->vf.L]);
     add_seg(v, hp + A * npi + A + nvf + 1, P, head_blocks, 1, A, A, h->cfg.log_std_off);
+    add_seg(v, hp + A * npi + A + nvf + 1 + A, P, head_blocks, 1, npi, npi, h->pi.b_off[h->pi.L - 1]);
+    add_seg(v, hp + A * npi + A + nvf + 1 + A + npi, P, head_blocks, 1, nvf, nvf, h->vf.b_off[h->vf.L - 1]);
     std::vector<int> sob;
     for (size_t i = 0; i < v.size(); ++i) {
         const long long count = static_cast<long long>(v[i].rows) * v[i].cols;
@@ -439,6 +454,10 @@ int dn_ppo_create(const dn_ppo_config* cfg, int device, float* params, float* gr
         if (cfg->pi_hidden[l] < 128 || cfg->pi_hidden[l] % 128) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: hidden widths must be multiples of 128");
     for (int l = 0; l < cfg->n_vf; ++l)
         if (cfg->vf_hidden[l] < 128 || cfg->vf_hidden[l] % 128) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: hidden widths must be multiples of 128");
+    for (int l = 0; l < cfg->n_pi; ++l)
+        if (cfg->pi_hidden[l] > MAX_COLSUM_COLS) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: hidden widths may be at most 1024");
+    for (int l = 0; l < cfg->n_vf; ++l)
+        if (cfg->vf_hidden[l] > MAX_COLSUM_COLS) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: hidden widths may be at most 1024");
     if (cfg->pi_hidden[cfg->n_pi - 1] > MAX_HEAD_COLS || cfg->vf_hidden[cfg->n_vf - 1] > MAX_HEAD_COLS)
         return dn_internal_fail(DN_EINVAL, "dn_ppo_create: the last hidden layer may be at most 512 wide");
     if (cfg->precision != DN_MLP_BF16X3 && cfg->precision != DN_MLP_BF16) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: unknown precision");
@@ -552,11 +571,8 @@ int dn_ppo_minibatch_grad(dn_ppo* h, const dn_ppo_rollout* r, const int64_t* idx
     Net* nets[2] = {&h->pi, &h->vf};
     for (Net* net : nets)
         for (int l = net->L; l >= 1; --l) {
+            // bias gradients ride along: layer L's in the head kernel, layer l-1's in the epilogue of this dgrad
             if ((rc = launch_gemm(net->wgrad[l], st))) return rc;
-            const __nv_bfloat16* dz = net->dz[l];
-            colsum_kernel<<<dim3(net->n[l] / 64, COLSUM_CHUNKS), 256, 0, st>>>(dz, (h->passes > 1) ? dz + R * net->n[l] : nullptr, rows, net->n[l],
-                                                                              net->bpart[l]);
-            PPO_CUDA(cudaGetLastError());
             if (l > 1 && (rc = launch_gemm(net->dgrad[l], st))) return rc;
         }
     // every partial -> the flat bucket; statistics; early-stop vote

@@ -617,6 +617,24 @@ class PPOLearner:
                 "clip_fraction": a[4], "epochs": epochs_run, "minibatches": n_done, "early_stop": bool(stop),
                 "std": float(self.policy.log_std.detach().exp().mean())}
 
+    def load_optimizer_state(self, state: Dict[int, dict]) -> None:
+        """Adam state by position in ``self.policy.parameters()`` ({"step", "exp_avg", "exp_avg_sq"} per entry), e.g. from an
+        SB3 ``policy.optimizer.pth`` re-indexed by checkpoint.load_sb3_zip.  Written into whatever owns the moments: the flat
+        vectors of the fused update, or torch.optim.Adam's own tensors."""
+        if self.fused is not None:
+            with torch.no_grad():
+                for i, p in enumerate(self.params):
+                    if i in state:
+                        st = self.opt.state[p]
+                        st["exp_avg"].copy_(state[i]["exp_avg"].to(self.device))
+                        st["exp_avg_sq"].copy_(state[i]["exp_avg_sq"].to(self.device))
+                        self.fused.step.copy_(torch.as_tensor(state[i]["step"], dtype=torch.float32).reshape(()))
+            return
+        own = self.opt.state_dict()
+        own["state"] = state
+        self.opt.load_state_dict(own)
+        self._graphs = None      # load_state_dict re-creates the state tensors: captured CUDA graphs must be rebuilt
+
     def flat_parameters(self) -> torch.Tensor:
         return torch.cat([p.detach().reshape(-1) for p in self.params])
 

@@ -695,7 +695,7 @@ class OracleDroneEnv:
 
     def _drag_link(self, rotation):
         """The forceObj BaseAviary._drag hands to p.applyExternalForce(..., flags=p.LINK_FRAME) (BaseAviary.py:855-865);
-        pinned against the reference's own function by tests/golden/ref_forces.npz."""
+        pinned against the reference's own function by tests/golden/forces_ref.npz."""
         drag_factors = -1 * self.DRAG_COEFF * np.sum(np.array(2 * np.pi * self.last_clipped_action / 60))
         return np.dot(rotation, drag_factors * np.array(self.vel))
 

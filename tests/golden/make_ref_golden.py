@@ -389,7 +389,7 @@ def _urdf_link_offsets(path):
 
 
 def mint_forces(ref, n_rollout=40, seed=77):
-    """ref_forces.npz: the reference's OWN BaseAviary._drag (BaseAviary.py:838-865) and BaseAviary._groundEffect (:798-834)
+    """forces_ref.npz: the reference's OWN BaseAviary._drag (BaseAviary.py:838-865) and BaseAviary._groundEffect (:798-834)
     evaluated on states of a DYN rollout plus hand-placed edge states; what is stored is the argument each of them hands
     to p.applyExternalForce (recorded by the pybullet shim), next to the state it was computed from.  These two functions
     only run under Physics.PYB_* in the reference (which needs Bullet's integrator); the oracle / the kernel apply the same
@@ -442,7 +442,7 @@ def mint_forces(ref, n_rollout=40, seed=77):
 
 if __name__ == "__main__":
     ref = _import_reference()
-    np.savez_compressed(os.path.join(HERE, "ref_forces.npz"), **mint_forces(ref))
+    np.savez_compressed(os.path.join(HERE, "forces_ref.npz"), **mint_forces(ref))
     print("HoverAviary imported from the reference:", ref[-1], file=sys.stderr)
     for name, cfg in CASES.items():
         out = run(ref, *cfg)

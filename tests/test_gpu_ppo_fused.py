@@ -105,7 +105,7 @@ def test_one_minibatch_matches_fp32_torch(arch, B):
     moved = (p_ref - p0).abs()
     rel_p = per_tensor_rel(ref, p_fus, p_ref)
     print("parameter rel errors:", {k: f"{v:.1e}" for k, v in rel_p.items()}, "mean step", float(moved.mean()))
-    assert max(rel_p.values()) < 1e-4, rel_p
+    assert max(rel_p.values()) < 1e-4, {k: v for k, v in rel_p.items() if v >= 1e-4}
     # and the step itself (not just the parameter) agrees: the update of a coordinate is ~lr in size
     dstep = ((p_fus - p0) - (p_ref - p0)).abs()
     assert float(dstep.mean()) < 2e-2 * float(moved.mean()), (float(dstep.mean()), float(moved.mean()))

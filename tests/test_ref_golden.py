@@ -118,6 +118,9 @@ def test_oracle_matches_reference(path):
 # Open loop over the whole fixture without re-synchronisation (up to 480 substeps = 2x the stated 1 s horizon;
 # the saturating-action cases reach |rates| ~ 60 rad/s): |dobs| <= 1e-3, |dreward| <= 1e-2, discrete outputs exact.
 OBS_TOL, REW_TOL = 1e-3, 1e-2
+# The STATED tolerance (north_star / SURVEY 8c / parity_utils.py): |dobs| <= 1e-4, |dreward| <= 1e-3 over a 240-substep (1 s)
+# open-loop horizon.  Asserted directly against the reference fixtures on the first 240 substeps of every one of them.
+STATED_OBS_TOL, STATED_REW_TOL, STATED_SUBSTEPS = 1e-4, 1e-3, 240
 
 
 def _resync(g, t, get_state, set_state):
@@ -144,6 +147,8 @@ def _compare_fp32(g, step_fn, obs0, norm, rel_reward=False, resync=None):
     np.testing.assert_allclose(obs0, g["obs0"], atol=2e-4 if norm else 1e-6)
     T, N = g["reward"].shape
     worst_obs = worst_rew = 0.0
+    stated_steps = STATED_SUBSTEPS // _meta(g)["S"]           # control steps inside the stated horizon
+    stated = {"obs": 0.0, "rew": 0.0, "steps": 0}
     for t in range(T):
         o, r, d, f, term = step_fn(g["actions"][t])
         if resync is not None:
@@ -165,6 +170,8 @@ def _compare_fp32(g, step_fn, obs0, norm, rel_reward=False, resync=None):
                     continue
                 e[3:6] = np.minimum(e[3:6], np.abs(2 - e[3:6]))        # +-pi wrap of the Euler angles
                 worst_obs = max(worst_obs, e[:9].max(), e[12] if e.size > 12 else 0.0)
+                if t < stated_steps:
+                    stated["obs"] = max(stated["obs"], e[:9].max(), e[12] if e.size > 12 else 0.0)
                 # obs[9:12] = ang_v/|ang_v| is ill-conditioned near |ang_v| = 0; bounded by the absolute ang_v error
                 angn = float(np.linalg.norm(g["ang_v"][t, i]))
                 if not d[i]:
@@ -175,8 +182,20 @@ def _compare_fp32(g, step_fn, obs0, norm, rel_reward=False, resync=None):
             np.testing.assert_allclose(r, g["reward"][t], rtol=2e-3, atol=REW_TOL)
         else:
             worst_rew = max(worst_rew, float(np.abs(r - g["reward"][t]).max()))
+            if t < stated_steps:
+                stated["rew"] = max(stated["rew"], float(np.abs(r - g["reward"][t]).max()))
+        if t < stated_steps:
+            stated["steps"] = t + 1
     assert worst_obs < OBS_TOL and worst_rew < REW_TOL, (worst_obs, worst_rew)
-    return worst_obs, worst_rew
+    # the stated tolerance, CUDA / host build vs REFERENCE fixture directly (not via the oracle).  Skipped only where the
+    # comparison above is relative by construction (normalised observations / normalised or 1e6-sized rewards) and for the
+    # step-by-step re-synchronised PID fixtures (their horizon is one step).
+    if not norm and resync is None:
+        assert stated["steps"] == min(T, stated_steps)
+        assert stated["obs"] <= STATED_OBS_TOL, ("stated obs tolerance", stated)
+        if not rel_reward:
+            assert stated["rew"] <= STATED_REW_TOL, ("stated reward tolerance", stated)
+    return worst_obs, worst_rew, stated
 
 
 def _env_args(g):

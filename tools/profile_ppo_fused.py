@@ -36,3 +36,11 @@ print(f"{'kernel':90s} {'calls':>6s} {'total us':>10s} {'us/call':>9s} {'share':
 for r in rows[:25]:
     print(f"{r.key[:90]:90s} {r.count:6d} {r.device_time_total:10.0f} {r.device_time_total / max(r.count, 1):9.1f} {100 * r.device_time_total / tot:5.1f}%")
 print("sum of kernel time per minibatch (us):", tot / n)
+
+# per-launch sequence of one minibatch (kernel order within dn_ppo_minibatch_grad / apply)
+evs = [e for e in prof.events() if e.device_time_total > 0 and ("dnmma" in e.name or "dnppo" in e.name)]
+evs.sort(key=lambda e: e.time_range.start)
+per_mb = len(evs) // n
+print("launch sequence of the second minibatch:")
+for e in evs[per_mb:2 * per_mb]:
+    print(f"  {e.name[:70]:70s} {e.device_time_total:8.1f} us")
