@@ -516,7 +516,7 @@ def run_sac(args, dev, world, rank, barrier, max_over_ranks):
     a = copy.copy(args)
     a.track = "circle"
     n = args.sac_envs
-    env = make_env(n, a, dev, env_id_offset=rank * n, physics=Physics.PYB_GND_DRAG_DW)
+    env = make_env(n, a, dev, env_id_offset=rank * n, physics=Physics.PYB_GND_DRAG_DW, normalize_obs=not args.no_norm_obs)
     tr = SACTrainer(env, SACConfig(learning_starts=2 * 3 * n * world))     # two collection-only iterations, then updates
     for _ in range(4):
         tr.train_iteration()                                               # warm-up (past learning_starts)
@@ -548,9 +548,10 @@ def run_ppo(args, dev, world, rank, barrier, max_over_ranks):
     import copy
     a = copy.copy(args)
     a.track = args.ppo_track
-    env = make_env(args.ppo_envs, a, dev, env_id_offset=rank * args.ppo_envs)
+    # the reference's wrapper stack: every env is wrapped in NormalizeObservation (PBDroneSimulator.py:181) -> the NORM kernel variant
+    env = make_env(args.ppo_envs, a, dev, env_id_offset=rank * args.ppo_envs, normalize_obs=not args.no_norm_obs)
     T = args.ppo_rollout
-    cfg = PPOConfig(n_steps=T, batch_size=max(512, (T * args.ppo_envs) // 32))
+    cfg = PPOConfig(n_steps=T, batch_size=max(512, (T * args.ppo_envs) // 32), update_impl=args.ppo_impl, mlp_precision=args.ppo_precision)
     tr = PPOTrainer(env, cfg, rollout_steps=T)
     tr.train_iteration()                                   # warm-up (cuBLAS heuristics, allocator)
     barrier()
@@ -568,7 +569,10 @@ def run_ppo(args, dev, world, rank, barrier, max_over_ranks):
            "rollout_s_each": [round(o["rollout_s"], 5) for o in outs], "update_s_each": [round(o["update_s"], 5) for o in outs],
            "env_share_of_rollout": None, "allreduce_calls": tr.learner.allreduce_calls, "allreduce_bytes": tr.learner.n_params * 4,
            "gpu_launches": int(env.launch_count - l0), "approx_kl": outs[-1]["approx_kl"],
-           "policy": "2 x MLP 13-512-512-256 (pi, vf), Tanh, TF32 GEMMs (cuBLAS)", "collective": "NCCL all-reduce of one flat FP32 gradient bucket per optimiser step" if world > 1 else "none (1 GPU)"}
+           "normalize_obs": not args.no_norm_obs, "update_impl": outs[-1].get("impl", "torch/" + cfg.matmul_precision),
+           "optimizer_steps": [o.get("optimizer_steps") for o in outs], "update_us_per_minibatch": 1e6 * sum(o["update_s"] for o in outs) / max(1, sum(o["minibatches"] for o in outs)),
+           "policy": "2 x MLP 13-512-512-256 (pi, vf), Tanh; update + rollout forward: hand-written sm_100a kernels (tcgen05 BF16 hi/lo planes, "
+                     "FP32 TMEM accumulation) unless update_impl says torch", "collective": "NCCL all-reduce of one flat FP32 gradient bucket per optimiser step" if world > 1 else "none (1 GPU)"}
     env.close()
     return res
 
@@ -850,6 +854,10 @@ def main():
     ap.add_argument("--sac-envs", type=int, default=16384, help="BASELINE configs[3]: 16384 envs")
     ap.add_argument("--sac-iters", type=int, default=20)
     ap.add_argument("--no-vecenv", action="store_true")
+    ap.add_argument("--no-norm-obs", dest="no_norm_obs", action="store_true",
+                    help="learner lines on raw observations (labelled deviation; the reference always normalises, PBDroneSimulator.py:181)")
+    ap.add_argument("--ppo-precision", default="bf16x3", choices=["bf16x3", "bf16"], help="arithmetic of the fused PPO update's contractions")
+    ap.add_argument("--ppo-impl", default="auto", choices=["auto", "fused", "torch"])
     ap.add_argument("--rotating-handles", type=int, default=None,
                     help="override the number of rotating handles of the headline measurement (default: enough for > 126 MB; "
                          "the ncu launch-list pass uses a small number so that the capture window covers the timed region)")

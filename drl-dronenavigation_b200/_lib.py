@@ -12,7 +12,7 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libdronenav.so")
 
-DN_ABI_VERSION = 3
+DN_ABI_VERSION = 4
 
 # enums of include/dronenav.h
 DN_ACT_THRUST, DN_ACT_RPM, DN_ACT_ONE_D_RPM, DN_ACT_PID, DN_ACT_VEL, DN_ACT_ONE_D_PID = 0, 1, 2, 3, 4, 5

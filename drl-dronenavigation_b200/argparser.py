@@ -52,6 +52,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--wandb_rootlog", type=str, default="/wandb")
     p.add_argument("--capture-video", type=_bool, default=False, nargs="?", const=True)
     # additions of this implementation
+    p.add_argument("--no_norm_obs", default=False, type=_bool, nargs="?", const=True,
+                   help="labelled deviation: train / evaluate on raw observations.  The reference always wraps every env in "
+                        "NormalizeObservation (PBDroneSimulator.py:181), which is the default here too (fused, per-env FP64 statistics)")
     p.add_argument("--pyb_freq", type=int, default=240)
     p.add_argument("--ctrl_freq", type=int, default=240)
     p.add_argument("--reward_id", type=int, default=0, help="DN_REWARD_* (include/dronenav.h): 0 PBDroneEnv, 1 dummy_env, "

@@ -34,7 +34,7 @@ _STATE_DTYPES = {
     "prev_ang_v": (torch.float32, 3), "dist": (torch.float32, 0), "prev_dist": (torch.float32, 0),
     "target_idx": (torch.int32, 0), "steps": (torch.int32, 0), "just_found": (torch.uint8, 0),
     "ep_return": (torch.float32, 0), "ep_length": (torch.int32, 0), "episode_count": (torch.int32, 0),
-    "last_rpm_sum": (torch.float32, 0), "obs_rms": (torch.float32, -1),
+    "last_rpm_sum": (torch.float32, 0), "obs_rms": (torch.float64, -1),
     "aux": (torch.float32, 4), "rew_rms": (torch.float32, 4), "spawn": (torch.float32, 4), "pid": (torch.float32, 9),
 }
 

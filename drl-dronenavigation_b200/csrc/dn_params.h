@@ -108,7 +108,7 @@ struct Params {
     const float4* segs;      // [T][2] {ext_p1.xyz, ext_len} {unit.xyz, seg_len}; non-circle cylinder
     float4* s[kPlanes];
     float* last_rpm_sum;     // [N], drag only
-    float* obs_rms;          // [(2*obs_dim+1)][N] mean planes | var planes | count, normalize_obs only
+    double* obs_rms;         // [(2*obs_dim+1)][N] FP64 mean planes | var planes | count, normalize_obs only
     float4* spawn;           // [N] {spawn point of the current episode, 0}; DN_SPAWN_LINE only (segment 0 of the tube starts there)
     float4* aux;             // [N] {_current_position.xyz (stale across resets), |_current_position - _last_position|} (RW_REACHING);
                              //     PBDroneEnv._last_action (RW_LITERATURE)

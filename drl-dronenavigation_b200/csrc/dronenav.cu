@@ -172,33 +172,40 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
                 // statistics in .step, the reset observation again in .reset (normalize.py:74-92).
                 // All 2 x obs_dim statistics are fetched first (independent loads in flight together; a
                 // load -> update -> store loop per entry serialised 13 L2 round trips: 9 us for a 12-env launch).
+                // The statistics are FP64 (the reference's dtype); they are fetched four entries at a time so that the
+                // independent loads are in flight together without holding all 2 x obs_dim doubles in registers.
                 const size_t N = P.n;
-                float* cnt_p = P.obs_rms + static_cast<size_t>(2 * D) * N + i;
-                const float cnt = *cnt_p;
-                float m[kMaxObs], v[kMaxObs];
+                double* cnt_p = P.obs_rms + static_cast<size_t>(2 * D) * N + i;
+                const double cnt = *cnt_p;
 #pragma unroll
-                for (int k = 0; k < kMaxObs; ++k) {
-                    if (k < D) {
-                        m[k] = P.obs_rms[static_cast<size_t>(k) * N + i];
-                        v[k] = P.obs_rms[static_cast<size_t>(D + k) * N + i];
-                    }
-                }
+                for (int k0 = 0; k0 < kMaxObs; k0 += 4) {
+                    double m[4], v[4];
 #pragma unroll
-                for (int k = 0; k < kMaxObs; ++k) {
-                    if (k < D) {
-                        const float tn = rms_update_normalize(obs_row[k], m[k], v[k], cnt);
-                        float ob = tn;
-                        if (r.finished) {
-                            if (term_out) term_out[k] = tn;
-                            const float raw = (k < 3) ? r.spawn_obs[k] : ((k < 12) ? P.init_obs[k] : r.reset_obs_dist);
-                            ob = rms_update_normalize(raw, m[k], v[k], cnt + 1.0f);
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = k0 + j;
+                        if (k < D) {
+                            m[j] = P.obs_rms[static_cast<size_t>(k) * N + i];
+                            v[j] = P.obs_rms[static_cast<size_t>(D + k) * N + i];
                         }
-                        obs_row[k] = ob;
-                        P.obs_rms[static_cast<size_t>(k) * N + i] = m[k];
-                        P.obs_rms[static_cast<size_t>(D + k) * N + i] = v[k];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = k0 + j;
+                        if (k < D) {
+                            const float tn = rms_update_normalize(obs_row[k], m[j], v[j], cnt);
+                            float ob = tn;
+                            if (r.finished) {
+                                if (term_out) term_out[k] = tn;
+                                const float raw = (k < 3) ? r.spawn_obs[k] : ((k < 12) ? P.init_obs[k] : r.reset_obs_dist);
+                                ob = rms_update_normalize(raw, m[j], v[j], cnt + 1.0);
+                            }
+                            obs_row[k] = ob;
+                            P.obs_rms[static_cast<size_t>(k) * N + i] = m[j];
+                            P.obs_rms[static_cast<size_t>(D + k) * N + i] = v[j];
+                        }
                     }
                 }
-                *cnt_p = cnt + (r.finished ? 2.0f : 1.0f);
+                *cnt_p = cnt + (r.finished ? 2.0 : 1.0);
             } else if (r.finished) {
                 if (term_out) {
 #pragma unroll
@@ -453,8 +460,8 @@ __global__ void init_kernel(const __grid_constant__ Params P, float d0) {
     if (P.pid[0]) { P.pid[0][i] = P.pid[1][i] = P.pid[2][i] = make_float4(0.f, 0.f, 0.f, 0.f); }   // DSLPIDControl.reset (DSLPIDControl.py:66-80)
     if (P.obs_rms) {
         const size_t N = P.n; const int D = P.obs_dim;
-        for (int k = 0; k < D; ++k) { P.obs_rms[k * N + i] = 0.f; P.obs_rms[(D + k) * N + i] = 1.f; }
-        P.obs_rms[2 * D * N + i] = 1e-4f;                   // RunningMeanStd(epsilon=1e-4), normalize.py:13-17
+        for (int k = 0; k < D; ++k) { P.obs_rms[k * N + i] = 0.0; P.obs_rms[(D + k) * N + i] = 1.0; }
+        P.obs_rms[2 * D * N + i] = 1e-4;                    // RunningMeanStd(epsilon=1e-4), normalize.py:13-17
     }
 }
 
@@ -501,16 +508,16 @@ __global__ void reset_kernel(const __grid_constant__ Params P, const uint8_t* ma
     o[12] = stale_dist * P.inv_max_target_dist;
     if (NORM) {
         const size_t N = P.n;
-        float* cnt_p = P.obs_rms + static_cast<size_t>(2 * D) * N + i;
-        const float cnt = *cnt_p;
+        double* cnt_p = P.obs_rms + static_cast<size_t>(2 * D) * N + i;
+        const double cnt = *cnt_p;
         for (int k = 0; k < D; ++k) {
-            float* mp = P.obs_rms + static_cast<size_t>(k) * N + i;
-            float* vp = P.obs_rms + static_cast<size_t>(D + k) * N + i;
-            float m = *mp, v = *vp;
+            double* mp = P.obs_rms + static_cast<size_t>(k) * N + i;
+            double* vp = P.obs_rms + static_cast<size_t>(D + k) * N + i;
+            double m = *mp, v = *vp;
             o[k] = rms_update_normalize(o[k], m, v, cnt);
             *mp = m; *vp = v;
         }
-        *cnt_p = cnt + 1.0f;
+        *cnt_p = cnt + 1.0;
     }
     if (obs_out) for (int k = 0; k < D; ++k) obs_out[static_cast<size_t>(i) * D + k] = o[k];
 }
@@ -541,7 +548,7 @@ __global__ void gae_kernel(const float* __restrict__ rew, const float* __restric
 struct StateView {   // device mirror of dn_state_view
     float *pos, *quat, *vel, *rpy_rates, *ang_v, *prev_vel, *prev_ang_v, *dist, *prev_dist;
     int32_t *target_idx, *steps; uint8_t* just_found; float* ep_return; int32_t* ep_length;
-    uint32_t* episode_count; float* last_rpm_sum; float* obs_rms; float* aux; float* rew_rms; float* spawn; float* pid;
+    uint32_t* episode_count; float* last_rpm_sum; double* obs_rms; float* aux; float* rew_rms; float* spawn; float* pid;
 };
 
 template <bool SET>
@@ -741,7 +748,7 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     const bool drag = (cfg->physics & DN_PHYS_DRAG) != 0;
     if (drag) bytes += fplane;
     const size_t rms_floats = e->normalize_obs ? static_cast<size_t>(2 * P.obs_dim + 1) * N : 0;
-    bytes += ((rms_floats * sizeof(float) + 255) / 256) * 256;
+    bytes += ((rms_floats * sizeof(double) + 255) / 256) * 256;
     const bool need_aux = (rw.mode == dn::RW_REACHING || rw.mode == dn::RW_LITERATURE), need_rew_rms = (cfg->normalize_reward != 0);
     const bool need_spawn = (cfg->spawn_mode != DN_SPAWN_FIXED), need_pid = (cfg->act_type >= DN_ACT_PID);
     if (need_pid) bytes += 3 * plane;
@@ -753,7 +760,7 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
     char* p = static_cast<char*>(e->state_mem);
     for (int k = 0; k < dn::kPlanes; ++k) { P.s[k] = reinterpret_cast<float4*>(p); p += plane; }
     if (drag) { P.last_rpm_sum = reinterpret_cast<float*>(p); p += fplane; }
-    if (rms_floats) { P.obs_rms = reinterpret_cast<float*>(p); p += ((rms_floats * sizeof(float) + 255) / 256) * 256; }
+    if (rms_floats) { P.obs_rms = reinterpret_cast<double*>(p); p += ((rms_floats * sizeof(double) + 255) / 256) * 256; }
     if (need_aux) { P.aux = reinterpret_cast<float4*>(p); p += plane; }
     if (need_rew_rms) { P.rew_rms = reinterpret_cast<float4*>(p); p += plane; }
     if (need_spawn) { P.spawn = reinterpret_cast<float4*>(p); p += plane; }

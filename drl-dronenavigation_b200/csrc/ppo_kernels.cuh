@@ -1,6 +1,6 @@
 // ppo_kernels.cuh -- the CUDA-core kernels of the PPO minibatch update around the tcgen05 contractions (dn_umma.cuh):
 // minibatch gather + BF16 plane split, Gaussian / value heads with the PPO losses and their gradients
-// (sb3_ppo.py:222-282 spelled out by hand), bias-gradient column sums, deterministic reduction of all partial
+// (sb3_ppo.py:222-282 spelled out by hand), deterministic reduction of all partial
 // gradients into the flat bucket, gradient-norm clipping + Adam (sb3_ppo.py:291-294), FP32 -> BF16 plane refresh.
 #pragma once
 #include <cuda_bf16.h>
@@ -14,9 +14,8 @@ namespace dnppo {
 constexpr int MAX_LAYERS = 4;       // hidden layers per network
 constexpr int MAX_ACT = 8;
 constexpr int XPAD = 64;            // observation width padded to one 64-element k-block
-constexpr int HEAD_WARPS = 8;
+constexpr int HEAD_WARPS = 4;       // 128-thread blocks: ~160 registers per thread still leave 3 blocks per SM
 constexpr int MAX_HEAD_COLS = 512;  // widest last hidden layer the head kernel keeps in registers (16 values per lane)
-constexpr int COLSUM_CHUNKS = 32;
 
 struct Ctrl {                       // device-resident control block of one update() call
     int stopped;                    // sticky: the KL early stop fired (sb3_ppo.py:283-287); later minibatches are no-ops
@@ -125,7 +124,8 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-template <int ACT>
+// NP = column pairs per lane = (widest of the two last hidden layers) / 64: sizes the per-lane register arrays
+template <int ACT, int NP>
 __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g) {
     extern __shared__ float hsm[];
     float* s_wpi = hsm;                                   // [ACT][n_pi]
@@ -162,43 +162,51 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
     const float inv_rows = 1.0f / static_cast<float>(g.rows);
 
     // per-lane accumulators of the head weight gradients (training)
-    float gw_pi[ACT][MAX_HEAD_COLS / 32], gw_vf[MAX_HEAD_COLS / 32], gbh_pi[MAX_HEAD_COLS / 32], gbh_vf[MAX_HEAD_COLS / 32];
+    float gw_pi[ACT][2 * NP], gw_vf[2 * NP], gbh_pi[2 * NP], gbh_vf[2 * NP];
     float gb_pi[ACT], gls[ACT], gb_vf = 0.0f, st_pg = 0.0f, st_v = 0.0f, st_kl = 0.0f, st_cf = 0.0f;
 #pragma unroll
     for (int a = 0; a < ACT; ++a) {
         gb_pi[a] = 0.0f; gls[a] = 0.0f;
 #pragma unroll
-        for (int i = 0; i < MAX_HEAD_COLS / 32; ++i) gw_pi[a][i] = 0.0f;
+        for (int i = 0; i < 2 * NP; ++i) gw_pi[a][i] = 0.0f;
     }
 #pragma unroll
-    for (int i = 0; i < MAX_HEAD_COLS / 32; ++i) { gw_vf[i] = 0.0f; gbh_pi[i] = 0.0f; gbh_vf[i] = 0.0f; }
+    for (int i = 0; i < 2 * NP; ++i) { gw_vf[i] = 0.0f; gbh_pi[i] = 0.0f; gbh_vf[i] = 0.0f; }
 
-    for (int row = blockIdx.x * HEAD_WARPS + warp; row < g.rows; row += gridDim.x * HEAD_WARPS) {
-        // ---- load the two activation rows (hi + lo) ----
-        float hp[MAX_HEAD_COLS / 32], hv[MAX_HEAD_COLS / 32];
+    // raw BF16 words of a row (hi / lo planes of both networks); the NEXT row's are requested before the current row is
+    // worked on, so a warp always has one row of loads in flight (the kernel is latency-bound otherwise: few warps, DRAM-cold rows)
+    uint32_t rp_h[NP], rp_l[NP], rv_h[NP], rv_l[NP];
+    auto fetch = [&](int row) {
         const long long op = static_cast<long long>(row) * g.n_pi, ov = static_cast<long long>(row) * g.n_vf;
 #pragma unroll
-        for (int i = 0; i < MAX_HEAD_COLS / 64; ++i) {
-            if (i < ip) {
-                const uint32_t wh = __ldg(reinterpret_cast<const uint32_t*>(g.hp_hi + op) + lane + 32 * i);
-                const uint32_t wl = g.hp_lo ? __ldg(reinterpret_cast<const uint32_t*>(g.hp_lo + op) + lane + 32 * i) : 0u;
-                hp[2 * i] = dnmma::bf16lo_f(wh) + dnmma::bf16lo_f(wl);
-                hp[2 * i + 1] = dnmma::bf16hi_f(wh) + dnmma::bf16hi_f(wl);
-            } else { hp[2 * i] = hp[2 * i + 1] = 0.0f; }
-            if (i < iv) {
-                const uint32_t wh = __ldg(reinterpret_cast<const uint32_t*>(g.hv_hi + ov) + lane + 32 * i);
-                const uint32_t wl = g.hv_lo ? __ldg(reinterpret_cast<const uint32_t*>(g.hv_lo + ov) + lane + 32 * i) : 0u;
-                hv[2 * i] = dnmma::bf16lo_f(wh) + dnmma::bf16lo_f(wl);
-                hv[2 * i + 1] = dnmma::bf16hi_f(wh) + dnmma::bf16hi_f(wl);
-            } else { hv[2 * i] = hv[2 * i + 1] = 0.0f; }
+        for (int i = 0; i < NP; ++i) {
+            rp_h[i] = (i < ip) ? __ldg(reinterpret_cast<const uint32_t*>(g.hp_hi + op) + lane + 32 * i) : 0u;
+            rp_l[i] = (i < ip && g.hp_lo) ? __ldg(reinterpret_cast<const uint32_t*>(g.hp_lo + op) + lane + 32 * i) : 0u;
+            rv_h[i] = (i < iv) ? __ldg(reinterpret_cast<const uint32_t*>(g.hv_hi + ov) + lane + 32 * i) : 0u;
+            rv_l[i] = (i < iv && g.hv_lo) ? __ldg(reinterpret_cast<const uint32_t*>(g.hv_lo + ov) + lane + 32 * i) : 0u;
         }
+    };
+    const int row_first = blockIdx.x * HEAD_WARPS + warp, row_step = gridDim.x * HEAD_WARPS;
+    if (row_first < g.rows) fetch(row_first);
+    for (int row = row_first; row < g.rows; row += row_step) {
+        // ---- the two activation rows (hi + lo) ----
+        float hp[2 * NP], hv[2 * NP];
+        const long long op = static_cast<long long>(row) * g.n_pi, ov = static_cast<long long>(row) * g.n_vf;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            hp[2 * i] = dnmma::bf16lo_f(rp_h[i]) + dnmma::bf16lo_f(rp_l[i]);
+            hp[2 * i + 1] = dnmma::bf16hi_f(rp_h[i]) + dnmma::bf16hi_f(rp_l[i]);
+            hv[2 * i] = dnmma::bf16lo_f(rv_h[i]) + dnmma::bf16lo_f(rv_l[i]);
+            hv[2 * i + 1] = dnmma::bf16hi_f(rv_h[i]) + dnmma::bf16hi_f(rv_l[i]);
+        }
+        if (row + row_step < g.rows) fetch(row + row_step);
         // ---- heads: mean[a] = W_pi[a] . hp + b, value = W_vf . hv + b ----
         float mean[ACT], value;
 #pragma unroll
         for (int a = 0; a < ACT; ++a) {
             float acc = 0.0f;
 #pragma unroll
-            for (int i = 0; i < MAX_HEAD_COLS / 64; ++i)
+            for (int i = 0; i < NP; ++i)
                 if (i < ip) {
                     const float2 w = *reinterpret_cast<const float2*>(s_wpi + a * g.n_pi + 2 * lane + 64 * i);
                     acc = fmaf(w.x, hp[2 * i], acc);
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
         {
             float acc = 0.0f;
 #pragma unroll
-            for (int i = 0; i < MAX_HEAD_COLS / 64; ++i)
+            for (int i = 0; i < NP; ++i)
                 if (i < iv) {
                     const float2 w = *reinterpret_cast<const float2*>(s_wvf + 2 * lane + 64 * i);
                     acc = fmaf(w.x, hv[2 * i], acc);
@@ -268,7 +276,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
         }
         // ---- gradient w.r.t. the last hidden pre-activations, head weight gradients ----
 #pragma unroll
-        for (int i = 0; i < MAX_HEAD_COLS / 64; ++i) {
+        for (int i = 0; i < NP; ++i) {
             if (i < ip) {
                 float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
@@ -311,7 +319,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
     const int o_bpi = ACT * g.n_pi, o_wvf = o_bpi + ACT, o_bvf = o_wvf + g.n_vf, o_ls = o_bvf + 1, o_bhp = o_ls + ACT, o_bhv = o_bhp + g.n_pi,
               o_st = o_bhv + g.n_vf;
 #pragma unroll
-    for (int i = 0; i < MAX_HEAD_COLS / 64; ++i) {
+    for (int i = 0; i < NP; ++i) {
         if (i < ip) {
 #pragma unroll
             for (int a = 0; a < ACT; ++a) {
@@ -344,34 +352,6 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// bias gradients: column sums of a pre-activation gradient [rows, n] (hi + lo planes), COLSUM_CHUNKS row chunks
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int rows, int n,
-                                                     float* __restrict__ partial /* [COLSUM_CHUNKS][n] */) {
-    // block: 64 columns x one row chunk; thread (rg = tid / 32, lane): column pair 2*lane, rows rg, rg + 8, ...
-    const int col0 = blockIdx.x * 64, chunk = blockIdx.y;
-    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int rows_per = rows / COLSUM_CHUNKS, r0 = chunk * rows_per;
-    float s0 = 0.0f, s1 = 0.0f;
-    for (int r = r0 + rg; r < r0 + rows_per; r += 8) {
-        const long long o = (static_cast<long long>(r) * n + col0) / 2 + lane;
-        const uint32_t wh = __ldg(reinterpret_cast<const uint32_t*>(hi) + o);
-        const uint32_t wl = lo ? __ldg(reinterpret_cast<const uint32_t*>(lo) + o) : 0u;
-        s0 += dnmma::bf16lo_f(wh) + dnmma::bf16lo_f(wl);
-        s1 += dnmma::bf16hi_f(wh) + dnmma::bf16hi_f(wl);
-    }
-    __shared__ float sh[8][64];
-    sh[rg][2 * lane] = s0; sh[rg][2 * lane + 1] = s1;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) acc += sh[w][threadIdx.x];
-        partial[static_cast<long long>(chunk) * n + col0 + threadIdx.x] = acc;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // deterministic reduction of every partial gradient into the flat bucket (+ statistics and the KL flag)
 // ---------------------------------------------------------------------------------------------------------------
 struct Seg {                 // dst[dst_off + r * cols + c] = sum_s src[s * slice_stride + r * ld + c]
@@ -379,8 +359,11 @@ struct Seg {                 // dst[dst_off + r * cols + c] = sum_s src[s * slic
     long long slice_stride, dst_off;
     int n_slices, rows, cols, ld;
     int first_block, n_blocks;
+    int deep;                // 1: few elements, many slices (head / bias partials): 32 elements per block, the slices split over its warps
 };
-constexpr int REDUCE_PER_BLOCK = 1024;
+constexpr int REDUCE_PER_BLOCK = 1024;       // wide segments: 4 elements per thread, every thread walks all slices
+constexpr int REDUCE_DEEP_PER_BLOCK = 32;    // deep segments: lane = element, warp w takes slices w, w + 8, ...
+constexpr int REDUCE_DEEP_MIN_SLICES = 48;
 
 struct ReduceArgs {
     const Seg* segs; int n_segs;
@@ -394,24 +377,27 @@ struct ReduceArgs {
     Ctrl* ctrl;
 };
 
+// Every sum below is evaluated in an order fixed by the launch geometry alone: gradients are bit-reproducible run to run.
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs g) {
     if (blockIdx.x == gridDim.x - 1) {
-        // statistics of this minibatch: sum the head blocks in order
+        // statistics of this minibatch: the head blocks' sums, strided over the threads, then a fixed-order tree
         __shared__ double sh[4][256];
         double a[4] = {0, 0, 0, 0};
         for (int b = threadIdx.x; b < g.head_blocks; b += 256)
             for (int k = 0; k < 4; ++k) a[k] += g.head_partial[static_cast<long long>(b) * g.head_psize + g.head_stats_off + k];
         for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] = a[k];
         __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o)
+                for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+            __syncthreads();
+        }
         if (threadIdx.x == 0) {
-            double t[4] = {0, 0, 0, 0};
-            for (int i = 0; i < 256; ++i)
-                for (int k = 0; k < 4; ++k) t[k] += sh[k][i];
             const double inv = 1.0 / g.rows;
-            const float kl = static_cast<float>(t[2] * inv);
+            const float kl = static_cast<float>(sh[2][0] * inv);
             const bool was_stopped = g.ctrl->stopped != 0;
             if (!was_stopped) {
-                for (int k = 0; k < 4; ++k) g.ctrl->stats[k] += t[k] * inv;
+                for (int k = 0; k < 4; ++k) g.ctrl->stats[k] += sh[k][0] * inv;
                 g.ctrl->n_done += 1;
                 g.ctrl->last_kl = kl;
             }
@@ -422,6 +408,35 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs g) {
     }
     const Seg s = g.segs[g.seg_of_block[blockIdx.x]];
     const long long count = static_cast<long long>(s.rows) * s.cols;
+    if (s.deep) {
+        __shared__ float part[8][REDUCE_DEEP_PER_BLOCK];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const long long i = static_cast<long long>(blockIdx.x - s.first_block) * REDUCE_DEEP_PER_BLOCK + lane;
+        float acc = 0.0f;
+        if (i < count) {
+            const int r = static_cast<int>(i / s.cols), c = static_cast<int>(i % s.cols);
+            const float* p = s.src + static_cast<long long>(r) * s.ld + c;
+            int sl = warp;
+            for (; sl + 56 < s.n_slices; sl += 64) {         // 8 loads in flight, added in slice order
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (sl + 8 * u) * s.slice_stride);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += v[u];
+            }
+            for (; sl < s.n_slices; sl += 8) acc += __ldg(p + sl * s.slice_stride);
+        }
+        part[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0 && i < count) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += part[w][lane];
+            if (s.dst_off == g.log_std_off) t -= g.ent_coef;      // entropy bonus, see below
+            g.grads[s.dst_off + i] = t;
+        }
+        return;
+    }
     const long long base = static_cast<long long>(blockIdx.x - s.first_block) * REDUCE_PER_BLOCK;
 #pragma unroll
     for (int k = 0; k < REDUCE_PER_BLOCK / 256; ++k) {

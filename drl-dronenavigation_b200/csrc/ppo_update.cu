@@ -46,33 +46,45 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// BF16 row-major [rows, cols] tensor, box = box_rows x 64 columns (one 128-byte swizzle row per box row)
-int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
+// BF16 row-major [rows, cols] tensor.  Operand maps: box = box_rows x 64 columns, 128-byte swizzle (one swizzle row per box
+// row).  Epilogue maps (results, tanh outputs): box = 32 x 32, 64-byte swizzle (the per-warp staging buffers of dn_umma.cuh).
+int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows, bool epilogue = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return dn_internal_fail(DN_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t box[2] = {epilogue ? 32u : 64u, static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    epilogue ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return dn_internal_fail(DN_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
     return DN_OK;
 }
 
-int pick_bn(int n) {
-    static int forced = -1;        // DN_MLP_BN=64|128|256: tile-width experiments
-    if (forced < 0) {
-        const char* e = getenv("DN_MLP_BN");
-        forced = e ? atoi(e) : 0;
+int env_int(const char* name) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+
+// Tile shape of a contraction whose accumulator is `rows` x `n`: CTA pairs (CG = 2, 256 x BN tiles) whenever the row count
+// allows it, else single CTAs (128 x BN).  DN_MLP_CG=1 forces single CTAs, DN_MLP_BN=64|128|256 the tile width (experiments).
+void pick_tile(int rows, int n, int* cg, int* bn) {
+    static int forced_cg = -1, forced_bn = -1;
+    if (forced_cg < 0) { forced_cg = env_int("DN_MLP_CG"); forced_bn = env_int("DN_MLP_BN"); }
+    *cg = (rows % 256 == 0 && n % 128 == 0 && forced_cg != 1) ? 2 : 1;
+    if (*cg == 2) *bn = (n % 256 == 0) ? 256 : 128;
+    else *bn = (n % 128 == 0) ? 128 : 64;
+    if (forced_bn == 64 || forced_bn == 128 || forced_bn == 256) {
+        const bool ok = n % forced_bn == 0 && ((*cg == 2) ? forced_bn >= 128 : forced_bn <= 128);
+        if (ok) *bn = forced_bn;
     }
-    if ((forced == 64 || forced == 128 || forced == 256) && n % forced == 0) return forced;
-    return (n % 256 == 0) ? 256 : (n % 128 == 0) ? 128 : 64;
 }
 
 struct GemmPlan {       // one contraction, ready to launch
-    int kind = 0, bn = 0, grid = 0;
-    CUtensorMap ma, mb;
+    int kind = 0, bn = 0, cg = 1, grid = 0;
+    int tiles_n = 0;    // accumulator columns / bn
+    CUtensorMap ma, mb, mc, mh;
     GemmArgs args;
 };
 
@@ -87,77 +99,104 @@ int num_sms() {
     return g_num_sms;
 }
 
-template <int KIND, int BN>
+// persistent grid: one CTA (pair) per SM (pair), never more than there are tiles
+int grid_for(int tiles, int cg) { return std::max(1, std::min(tiles, num_sms() / cg)) * cg; }
+
+template <int KIND, int BN, int CG>
 int launch_one(const GemmPlan& p, cudaStream_t st) {
-    auto kern = umma_gemm<KIND, BN>;
+    auto kern = umma_gemm<KIND, BN, CG>;
     static bool attr_set = false;
     if (!attr_set) {
-        PPO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg<BN>::SMEM_BYTES)));
+        PPO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM_BYTES)));
         attr_set = true;
     }
-    kern<<<p.grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(p.ma, p.mb, p.args);
-    PPO_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(p.grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PPO_CUDA(cudaLaunchKernelEx(&cfg, kern, p.ma, p.mb, p.mc, p.mh, p.args));
     return DN_OK;
 }
 
 int launch_gemm(const GemmPlan& p, cudaStream_t st) {
-#define DN_CASE(K, B) \
-    if (p.kind == K && p.bn == B) return launch_one<K, B>(p, st);
-    DN_CASE(K_FWD, 256) DN_CASE(K_FWD, 128) DN_CASE(K_FWD, 64)
-    DN_CASE(K_DGRAD, 256) DN_CASE(K_DGRAD, 128) DN_CASE(K_DGRAD, 64)
-    DN_CASE(K_WGRAD, 256) DN_CASE(K_WGRAD, 128) DN_CASE(K_WGRAD, 64)
+#define DN_CASE(K, B, G) \
+    if (p.kind == K && p.bn == B && p.cg == G) return launch_one<K, B, G>(p, st);
+    DN_CASE(K_FWD, 256, 2) DN_CASE(K_FWD, 128, 2) DN_CASE(K_FWD, 128, 1) DN_CASE(K_FWD, 64, 1)
+    DN_CASE(K_DGRAD, 256, 2) DN_CASE(K_DGRAD, 128, 2) DN_CASE(K_DGRAD, 128, 1) DN_CASE(K_DGRAD, 64, 1)
+    DN_CASE(K_WGRAD, 256, 2) DN_CASE(K_WGRAD, 128, 2) DN_CASE(K_WGRAD, 128, 1) DN_CASE(K_WGRAD, 64, 1)
 #undef DN_CASE
     return dn_internal_fail(DN_EINVAL, "launch_gemm: no such kernel instantiation");
 }
 
-// Plans.  `*_planes` point at the hi plane; the lo plane starts `rows * cols` elements later.
+// Plans.  `*_planes` point at the hi plane; the lo plane starts `plane_rows * cols` elements later.  `rows_now` <= plane_rows
+// is the number of rows the launch covers (tile counts); the tensor maps always span the whole planes.
+void set_grid(GemmPlan* p) {
+    const GemmArgs& g = p->args;
+    p->grid = grid_for(g.m_tiles * g.n_tiles * g.slices, p->cg);
+}
 // forward: out[M,N] = act(A[M,K] W[N,K]^T + bias)
-int plan_fwd(GemmPlan* p, int passes, int M, int N, int K, const void* a, const void* w, const float* bias, int act, void* out) {
-    if (M % BM || N % 64 || K % 64) return dn_internal_fail(DN_EINVAL, "mlp forward: M % 128, N % 64, K % 64 must be 0");
+int plan_fwd(GemmPlan* p, int passes, int M, int N, int K, const void* a, const void* w, const float* bias, int act, void* out,
+             int rows_now = 0) {
+    if (!rows_now) rows_now = M;
+    if (M % BM || rows_now % BM || N % 64 || K % 64) return dn_internal_fail(DN_EINVAL, "mlp forward: M % 128, N % 64, K % 64 must be 0");
     p->kind = K_FWD;
-    p->bn = pick_bn(N);
+    pick_tile(rows_now, N, &p->cg, &p->bn);
     int rc;
-    if ((rc = make_map(&p->ma, a, 2LL * M, K, BM)) || (rc = make_map(&p->mb, w, 2LL * N, K, p->bn))) return rc;
+    if ((rc = make_map(&p->ma, a, 2LL * M, K, BM)) || (rc = make_map(&p->mb, w, 2LL * N, K, p->bn / p->cg)) ||
+        (rc = make_map(&p->mc, out, 2LL * M, N, 32, true)))
+        return rc;
+    p->mh = p->mc;
     GemmArgs& g = p->args;
     memset(&g, 0, sizeof(g));
-    g.m_tiles = M / BM; g.n_tiles = N / p->bn; g.slices = 1; g.k_blocks = K / BK; g.passes = passes;
-    g.a_lo_row = M; g.b_lo_row = N; g.act = act; g.write_lo = passes > 1; g.bias = bias;
-    g.out_hi = static_cast<__nv_bfloat16*>(out); g.out_lo = g.out_hi + static_cast<long long>(M) * N; g.ld_out = N;
-    p->grid = std::min(g.m_tiles * g.n_tiles, num_sms());
+    g.m_tiles = rows_now / (BM * p->cg); g.n_tiles = N / p->bn; g.slices = 1; g.k_blocks = K / BK; g.passes = passes;
+    g.a_lo_row = M; g.b_lo_row = N; g.c_lo_row = M; g.act = act; g.bias = bias; g.ld_out = N;
+    set_grid(p);
     return DN_OK;
 }
 // dgrad: out[M,N] = (A[M,K] W[K,N]) * (1 - H[M,N]^2)
-int plan_dgrad(GemmPlan* p, int passes, int M, int N, int K, const void* a, const void* w, const void* h, void* out) {
-    if (M % BM || N % 64 || K % 64) return dn_internal_fail(DN_EINVAL, "mlp dgrad: M % 128, N % 64, K % 64 must be 0");
+int plan_dgrad(GemmPlan* p, int passes, int M, int N, int K, const void* a, const void* w, const void* h, void* out, int rows_now = 0) {
+    if (!rows_now) rows_now = M;
+    if (M % BM || rows_now % BM || N % 64 || K % 64) return dn_internal_fail(DN_EINVAL, "mlp dgrad: M % 128, N % 64, K % 64 must be 0");
     p->kind = K_DGRAD;
-    p->bn = pick_bn(N);
+    pick_tile(rows_now, N, &p->cg, &p->bn);
     int rc;
-    if ((rc = make_map(&p->ma, a, 2LL * M, K, BM)) || (rc = make_map(&p->mb, w, 2LL * K, N, 64))) return rc;
+    if ((rc = make_map(&p->ma, a, 2LL * M, K, BM)) || (rc = make_map(&p->mb, w, 2LL * K, N, 64)) ||
+        (rc = make_map(&p->mc, out, 2LL * M, N, 32, true)) || (rc = make_map(&p->mh, h, 2LL * M, N, 32, true)))
+        return rc;
     GemmArgs& g = p->args;
     memset(&g, 0, sizeof(g));
-    g.m_tiles = M / BM; g.n_tiles = N / p->bn; g.slices = 1; g.k_blocks = K / BK; g.passes = passes;
-    g.a_lo_row = M; g.b_lo_row = K; g.write_lo = passes > 1;
-    g.out_hi = static_cast<__nv_bfloat16*>(out); g.out_lo = g.out_hi + static_cast<long long>(M) * N; g.ld_out = N;
-    g.h_hi = static_cast<const __nv_bfloat16*>(h); g.h_lo = passes > 1 ? g.h_hi + static_cast<long long>(M) * N : nullptr;
-    p->grid = std::min(g.m_tiles * g.n_tiles, num_sms());
+    g.m_tiles = rows_now / (BM * p->cg); g.n_tiles = N / p->bn; g.slices = 1; g.k_blocks = K / BK; g.passes = passes;
+    g.a_lo_row = M; g.b_lo_row = K; g.c_lo_row = M; g.ld_out = N;
+    set_grid(p);
     return DN_OK;
 }
 // wgrad: partial[s][Mo][No] = A[rows_s, Mo]^T B[rows_s, No], rows split into `slices`
-int plan_wgrad(GemmPlan* p, int passes, int Mo, int No, int rows, int slices, const void* a, const void* b, float* partial) {
-    if (Mo % BM || No % 64 || slices < 1 || rows % (64 * slices)) return dn_internal_fail(DN_EINVAL, "mlp wgrad: Mo % 128, No % 64, rows % (64 slices) must be 0");
+int plan_wgrad(GemmPlan* p, int passes, int Mo, int No, int rows, int slices, const void* a, const void* b, float* partial, int rows_now = 0) {
+    if (!rows_now) rows_now = rows;
+    if (Mo % BM || No % 64 || slices < 1 || rows_now % (64 * slices)) return dn_internal_fail(DN_EINVAL, "mlp wgrad: Mo % 128, No % 64, rows % (64 slices) must be 0");
     p->kind = K_WGRAD;
-    p->bn = pick_bn(No);
+    pick_tile(Mo, No, &p->cg, &p->bn);
     int rc;
     if ((rc = make_map(&p->ma, a, 2LL * rows, Mo, 64)) || (rc = make_map(&p->mb, b, 2LL * rows, No, 64))) return rc;
+    p->mc = p->ma;
+    p->mh = p->ma;
     GemmArgs& g = p->args;
     memset(&g, 0, sizeof(g));
-    g.m_tiles = Mo / BM; g.n_tiles = No / p->bn; g.slices = slices; g.k_blocks = rows / slices / BK; g.passes = passes;
+    g.m_tiles = Mo / (BM * p->cg); g.n_tiles = No / p->bn; g.slices = slices; g.k_blocks = rows_now / slices / BK; g.passes = passes;
     g.a_lo_row = rows; g.b_lo_row = rows;
     g.partial = partial; g.ld_partial = No; g.slice_stride = static_cast<long long>(Mo) * No;
-    p->grid = std::min(g.m_tiles * g.n_tiles * slices, num_sms());
+    set_grid(p);
     return DN_OK;
 }
-
 
 // ====================================================================================================================
 // the update handle
@@ -197,14 +236,15 @@ struct dn_ppo {
     Seg* segs_dev = nullptr; int* seg_of_block_dev = nullptr; int n_segs = 0, reduce_blocks = 0;
     std::vector<Seg> segs_host;
     PlaneSeg* psegs_dev = nullptr; int* pseg_of_block_dev = nullptr; int plane_blocks = 0;
-    int cur_rows = -1;
+    int cur_rows = -1, table_rows = -1;
     std::vector<void*> allocs;
 };
 
 namespace {
 
-int wgrad_slices(int rows, int tiles, int sms) {
-    const int target = std::max(1, sms / std::max(tiles, 1));
+// split of the batch rows of a weight-gradient contraction: as many slices as it takes to give every CTA (pair) a work item
+int wgrad_slices(int rows, int tiles, int units) {
+    const int target = std::max(1, units / std::max(tiles, 1));
     int s = 1;
     while (s * 2 <= target && rows % (64 * s * 2) == 0 && rows / (s * 2) >= 256) s *= 2;
     return s;
@@ -220,6 +260,14 @@ int dev_alloc(dn_ppo* h, T** p, size_t count) {
     return DN_OK;
 }
 
+// tiles of the weight-gradient contraction of a layer [N, K] (accumulator N x K) and the CTAs (pairs) available for them
+int wgrad_tiles(int N, int K, int sms, int* units) {
+    int cg, bn;
+    pick_tile(N, K, &cg, &bn);
+    *units = sms / cg;
+    return (N / (BM * cg)) * (K / bn);
+}
+
 int setup_net(dn_ppo* h, Net& net, int L, const int32_t* hidden, const int64_t* w_off, const int64_t* b_off) {
     net.L = L;
     net.n[0] = XPAD;
@@ -233,46 +281,41 @@ int setup_net(dn_ppo* h, Net& net, int L, const int32_t* hidden, const int64_t* 
         if ((rc = dev_alloc(h, &net.h[l], 2 * R * N)) || (rc = dev_alloc(h, &net.dz[l], 2 * R * N)) ||
             (rc = dev_alloc(h, &net.w[l], 2LL * N * K)))
             return rc;
-        const int tiles = (N / BM) * (K / pick_bn(K));
-        net.slices_max[l] = wgrad_slices(h->max_rows, tiles, h->sms);
+        int units = 0;
+        const int wt = wgrad_tiles(N, K, h->sms, &units);
+        net.slices_max[l] = wgrad_slices(h->max_rows, wt, units);
         if ((rc = dev_alloc(h, &net.wpart[l], static_cast<size_t>(net.slices_max[l]) * N * K)) ||
-            (rc = dev_alloc(h, &net.bpart[l], static_cast<size_t>(std::max(h->sms, COLSUM_CHUNKS)) * N)))
+            (rc = dev_alloc(h, &net.bpart[l], static_cast<size_t>(h->sms) * N)))
             return rc;
-        // plans: tensor maps over the full workspaces (lo plane max_rows rows after the hi plane), tile counts set per call
-        const float* bias = h->params + net.b_off[l - 1];
-        if ((rc = plan_fwd(&net.fwd[l], h->passes, h->max_rows, N, K, net.h[l - 1], net.w[l], bias, 1, net.h[l]))) return rc;
-        if (l > 1) {
-            if ((rc = plan_dgrad(&net.dgrad[l], h->passes, h->max_rows, K, N, net.dz[l], net.w[l], net.h[l - 1], net.dz[l - 1]))) return rc;
-            net.dgrad[l].args.colsum = net.bpart[l - 1];      // bias gradient of layer l-1 = column sums of dz[l-1], per CTA
-        }
-        if ((rc = plan_wgrad(&net.wgrad[l], h->passes, N, K, h->max_rows, 1, net.dz[l], net.h[l - 1], net.wpart[l]))) return rc;
     }
     return DN_OK;
 }
 
-void set_rows(dn_ppo* h, Net& net, int rows) {
+// Plans for `rows` rows: tensor maps over the full workspaces (lo plane max_rows rows after the hi plane), tile shapes and
+// counts for this row count (CTA pairs need multiples of 256 rows).
+int build_plans(dn_ppo* h, Net& net, int rows) {
+    int rc;
     for (int l = 1; l <= net.L; ++l) {
-        GemmPlan& f = net.fwd[l];
-        f.args.m_tiles = rows / BM;
-        f.grid = std::min(f.args.m_tiles * f.args.n_tiles, h->sms);
+        const int N = net.n[l], K = net.n[l - 1];
+        const float* bias = h->params + net.b_off[l - 1];
+        if ((rc = plan_fwd(&net.fwd[l], h->passes, h->max_rows, N, K, net.h[l - 1], net.w[l], bias, 1, net.h[l], rows))) return rc;
         if (l > 1) {
-            GemmPlan& d = net.dgrad[l];
-            d.args.m_tiles = rows / BM;
-            d.grid = std::min(d.args.m_tiles * d.args.n_tiles, h->sms);
+            if ((rc = plan_dgrad(&net.dgrad[l], h->passes, h->max_rows, K, N, net.dz[l], net.w[l], net.h[l - 1], net.dz[l - 1], rows))) return rc;
+            net.dgrad[l].args.colsum = net.bpart[l - 1];      // bias gradient of layer l-1 = column sums of dz[l-1], per CTA
         }
-        GemmPlan& w = net.wgrad[l];
-        const int tiles = w.args.m_tiles * w.args.n_tiles;
-        w.args.slices = wgrad_slices(rows, tiles, h->sms);
-        w.args.k_blocks = rows / w.args.slices / BK;
-        w.grid = std::min(tiles * w.args.slices, h->sms);
+        int units = 0;
+        const int wt = wgrad_tiles(N, K, h->sms, &units);
+        const int slices = std::min(wgrad_slices(rows, wt, units), net.slices_max[l]);
+        if ((rc = plan_wgrad(&net.wgrad[l], h->passes, N, K, h->max_rows, slices, net.dz[l], net.h[l - 1], net.wpart[l], rows))) return rc;
     }
+    return DN_OK;
 }
 
 // reduction table: every parameter tensor <- its partials
 void add_seg(std::vector<Seg>& v, const float* src, long long stride, int n_slices, int rows, int cols, int ld, long long dst) {
     Seg s;
     s.src = src; s.slice_stride = stride; s.dst_off = dst; s.n_slices = n_slices; s.rows = rows; s.cols = cols; s.ld = ld;
-    s.first_block = 0; s.n_blocks = 0;
+    s.first_block = 0; s.n_blocks = 0; s.deep = 0;
     v.push_back(s);
 }
 
@@ -304,7 +347,9 @@ int build_reduce_table(dn_ppo* h, int rows) {
     for (size_t i = 0; i < v.size(); ++i) {
         const long long count = static_cast<long long>(v[i].rows) * v[i].cols;
         v[i].first_block = static_cast<int>(sob.size());
-        v[i].n_blocks = static_cast<int>((count + REDUCE_PER_BLOCK - 1) / REDUCE_PER_BLOCK);
+        v[i].deep = v[i].n_slices >= REDUCE_DEEP_MIN_SLICES;
+        const int per = v[i].deep ? REDUCE_DEEP_PER_BLOCK : REDUCE_PER_BLOCK;
+        v[i].n_blocks = static_cast<int>((count + per - 1) / per);
         for (int b = 0; b < v[i].n_blocks; ++b) sob.push_back(static_cast<int>(i));
     }
     if (static_cast<int>(v.size()) > h->n_segs || static_cast<int>(sob.size()) > h->reduce_blocks) {
@@ -344,33 +389,45 @@ int build_plane_table(dn_ppo* h) {
     return DN_OK;
 }
 
-int ensure_rows(dn_ppo* h, int rows) {
-    if (rows == h->cur_rows) return DN_OK;
-    set_rows(h, h->pi, rows);
-    set_rows(h, h->vf, rows);
-    int rc = build_reduce_table(h, rows);
-    if (rc) return rc;
-    h->cur_rows = rows;
+// (re)plans the contractions for `rows` rows; the reduction table of the partial gradients only when training with a new row count
+int ensure_rows(dn_ppo* h, int rows, bool train) {
+    int rc;
+    if (rows != h->cur_rows) {
+        if ((rc = build_plans(h, h->pi, rows)) || (rc = build_plans(h, h->vf, rows))) return rc;
+        h->cur_rows = rows;
+    }
+    if (train && rows != h->table_rows) {
+        if ((rc = build_reduce_table(h, rows))) return rc;
+        h->table_rows = rows;
+    }
     return DN_OK;
 }
 
-template <int ACT>
+template <int ACT, int NP>
 int launch_head(dn_ppo* h, const HeadArgs& a, int blocks, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        PPO_CUDA(cudaFuncSetAttribute(head_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PPO_CUDA(cudaFuncSetAttribute(head_kernel<ACT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    head_kernel<ACT><<<blocks, HEAD_WARPS * 32, h->head_smem, st>>>(a);
+    head_kernel<ACT, NP><<<blocks, HEAD_WARPS * 32, h->head_smem, st>>>(a);
     PPO_CUDA(cudaGetLastError());
     return DN_OK;
 }
 
+template <int ACT>
+int run_head_np(dn_ppo* h, HeadArgs& a, int blocks, cudaStream_t st) {
+    const int np = std::max(a.n_pi, a.n_vf) / 64;       // widths are multiples of 128
+    if (np <= 2) return launch_head<ACT, 2>(h, a, blocks, st);
+    if (np <= 4) return launch_head<ACT, 4>(h, a, blocks, st);
+    return launch_head<ACT, 8>(h, a, blocks, st);
+}
+
 int run_head(dn_ppo* h, HeadArgs& a, int blocks, cudaStream_t st) {
     switch (h->cfg.act_dim) {
-        case 1: return launch_head<1>(h, a, blocks, st);
-        case 3: return launch_head<3>(h, a, blocks, st);
-        case 4: return launch_head<4>(h, a, blocks, st);
+        case 1: return run_head_np<1>(h, a, blocks, st);
+        case 3: return run_head_np<3>(h, a, blocks, st);
+        case 4: return run_head_np<4>(h, a, blocks, st);
         default: return dn_internal_fail(DN_EINVAL, "dn_ppo: act_dim must be 1, 3 or 4");
     }
 }
@@ -455,9 +512,9 @@ int dn_ppo_create(const dn_ppo_config* cfg, int device, float* params, float* gr
     for (int l = 0; l < cfg->n_vf; ++l)
         if (cfg->vf_hidden[l] < 128 || cfg->vf_hidden[l] % 128) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: hidden widths must be multiples of 128");
     for (int l = 0; l < cfg->n_pi; ++l)
-        if (cfg->pi_hidden[l] > MAX_COLSUM_COLS) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: hidden widths may be at most 1024");
+        if (cfg->pi_hidden[l] > MAX_COLSUM_COLS) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: hidden widths may be at most 512");
     for (int l = 0; l < cfg->n_vf; ++l)
-        if (cfg->vf_hidden[l] > MAX_COLSUM_COLS) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: hidden widths may be at most 1024");
+        if (cfg->vf_hidden[l] > MAX_COLSUM_COLS) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: hidden widths may be at most 512");
     if (cfg->pi_hidden[cfg->n_pi - 1] > MAX_HEAD_COLS || cfg->vf_hidden[cfg->n_vf - 1] > MAX_HEAD_COLS)
         return dn_internal_fail(DN_EINVAL, "dn_ppo_create: the last hidden layer may be at most 512 wide");
     if (cfg->precision != DN_MLP_BF16X3 && cfg->precision != DN_MLP_BF16) return dn_internal_fail(DN_EINVAL, "dn_ppo_create: unknown precision");
@@ -491,7 +548,7 @@ int dn_ppo_create(const dn_ppo_config* cfg, int device, float* params, float* gr
     if ((rc = dev_alloc(h, &h->adv_partial, 2 * ((R * 8 + 255) / 256))) || (rc = dev_alloc(h, &h->norm_partial, NORM_BLOCKS))) return bail(rc);
     const int npi = h->pi.n[h->pi.L], nvf = h->vf.n[h->vf.L];
     h->head_psize = head_partial_size(A, npi, nvf);
-    h->head_blocks_max = 2 * h->sms;
+    h->head_blocks_max = 3 * h->sms;
     h->head_smem = static_cast<size_t>(A * npi + nvf + HEAD_WARPS * h->head_psize) * sizeof(float);
     if (h->head_smem > 200 * 1024) return bail(dn_internal_fail(DN_EINVAL, "dn_ppo_create: head kernel shared memory exceeds 200 KB"));
     if ((rc = dev_alloc(h, &h->head_partial, static_cast<size_t>(h->head_blocks_max) * h->head_psize))) return bail(rc);
@@ -508,7 +565,7 @@ int dn_ppo_create(const dn_ppo_config* cfg, int device, float* params, float* gr
         h->mirror_dev = static_cast<int*>(d);
     }
     if ((rc = build_plane_table(h))) return bail(rc);
-    if ((rc = ensure_rows(h, h->max_rows))) return bail(rc);
+    if ((rc = ensure_rows(h, h->max_rows, true))) return bail(rc);
     if ((rc = dn_ppo_sync_weights(h, nullptr))) return bail(rc);
     PPO_CUDA(cudaStreamSynchronize(nullptr));
     *out = h;
@@ -549,7 +606,7 @@ int dn_ppo_minibatch_grad(dn_ppo* h, const dn_ppo_rollout* r, const int64_t* idx
         return dn_internal_fail(DN_EINVAL, "dn_ppo_minibatch_grad: null rollout array");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
-    if ((rc = ensure_rows(h, rows))) return rc;
+    if ((rc = ensure_rows(h, rows, true))) return rc;
     if ((rc = run_gather(h, r->obs, r, reinterpret_cast<const long long*>(idx), rows, true, st))) return rc;
     if ((rc = run_forward_chain(h, st))) return rc;
     // heads, losses, gradients w.r.t. the last hidden pre-activations
@@ -640,7 +697,7 @@ int dn_ppo_forward(dn_ppo* h, const float* obs, int32_t rows, float* mean, float
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int rows_pad = (rows + BM - 1) / BM * BM;
     int rc;
-    if ((rc = ensure_rows(h, rows_pad))) return rc;
+    if ((rc = ensure_rows(h, rows_pad, false))) return rc;
     if ((rc = run_gather(h, obs, nullptr, nullptr, rows, false, st))) return rc;
     if ((rc = run_forward_chain(h, st))) return rc;
     HeadArgs a;

@@ -180,9 +180,19 @@ class ReplayBuffer:
                 a = a[:pos]
             return a[-self.cap:]
         fields = {"obs": "observations", "next_obs": "next_observations", "act": "actions", "rew": "rewards", "done": "dones"}
+        # SB3 samples dones * (1 - timeouts) (ReplayBuffer._get_samples with handle_timeout_termination): a time-limit truncation is
+        # not a terminal state and must keep its bootstrap.  This buffer stores terminated-only flags in `done`, so an SB3 object
+        # that carries `timeouts` is converted on the way in.
+        timeouts = None
+        try:
+            timeouts = get("timeouts")
+        except (KeyError, AttributeError):
+            pass
         n = 0
         for ours, theirs in fields.items():
             a = ordered(get(theirs))
+            if ours == "done" and timeouts is not None:
+                a = a * (1.0 - ordered(timeouts).reshape(a.shape))
             dst = getattr(self, ours)
             a = a.reshape((a.shape[0],) + tuple(dst.shape[1:]))
             n = a.shape[0]

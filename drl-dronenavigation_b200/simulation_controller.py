@@ -32,7 +32,8 @@ def _reject_out_of_scope(args):
     for flag, why in (("wandb", "wandb logging is out of scope (no network); use --tensorboard DIR"),
                       ("capture_video", "video capture needs the PyBullet renderer"), ("gui", "the PyBullet GUI is outside the CUDA hot path"),
                       ("vec_normalize", "the reference wraps a single gym env in VecNormalize here, which raises (PBDroneSimulator.py:186-189); "
-                                        "NormalizeObservation is always fused, --norm_rew / --clip_rew select the reward wrappers"),
+                                        "NormalizeObservation is fused into the step kernel and on by default for every env (train, evaluation, VecEnv), "
+                                        "--no_norm_obs turns it off, --norm_rew / --clip_rew select the reward wrappers"),
                       ("vec_check_nan", "the reference wraps a single gym env in VecCheckNan here, which raises (PBDroneSimulator.py:186-189)")):
         if getattr(args, flag, False):
             raise NotImplementedError(f"--{flag}: {why}")

@@ -71,8 +71,12 @@ class PBDroneSimulator:
             return GpuDroneVecEnv(num_envs, self.targets, normalize_obs=True, collect_rollouts=collect_rollouts, **kw)
         return _init if multi else _init()
 
-    def make_device_env(self, num_envs: int, normalize_obs: bool = False, device=None, env_id_offset: int = 0):
-        """The device-resident shard the torch-native learner steps (no host hop)."""
+    def make_device_env(self, num_envs: int, normalize_obs: bool = None, device=None, env_id_offset: int = 0):
+        """The device-resident shard the torch-native learner steps (no host hop).  Like every env ``make_env`` builds
+        (PBDroneSimulator.py:181) it is wrapped in NormalizeObservation -- fused into the step kernel, per-env running
+        statistics -- unless ``--no_norm_obs`` asks for raw observations (a labelled deviation)."""
+        if normalize_obs is None:
+            normalize_obs = not bool(getattr(self.args, "no_norm_obs", False))
         kw = self._env_kwargs(None, self.aviary_dim, True, True)
         return BatchedDroneEnv(num_envs, self.targets, normalize_obs=normalize_obs, device=device,
                                env_id_offset=env_id_offset, **kw)
@@ -98,6 +102,12 @@ class PBDroneSimulator:
         """EvalCallback's protocol (:719-729): stochastic actions, mean episode reward / length, plus the
         success rate defined in BASELINE.md (episodes ending with all targets found)."""
         env = self.make_device_env(n_envs, device=trainer.dev)
+        # The reference's eval_env keeps ITS NormalizeObservation statistics across the periodic evaluations of a run, so they
+        # converge; this eval env lives for one call, so it starts from the pooled statistics of the training shard instead of
+        # (mean 0, var 1, count 1e-4) -- otherwise the first episodes of every evaluation would see badly scaled inputs
+        src = getattr(trainer, "env", None)
+        if getattr(env, "normalize_obs", False) and getattr(src, "normalize_obs", False) and src.obs_dim == env.obs_dim:
+            env.set_state({"obs_rms": self._pool_obs_rms(src.get_state()["obs_rms"].double().cpu(), env.obs_dim, n_envs)})
         obs = env.reset()
         gen = torch.Generator(device=trainer.dev).manual_seed(123)
         sac = not hasattr(trainer.learner, "policy")
@@ -129,6 +139,8 @@ class PBDroneSimulator:
             if not os.path.exists(self.continued_agent):
                 raise FileNotFoundError(f"--run_type cont: {self.continued_agent} not found (pass --model_path)")
             load_sb3_zip(self.continued_agent, trainer.learner, load_optimizer=True)
+            if self._load_obs_rms(train_env, self.continued_agent[:-4] + "_obs_rms.pt"):
+                log("restored the NormalizeObservation statistics saved next to the archive")
             if args.agent == "SAC":              # model.load_replay_buffer(load_most_recent_replay_buffer(chkpt_path)), :357
                 rb = load_most_recent_replay_buffer(os.path.dirname(self.continued_agent))
                 if rb:
@@ -178,14 +190,19 @@ class PBDroneSimulator:
                         f"critic_loss {out.get('critic_loss', float('nan')):.4g}  ent_coef {out.get('ent_coef', float('nan')):.4g}")
                 log(f"[{time.time() - t0:7.1f}s] steps {trainer.total_steps:>12d}  sps {out['sps']:.3g}  ep_rew {st['return_sum'] / e:8.3f}  "
                     f"ep_len {st['length_sum'] / e:7.1f}  found {st['found_targets'] / e:5.2f}  success {st['successes'] / e:5.3f}  {tail}")
-                if chk and st["return_sum"] / e > best:
+                # EvalCallback(best_model_save_path), :719-729.  The criterion here is the mean return of the training episodes that
+                # finished since the last check (the reference runs a separate 10-episode evaluation); an interval without a single
+                # finished episode says nothing and must not count as a return of 0
+                if chk and st["episodes"] > 0 and st["return_sum"] / e > best:
                     best = st["return_sum"] / e
-                    save_sb3_zip(os.path.join(chk, "best_model.zip"), trainer.learner)     # EvalCallback(best_model_save_path), :719-729
+                    save_sb3_zip(os.path.join(chk, "best_model.zip"), trainer.learner)
+                    self._save_obs_rms(train_env, os.path.join(chk, "best_model_obs_rms.pt"))
             if chk and args.agent == "SAC" and (trainer.total_steps // max(self.num_envs * world, 1)) // 100_000 > rb_saves:
                 rb_saves = (trainer.total_steps // max(self.num_envs * world, 1)) // 100_000
                 trainer.buffer.save(os.path.join(chk, "replay_buffer.pkl"))
         if chk:
             save_sb3_zip(os.path.join(chk, "success_model.zip"), trainer.learner)          # model.save(...), :741-746
+            self._save_obs_rms(train_env, os.path.join(chk, "success_model_obs_rms.pt"))   # eval_env.save(...), :746
             if args.agent == "SAC":
                 trainer.buffer.save(os.path.join(chk, "replay_buffer.pkl"))
         if tb is not None:
@@ -194,6 +211,37 @@ class PBDroneSimulator:
         log(f"final evaluation: {ev}")
         train_env.close()
         return trainer, ev
+
+    @staticmethod
+    def _save_obs_rms(env, path: str) -> None:
+        """The running observation statistics belong to a policy trained on normalised observations (what ``VecNormalize.save``
+        keeps in the reference, :746): per-env FP64 mean | var | count rows of the training shard."""
+        if getattr(env, "normalize_obs", False):
+            torch.save({"obs_rms": env.get_state()["obs_rms"].cpu(), "obs_dim": env.obs_dim}, path)
+
+    @staticmethod
+    def _load_obs_rms(env, path: str) -> bool:
+        """Restores statistics saved by :meth:`_save_obs_rms` into an env of the same size (or broadcasts their mean over the
+        envs otherwise: count-weighted pooled mean / variance of the saved rows)."""
+        if not (getattr(env, "normalize_obs", False) and os.path.exists(path)):
+            return False
+        d = torch.load(path, map_location="cpu")
+        rms = d["obs_rms"].double()
+        if int(d.get("obs_dim", env.obs_dim)) != env.obs_dim:
+            return False
+        if rms.shape[0] != env.num_envs:
+            rms = PBDroneSimulator._pool_obs_rms(rms, env.obs_dim, env.num_envs)
+        env.set_state({"obs_rms": rms})
+        return True
+
+    @staticmethod
+    def _pool_obs_rms(rms: torch.Tensor, D: int, n: int) -> torch.Tensor:
+        """Count-weighted pooled mean / variance of per-env rows [*, 2 D + 1], replicated for `n` envs (count = the mean count)."""
+        cnt = rms[:, 2 * D:]
+        tot = cnt.sum()
+        mean = (rms[:, :D] * cnt).sum(0) / tot
+        var = ((rms[:, D:2 * D] + (rms[:, :D] - mean) ** 2) * cnt).sum(0) / tot
+        return torch.cat([mean, var, (tot / rms.shape[0]).reshape(1)]).repeat(n, 1)
 
     def run_test(self, max_steps: int = 2000, log=print):
         """--run_type test (:390-436): constant action 0.1 on every motor on the `up` track until termination."""

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 3
+#define DN_ABI_VERSION 4
 
 /* error codes */
 #define DN_OK        0
@@ -173,7 +173,8 @@ typedef struct dn_state_view {
     int32_t*  ep_length;      /* [N]    Monitor running length                           */
     uint32_t* episode_count;  /* [N]    episodes finished so far (Philox counter)        */
     float*    last_rpm_sum;   /* [N]    sum(last_clipped_action) (drag only, BaseAviary.py:429,442) */
-    float*    obs_rms;        /* [N,2*obs_dim+1] mean | var | count (normalize.py:10-47); only if normalize_obs */
+    double*   obs_rms;        /* [N,2*obs_dim+1] FP64 mean | var | count, the dtype of the reference's RunningMeanStd
+                                 (normalize.py:10-47); only if normalize_obs */
     float*    aux;            /* [N,4] _current_position.xyz | last travel with DN_REWARD_REACHING; PBDroneEnv._last_action with
                                  DN_REWARD_BOOTSTRAPPED / DN_REWARD_CHAMP; absent otherwise */
     float*    rew_rms;        /* [N,4] returns | mean | var | count (normalize.py:100-147); only if normalize_reward */

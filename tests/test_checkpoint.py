@@ -190,3 +190,22 @@ def test_replay_buffer_save_and_load(tmp_path):
     assert Q.load(path) == N and Q.pos == 1 and not Q.full and torch.equal(Q.obs[0], rows[0][0])
     with pytest.raises(ValueError, match="n_envs"):
         ReplayBuffer(8, 2, D, 4, "cpu").load(path)
+
+
+def test_replay_buffer_load_honours_sb3_timeouts(tmp_path):
+    """An SB3 ReplayBuffer pickle stores `dones` (terminated OR truncated) next to `timeouts`; SB3 samples dones * (1 - timeouts).
+    Loading such an object must not turn time-limit truncations into terminal states (no bootstrap)."""
+    import pickle
+    import numpy as np
+    from drl_dronenavigation_b200.sac import ReplayBuffer
+    N, D, T = 2, 13, 3
+    rng = np.random.default_rng(0)
+    obj = {"observations": rng.normal(size=(T, N, D)).astype(np.float32), "next_observations": rng.normal(size=(T, N, D)).astype(np.float32),
+           "actions": rng.uniform(-1, 1, size=(T, N, 4)).astype(np.float32), "rewards": rng.normal(size=(T, N)).astype(np.float32),
+           "dones": np.array([[1, 0], [1, 1], [0, 0]], np.float32), "timeouts": np.array([[1, 0], [0, 1], [0, 0]], np.float32),
+           "pos": 3, "full": False, "buffer_size": 8, "n_envs": N}
+    path = str(tmp_path / "sb3_like.pkl")
+    pickle.dump(obj, open(path, "wb"))
+    B = ReplayBuffer(8 * N, N, D, 4, "cpu")
+    assert B.load(path) == T * N
+    assert B.done[:T].tolist() == [[0.0, 0.0], [1.0, 0.0], [0.0, 0.0]]

@@ -11,7 +11,7 @@ from tests import parity_utils as PU
 from tests.golden.make_golden import CASES, run
 
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-              if not os.path.basename(p).startswith("ref_"))      # ref_*: tests/test_ref_golden.py
+              if not os.path.basename(p).startswith(("ref_", "forces_")))      # ref_*: tests/test_ref_golden.py, forces_ref: tests/test_ref_pins.py
 PHYS = {"dyn": 0, "dyn_drag": 1, "dyn_gnd": 2, "dyn_gnd_drag": 3}
 
 

@@ -121,6 +121,7 @@ OBS_TOL, REW_TOL = 1e-3, 1e-2
 # The STATED tolerance (north_star / SURVEY 8c / parity_utils.py): |dobs| <= 1e-4, |dreward| <= 1e-3 over a 240-substep (1 s)
 # open-loop horizon.  Asserted directly against the reference fixtures on the first 240 substeps of every one of them.
 STATED_OBS_TOL, STATED_REW_TOL, STATED_SUBSTEPS = 1e-4, 1e-3, 240
+NORM_OBS_TOL = 2e-4          # normalised observations (abs + rel), FP64 running statistics on both sides
 
 
 def _resync(g, t, get_state, set_state):
@@ -162,11 +163,12 @@ def _compare_fp32(g, step_fn, obs0, norm, rel_reward=False, resync=None):
             for a, b in rows:
                 e = np.abs(a.astype(np.float64) - b)
                 if norm:
-                    # NormalizeObservation divides by sqrt(var + 1e-8) of a per-env running variance that is tiny for
-                    # the first steps of an episode: FP32 statistics vs the reference's FP64 (cf. test_gpu_parity)
-                    np.testing.assert_allclose(a[:9], b[:9], atol=2e-3, rtol=2e-3)
-                    if a.size > 12:
-                        np.testing.assert_allclose(a[12], b[12], atol=2e-3, rtol=2e-3)
+                    # NormalizeObservation divides by sqrt(var + 1e-8) of a per-env running variance that is tiny for the
+                    # first steps of an episode (gain up to 1e4 on the raw observation's FP32 error).  The statistics
+                    # themselves are FP64 on the device, like the reference's.
+                    keep = list(range(9)) + ([12] if a.size > 12 else [])
+                    stated["norm"] = max(stated.get("norm", 0.0), float(np.max(e[keep] / (1.0 + np.abs(b[keep])))))
+                    np.testing.assert_allclose(a[keep], b[keep], atol=NORM_OBS_TOL, rtol=NORM_OBS_TOL)
                     continue
                 e[3:6] = np.minimum(e[3:6], np.abs(2 - e[3:6]))        # +-pi wrap of the Euler angles
                 worst_obs = max(worst_obs, e[:9].max(), e[12] if e.size > 12 else 0.0)
