@@ -716,31 +716,64 @@ def run_b200(args):
             line["roofline_hbm_s1"] = {"error": str(ex)[:200]}
 
     # ---- e2e: C-ABI host-buffer call, pinned host actions -> H2D -> kernel -> D2H results ---------
+    # Headline form: the handle's own pinned slab (dn_host_buffers): per step the caller writes that step's actions into the
+    # pinned slab, dn_step_host replays one captured graph (H2D DMA of the actions, fused kernel, D2H DMA of the packed
+    # results) and returns when the results are in the slab.  K steps form a block; blocks are repeated until the timed
+    # region is >= 50 ms (wall clock needs it), the mean block is reported.
     D = env.obs_dim
     h_act = torch.empty(A, N, 4, dtype=torch.float32).pin_memory()
     h_act.copy_(acts.cpu())
+    a_np = h_act.numpy()
+    torch.cuda.synchronize()
+    slab_io, slab = env.host_buffers(with_episode_info=False)
+
+    def e2e_block(step_fn, n_steps, k0):
+        t0 = time.perf_counter()
+        for k in range(n_steps):
+            step_fn((k0 + k) % A)
+        return time.perf_counter() - t0
+
+    def e2e_measure(step_fn):
+        for k in range(W):
+            step_fn(k % A)
+        est = max(e2e_block(step_fn, K, W), 1e-6)
+        R = int(max(1, min(100000, np.ceil(0.05 / est))))
+        barrier()
+        l0 = env.launch_count
+        tot = 0.0
+        for r in range(R):
+            tot += e2e_block(step_fn, K, W + r * K)
+        launches_ = env.launch_count - l0
+        barrier()
+        return max_over_ranks(tot / R), R, launches_
+
+    def step_slab(k):
+        np.copyto(slab["actions"], a_np[k])
+        env.step_host(slab_io)
+    e2e_sec, e2e_reps, e2e_launches = e2e_measure(step_slab)
+    checksum = float(slab["reward"][:8].sum())           # the results are read on the host
+    e2e_slab = {"value": world * N * K / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": N * 16,
+                   "d2h_bytes_per_step": N * (D * 4 + 4 + 1 + 4), "us_per_step": 1e6 * e2e_sec / K, "reps": e2e_reps,
+                   "api": "dn_host_buffers + dn_step_host (C ABI): the step's actions are written into the handle's pinned host slab, one "
+                          "captured graph per step = H2D DMA (actions) -> fused kernel -> D2H DMA (obs, reward, found_targets, done, "
+                          "completion word); the host polls the completion word",
+                   "gpu_launches": int(e2e_launches), "reward_checksum": checksum}
+    # the previous form, kept as a comparison line: caller-owned pinned buffers, the kernel reads / writes them over PCIe itself
     h_obs = torch.empty(N, D, dtype=torch.float32).pin_memory()
     h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
     h_done = torch.empty(N, dtype=torch.uint8).pin_memory()
     h_found = torch.empty(N, dtype=torch.int32).pin_memory()
-    torch.cuda.synchronize()
     ios = [env._make_io(h_act[k], h_obs, h_rew, h_done, None, h_found) for k in range(A)]
-    for k in range(W):
-        env.step_host(ios[k % A])
-    barrier()
-    l0 = env.launch_count
-    t0 = time.perf_counter()
-    for k in range(K):
-        env.step_host(ios[(W + k) % A])
-    e2e_sec = time.perf_counter() - t0
-    e2e_launches = env.launch_count - l0
-    barrier()
-    e2e_sec = max_over_ranks(e2e_sec)
-    line["e2e"] = {"value": world * N * K / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": N * 16,
-                   "d2h_bytes_per_step": N * (D * 4 + 4 + 1 + 4), "us_per_step": 1e6 * e2e_sec / K,
-                   "api": "dn_step_host (C ABI, pinned host buffers, zero copy): step_kernel reads the actions and writes obs,reward,done,"
-                          "found_targets in host memory over PCIe; one launch + one stream synchronise per step",
-                   "gpu_launches": int(e2e_launches)}
+    zc_sec, zc_reps, zc_launches = e2e_measure(lambda k: env.step_host(ios[k]))
+    e2e_zc = {"value": world * N * K / zc_sec, "unit": UNIT, "h2d_bytes_per_step": N * 16, "d2h_bytes_per_step": N * (D * 4 + 4 + 1 + 4),
+              "us_per_step": 1e6 * zc_sec / K, "reps": zc_reps, "gpu_launches": int(zc_launches), "reward_checksum": float(h_rew[:8].sum()),
+              "api": "dn_step_host (C ABI) with caller-owned pinned host buffers, zero copy: the fused kernel reads that step's actions from and "
+                     "writes obs, reward, found_targets, done to host memory over PCIe (64 KiB in, 244 KiB out per step); its last CTA "
+                     "writes a completion word the host polls -- one launch per step, no DMA engine, no stream query"}
+    # both forms move the same bytes between host and device inside the timed region; the headline is the faster one at this batch size
+    best, other = (e2e_zc, e2e_slab) if e2e_zc["value"] >= e2e_slab["value"] else (e2e_slab, e2e_zc)
+    line["e2e"] = best
+    line["e2e_alternative"] = other
     if world == 1:
         # the staged variant of the same call (pageable numpy buffers: H2D copy -> kernel -> D2H copies)
         p_act = h_act.numpy().copy()

@@ -113,6 +113,9 @@ SYMBOLS = {
     "dn_step": (C.c_int, [C.c_void_p, C.POINTER(dn_step_io), C.c_void_p]),
     "dn_step_many": (C.c_int, [C.c_void_p, C.POINTER(dn_step_io), C.c_int, C.c_int, C.c_void_p]),
     "dn_step_host": (C.c_int, [C.c_void_p, C.POINTER(dn_step_io)]),
+    "dn_host_buffers": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(dn_step_io)]),
+    "dn_step_host_async": (C.c_int, [C.c_void_p, C.POINTER(dn_step_io)]),
+    "dn_step_host_wait": (C.c_int, [C.c_void_p]),
     "dn_action_to_rpm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dn_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                          C.c_int32, C.c_int32, C.c_void_p]),

@@ -184,6 +184,34 @@ class BatchedDroneEnv:
         see :meth:`_make_io`); returns when the results are in the host buffers."""
         L.check(self._lib.dn_step_host(self._handle, C.byref(host_io)), "dn_step_host")
 
+    def host_buffers(self, with_episode_info: bool = False):
+        """dn_host_buffers: the handle's pinned host slab as numpy views (``actions`` to write, the rest to read) plus the
+        ``dn_step_io`` of their pointers.  ``step_host(io)`` / ``step_host_async(io)`` with that io replay one captured graph
+        (one H2D DMA, the fused kernel, one D2H DMA) -- the lowest-latency way to step from the host."""
+        io = L.dn_step_io()
+        L.check(self._lib.dn_host_buffers(self._handle, int(bool(with_episode_info)), C.byref(io)), "dn_host_buffers")
+        N, D = self.num_envs, self.obs_dim
+
+        def view(ptr, ctype, shape, dtype):
+            if not ptr:
+                return None
+            n = int(np.prod(shape))
+            return np.frombuffer((ctype * n).from_address(ptr), dtype=dtype).reshape(shape)
+        bufs = {"actions": view(io.actions, C.c_float, (N, 4), np.float32), "obs": view(io.obs, C.c_float, (N, D), np.float32),
+                "reward": view(io.reward, C.c_float, (N,), np.float32), "done": view(io.done, C.c_uint8, (N,), np.uint8),
+                "found_targets": view(io.found_targets, C.c_int32, (N,), np.int32),
+                "terminal_obs": view(io.terminal_obs, C.c_float, (N, D), np.float32),
+                "episode_return": view(io.episode_return, C.c_float, (N,), np.float32),
+                "episode_length": view(io.episode_length, C.c_int32, (N,), np.int32)}
+        return io, bufs
+
+    def step_host_async(self, host_io) -> None:
+        """dn_step_host_async (buffers of :meth:`host_buffers` only): returns once the step is launched."""
+        L.check(self._lib.dn_step_host_async(self._handle, C.byref(host_io)), "dn_step_host_async")
+
+    def step_host_wait(self) -> None:
+        L.check(self._lib.dn_step_host_wait(self._handle), "dn_step_host_wait")
+
     def step_many(self, actions: torch.Tensor, per_step_outputs: bool = True, out: Optional[Dict] = None):
         """T control steps in one launch (state stays in registers); actions [T, N, 4]."""
         T = int(actions.shape[0])

@@ -135,6 +135,10 @@ struct StepIO {
     float*    episode_return;
     int32_t*  episode_length;
     int       pdl_prefetch;   // 1: launched as a programmatic dependent grid -> prefetch this thread's lines to L2 while waiting
+    // dn_step_host, zero-copy path: the last CTA to finish writes `seq` to a pinned host word, which the host polls instead of the stream
+    unsigned int* done_counter;   // device, zero between launches
+    unsigned int* host_flag;      // device alias of the pinned word; nullptr: not a host call
+    unsigned int  seq;
 };
 
 }  // namespace dn

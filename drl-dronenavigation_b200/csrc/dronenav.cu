@@ -265,6 +265,23 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
         }
     }
     flush_stats(P, acc, tid);
+    if (io.host_flag != nullptr) {
+        // Host call on mapped host buffers: completion is announced through host memory.  Every thread's stores (the bulk
+        // stores of the observation rows included) are made visible system-wide, the CTA counts itself done, and the last
+        // CTA writes the step's sequence number to the pinned word the host is polling -- no stream query, no interrupt.
+        if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int prev = atomicAdd(io.done_counter, 1u);
+            if (prev == gridDim.x - 1) {
+                *io.done_counter = 0u;
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int*>(io.host_flag) = io.seq;
+            }
+        }
+        return;
+    }
     if ((tid & 31) == 0) bulk_store_wait_read();   // shared memory must outlive the bulk read
 }
 
@@ -650,6 +667,18 @@ struct dn_env {
     dn_step_io host_seen;   // last host io whose pointers were classified
     dn_step_io host_mapped; // device aliases of those pointers when all of them are pinned + mapped (UVA)
     int host_direct;        // 1: the kernel reads / writes the caller's pinned buffers directly (zero copy)
+    // dn_host_buffers: handle-owned pinned slab + device slab, stepped by replaying one captured graph
+    char* slab_h; char* slab_d;
+    size_t slab_out_off, slab_out_bytes, slab_seq_off;   // outputs [slab_out_off, +slab_out_bytes) incl. the completion word
+    dn_step_io slab_io_h, slab_io_d;
+    cudaGraphExec_t slab_exec;
+    int slab_pending;       // a graph launch whose completion word has not been consumed yet
+    int no_pdl;             // launch_step: plain launch (inside the slab graph the predecessor is a copy node)
+    long long graph_replays;
+    // zero-copy host call: completion word in pinned host memory, written by the last CTA of the step kernel
+    unsigned int* zc_flag_h; unsigned int* zc_flag_d; unsigned int* zc_counter; unsigned int zc_seq;
+    int zc_signal;          // launch_step: pass the completion word to the kernel (set around the zero-copy launch only)
+    int zc_signalled;       // the launch in flight announces completion through the word (else: poll the stream)
 };
 
 static thread_local std::string g_err;
@@ -802,6 +831,12 @@ int dn_destroy(dn_env* env) {
     cudaFree(env->state_mem); cudaFree(env->d_targets); cudaFree(env->d_segs); cudaFree(env->d_stats);
     cudaFree(env->d_block_stats);
     if (env->stage) cudaFree(env->stage);
+    if (env->zc_flag_h) cudaFreeHost(env->zc_flag_h);
+    if (env->zc_counter) cudaFree(env->zc_counter);
+    if (env->slab_pending) cudaStreamSynchronize(env->host_stream);
+    if (env->slab_exec) cudaGraphExecDestroy(env->slab_exec);
+    if (env->slab_h) cudaFreeHost(env->slab_h);
+    if (env->slab_d) cudaFree(env->slab_d);
     if (env->host_stream) cudaStreamDestroy(env->host_stream);
     delete env;
     return DN_OK;
@@ -834,6 +869,8 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
     k.actions = reinterpret_cast<const float4*>(io->actions);
     k.obs = io->obs; k.reward = io->reward; k.done = io->done; k.terminal_obs = io->terminal_obs;
     k.found_targets = io->found_targets; k.episode_return = io->episode_return; k.episode_length = io->episode_length;
+    k.done_counter = nullptr; k.host_flag = nullptr; k.seq = 0u;
+    if (env->zc_signal && num_steps == 1) { k.done_counter = env->zc_counter; k.host_flag = env->zc_flag_d; k.seq = env->zc_seq; }
     const int N = env->P.n;
     const dim3 grid((N + dn::kBlock - 1) / dn::kBlock), block(dn::kBlock);
     const int phys = env->P.physics & 3;
@@ -851,7 +888,7 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
     // two consecutive small grids each get SMs of their own.  With mid-size grids (0.3 - 1 wave) the early-resident
     // CTAs of the next step pile up on the SMs that had free slots, and the step then runs unbalanced (measured:
     // 65 536 envs 7.7 -> 9.8 us, 16 384 envs with drag / ground effect 7.4 -> 9.1 us per replayed step).
-    lc.attrs = attr; lc.numAttrs = (use_pdl && static_cast<int>(grid.x) * 2 <= env->sms) ? 1 : 0;
+    lc.attrs = attr; lc.numAttrs = (use_pdl && !env->no_pdl && static_cast<int>(grid.x) * 2 <= env->sms) ? 1 : 0;
     k.pdl_prefetch = static_cast<int>(lc.numAttrs);
     cudaError_t lerr = cudaSuccess;
     // large batches: persistent software-pipelined kernel (>= 2 tiles per resident CTA, single step, no fused obs-RMS)
@@ -900,41 +937,214 @@ int dn_step_many(dn_env* env, const dn_step_io* io, int num_steps, int per_step_
     return launch_step(env, io, num_steps, per_step_outputs ? 1 : 0, stream);
 }
 
+// Zero-copy classification: if every buffer is pinned host memory mapped into the device address space (torch /
+// cudaHostAlloc / cudaHostRegister), the fused kernel reads the actions and writes its outputs over PCIe itself -- one
+// launch per step, no staging copies.  The classification is cached on the pointer set.
+static int host_classify(dn_env* env, const dn_step_io* h) {
+    if (std::memcmp(&env->host_seen, h, sizeof(*h)) == 0) return DN_OK;
+    env->host_seen = *h;
+    env->host_direct = getenv("DN_HOST_STAGED") ? 0 : 1;
+    const void* src[8] = {h->actions, h->obs, h->reward, h->done, h->terminal_obs, h->found_targets, h->episode_return, h->episode_length};
+    void* dst[8] = {nullptr};
+    for (int k = 0; k < 8 && env->host_direct; ++k) {
+        if (!src[k]) continue;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src[k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+            cudaGetLastError();
+            env->host_direct = 0;
+        } else {
+            dst[k] = at.devicePointer;
+        }
+    }
+    if (env->host_direct && (reinterpret_cast<uintptr_t>(dst[0]) & 15u)) env->host_direct = 0;
+    env->host_mapped.actions = static_cast<const float*>(dst[0]); env->host_mapped.obs = static_cast<float*>(dst[1]);
+    env->host_mapped.reward = static_cast<float*>(dst[2]); env->host_mapped.done = static_cast<uint8_t*>(dst[3]);
+    env->host_mapped.terminal_obs = static_cast<float*>(dst[4]); env->host_mapped.found_targets = static_cast<int32_t*>(dst[5]);
+    env->host_mapped.episode_return = static_cast<float*>(dst[6]); env->host_mapped.episode_length = static_cast<int32_t*>(dst[7]);
+    return DN_OK;
+}
+
+// One launch of the step kernel on the mapped host buffers.  Completion is announced through a pinned word that the last CTA
+// of the kernel writes after a system-scope fence (DN_HOST_POLL_STREAM=1: poll the stream instead, the first version).
+static int zero_copy_launch(dn_env* env) {
+    if (!env->zc_flag_h && !env->use_pipe) {
+        void* hp = nullptr; void* dp = nullptr;
+        DN_CUDA(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+        DN_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+        std::memset(hp, 0, 64);
+        env->zc_flag_h = static_cast<unsigned int*>(hp); env->zc_flag_d = static_cast<unsigned int*>(dp);
+        DN_CUDA(cudaMalloc(reinterpret_cast<void**>(&env->zc_counter), 64));
+        DN_CUDA(cudaMemset(env->zc_counter, 0, 64));
+    }
+    const bool signal = env->zc_flag_h != nullptr && getenv("DN_HOST_POLL_STREAM") == nullptr;
+    env->zc_signalled = signal ? 1 : 0;
+    if (signal) { env->zc_seq += 1; if (env->zc_seq == 0u) env->zc_seq = 1u; env->zc_signal = 1; }
+    const int rc = launch_step(env, &env->host_mapped, 1, 1, env->host_stream);
+    env->zc_signal = 0;
+    return rc;
+}
+
+static int zero_copy_wait(dn_env* env) {
+    if (!env->zc_signalled) {
+        DN_CUDA(spin_until_done(env->host_stream));
+        return DN_OK;
+    }
+    volatile unsigned int* flag = env->zc_flag_h;
+    const unsigned int want = env->zc_seq;
+    uint32_t spins = 0;
+    while (*flag != want) {
+        if ((++spins & 0xFFFFu) == 0u) {           // a failed launch must end in an error, not in an endless spin
+            const cudaError_t e = cudaStreamQuery(env->host_stream);
+            if (e != cudaErrorNotReady && *flag != want) {
+                if (e == cudaSuccess) return fail(DN_ECUDA, "dn_step_host: the step finished without writing the completion word");
+                return fail(DN_ECUDA, std::string("dn_step_host: ") + cudaGetErrorString(e));
+            }
+        }
+    }
+    return DN_OK;
+}
+
+int dn_host_buffers(dn_env* env, int with_episode_info, dn_step_io* out) {
+    if (!env || !out) return fail(DN_EINVAL, "dn_host_buffers: null argument");
+    DeviceGuard guard(env->device);
+    if (!env->host_stream) DN_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
+    if (env->slab_h && (env->slab_io_h.terminal_obs != nullptr) != (with_episode_info != 0)) {
+        if (env->slab_pending) return fail(DN_EINVAL, "dn_host_buffers: a step is pending");
+        if (env->slab_exec) { cudaGraphExecDestroy(env->slab_exec); env->slab_exec = nullptr; }
+        cudaFreeHost(env->slab_h); cudaFree(env->slab_d);
+        env->slab_h = env->slab_d = nullptr;
+    }
+    if (!env->slab_h) {
+        const size_t N = env->P.n, D = env->P.obs_dim;
+        auto up = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+        size_t o = 0;
+        const size_t o_act = o; o += up(N * 16);
+        const size_t o_obs = o; o += up(N * D * 4);
+        const size_t o_rew = o; o += up(N * 4);
+        const size_t o_fnd = o; o += up(N * 4);
+        const size_t o_done = o; o += up(N);
+        size_t o_epr = 0, o_epl = 0, o_term = 0;
+        if (with_episode_info) {
+            o_epr = o; o += up(N * 4);
+            o_epl = o; o += up(N * 4);
+            o_term = o; o += up(N * D * 4);
+        }
+        const size_t o_seq = o; o += 256;
+        void* hp = nullptr; void* dp = nullptr;
+        DN_CUDA(cudaHostAlloc(&hp, o, cudaHostAllocDefault));
+        cudaError_t ce = cudaMalloc(&dp, o);
+        if (ce != cudaSuccess) { cudaFreeHost(hp); return fail(DN_ENOMEM, std::string("dn_host_buffers: cudaMalloc: ") + cudaGetErrorString(ce)); }
+        std::memset(hp, 0, o);
+        DN_CUDA(cudaMemset(dp, 0, o));
+        const uint32_t one = 1;                        // the completion word: constant 1 on the device, cleared on the host before a launch
+        DN_CUDA(cudaMemcpy(static_cast<char*>(dp) + o_seq, &one, 4, cudaMemcpyHostToDevice));
+        env->slab_h = static_cast<char*>(hp); env->slab_d = static_cast<char*>(dp);
+        env->slab_out_off = o_obs; env->slab_out_bytes = o_seq + 4 - o_obs; env->slab_seq_off = o_seq;
+        auto fill = [&](dn_step_io& io, char* b) {
+            io.actions = reinterpret_cast<const float*>(b + o_act); io.obs = reinterpret_cast<float*>(b + o_obs);
+            io.reward = reinterpret_cast<float*>(b + o_rew); io.found_targets = reinterpret_cast<int32_t*>(b + o_fnd);
+            io.done = reinterpret_cast<uint8_t*>(b + o_done);
+            io.episode_return = with_episode_info ? reinterpret_cast<float*>(b + o_epr) : nullptr;
+            io.episode_length = with_episode_info ? reinterpret_cast<int32_t*>(b + o_epl) : nullptr;
+            io.terminal_obs = with_episode_info ? reinterpret_cast<float*>(b + o_term) : nullptr;
+        };
+        fill(env->slab_io_h, env->slab_h);
+        fill(env->slab_io_d, env->slab_d);
+    }
+    *out = env->slab_io_h;
+    return DN_OK;
+}
+
+int dn_step_host_async(dn_env* env, const dn_step_io* h) {
+    if (!env || !h) return fail(DN_EINVAL, "dn_step_host_async: null argument");
+    if (env->slab_pending) return fail(DN_EINVAL, "dn_step_host_async: the previous step has not been waited for");
+    if (!env->slab_h || std::memcmp(h, &env->slab_io_h, sizeof(*h)) != 0) {
+        // caller-owned buffers: only the zero-copy form (pinned + mapped) can be left in flight
+        if (!h->actions || !h->obs || !h->reward || !h->done) return fail(DN_EINVAL, "dn_step_host_async: actions/obs/reward/done are required");
+        DeviceGuard guard(env->device);
+        if (!env->host_stream) DN_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
+        const int rc = host_classify(env, h);
+        if (rc != DN_OK) return rc;
+        if (!env->host_direct)
+            return fail(DN_EINVAL, "dn_step_host_async: needs pinned, device-mapped host buffers or the buffers dn_host_buffers returned");
+        const int rl = zero_copy_launch(env);
+        if (rl != DN_OK) return rl;
+        env->slab_pending = 2;
+        return DN_OK;
+    }
+    DeviceGuard guard(env->device);
+    cudaStream_t st = env->host_stream;
+    if (!env->slab_exec) {
+        // capture once: H2D(actions) -> fused step kernel -> D2H(outputs + completion word)
+        cudaGraph_t graph = nullptr;
+        DN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        cudaError_t ce = cudaMemcpyAsync(env->slab_d, env->slab_h, static_cast<size_t>(env->P.n) * 16, cudaMemcpyHostToDevice, st);
+        env->no_pdl = 1;
+        const int rc = (ce == cudaSuccess) ? launch_step(env, &env->slab_io_d, 1, 1, st) : DN_ECUDA;
+        env->no_pdl = 0;
+        if (ce == cudaSuccess && rc == DN_OK)
+            ce = cudaMemcpyAsync(env->slab_h + env->slab_out_off, env->slab_d + env->slab_out_off, env->slab_out_bytes, cudaMemcpyDeviceToHost, st);
+        cudaError_t ce2 = cudaStreamEndCapture(st, &graph);
+        if (rc != DN_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess || ce2 != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return fail(DN_ECUDA, std::string("dn_step_host_async: graph capture: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
+        }
+        ce = cudaGraphInstantiate(&env->slab_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { env->slab_exec = nullptr; return fail(DN_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+        env->launches -= 1;                            // the captured launch is counted per replay below
+    }
+    *reinterpret_cast<volatile uint32_t*>(env->slab_h + env->slab_seq_off) = 0u;
+    DN_CUDA(cudaGraphLaunch(env->slab_exec, st));
+    env->slab_pending = 1;
+    env->launches += 1;
+    env->graph_replays += 1;
+    return DN_OK;
+}
+
+int dn_step_host_wait(dn_env* env) {
+    if (!env) return fail(DN_EINVAL, "dn_step_host_wait: null handle");
+    if (!env->slab_pending) return DN_OK;
+    if (env->slab_pending == 2) {
+        env->slab_pending = 0;
+        return zero_copy_wait(env);
+    }
+    volatile uint32_t* seq = reinterpret_cast<volatile uint32_t*>(env->slab_h + env->slab_seq_off);
+    // the D2H copy writes the completion word last; poll it, and look at the stream now and then so that a failed
+    // launch ends in an error instead of an endless spin
+    uint32_t spins = 0;
+    while (*seq == 0u) {
+        if ((++spins & 0xFFFFu) == 0u) {
+            DeviceGuard guard(env->device);
+            const cudaError_t e = cudaStreamQuery(env->host_stream);
+            if (e != cudaErrorNotReady && *seq == 0u) {
+                env->slab_pending = 0;
+                if (e == cudaSuccess) return fail(DN_ECUDA, "dn_step_host_wait: the graph finished without setting the completion word");
+                return fail(DN_ECUDA, std::string("dn_step_host_wait: ") + cudaGetErrorString(e));
+            }
+        }
+    }
+    env->slab_pending = 0;
+    return DN_OK;
+}
+
 int dn_step_host(dn_env* env, const dn_step_io* h) {
     if (!env || !h) return fail(DN_EINVAL, "dn_step_host: null argument");
     if (!h->actions || !h->obs || !h->reward || !h->done) return fail(DN_EINVAL, "dn_step_host: actions/obs/reward/done are required");
+    if (env->slab_h && std::memcmp(h, &env->slab_io_h, sizeof(*h)) == 0) {     // the handle's own slab: graph replay
+        const int rc = dn_step_host_async(env, h);
+        return rc != DN_OK ? rc : dn_step_host_wait(env);
+    }
     DeviceGuard guard(env->device);
     if (!env->host_stream) DN_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
-    // Zero-copy path: if every buffer is pinned host memory mapped into the device address space (torch /
-    // cudaHostAlloc / cudaHostRegister), the fused kernel reads the actions and writes its outputs over
-    // PCIe itself -- one launch + one stream synchronise per step, no staging copies.  The classification
-    // is cached on the pointer set.  Pageable buffers take the staged path below.
-    if (std::memcmp(&env->host_seen, h, sizeof(*h)) != 0) {
-        env->host_seen = *h;
-        env->host_direct = getenv("DN_HOST_STAGED") ? 0 : 1;
-        const void* src[8] = {h->actions, h->obs, h->reward, h->done, h->terminal_obs, h->found_targets, h->episode_return, h->episode_length};
-        void* dst[8] = {nullptr};
-        for (int k = 0; k < 8 && env->host_direct; ++k) {
-            if (!src[k]) continue;
-            cudaPointerAttributes at;
-            if (cudaPointerGetAttributes(&at, src[k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
-                cudaGetLastError();
-                env->host_direct = 0;
-            } else {
-                dst[k] = at.devicePointer;
-            }
-        }
-        if (env->host_direct && (reinterpret_cast<uintptr_t>(dst[0]) & 15u)) env->host_direct = 0;
-        env->host_mapped.actions = static_cast<const float*>(dst[0]); env->host_mapped.obs = static_cast<float*>(dst[1]);
-        env->host_mapped.reward = static_cast<float*>(dst[2]); env->host_mapped.done = static_cast<uint8_t*>(dst[3]);
-        env->host_mapped.terminal_obs = static_cast<float*>(dst[4]); env->host_mapped.found_targets = static_cast<int32_t*>(dst[5]);
-        env->host_mapped.episode_return = static_cast<float*>(dst[6]); env->host_mapped.episode_length = static_cast<int32_t*>(dst[7]);
+    {
+        const int rc = host_classify(env, h);
+        if (rc != DN_OK) return rc;
     }
     if (env->host_direct) {
-        const int rc = launch_step(env, &env->host_mapped, 1, 1, env->host_stream);
-        if (rc != DN_OK) return rc;
-        DN_CUDA(spin_until_done(env->host_stream));
-        return DN_OK;
+        const int rc = zero_copy_launch(env);
+        return rc != DN_OK ? rc : zero_copy_wait(env);
     }
     const size_t N = env->P.n, D = env->P.obs_dim;
     const size_t a256 = 255;

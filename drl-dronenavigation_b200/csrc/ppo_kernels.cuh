@@ -55,11 +55,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherArgs g) {
         }
         uint32_t h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-            h[j] = dnmma::pack_bf16(h0, h1);
-            l[j] = dnmma::pack_bf16(__float2bfloat16_rn(v[2 * j] - __bfloat162float(h0)), __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1)));
-        }
+        for (int j = 0; j < 4; ++j) dnmma::split_pair(v[2 * j], v[2 * j + 1], h[j], l[j]);
         reinterpret_cast<uint4*>(g.x_hi + static_cast<long long>(row) * XPAD)[chunk] = make_uint4(h[0], h[1], h[2], h[3]);
         if (g.x_lo) reinterpret_cast<uint4*>(g.x_lo + static_cast<long long>(row) * XPAD)[chunk] = make_uint4(l[0], l[1], l[2], l[3]);
         if (chunk == 0 && g.m_act) {
@@ -290,11 +286,10 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
                 d0 *= fmaf(-hp[2 * i], hp[2 * i], 1.0f);
                 d1 *= fmaf(-hp[2 * i + 1], hp[2 * i + 1], 1.0f);
                 gbh_pi[2 * i] += d0; gbh_pi[2 * i + 1] += d1;
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(d0), h1 = __float2bfloat16_rn(d1);
-                reinterpret_cast<uint32_t*>(g.dzp_hi + op)[lane + 32 * i] = dnmma::pack_bf16(h0, h1);
-                if (g.dzp_lo)
-                    reinterpret_cast<uint32_t*>(g.dzp_lo + op)[lane + 32 * i] =
-                        dnmma::pack_bf16(__float2bfloat16_rn(d0 - __bfloat162float(h0)), __float2bfloat16_rn(d1 - __bfloat162float(h1)));
+                uint32_t wh, wl;
+                dnmma::split_pair(d0, d1, wh, wl);
+                reinterpret_cast<uint32_t*>(g.dzp_hi + op)[lane + 32 * i] = wh;
+                if (g.dzp_lo) reinterpret_cast<uint32_t*>(g.dzp_lo + op)[lane + 32 * i] = wl;
             }
             if (i < iv) {
                 const float2 w = *reinterpret_cast<const float2*>(s_wvf + 2 * lane + 64 * i);
@@ -304,11 +299,10 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs g)
                 d0 *= fmaf(-hv[2 * i], hv[2 * i], 1.0f);
                 d1 *= fmaf(-hv[2 * i + 1], hv[2 * i + 1], 1.0f);
                 gbh_vf[2 * i] += d0; gbh_vf[2 * i + 1] += d1;
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(d0), h1 = __float2bfloat16_rn(d1);
-                reinterpret_cast<uint32_t*>(g.dzv_hi + ov)[lane + 32 * i] = dnmma::pack_bf16(h0, h1);
-                if (g.dzv_lo)
-                    reinterpret_cast<uint32_t*>(g.dzv_lo + ov)[lane + 32 * i] =
-                        dnmma::pack_bf16(__float2bfloat16_rn(d0 - __bfloat162float(h0)), __float2bfloat16_rn(d1 - __bfloat162float(h1)));
+                uint32_t wh, wl;
+                dnmma::split_pair(d0, d1, wh, wl);
+                reinterpret_cast<uint32_t*>(g.dzv_hi + ov)[lane + 32 * i] = wh;
+                if (g.dzv_lo) reinterpret_cast<uint32_t*>(g.dzv_lo + ov)[lane + 32 * i] = wl;
             }
         }
     }
@@ -553,11 +547,10 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlaneSeg* __restrict_
     const int r = static_cast<int>(i / s.ld), c = static_cast<int>(i % s.ld);
     const float v0 = (c < s.cols) ? params[s.param_off + static_cast<long long>(r) * s.cols + c] : 0.0f;
     const float v1 = (c + 1 < s.cols) ? params[s.param_off + static_cast<long long>(r) * s.cols + c + 1] : 0.0f;
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-    reinterpret_cast<uint32_t*>(s.planes)[i / 2] = dnmma::pack_bf16(h0, h1);
-    if (write_lo)
-        reinterpret_cast<uint32_t*>(s.planes + count)[i / 2] =
-            dnmma::pack_bf16(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+    uint32_t wh, wl;
+    dnmma::split_pair(v0, v1, wh, wl);
+    reinterpret_cast<uint32_t*>(s.planes)[i / 2] = wh;
+    if (write_lo) reinterpret_cast<uint32_t*>(s.planes + count)[i / 2] = wl;
 }
 
 }  // namespace dnppo

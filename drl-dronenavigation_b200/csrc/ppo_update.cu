@@ -46,17 +46,20 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// BF16 row-major [rows, cols] tensor.  Operand maps: box = box_rows x 64 columns, 128-byte swizzle (one swizzle row per box
-// row).  Epilogue maps (results, tanh outputs): box = 32 x 32, 64-byte swizzle (the per-warp staging buffers of dn_umma.cuh).
-int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows, bool epilogue = false) {
+// BF16 row-major [rows, cols] tensor maps (dn_umma.cuh):
+//   MAP_KMAJOR   operand read along its rows: box = box_rows x BK (32) columns, 64-byte swizzle (one swizzle row per box row)
+//   MAP_MNMAJOR  operand read across its rows: box = BK (32) rows x 64 columns, 128-byte swizzle
+//   MAP_EPILOGUE results / tanh outputs: box = 32 x 32, 64-byte swizzle (the per-warp staging buffers)
+enum MapKind { MAP_KMAJOR, MAP_MNMAJOR, MAP_EPILOGUE };
+int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows, MapKind kind) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return dn_internal_fail(DN_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
-    cuuint32_t box[2] = {epilogue ? 32u : 64u, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t box[2] = {kind == MAP_MNMAJOR ? 64u : 32u, static_cast<cuuint32_t>(kind == MAP_MNMAJOR ? BK : (kind == MAP_EPILOGUE ? 32 : box_rows))};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    epilogue ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    kind == MAP_MNMAJOR ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return dn_internal_fail(DN_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
     return DN_OK;
@@ -151,14 +154,15 @@ int plan_fwd(GemmPlan* p, int passes, int M, int N, int K, const void* a, const 
     p->kind = K_FWD;
     pick_tile(rows_now, N, &p->cg, &p->bn);
     int rc;
-    if ((rc = make_map(&p->ma, a, 2LL * M, K, BM)) || (rc = make_map(&p->mb, w, 2LL * N, K, p->bn / p->cg)) ||
-        (rc = make_map(&p->mc, out, 2LL * M, N, 32, true)))
+    if ((rc = make_map(&p->ma, a, 2LL * M, K, BM, MAP_KMAJOR)) || (rc = make_map(&p->mb, w, 2LL * N, K, p->bn / p->cg, MAP_KMAJOR)) ||
+        (rc = make_map(&p->mc, out, 2LL * M, N, 32, MAP_EPILOGUE)))
         return rc;
     p->mh = p->mc;
     GemmArgs& g = p->args;
     memset(&g, 0, sizeof(g));
     g.m_tiles = rows_now / (BM * p->cg); g.n_tiles = N / p->bn; g.slices = 1; g.k_blocks = K / BK; g.passes = passes;
     g.a_lo_row = M; g.b_lo_row = N; g.c_lo_row = M; g.act = act; g.bias = bias; g.ld_out = N;
+    g.dbg = env_int("DN_MLP_DBG");
     set_grid(p);
     return DN_OK;
 }
@@ -169,13 +173,14 @@ int plan_dgrad(GemmPlan* p, int passes, int M, int N, int K, const void* a, cons
     p->kind = K_DGRAD;
     pick_tile(rows_now, N, &p->cg, &p->bn);
     int rc;
-    if ((rc = make_map(&p->ma, a, 2LL * M, K, BM)) || (rc = make_map(&p->mb, w, 2LL * K, N, 64)) ||
-        (rc = make_map(&p->mc, out, 2LL * M, N, 32, true)) || (rc = make_map(&p->mh, h, 2LL * M, N, 32, true)))
+    if ((rc = make_map(&p->ma, a, 2LL * M, K, BM, MAP_KMAJOR)) || (rc = make_map(&p->mb, w, 2LL * K, N, 0, MAP_MNMAJOR)) ||
+        (rc = make_map(&p->mc, out, 2LL * M, N, 32, MAP_EPILOGUE)) || (rc = make_map(&p->mh, h, 2LL * M, N, 32, MAP_EPILOGUE)))
         return rc;
     GemmArgs& g = p->args;
     memset(&g, 0, sizeof(g));
     g.m_tiles = rows_now / (BM * p->cg); g.n_tiles = N / p->bn; g.slices = 1; g.k_blocks = K / BK; g.passes = passes;
     g.a_lo_row = M; g.b_lo_row = K; g.c_lo_row = M; g.ld_out = N;
+    g.dbg = env_int("DN_MLP_DBG");
     set_grid(p);
     return DN_OK;
 }
@@ -186,7 +191,7 @@ int plan_wgrad(GemmPlan* p, int passes, int Mo, int No, int rows, int slices, co
     p->kind = K_WGRAD;
     pick_tile(Mo, No, &p->cg, &p->bn);
     int rc;
-    if ((rc = make_map(&p->ma, a, 2LL * rows, Mo, 64)) || (rc = make_map(&p->mb, b, 2LL * rows, No, 64))) return rc;
+    if ((rc = make_map(&p->ma, a, 2LL * rows, Mo, 0, MAP_MNMAJOR)) || (rc = make_map(&p->mb, b, 2LL * rows, No, 0, MAP_MNMAJOR))) return rc;
     p->mc = p->ma;
     p->mh = p->ma;
     GemmArgs& g = p->args;

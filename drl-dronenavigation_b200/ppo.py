@@ -454,21 +454,21 @@ class PPOLearner:
                 "grad_norm": st.last_grad_norm, "std": float(self.policy.log_std.detach().exp().mean()), "impl": "fused/" + cfg.mlp_precision}
 
     # ---- the only collective: one flat bucket per optimiser step (between backward and clip, sb3_ppo.py:291-293)
-    def _allreduce_grads(self):
-        w = _world()
+    def _allreduce_grads(self, approx_kl=None) -> bool:
+        """ONE collective per minibatch: the flat gradient bucket, whose extra last element carries this rank's KL early-stop
+        vote (sb3_ppo.py:283-287) -- a sum > 0 is the MAX over ranks, so ranks leave the epoch loop together without a second
+        all-reduce.  Returns the joint stop decision (one host read per minibatch, as in SB3)."""
+        cfg, w = self.cfg, _world()
+        vote = None
+        if cfg.target_kl is not None and approx_kl is not None:
+            vote = (approx_kl > 1.5 * cfg.target_kl).to(self._bucket.dtype)
         if w == 1:
-            return
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+            return bool(vote.item() > 0) if vote is not None else False
+        self._bucket[-1] = vote if vote is not None else 0.0
+        dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM)
         self._flat.div_(w)
         self.allreduce_calls += 1
-
-    def _sync_stop(self, stop: bool) -> bool:
-        """Ranks must leave the epoch loop together (sb3_ppo.py:283-287): all-reduce(MAX) of the decision."""
-        if _world() == 1:
-            return stop
-        t = torch.tensor([1.0 if stop else 0.0], device=self.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return bool(t.item() > 0)
+        return bool(self._bucket[-1].item() > 0) if vote is not None else False
 
     # ---- one minibatch, in two halves around the gradient all-reduce --------------------------------------
     def _forward_backward(self, obs, actions, old_logp, old_values, advantages, returns, acc):
@@ -599,11 +599,9 @@ class PPOLearner:
                     approx_kl = self._forward_backward(obs[idx], actions[idx], old_logp[idx], old_values[idx],
                                                        advantages[idx], returns[idx], acc)
                 n_done += 1
-                if cfg.target_kl is not None:
-                    stop = self._sync_stop(bool(approx_kl.item() > 1.5 * cfg.target_kl))   # one host sync per minibatch, as in SB3
-                    if stop:
-                        break
-                self._allreduce_grads()
+                stop = self._allreduce_grads(approx_kl)      # gradients + the early-stop vote in one collective
+                if stop:
+                    break                                    # the reduced gradients of this minibatch are discarded, as in SB3
                 if graphed:
                     gb.replay()
                 else:

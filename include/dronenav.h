@@ -231,6 +231,19 @@ int dn_step_many(dn_env* env, const dn_step_io* io, int num_steps, int per_step_
  * belong to the handle.  Set DN_HOST_STAGED=1 to force the staged path. */
 int dn_step_host(dn_env* env, const dn_step_io* host_io);
 
+/* The lowest-latency form of the host-buffer call: the HANDLE owns one pinned host slab laid out
+ *   actions | obs | reward | found_targets | done | [episode_return | episode_length | terminal_obs]
+ * and a device slab of the same layout.  dn_host_buffers fills `out` with HOST pointers into that slab (write actions
+ * there, read results there: no copy on either side); `with_episode_info` = 0 leaves the three bracketed outputs NULL.
+ * A dn_step_host / dn_step_host_async call that is given exactly these pointers replays ONE captured CUDA graph:
+ * one H2D DMA of the actions, the fused kernel, one D2H DMA of the contiguous outputs (whose last word is the completion
+ * flag the host waits on) -- instead of a kernel that reads and writes host memory over PCIe word by word plus a poll of the
+ * stream.  dn_step_host_async returns as soon as the graph is launched, dn_step_host_wait when the results are in the slab
+ * (SB3 VecEnv.step_async / step_wait).  Any other pointer set takes the paths described above. */
+int dn_host_buffers(dn_env* env, int with_episode_info, dn_step_io* out);
+int dn_step_host_async(dn_env* env, const dn_step_io* host_io);
+int dn_step_host_wait(dn_env* env);
+
 /* The action map alone, elementwise over `n` action components (device pointers):
  * PBDroneEnv._preprocessAction(rescale_action(a)) (PBDroneEnv.py:872-895,949-971) or the RPM map
  * (BaseSingleAgentAviary.py:176-179), whichever the handle was created with.  Bit-identical to

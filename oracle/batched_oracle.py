@@ -45,12 +45,17 @@ class BatchedOracle:
     def __init__(self, num_envs, track="circle", pyb_freq=240, ctrl_freq=240, max_steps=4096, act=O.ACT_THRUST,
                  normalize_actions=True, include_distance=True, reward_id="default", threshold=0.3, cylinder=True,
                  drone_model=O.MODEL_CF2X, numpy_legacy_cast=True, normalize_obs=False, normalize_reward=False, clip_reward=0.0,
-                 reward_gamma=0.99):
+                 reward_gamma=0.99, physics=O.PHYSICS_DYN, ground_contact=False):
         if reward_id not in _REWARDS:
             raise ValueError(f"reward {reward_id!r} is only in the per-environment oracle")
         if act not in (O.ACT_THRUST, O.ACT_RPM, O.ACT_ONE_D_RPM):
             raise ValueError(f"action type {act!r} is only in the per-environment oracle")
         self.N = int(num_envs)
+        # the documented DYN extensions: drag and ground effect (formulas pinned against the reference's own
+        # functions by tests/test_ref_pins.py) and the analytic ground-plane contact
+        self.drag = physics in (O.PHYSICS_DYN_DRAG, O.PHYSICS_DYN_GND_DRAG)
+        self.gnd = physics in (O.PHYSICS_DYN_GND, O.PHYSICS_DYN_GND_DRAG)
+        self.ground_contact = bool(ground_contact)
         self.C = O.AIRFRAMES[drone_model]
         self.DRONE_MODEL = drone_model
         self.targets, init, dim = O.circle_track() if track == "circle" else O.reaching_track()
@@ -88,6 +93,7 @@ class BatchedOracle:
         self.just_found = np.zeros(N, bool)
         self.ep_return, self.ep_len = np.zeros(N), np.zeros(N, np.int64)
         self.last_rpm = np.zeros((N, 4))
+        self.last_clipped = np.zeros((N, 4))    # BaseAviary.last_clipped_action (drag reads the PREVIOUS substep's), float64 zeros at reset
         # the wrappers of PBDroneSimulator.make_env (:181-195), per environment as each worker process has its own:
         # NormalizeObservation / NormalizeReward (normalize.py:50-147) with RunningMeanStd batches of one, TransformReward clip
         self.normalize_obs, self.normalize_reward, self.clip_reward, self.reward_gamma = normalize_obs, normalize_reward, clip_reward, reward_gamma
@@ -175,9 +181,24 @@ class BatchedOracle:
         c, dt = self.C, self.dt
         R = self._rotation(self.quat)
         forces = np.array(rpm ** 2) * c.KF                          # float32 on the THRUST path
+        if self.gnd:                                                # dyn_oracle._ground_effect (BaseAviary.py:798-834)
+            rpy = self._euler(self.quat)
+            offs = np.array(c.PROP_XY, dtype=np.float64)            # [4, 2]
+            heights = self.pos[:, 2:3] + R[:, 2, 0:1] * offs[None, :, 0] + R[:, 2, 1:2] * offs[None, :, 1]
+            heights = np.clip(heights, c.GND_EFF_H_CLIP, np.inf)
+            gnd = np.array(rpm, dtype=np.float64) ** 2 * c.KF * c.GND_EFF_COEFF * (c.PROP_RADIUS / (4 * heights)) ** 2
+            ok = (np.abs(rpy[:, 0]) < np.pi / 2) & (np.abs(rpy[:, 1]) < np.pi / 2)
+            forces = forces + np.where(ok[:, None], gnd, 0.0)
         total = forces[:, 0] + forces[:, 1] + forces[:, 2] + forces[:, 3]      # np.sum over four elements, left to right
         thrust_world = R[:, :, 2] * np.float64(total)[:, None]
         force_world = thrust_world - np.array([0, 0, c.GRAVITY])
+        if self.drag:                                               # dyn_oracle._drag (BaseAviary.py:838-865), LINK_FRAME: rotated twice
+            last = self.last_clipped
+            per = 2 * np.pi * last / 60                             # float32 arithmetic when `last` is the float32 action-map output
+            ssum = per[:, 0] + per[:, 1] + per[:, 2] + per[:, 3]
+            factors = -1 * np.array([c.DRAG_COEFF_XY, c.DRAG_COEFF_XY, c.DRAG_COEFF_Z])[None, :] * np.float64(ssum)[:, None]
+            link = np.einsum("nij,nj->ni", R, factors * self.vel)
+            force_world = force_world + np.einsum("nij,nj->ni", R, link)
         z_t = np.array(rpm ** 2) * c.KM
         if self.DRONE_MODEL == O.MODEL_RACE:
             z_t = -z_t
@@ -212,6 +233,7 @@ class BatchedOracle:
         self.quat = newq / _norm(newq)[:, None]                     # Bullet pose read-back
         self.ang_v = np.einsum("nij,nj->ni", R, w)
         self.rpy_rates = w
+        self.last_clipped = np.array(rpm)                            # BaseAviary.py:442, inside the substep loop
 
     # ---- PBDroneEnv._computeObs (dyn_oracle._computeObs) ---------------------------------------------------------------
     def _obs(self, pos, rpy, vel, ang_v, dist):
@@ -234,6 +256,10 @@ class BatchedOracle:
             for m in (p[:, 0] - self.x_high, p[:, 0] - self.x_low, p[:, 1] - self.y_high, p[:, 1] - self.y_low, p[:, 2] - self.z_high):
                 self._m(m)
         out = (p[:, 0] > self.x_high) | (p[:, 0] < self.x_low) | (p[:, 1] > self.y_high) | (p[:, 1] < self.y_low) | (p[:, 2] > self.z_high)
+        if self.ground_contact:                                     # analytic substitute for p.getContactPoints() (dyn_oracle._has_collision_occurred)
+            if record:
+                self._m(p[:, 2] - self.C.COLLISION_H / 2)
+            out = out | (p[:, 2] < self.C.COLLISION_H / 2)
         if not self.cylinder:
             return out
         if self.circle:
@@ -372,6 +398,7 @@ class BatchedOracle:
                 a[d] = 0.0
             self.ep_return[d], self.ep_len[d] = 0.0, 0
             self.last_rpm[d] = 0.0
+            self.last_clipped[d] = 0.0        # _housekeeping zeroes last_clipped_action (zeros are exact in either dtype)
         return obs, reward, bits, found, terminal_obs, ep_r, ep_l
 
     def reset_obs(self):
@@ -384,4 +411,5 @@ class BatchedOracle:
         return dict(pos=self.pos, quat=self.quat, vel=self.vel, rpy_rates=self.rpy_rates, ang_v=self.ang_v,
                     prev_vel=self.prev_vel, prev_ang_v=self.prev_ang_v, dist=self.dist, prev_dist=self.prev_dist,
                     target_idx=self.idx.astype(np.int32), steps=self.steps.astype(np.int32),
-                    just_found=self.just_found.astype(np.uint8), ep_return=self.ep_return, ep_length=self.ep_len.astype(np.int32))
+                    just_found=self.just_found.astype(np.uint8), ep_return=self.ep_return, ep_length=self.ep_len.astype(np.int32),
+                    **({"last_rpm_sum": np.sum(np.float64(self.last_clipped), axis=1)} if self.drag else {}))

@@ -587,7 +587,7 @@ class OracleDroneEnv:
             # (BaseAviary.py:413-415) and after the last one (:444); with the DYN
             # set/get pair that is the pose read-back applied in _dynamics below.
             self._dynamics(rpm)
-            self.last_clipped_action = np.array(rpm, dtype=np.float64)
+            self.last_clipped_action = np.array(rpm)      # keeps the action map's dtype (float32 on the THRUST path), BaseAviary.py:442
         self.rpy = bullet_euler_from_quaternion(self.quat)
         obs = self._computeObs()
         reward = self._computeReward()

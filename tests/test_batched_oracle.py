@@ -29,6 +29,11 @@ def _actions(mode, T, N, seed):
     ("circle", 8, "mixed", {"normalize_obs": True}),
     ("reaching", 8, "saturating", {"normalize_obs": True, "normalize_reward": True, "clip_reward": 10.0}),
     ("circle", 1, "saturating", {"normalize_reward": True, "max_steps": 40}),
+    # the documented DYN extensions: drag / ground effect (formulas pinned to the reference's own functions, test_ref_pins.py)
+    # and the analytic ground-plane contact
+    ("circle", 8, "mixed", {"physics": O.PHYSICS_DYN_GND_DRAG}), ("reaching", 8, "saturating", {"physics": O.PHYSICS_DYN_DRAG}),
+    ("circle", 1, "hover_band", {"physics": O.PHYSICS_DYN_GND}),
+    ("circle", 8, "saturating", {"ground_contact": True}), ("reaching", 8, "mixed", {"ground_contact": True, "physics": O.PHYSICS_DYN_GND_DRAG}),
 ])
 def test_batched_oracle_equals_per_environment_oracle(track, S, mode, kw):
     N, T = 12, 240 if S == 1 else 80

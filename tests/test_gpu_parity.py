@@ -251,6 +251,50 @@ def test_step_host_zero_copy_and_staged_paths_equal_device_step():
         e.close()
 
 
+@pytest.mark.parametrize("N,with_info", [(777, True), (4096, False), (1, True)])
+def test_step_host_slab_graph_path_equals_device_step(N, with_info):
+    """dn_host_buffers + dn_step_host / dn_step_host_async + dn_step_host_wait (the handle's pinned slab, one captured graph per
+    step: H2D DMA, fused kernel, D2H DMA) == dn_step on device buffers, including the optional episode outputs."""
+    from drl_dronenavigation_b200 import _lib as L
+    envs = [_make("circle", N, 8)[0] for _ in range(2)]
+    for e in envs:
+        e.reset()
+    acts = _actions("saturating", 14, N, seed=6)
+    io, b = envs[1].host_buffers(with_episode_info=with_info)
+    assert (b["terminal_obs"] is not None) == with_info and b["actions"].shape == (N, 4) and b["obs"].shape == (N, 13)
+    l0 = envs[1].launch_count
+    n_done = 0
+    for t in range(14):
+        o, r, d, f = envs[0].step(torch.from_numpy(acts[t]).cuda())
+        b["actions"][...] = acts[t]
+        if t % 2:
+            envs[1].step_host(io)
+        else:
+            envs[1].step_host_async(io)
+            with pytest.raises(L.DroneNavError, match="not been waited"):
+                envs[1].step_host_async(io)                       # one step in flight at a time
+            envs[1].step_host_wait()
+        for name, dev_t in (("obs", o), ("reward", r), ("done", d), ("found_targets", f)):
+            np.testing.assert_array_equal(b[name], dev_t.cpu().numpy(), err_msg=f"{name} t={t}")
+        done = d.cpu().numpy() != 0
+        n_done += int(done.sum())
+        if with_info:
+            np.testing.assert_array_equal(b["terminal_obs"][done], envs[0].terminal_obs.cpu().numpy()[done])
+            np.testing.assert_array_equal(b["episode_length"][done], envs[0].episode_length.cpu().numpy()[done])
+            np.testing.assert_array_equal(b["episode_return"][done], envs[0].episode_return.cpu().numpy()[done])
+    assert envs[1].launch_count - l0 == 14                        # every graph replay counts as one launch of the step kernel
+    assert n_done > 0 or N == 1
+    # any other pointer set still takes the zero-copy / staged paths
+    other = L.dn_step_io()
+    pa, po, pr, pd = np.zeros((N, 4), np.float32), np.zeros((N, 13), np.float32), np.zeros(N, np.float32), np.zeros(N, np.uint8)
+    other.actions, other.obs, other.reward, other.done = pa.ctypes.data, po.ctypes.data, pr.ctypes.data, pd.ctypes.data
+    with pytest.raises(L.DroneNavError, match="dn_host_buffers"):
+        envs[1].step_host_async(other)
+    envs[1].step_host(other)
+    for e in envs:
+        e.close()
+
+
 def test_ragged_sizes_and_obs12():
     """N not a multiple of the CTA size (tail CTA takes the non-TMA store path), N = 1, 12-dim obs."""
     from drl_dronenavigation_b200.batched_env import BatchedDroneEnv

@@ -109,7 +109,7 @@ def _worker(rank, world, port, tmp):
         with torch.no_grad():
             v, logp, _ = L2.policy.evaluate(obs, act)
         out2 = L2.update(obs, act, logp, v, adv, ret, generator=torch.Generator().manual_seed(5))
-        torch.save({"out2": out2, "p": L2.flat_parameters()}, os.path.join(tmp, f"s{rank}.pt"))
+        torch.save({"out2": out2, "p": L2.flat_parameters(), "calls": L2.allreduce_calls}, os.path.join(tmp, f"s{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -148,4 +148,7 @@ def test_two_rank_gloo_gradient_allreduce(tmp_path):
     s = [torch.load(os.path.join(tmp_path, f"s{k}.pt"), weights_only=False) for k in range(world)]
     assert s[0]["out2"]["early_stop"] and s[1]["out2"]["early_stop"]
     assert s[0]["out2"]["minibatches"] == s[1]["out2"]["minibatches"]
+    # the early-stop vote rides in the gradient bucket: ONE collective per minibatch, none besides
+    assert s[0]["calls"] == s[1]["calls"] == s[0]["out2"]["minibatches"]
+    assert torch.equal(s[0]["p"], s[1]["p"])
     assert torch.equal(s[0]["p"], s[1]["p"])
