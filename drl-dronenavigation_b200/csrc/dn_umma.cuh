@@ -53,7 +53,7 @@ enum Kind { K_FWD = 0, K_DGRAD = 1, K_WGRAD = 2 };
 
 struct GemmArgs {
     int m_tiles, n_tiles, slices;   // tile grid: accumulator rows / (128 CG), accumulator columns / BN, split of the reduction
-    int k_blocks;                   // BK-wide k-blocks per tile
+    int k_blocks;                   // BK-wide k-blocks of the reduction (WGRAD: of ALL slices; slice s takes [s KB / S, (s + 1) KB / S))
     int passes;                     // 1 (BF16) or 3 (hi*hi + hi*lo + lo*hi)
     int a_lo_row, b_lo_row;         // row of the lo plane inside the A / B tensor maps (rows of plane 0)
     int c_lo_row;                   // row of the lo plane inside the result / H tensor maps
@@ -385,7 +385,9 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const int nt = t % g.n_tiles, mt = (t / g.n_tiles) % g.m_tiles, sl = t / (g.n_tiles * g.m_tiles);
                 const int m0 = (mt * CG + rank) * BM;             // this CTA's accumulator rows
                 const int n0 = nt * BN + rank * BNL;              // this CTA's share of the B tile
-                for (int kb = 0; kb < g.k_blocks; ++kb) {
+                const int kb0 = (KIND == K_WGRAD) ? static_cast<int>(static_cast<long long>(sl) * g.k_blocks / g.slices) : 0;
+                const int kb1 = (KIND == K_WGRAD) ? static_cast<int>(static_cast<long long>(sl + 1) * g.k_blocks / g.slices) : g.k_blocks;
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * stage_bytes;
                     uint8_t* sb = sa + planes * A_BYTES;
@@ -404,7 +406,7 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             for (int j = 0; j < BNL / 64; ++j)                                                       // W rows = reduction
                                 tma_load_2d<CG>(&tmB, &full_bar[stage], db + j * MN_BOX_BYTES, n0 + j * 64, b_row + kb * BK);
                         } else {
-                            const int r0 = (sl * g.k_blocks + kb) * BK;                                              // batch rows = reduction
+                            const int r0 = kb * BK;                                                                  // batch rows = reduction
 #pragma unroll
                             for (int j = 0; j < BM / 64; ++j)
                                 tma_load_2d<CG>(&tmA, &full_bar[stage], da + j * MN_BOX_BYTES, m0 + j * 64, a_row + r0);
@@ -428,7 +430,12 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < g.k_blocks; ++kb) {
+                int n_kb = g.k_blocks;
+                if constexpr (KIND == K_WGRAD) {
+                    const int sl = t / (g.n_tiles * g.m_tiles);
+                    n_kb = static_cast<int>(static_cast<long long>(sl + 1) * g.k_blocks / g.slices) - static_cast<int>(static_cast<long long>(sl) * g.k_blocks / g.slices);
+                }
+                for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes), sb = sa + planes * A_BYTES;

@@ -187,7 +187,8 @@ int plan_dgrad(GemmPlan* p, int passes, int M, int N, int K, const void* a, cons
 // wgrad: partial[s][Mo][No] = A[rows_s, Mo]^T B[rows_s, No], rows split into `slices`
 int plan_wgrad(GemmPlan* p, int passes, int Mo, int No, int rows, int slices, const void* a, const void* b, float* partial, int rows_now = 0) {
     if (!rows_now) rows_now = rows;
-    if (Mo % BM || No % 64 || slices < 1 || rows_now % (64 * slices)) return dn_internal_fail(DN_EINVAL, "mlp wgrad: Mo % 128, No % 64, rows % (64 slices) must be 0");
+    if (Mo % BM || No % 64 || slices < 1 || rows_now % 64 || rows_now / BK < slices)
+        return dn_internal_fail(DN_EINVAL, "mlp wgrad: Mo % 128, No % 64, rows % 64 must be 0 and every slice needs at least one k-block");
     p->kind = K_WGRAD;
     pick_tile(Mo, No, &p->cg, &p->bn);
     int rc;
@@ -196,7 +197,7 @@ int plan_wgrad(GemmPlan* p, int passes, int Mo, int No, int rows, int slices, co
     p->mh = p->ma;
     GemmArgs& g = p->args;
     memset(&g, 0, sizeof(g));
-    g.m_tiles = Mo / (BM * p->cg); g.n_tiles = No / p->bn; g.slices = slices; g.k_blocks = rows_now / slices / BK; g.passes = passes;
+    g.m_tiles = Mo / (BM * p->cg); g.n_tiles = No / p->bn; g.slices = slices; g.k_blocks = rows_now / BK; g.passes = passes;
     g.a_lo_row = rows; g.b_lo_row = rows;
     g.partial = partial; g.ld_partial = No; g.slice_stride = static_cast<long long>(Mo) * No;
     set_grid(p);
@@ -248,11 +249,11 @@ struct dn_ppo {
 namespace {
 
 // split of the batch rows of a weight-gradient contraction: as many slices as it takes to give every CTA (pair) a work item
+// (slices need not divide the rows: slice s covers k-blocks [s KB / S, (s + 1) KB / S) of the KB = rows / BK blocks), but every
+// slice keeps at least 256 rows so that the partial-sum traffic stays small against the contraction
 int wgrad_slices(int rows, int tiles, int units) {
     const int target = std::max(1, units / std::max(tiles, 1));
-    int s = 1;
-    while (s * 2 <= target && rows % (64 * s * 2) == 0 && rows / (s * 2) >= 256) s *= 2;
-    return s;
+    return std::max(1, std::min(target, rows / 256));
 }
 
 template <typename T>

@@ -380,6 +380,7 @@ class PPOLearner:
                 self.fused.close()
             self.fused = FusedUpdate(self, rows)
             self._graphs = None            # parameters were re-seated: graphs of the torch path are stale
+            self._fused_graphs = None
         return self.fused
 
     def forward(self, obs):
@@ -422,24 +423,57 @@ class PPOLearner:
                              "use update_impl='torch' for ragged batches")
         n_mb = B // mb
         fu = self.ensure_fused(mb)
+        world = _world()
         ro = fu.L.dn_ppo_rollout()
-        keep = [t.contiguous().float() for t in (obs, actions, old_logp, old_values, advantages, returns)]
+        graphs = None
+        if cfg.cuda_graph:
+            # the ~25 kernels of a minibatch step replayed from CUDA graphs (one for the gradient half, one for the apply half; a
+            # single one when there is no all-reduce in between): removes the launch gaps between the short dependent kernels.
+            # Graphs bake pointers in, so the rollout is staged in static tensors and the minibatch indices in a static buffer.
+            fg = self._fused_graphs
+            key = (B, mb, obs.shape[1], actions.shape[1], world)
+            if fg is None or fg["key"] != key or fg["fu"] is not fu:
+                fg = self._capture_fused(fu, key)
+            for dst, src in zip(fg["static"], (obs, actions, old_logp, old_values, advantages, returns)):
+                dst.copy_(src)
+            keep = list(fg["static"])
+            graphs = fg
+        else:
+            keep = [t.contiguous().float() for t in (obs, actions, old_logp, old_values, advantages, returns)]
         ro.obs, ro.actions, ro.old_log_prob, ro.old_values, ro.advantages, ro.returns = [t.data_ptr() for t in keep]
         fu.begin_update()
-        world = _world()
         launched = 0
         stop = False
+        # When does the host learn that the device stopped?  One rank: a non-blocking look at the pinned mirror after every
+        # minibatch (it may lag by a few launches; those are no-ops on the device).  Several ranks: every rank must issue the
+        # SAME number of all-reduces, so the decision has to be taken at the same loop positions from a value that is the same
+        # everywhere -- the device-side `stopped` state (derived from the all-reduced vote), read with a stream synchronisation
+        # every `check_every` minibatches and at the end of every epoch.
+        check_every = 4
         for epoch in range(cfg.n_epochs):
             perm = torch.randperm(B, device=self.device, generator=generator)
             keep.append(perm)
             for k in range(n_mb):
-                fu.minibatch_grad(ro, perm[k * mb:(k + 1) * mb])
-                if world > 1:
-                    dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM)
-                    self.allreduce_calls += 1
-                fu.minibatch_apply()
+                if graphs is not None:
+                    graphs["idx"].copy_(perm[k * mb:(k + 1) * mb])
+                    graphs["grad"].replay()
+                    if world > 1:
+                        dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM)
+                        self.allreduce_calls += 1
+                        graphs["apply"].replay()
+                else:
+                    fu.minibatch_grad(ro, perm[k * mb:(k + 1) * mb])
+                    if world > 1:
+                        dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM)
+                        self.allreduce_calls += 1
+                    fu.minibatch_apply()
                 launched += 1
-                stop = fu.poll()[0]
+                if cfg.target_kl is None:
+                    continue
+                if world == 1:
+                    stop = fu.poll()[0]
+                elif (k + 1) % check_every == 0 or k == n_mb - 1:
+                    stop = bool(fu.stats().early_stop)
                 if stop:
                     break
             if stop:
@@ -452,6 +486,42 @@ class PPOLearner:
                 "approx_kl": st.approx_kl, "clip_fraction": st.clip_fraction, "epochs": epochs_run, "minibatches": st.minibatches,
                 "optimizer_steps": st.optimizer_steps, "early_stop": bool(st.early_stop), "launched_minibatches": launched,
                 "grad_norm": st.last_grad_norm, "std": float(self.policy.log_std.detach().exp().mean()), "impl": "fused/" + cfg.mlp_precision}
+
+    _fused_graphs = None
+
+    def _capture_fused(self, fu: FusedUpdate, key):
+        """CUDA graphs of the fused minibatch step for rollouts of `key` = (B, mb, D, A, world).  With one rank the two halves are one
+        graph; with several the flat-bucket all-reduce sits between two graphs."""
+        B, mb, D, A, world = key
+        dev = self.device
+        f = dict(dtype=torch.float32, device=dev)
+        static = [torch.zeros(B, D, **f), torch.zeros(B, A, **f), torch.zeros(B, **f), torch.zeros(B, **f), torch.zeros(B, **f), torch.zeros(B, **f)]
+        idx = torch.arange(mb, dtype=torch.long, device=dev)
+        ro = fu.L.dn_ppo_rollout()
+        ro.obs, ro.actions, ro.old_log_prob, ro.old_values, ro.advantages, ro.returns = [t.data_ptr() for t in static]
+        # warm-up outside the capture (lazy kernel loading, launch attributes, plans for `mb` rows): one gradient half on zeros, then
+        # an apply half that is a no-op because the early-stop vote in the bucket's extra element is forced to "stop"
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            fu.begin_update()
+            fu.minibatch_grad(ro, idx)
+            self._bucket[-1] = 1.0
+            fu.minibatch_apply()
+            fu.begin_update()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g_grad, g_apply = torch.cuda.CUDAGraph(), None
+        with torch.cuda.graph(g_grad):
+            fu.minibatch_grad(ro, idx)
+            if world == 1:
+                fu.minibatch_apply()
+        if world > 1:
+            g_apply = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_apply):
+                fu.minibatch_apply()
+        self._fused_graphs = {"key": key, "fu": fu, "static": static, "idx": idx, "ro": ro, "grad": g_grad, "apply": g_apply}
+        return self._fused_graphs
 
     # ---- the only collective: one flat bucket per optimiser step (between backward and clip, sb3_ppo.py:291-293)
     def _allreduce_grads(self, approx_kl=None) -> bool:

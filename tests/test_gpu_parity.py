@@ -633,18 +633,26 @@ def test_airframes_and_controller_action_types_lockstep(model, act, track, S, T,
     ("reaching", 8, "mixed", 65536, 45, {}),             # BASELINE config 3's per-GPU shard (segment tube)
     ("circle", 1, "saturating", 4096, 480, {"reward_id": "dummy"}),
     ("reaching", 8, "saturating", 16384, 60, {"reward_id": "thrustenv"}),
-], ids=["config2_saturating", "config2_hover_band", "config3_65536", "circle_s1_dummy", "reaching_thrustenv"])
+    ("circle", 8, "mixed", 16384, 60, {"physics": "dyn_gnd_drag"}),              # BASELINE config 4: drag + ground effect, every env
+    ("circle", 8, "saturating", 16384, 40, {"physics": "dyn_gnd_drag"}),
+    ("circle", 8, "saturating", 131072, 30, {"reward_id": "thrustenv"}),         # BASELINE config 5's per-GPU shard, one reward of the sweep
+    ("circle", 8, "saturating", 4096, 60, {"ground_contact": True}),             # analytic ground-plane contact
+    ("reaching", 8, "mixed", 4096, 60, {"ground_contact": True, "physics": "dyn_gnd_drag"}),
+], ids=["config2_saturating", "config2_hover_band", "config3_65536", "circle_s1_dummy", "reaching_thrustenv", "config4_16384_mixed",
+        "config4_16384_saturating", "config5_131072_thrustenv", "ground_contact_circle", "ground_contact_reaching_gnd_drag"])
 def test_full_size_lockstep_against_batched_oracle(track, S, mode, N, T, kw):
     """EVERY environment of the BASELINE shapes compared with the FP64 oracle at EVERY step (oracle/batched_oracle.py,
     itself checked against the per-environment oracle and the reference fixtures in tests/test_batched_oracle.py)."""
     from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
     from oracle.batched_oracle import BatchedOracle
     from oracle.dyn_oracle import circle_track, reaching_track
+    from drl_dronenavigation_b200 import Physics
     rid = {"default": 0, "dummy": 1, "thrustenv": 2}[kw.get("reward_id", "default")]
+    phys = {"dyn": Physics.DYN, "dyn_gnd_drag": Physics.PYB_GND_DRAG_DW}[kw.get("physics", "dyn")]
     targets, init, dim = circle_track() if track == "circle" else reaching_track()
     env = BatchedDroneEnv(N, targets, threshold=0.3, discount=0.999, max_steps=4096, aviary_dim=dim, initial_xyzs=init,
                           pyb_freq=240, ctrl_freq=240 // S, cylinder=True, circle=(track == "circle"), include_distance=True,
-                          normalize_actions=True, reward_id=rid)
+                          normalize_actions=True, reward_id=rid, physics=phys, ground_contact=kw.get("ground_contact", False))
     B = BatchedOracle(N, track, pyb_freq=240, ctrl_freq=240 // S, **kw)
     np.testing.assert_allclose(env.reset().cpu().numpy(), B.reset_obs(), atol=1e-6)
     rep = PU.run_lockstep_batched(env, B, _actions(mode, T, N, seed=N % 97 + S), resync_every=240 // S)

@@ -194,3 +194,27 @@ def test_trainer_uses_the_fused_update_and_learns_to_reduce_value_loss():
     assert all(o["impl"].startswith("fused") for o in outs)
     assert np.isfinite([o["value_loss"] for o in outs]).all() and outs[-1]["value_loss"] < outs[0]["value_loss"]
     env.close()
+
+
+@pytest.mark.skipif(not _cc10(), reason="needs an sm_100 device")
+def test_graph_replay_of_the_fused_step_is_bit_identical():
+    """The fused minibatch step replayed from CUDA graphs (static rollout / index buffers) is the same computation as the
+    launch-by-launch path: every kernel reduces in an order fixed by its geometry, so the parameters agree BIT FOR BIT, over two
+    updates (Adam state carried across replays) and through a KL early stop."""
+    from drl_dronenavigation_b200.ppo import PPOConfig, PPOLearner
+    outs = {}
+    for graph in (False, True):
+        L = PPOLearner(13, 4, PPOConfig(batch_size=1024, n_epochs=3, target_kl=None, cuda_graph=graph, update_impl="fused"), device="cuda")
+        ro = make_rollout(L, 8192, seed=4)
+        r1 = L.update(*ro, generator=torch.Generator(device="cuda").manual_seed(1))
+        ro2 = make_rollout(L, 8192, seed=5)
+        r2 = L.update(*ro2, generator=torch.Generator(device="cuda").manual_seed(2))
+        L.cfg.target_kl = 1e-7                       # third update: stops at once, nothing applied
+        L.fused.close(); L.fused = None
+        p_before = L.flat_parameters().clone()
+        r3 = L.update(*ro2, generator=torch.Generator(device="cuda").manual_seed(3))
+        assert r3["early_stop"] and r3["optimizer_steps"] == 0 and torch.equal(p_before, L.flat_parameters())
+        outs[graph] = (L.flat_parameters().clone(), r1, r2)
+    assert torch.equal(outs[False][0], outs[True][0])
+    for k in ("policy_gradient_loss", "value_loss", "approx_kl", "clip_fraction", "minibatches", "optimizer_steps"):
+        assert outs[False][1][k] == outs[True][1][k] and outs[False][2][k] == outs[True][2][k], k
