@@ -267,9 +267,18 @@ def baseline_configs(args, dev, K):
             k -= k % 50
             sec, group = time_graph(env, acts, k, 24, group=50)
             st = env.episode_stats()
-            bytes_per = BYTES_PER_ENV_STEP + (216 if kw.get("normalize_obs") else 0) + (8 if kw.get("physics") else 0)
+            # algorithmic bytes per env-step of the variant: + the FP64 RunningMeanStd planes (27 doubles read and written),
+            # + last_rpm_sum (drag / ground effect), + the [N,4] aux plane of the rewards that keep one (read and written)
+            rid = kw.get("reward_id", L.DN_REWARD_DEFAULT)
+            bytes_per = (BYTES_PER_ENV_STEP + (2 * 27 * 8 if kw.get("normalize_obs") else 0) + (8 if kw.get("physics") else 0)
+                         + (32 if rid in (L.DN_REWARD_REACHING, L.DN_REWARD_BOOTSTRAPPED, L.DN_REWARD_CHAMP) else 0))
+            variant = "norm_" if kw.get("normalize_obs") else "phys3_" if kw.get("physics") else f"full_rw{rid}_" if "reward_id" in kw and rid else ""
+            kern = "dn::step_kernel<%d,%s,false,%s>" % (3 if kw.get("physics") else 0, "true" if kw.get("normalize_obs") else "false",
+                                                        "true" if ("reward_id" in kw and rid) else "false")
+            rl = roofline(n, sec / k, substeps=S, bytes_per=bytes_per, variant=variant, kernel=kern)
+            rl["l2"] = "fits L2 (graph replay over one handle)" if n * (bytes_per - 112) < 126e6 else "larger than L2"
             out.append({"config": cid, "shape": name, "envs": n, "substeps": S, "value": n * k / sec, "unit": UNIT,
-                        "us_per_launch": 1e6 * sec / k, "achieved_gbs": bytes_per * n * k / sec / 1e9, "steps": k,
+                        "us_per_launch": 1e6 * sec / k, "achieved_gbs": rl["achieved"], "roofline": rl, "steps": k,
                         "episodes_finished": int(st["episodes"]), "timing": "CUDA-graph replay, 50 steps per graph"})
             env.close()
             del env, acts
@@ -477,17 +486,18 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(n_envs, substeps):
+def ncu_traffic(n_envs, substeps, variant=""):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of step_kernel from the committed `ncu --set full`
-    capture of the same (envs, substeps) configuration (profiles/ncu_summary_r*.json, written by
-    tools/summarize_profiles.py from the .ncu-rep files); None if that configuration was not captured."""
+    capture of the same configuration (profiles/ncu_summary_r*.json, written by tools/summarize_profiles*.py from the
+    reports; `variant` = the capture's prefix: "" plain, "norm_", "phys3_", "full_rw<id>_"); the latest round that
+    holds the capture wins; None if that configuration was not captured."""
     import glob
     best = None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_summary_r*.json"))):
         try:
             with open(path) as f:
                 d = json.load(f)
-            rec = d.get(f"prof_n{n_envs}_s{substeps}.ncu-rep")
+            rec = d.get(f"{variant}n{n_envs}_s{substeps}") or (d.get(f"prof_n{n_envs}_s{substeps}.ncu-rep") if not variant else None)
             if rec and "traffic_bytes" in rec:
                 best = float(rec["traffic_bytes"])
         except Exception:  # noqa: BLE001
@@ -495,14 +505,14 @@ def ncu_traffic(n_envs, substeps):
     return best
 
 
-def roofline(n_envs, sec_per_launch, traffic=None, substeps=None):
+def roofline(n_envs, sec_per_launch, traffic=None, substeps=None, bytes_per=BYTES_PER_ENV_STEP, variant="", kernel="dn::step_kernel<0,false,false,false>"):
     peak, src = peaks()
     if traffic is None and substeps is not None:
-        traffic = ncu_traffic(n_envs, substeps)
-    achieved = BYTES_PER_ENV_STEP * n_envs / sec_per_launch / 1e9
+        traffic = ncu_traffic(n_envs, substeps, variant)
+    achieved = bytes_per * n_envs / sec_per_launch / 1e9
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "kernel": "dn::step_kernel<0,false>", "bytes_per_env_step": BYTES_PER_ENV_STEP, "envs_per_launch": n_envs,
-            "us_per_launch": sec_per_launch * 1e6, "peak_source": src}
+            "kernel": kernel, "bytes_per_env_step": bytes_per, "envs_per_launch": n_envs,
+            "algorithmic_bytes_per_launch": bytes_per * n_envs, "us_per_launch": sec_per_launch * 1e6, "peak_source": src}
 
 
 def run_sac(args, dev, world, rank, barrier, max_over_ranks):
@@ -553,7 +563,8 @@ def run_ppo(args, dev, world, rank, barrier, max_over_ranks):
     T = args.ppo_rollout
     cfg = PPOConfig(n_steps=T, batch_size=max(512, (T * args.ppo_envs) // 32), update_impl=args.ppo_impl, mlp_precision=args.ppo_precision)
     tr = PPOTrainer(env, cfg, rollout_steps=T)
-    tr.train_iteration()                                   # warm-up (cuBLAS heuristics, allocator)
+    for _ in range(2):
+        tr.train_iteration()                               # warm-up (kernel loading, plans, graph capture, allocator)
     barrier()
     l0 = env.launch_count
     t0 = time.perf_counter()
