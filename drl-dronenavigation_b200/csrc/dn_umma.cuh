@@ -343,6 +343,11 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int stages = (RING_BYTES / stage_bytes) > MAX_STAGES ? MAX_STAGES : static_cast<int>(RING_BYTES / stage_bytes);
     const int total_tiles = g.m_tiles * g.n_tiles * g.slices;
 
+    // Programmatic dependent launch (launch_one sets the attribute): the next kernel of the stream may be scheduled as soon as
+    // this one's CTAs leave their SMs, and this kernel sets up (barriers, TMEM, descriptors) while its predecessor drains;
+    // nothing below touches global memory before griddepcontrol.wait, which returns once the predecessor has completed and its
+    // writes are visible.  Both instructions are no-ops for a normal launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -363,6 +368,7 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         fence_proxy_async();
     }
     if (warp == 2) tmem_alloc<CG>(tmem_ptr, TMEM_COLS);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if constexpr (KIND == K_DGRAD) {
         if (g.colsum != nullptr)
             for (int i = threadIdx.x; i < 4 * g.ld_out; i += NUM_THREADS) colsum_s[i] = 0.0f;

@@ -119,13 +119,18 @@ int launch_one(const GemmPlan& p, cudaStream_t st) {
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    // programmatic dependent launch: the kernel's set-up overlaps the tail of its predecessor in the stream (umma_gemm waits
+    // with griddepcontrol.wait before its first global access); DN_MLP_NO_PDL=1 launches normally (A/B measurements)
+    static const bool use_pdl = (getenv("DN_MLP_NO_PDL") == nullptr);
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = use_pdl ? 2 : 1;
     PPO_CUDA(cudaLaunchKernelEx(&cfg, kern, p.ma, p.mb, p.mc, p.mh, p.args));
     return DN_OK;
 }
