@@ -781,10 +781,30 @@ def run_b200(args):
               "api": "dn_step_host (C ABI) with caller-owned pinned host buffers, zero copy: the fused kernel reads that step's actions from and "
                      "writes obs, reward, found_targets, done to host memory over PCIe (64 KiB in, 244 KiB out per step); its last CTA "
                      "writes a completion word the host polls -- one launch per step, no DMA engine, no stream query"}
-    # both forms move the same bytes between host and device inside the timed region; the headline is the faster one at this batch size
-    best, other = (e2e_zc, e2e_slab) if e2e_zc["value"] >= e2e_slab["value"] else (e2e_slab, e2e_zc)
-    line["e2e"] = best
-    line["e2e_alternative"] = other
+    # third form: the same call and the same caller-owned pinned buffers with the resident step server on (dn_host_server): the
+    # step kernel stays on the GPU between calls, the host rings a doorbell word per step instead of launching
+    forms = {"zero_copy": e2e_zc, "slab_graph": e2e_slab}
+    try:
+        env.host_server(args.server_idle_us)
+        s0 = env.host_server_stats()
+        srv_sec, srv_reps, srv_launches = e2e_measure(lambda k: env.step_host(ios[k]))
+        s1 = env.host_server_stats()
+        env.host_server(0)
+        forms["server"] = {"value": world * N * K / srv_sec, "unit": UNIT, "h2d_bytes_per_step": N * 16, "d2h_bytes_per_step": N * (D * 4 + 4 + 1 + 4),
+                           "us_per_step": 1e6 * srv_sec / K, "reps": srv_reps, "gpu_launches": int(srv_launches),
+                           "server_steps": s1["steps"] - s0["steps"], "server_residencies": s1["residencies"] - s0["residencies"],
+                           "server_idle_us": args.server_idle_us, "reward_checksum": float(h_rew[:8].sum()),
+                           "api": "dn_host_server + dn_step_host (C ABI) with caller-owned pinned host buffers: the step kernel (dn_step_many "
+                                  "variant) is RESIDENT; per step the host writes that step's actions, rings a doorbell word in pinned memory "
+                                  "and polls the completion word; the kernel reads the actions from and writes obs, reward, found_targets, "
+                                  "done to host memory over PCIe (64 KiB in, 244 KiB out per step) -- no launch per step"}
+    except Exception as ex:  # noqa: BLE001
+        forms["server"] = {"error": str(ex)[:200], "value": 0.0}
+    # all forms move the same bytes between host and device inside the timed region; the headline is the fastest one at this batch size
+    order = sorted(forms, key=lambda k: -forms[k]["value"])
+    line["e2e"] = dict(forms[order[0]], form=order[0])
+    line["e2e_alternative"] = dict(forms[order[1]], form=order[1])
+    line["e2e_forms"] = {k: {kk: v.get(kk) for kk in ("value", "us_per_step", "gpu_launches", "error") if kk in v} for k, v in forms.items()}
     if world == 1:
         # the staged variant of the same call (pageable numpy buffers: H2D copy -> kernel -> D2H copies)
         p_act = h_act.numpy().copy()
@@ -830,21 +850,24 @@ def run_b200(args):
             import copy
             a0 = copy.copy(args); a0.substeps, a0.track = 1, "circle"
             t12, i12, d12, c12 = track_setup("circle")
-            v12 = GpuDroneVecEnv(12, t12, aviary_dim=d12, initial_xyzs=i12, pyb_freq=240, ctrl_freq=240, circle=c12,
-                                 include_distance=True, normalize_actions=True, normalize_obs=True, device=dev)
-            v12.reset()
             a12 = (np.random.default_rng(0).uniform(-1, 1, size=(64, 12, 4))).astype(np.float32)
-            for k in range(200):
-                v12.step(a12[k % 64])
-            t0 = time.perf_counter()
-            k12 = 3000
-            for k in range(k12):
-                v12.step(a12[k % 64])
-            dt12 = time.perf_counter() - t0
-            line["e2e_vecenv_config1"] = {"value": 12 * k12 / dt12, "unit": UNIT, "us_per_step": 1e6 * dt12 / k12, "num_envs": 12,
-                                          "substeps": 1, "api": "GpuDroneVecEnv.step, README configuration (12 envs, 240/240 Hz)",
+            k12, us12 = 3000, {}
+            for path in ("zero_copy", "server"):
+                v12 = GpuDroneVecEnv(12, t12, aviary_dim=d12, initial_xyzs=i12, pyb_freq=240, ctrl_freq=240, circle=c12,
+                                     include_distance=True, normalize_actions=True, normalize_obs=True, device=dev, host_path=path)
+                v12.reset()
+                for k in range(200):
+                    v12.step(a12[k % 64])
+                t0 = time.perf_counter()
+                for k in range(k12):
+                    v12.step(a12[k % 64])
+                us12[path] = 1e6 * (time.perf_counter() - t0) / k12
+                v12.close()
+            best12 = min(us12, key=us12.get)
+            line["e2e_vecenv_config1"] = {"value": 12 * 1e6 / us12[best12], "unit": UNIT, "us_per_step": us12[best12], "num_envs": 12,
+                                          "substeps": 1, "host_path": best12, "us_per_step_by_host_path": us12,
+                                          "api": "GpuDroneVecEnv.step, README configuration (12 envs, 240/240 Hz)",
                                           "note": "the reference's 4 h / 1e7 steps anecdote corresponds to ~700 env-steps/s end to end incl. PPO"}
-            v12.close()
         except Exception as ex:  # noqa: BLE001
             line["e2e_vecenv_config1"] = {"error": str(ex)[:200]}
 
@@ -902,6 +925,8 @@ def main():
                     help="learner lines on raw observations (labelled deviation; the reference always normalises, PBDroneSimulator.py:181)")
     ap.add_argument("--ppo-precision", default="bf16x3", choices=["bf16x3", "bf16"], help="arithmetic of the fused PPO update's contractions")
     ap.add_argument("--ppo-impl", default="auto", choices=["auto", "fused", "torch"])
+    ap.add_argument("--server-idle-us", type=int, default=2000,
+                    help="idle time after which the resident step server of the e2e 'server' form leaves the GPU")
     ap.add_argument("--rotating-handles", type=int, default=None,
                     help="override the number of rotating handles of the headline measurement (default: enough for > 126 MB; "
                          "the ncu launch-list pass uses a small number so that the capture window covers the timed region)")

@@ -116,6 +116,8 @@ SYMBOLS = {
     "dn_host_buffers": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(dn_step_io)]),
     "dn_step_host_async": (C.c_int, [C.c_void_p, C.POINTER(dn_step_io)]),
     "dn_step_host_wait": (C.c_int, [C.c_void_p]),
+    "dn_host_server": (C.c_int, [C.c_void_p, C.c_int]),
+    "dn_host_server_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dn_action_to_rpm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dn_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                          C.c_int32, C.c_int32, C.c_void_p]),

@@ -212,6 +212,16 @@ class BatchedDroneEnv:
     def step_host_wait(self) -> None:
         L.check(self._lib.dn_step_host_wait(self._handle), "dn_step_host_wait")
 
+    def host_server(self, idle_us: int) -> None:
+        """dn_host_server: keep the step kernel resident between :meth:`step_host` calls on pinned, device-mapped buffers
+        (no launch per step); it leaves after ``idle_us`` microseconds without a step.  0 switches it off."""
+        L.check(self._lib.dn_host_server(self._handle, int(idle_us)), "dn_host_server")
+
+    def host_server_stats(self):
+        r, s = C.c_int64(0), C.c_int64(0)
+        L.check(self._lib.dn_host_server_stats(self._handle, C.byref(r), C.byref(s)), "dn_host_server_stats")
+        return {"residencies": int(r.value), "steps": int(s.value)}
+
     def step_many(self, actions: torch.Tensor, per_step_outputs: bool = True, out: Optional[Dict] = None):
         """T control steps in one launch (state stays in registers); actions [T, N, 4]."""
         T = int(actions.shape[0])

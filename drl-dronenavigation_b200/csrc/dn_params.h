@@ -139,6 +139,15 @@ struct StepIO {
     unsigned int* done_counter;   // device, zero between launches
     unsigned int* host_flag;      // device alias of the pinned word; nullptr: not a host call
     unsigned int  seq;
+    // resident step server (dn_host_server; MULTI kernels only): the kernel stays on the GPU between host steps.  The host rings
+    // `srv_doorbell` (pinned + mapped) with (sequence << 48) | device pointer of the step's actions (pointer 0: quit); CTA 0 polls
+    // it and publishes every command -- or, after `srv_idle_us` without one, "leave" -- through `srv_cmd` (device memory) to the
+    // other CTAs, so that all CTAs run exactly the same steps; completion of a step = the sequence number in `host_flag`.
+    unsigned long long* srv_doorbell;
+    unsigned long long* srv_cmd;
+    unsigned long long  srv_word0;    // the word `srv_cmd` holds at launch (the last command of the previous residency)
+    unsigned int        srv_idle_us;
 };
+constexpr unsigned long long kSrvPtrMask = (1ull << 48) - 1ull;
 
 }  // namespace dn

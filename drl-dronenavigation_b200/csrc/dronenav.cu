@@ -53,6 +53,61 @@ __device__ __forceinline__ void bulk_store_g2s_commit(void* gdst, const void* ss
 __device__ __forceinline__ void bulk_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// resident step server: polling loads (host doorbell / device command word), the step's actions straight from host memory (the
+// same host addresses are read again in later steps of the SAME kernel: never through the non-coherent path), timer for the idle bound
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// The next command of the resident step server, the same for every thread of every CTA.  0 in the pointer field = leave.
+// Every wait is bounded: the leader leaves after `srv_idle_us` without a command (and publishes that), the others after the
+// leader says so -- or, as a last resort, after a spin cap (a kernel that cannot hear its leader must not stay forever).
+__device__ __forceinline__ unsigned long long srv_next_command(const StepIO& io, unsigned long long last, unsigned long long* s_cmd, int tid) {
+    if (tid == 0) {
+        unsigned long long w = last;
+        if (blockIdx.x == 0) {
+            const unsigned long long t0 = globaltimer_ns(), idle_ns = 1000ull * io.srv_idle_us;
+            unsigned int spins = 0;
+            for (;;) {
+                w = ld_volatile_u64(io.srv_doorbell);
+                if ((w >> 48) != (last >> 48)) break;
+                ++spins;
+                if (((spins & 15u) == 0u && globaltimer_ns() - t0 > idle_ns) || spins > (1u << 24)) { w = last & ~kSrvPtrMask; break; }
+            }
+            st_release_gpu_u64(io.srv_cmd, w);
+        } else {
+            unsigned int spins = 0;
+            for (;;) {
+                w = ld_acquire_gpu_u64(io.srv_cmd);
+                if (w != last) break;
+                if (++spins > (1u << 26)) { w = last & ~kSrvPtrMask; break; }
+            }
+        }
+        *s_cmd = w;
+    }
+    __syncthreads();
+    return *s_cmd;
+}
+
 // fire-and-forget L2 prefetch: raises the number of DRAM requests in flight without holding registers
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
@@ -151,12 +206,20 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
         }
     }
     BlockAcc acc = {0.f, 0, 0, 0, 0};            // this thread's finished episodes over the launch
+    __shared__ unsigned long long srv_cmd_s;
+    const bool srv = MULTI && io.srv_doorbell != nullptr;      // resident step server: one host command per loop iteration
+    unsigned long long srv_word = io.srv_word0;
 
     for (int t = 0; t < num_steps; ++t) {
-        const bool write_out = per_step || (t == num_steps - 1);
+        if (MULTI && srv) {
+            srv_word = srv_next_command(io, srv_word, &srv_cmd_s, tid);
+            if ((srv_word & kSrvPtrMask) == 0ull) break;             // quit / idle: every CTA leaves after the same step
+        }
+        const bool write_out = per_step || (t == num_steps - 1) || srv;
         const size_t o = (per_step ? static_cast<size_t>(t) * P.n : 0) + i;      // output element index of this env
         if (active) {
-            const float4 act = __ldg(io.actions + static_cast<size_t>(t) * P.n + i);
+            const float4 act = (MULTI && srv) ? ld_volatile_f4(reinterpret_cast<const float4*>(srv_word & kSrvPtrMask) + i)
+                                              : __ldg(io.actions + static_cast<size_t>(t) * P.n + i);
             const StepResult r = env_step<PHYS, FULL>(P, i, s, act, last_rpm_sum, obs_row,   // obs_row: obs of the step (terminal obs if finished)
                                                 MULTI ? nullptr : &aux_stage[tid], kBlock);
             float* term_out = (write_out && r.finished && io.terminal_obs) ? io.terminal_obs + o * D : nullptr;
@@ -263,7 +326,25 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
                 }
             }
         }
+        if (MULTI && srv) {
+            // the step is complete for the host when every CTA's stores (bulk stores of the observation rows included) are
+            // visible system-wide: count this CTA done; the last one writes the step's sequence number to the pinned word
+            flush_stats(P, acc, tid);
+            acc = BlockAcc{0.f, 0, 0, 0, 0};
+            if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned int prev = atomicAdd(io.done_counter, 1u);
+                if (prev == gridDim.x - 1) {
+                    *io.done_counter = 0u;
+                    __threadfence_system();
+                    *reinterpret_cast<volatile unsigned int*>(io.host_flag) = static_cast<unsigned int>(srv_word >> 48);
+                }
+            }
+        }
     }
+    if (MULTI && srv) return;
     flush_stats(P, acc, tid);
     if (io.host_flag != nullptr) {
         // Host call on mapped host buffers: completion is announced through host memory.  Every thread's stores (the bulk
@@ -667,6 +748,7 @@ struct dn_env {
     dn_step_io host_seen;   // last host io whose pointers were classified
     dn_step_io host_mapped; // device aliases of those pointers when all of them are pinned + mapped (UVA)
     int host_direct;        // 1: the kernel reads / writes the caller's pinned buffers directly (zero copy)
+    const void* ptr_cache_h[32]; void* ptr_cache_d[32]; int ptr_cache_n; unsigned ptr_cache_next;   // pinned + mapped pointers seen so far
     // dn_host_buffers: handle-owned pinned slab + device slab, stepped by replaying one captured graph
     char* slab_h; char* slab_d;
     size_t slab_out_off, slab_out_bytes, slab_seq_off;   // outputs [slab_out_off, +slab_out_bytes) incl. the completion word
@@ -679,11 +761,23 @@ struct dn_env {
     unsigned int* zc_flag_h; unsigned int* zc_flag_d; unsigned int* zc_counter; unsigned int zc_seq;
     int zc_signal;          // launch_step: pass the completion word to the kernel (set around the zero-copy launch only)
     int zc_signalled;       // the launch in flight announces completion through the word (else: poll the stream)
+    // resident step server (dn_host_server): a dn_step_many kernel that stays on the GPU and takes one host command per step
+    int srv_idle_us;        // > 0: dn_step_host on pinned + mapped buffers goes through the server
+    int srv_alive;          // a server kernel has been launched on srv_stream and has not been seen to finish
+    int srv_launch;         // launch_step: fill the server fields of StepIO (set around the server launch only)
+    cudaStream_t srv_stream;
+    unsigned long long* srv_doorbell_h; unsigned long long* srv_doorbell_d;   // pinned + mapped
+    unsigned long long* srv_word_h;     // pinned staging word for the initial value of srv_cmd
+    unsigned long long* srv_cmd;        // device
+    unsigned int srv_seq;   // sequence number of the last command (16 bits, never 0)
+    dn_step_io srv_io;      // mapped output pointers the running server writes
+    long long srv_launches, srv_steps;
 };
 
 static thread_local std::string g_err;
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
 int dn_internal_fail(int code, const std::string& msg) { return fail(code, msg); }   // other translation units (ppo_update.cu)
 
 #define DN_CUDA(expr)                                                                    \
@@ -715,6 +809,8 @@ inline cudaError_t spin_until_done(cudaStream_t st) {
 }  // namespace
 
 extern "C" {
+
+static int srv_quiesce(dn_env* env);     // stops the resident step server (if one is running) before anything else touches the state
 
 int dn_abi_version(void) { return DN_ABI_VERSION; }
 const char* dn_last_error(void) { return g_err.c_str(); }
@@ -827,7 +923,11 @@ int dn_create(const dn_config* cfg, int device, dn_env** out) {
 
 int dn_destroy(dn_env* env) {
     if (!env) return DN_OK;
+    srv_quiesce(env);
     DeviceGuard guard(env->device);
+    if (env->srv_stream) cudaStreamDestroy(env->srv_stream);
+    if (env->srv_doorbell_h) cudaFreeHost(env->srv_doorbell_h);
+    if (env->srv_cmd) cudaFree(env->srv_cmd);
     cudaFree(env->state_mem); cudaFree(env->d_targets); cudaFree(env->d_segs); cudaFree(env->d_stats);
     cudaFree(env->d_block_stats);
     if (env->stage) cudaFree(env->stage);
@@ -848,6 +948,7 @@ int64_t dn_launch_count(const dn_env* env) { return env ? env->launches : 0; }
 
 int dn_reset(dn_env* env, const uint8_t* mask, float* obs_out, void* stream) {
     if (!env) return fail(DN_EINVAL, "dn_reset: null handle");
+    { const int rq = srv_quiesce(env); if (rq != DN_OK) return rq; }
     DeviceGuard guard(env->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int N = env->P.n;
@@ -871,6 +972,12 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
     k.found_targets = io->found_targets; k.episode_return = io->episode_return; k.episode_length = io->episode_length;
     k.done_counter = nullptr; k.host_flag = nullptr; k.seq = 0u;
     if (env->zc_signal && num_steps == 1) { k.done_counter = env->zc_counter; k.host_flag = env->zc_flag_d; k.seq = env->zc_seq; }
+    k.srv_doorbell = nullptr; k.srv_cmd = nullptr; k.srv_word0 = 0ull; k.srv_idle_us = 0u;
+    if (env->srv_launch) {
+        k.done_counter = env->zc_counter; k.host_flag = env->zc_flag_d;
+        k.srv_doorbell = env->srv_doorbell_d; k.srv_cmd = env->srv_cmd; k.srv_word0 = *env->srv_word_h;
+        k.srv_idle_us = static_cast<unsigned int>(env->srv_idle_us);
+    }
     const int N = env->P.n;
     const dim3 grid((N + dn::kBlock - 1) / dn::kBlock), block(dn::kBlock);
     const int phys = env->P.physics & 3;
@@ -888,7 +995,7 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
     // two consecutive small grids each get SMs of their own.  With mid-size grids (0.3 - 1 wave) the early-resident
     // CTAs of the next step pile up on the SMs that had free slots, and the step then runs unbalanced (measured:
     // 65 536 envs 7.7 -> 9.8 us, 16 384 envs with drag / ground effect 7.4 -> 9.1 us per replayed step).
-    lc.attrs = attr; lc.numAttrs = (use_pdl && !env->no_pdl && static_cast<int>(grid.x) * 2 <= env->sms) ? 1 : 0;
+    lc.attrs = attr; lc.numAttrs = (use_pdl && !env->no_pdl && !env->srv_launch && static_cast<int>(grid.x) * 2 <= env->sms) ? 1 : 0;
     k.pdl_prefetch = static_cast<int>(lc.numAttrs);
     cudaError_t lerr = cudaSuccess;
     // large batches: persistent software-pipelined kernel (>= 2 tiles per resident CTA, single step, no fused obs-RMS)
@@ -931,9 +1038,13 @@ static int launch_step(dn_env* env, const dn_step_io* io, int num_steps, int per
     return DN_OK;
 }
 
-int dn_step(dn_env* env, const dn_step_io* io, void* stream) { return launch_step(env, io, 1, 1, stream); }
+int dn_step(dn_env* env, const dn_step_io* io, void* stream) {
+    { const int rq = srv_quiesce(env); if (rq != DN_OK) return rq; }
+    return launch_step(env, io, 1, 1, stream);
+}
 
 int dn_step_many(dn_env* env, const dn_step_io* io, int num_steps, int per_step_outputs, void* stream) {
+    { const int rq = srv_quiesce(env); if (rq != DN_OK) return rq; }
     return launch_step(env, io, num_steps, per_step_outputs ? 1 : 0, stream);
 }
 
@@ -948,12 +1059,19 @@ static int host_classify(dn_env* env, const dn_step_io* h) {
     void* dst[8] = {nullptr};
     for (int k = 0; k < 8 && env->host_direct; ++k) {
         if (!src[k]) continue;
+        // callers rotate a few action buffers over fixed output buffers: remember what each pointer turned out to be
+        // (cudaPointerGetAttributes costs about a microsecond per pointer)
+        int hit = -1;
+        for (int c = 0; c < env->ptr_cache_n; ++c) if (env->ptr_cache_h[c] == src[k]) { hit = c; break; }
+        if (hit >= 0) { dst[k] = env->ptr_cache_d[hit]; continue; }
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, src[k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
             cudaGetLastError();
             env->host_direct = 0;
         } else {
             dst[k] = at.devicePointer;
+            const int slot = env->ptr_cache_n < 32 ? env->ptr_cache_n++ : (env->ptr_cache_next++ & 31);
+            env->ptr_cache_h[slot] = src[k]; env->ptr_cache_d[slot] = at.devicePointer;
         }
     }
     if (env->host_direct && (reinterpret_cast<uintptr_t>(dst[0]) & 15u)) env->host_direct = 0;
@@ -1004,8 +1122,121 @@ static int zero_copy_wait(dn_env* env) {
     return DN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Resident step server.  A host step through a kernel LAUNCH costs 13 us before any byte has moved (launch, scheduling,
+// completion hand-off: tools/e2e_breakdown.py).  With dn_host_server(env, idle_us) the step kernel (the dn_step_many variant:
+// state in registers, stored every step) stays resident instead: the host writes the step's actions, rings a doorbell word in
+// pinned memory and polls the completion word; the kernel leaves by itself after `idle_us` without a command and is launched
+// again by the next dn_step_host.  Every other call that touches the handle's state stops the server first (srv_quiesce).
+// ---------------------------------------------------------------------------------------------------------------------------
+static int srv_quiesce(dn_env* env) {
+    if (!env || !env->srv_alive) return DN_OK;
+    DeviceGuard guard(env->device);
+    env->srv_seq = (env->srv_seq % 0xFFFFu) + 1u;
+    *reinterpret_cast<volatile unsigned long long*>(env->srv_doorbell_h) = static_cast<unsigned long long>(env->srv_seq) << 48;   // pointer 0: quit
+    env->srv_alive = 0;
+    DN_CUDA(cudaStreamSynchronize(env->srv_stream));
+    return DN_OK;
+}
+
+static int srv_start(dn_env* env, unsigned int seq_done) {
+    if (!env->srv_stream) {
+        DN_CUDA(cudaStreamCreateWithFlags(&env->srv_stream, cudaStreamNonBlocking));
+        void* hp = nullptr; void* dp = nullptr;
+        DN_CUDA(cudaHostAlloc(&hp, 128, cudaHostAllocMapped));
+        DN_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+        std::memset(hp, 0, 128);
+        env->srv_doorbell_h = static_cast<unsigned long long*>(hp); env->srv_doorbell_d = static_cast<unsigned long long*>(dp);
+        env->srv_word_h = env->srv_doorbell_h + 8;
+        DN_CUDA(cudaMalloc(reinterpret_cast<void**>(&env->srv_cmd), 64));
+    }
+    // the command word the kernel starts from: "step seq_done has been run" (any non-zero pointer field)
+    *env->srv_word_h = (static_cast<unsigned long long>(seq_done) << 48) | 1ull;
+    DN_CUDA(cudaMemcpyAsync(env->srv_cmd, env->srv_word_h, 8, cudaMemcpyHostToDevice, env->srv_stream));
+    dn_step_io io = env->srv_io;
+    io.actions = reinterpret_cast<const float*>(env->srv_doorbell_d);   // placeholder (16-byte aligned); the commands carry the real pointer
+    env->srv_launch = 1;
+    const int rc = launch_step(env, &io, 0x7fffffff, 0, env->srv_stream);
+    env->srv_launch = 0;
+    if (rc != DN_OK) return rc;
+    env->srv_alive = 1;
+    env->srv_launches += 1;
+    return DN_OK;
+}
+
+// one step through the server; env->host_mapped holds the mapped pointers of this call
+static int srv_step(dn_env* env) {
+    const dn_step_io& m = env->host_mapped;
+    if (reinterpret_cast<uintptr_t>(m.actions) >> 48) return fail(DN_EINVAL, "dn_step_host: device pointer does not fit the doorbell word");
+    dn_step_io outs = m; outs.actions = nullptr;
+    if (env->srv_alive && std::memcmp(&outs, &env->srv_io, sizeof(outs)) != 0) {      // other output buffers: new residency
+        const int rq = srv_quiesce(env);
+        if (rq != DN_OK) return rq;
+    }
+    if (!env->zc_flag_h) {
+        void* hp = nullptr; void* dp = nullptr;
+        DN_CUDA(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+        DN_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+        std::memset(hp, 0, 64);
+        env->zc_flag_h = static_cast<unsigned int*>(hp); env->zc_flag_d = static_cast<unsigned int*>(dp);
+        DN_CUDA(cudaMalloc(reinterpret_cast<void**>(&env->zc_counter), 64));
+        DN_CUDA(cudaMemset(env->zc_counter, 0, 64));
+    }
+    const unsigned int prev = env->srv_seq;
+    const unsigned int seq = (prev % 0xFFFFu) + 1u;
+    if (!env->srv_alive) {
+        env->srv_io = outs;
+        *reinterpret_cast<volatile unsigned int*>(env->zc_flag_h) = 0u;
+        const int rs = srv_start(env, prev);
+        if (rs != DN_OK) return rs;
+    }
+    env->srv_seq = seq;
+    volatile unsigned int* flag = env->zc_flag_h;
+    *reinterpret_cast<volatile unsigned long long*>(env->srv_doorbell_h) =
+        (static_cast<unsigned long long>(seq) << 48) | static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(m.actions));
+    uint32_t spins = 0, restarts = 0;
+    while (*flag != seq) {
+        if ((++spins & 0x3FFFu) == 0u) {
+            // the server may have left (idle) just before the doorbell rang: its stream is then idle -- start another residency,
+            // which finds the pending command at once.  An error on the stream must surface, not spin.
+            const cudaError_t e = cudaStreamQuery(env->srv_stream);
+            if (e == cudaErrorNotReady) continue;
+            if (*flag == seq) break;
+            env->srv_alive = 0;
+            if (e != cudaSuccess) return fail(DN_ECUDA, std::string("dn_step_host (server): ") + cudaGetErrorString(e));
+            if (++restarts > 8u) return fail(DN_ECUDA, "dn_step_host (server): the resident kernel keeps leaving without running the step");
+            const int rs = srv_start(env, prev);
+            if (rs != DN_OK) return rs;
+        }
+    }
+    env->srv_steps += 1;
+    env->launches += 0;
+    return DN_OK;
+}
+
+int dn_host_server(dn_env* env, int idle_us) {
+    if (!env) return fail(DN_EINVAL, "dn_host_server: null handle");
+    if (idle_us < 0 || idle_us > 1000000) return fail(DN_EINVAL, "dn_host_server: idle_us must be in [0, 1000000]");
+    const int rq = srv_quiesce(env);
+    if (rq != DN_OK) return rq;
+    // every CTA of the resident grid must fit on the device at once (they wait for each other's commands)
+    const int grid = (env->P.n + dn::kBlock - 1) / dn::kBlock;
+    if (idle_us > 0 && grid > 4 * env->sms) return fail(DN_EINVAL, "dn_host_server: more environments than a resident grid can hold (4 CTAs per SM)");
+    if (idle_us > 0 && env->use_pipe) return fail(DN_EINVAL, "dn_host_server: not with DN_PIPE");
+    env->srv_idle_us = idle_us;
+    return DN_OK;
+}
+
+int dn_host_server_stats(dn_env* env, int64_t* residencies, int64_t* steps) {
+    if (!env) return fail(DN_EINVAL, "dn_host_server_stats: null handle");
+    if (residencies) *residencies = env->srv_launches;
+    if (steps) *steps = env->srv_steps;
+    return DN_OK;
+}
+
 int dn_host_buffers(dn_env* env, int with_episode_info, dn_step_io* out) {
     if (!env || !out) return fail(DN_EINVAL, "dn_host_buffers: null argument");
+    { const int rq = srv_quiesce(env); if (rq != DN_OK) return rq; }
     DeviceGuard guard(env->device);
     if (!env->host_stream) DN_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
     if (env->slab_h && (env->slab_io_h.terminal_obs != nullptr) != (with_episode_info != 0)) {
@@ -1058,6 +1289,7 @@ int dn_host_buffers(dn_env* env, int with_episode_info, dn_step_io* out) {
 int dn_step_host_async(dn_env* env, const dn_step_io* h) {
     if (!env || !h) return fail(DN_EINVAL, "dn_step_host_async: null argument");
     if (env->slab_pending) return fail(DN_EINVAL, "dn_step_host_async: the previous step has not been waited for");
+    { const int rq = srv_quiesce(env); if (rq != DN_OK) return rq; }
     if (!env->slab_h || std::memcmp(h, &env->slab_io_h, sizeof(*h)) != 0) {
         // caller-owned buffers: only the zero-copy form (pinned + mapped) can be left in flight
         if (!h->actions || !h->obs || !h->reward || !h->done) return fail(DN_EINVAL, "dn_step_host_async: actions/obs/reward/done are required");
@@ -1142,6 +1374,11 @@ int dn_step_host(dn_env* env, const dn_step_io* h) {
         const int rc = host_classify(env, h);
         if (rc != DN_OK) return rc;
     }
+    if (env->host_direct && env->srv_idle_us > 0) return srv_step(env);
+    {
+        const int rq = srv_quiesce(env);
+        if (rq != DN_OK) return rq;
+    }
     if (env->host_direct) {
         const int rc = zero_copy_launch(env);
         return rc != DN_OK ? rc : zero_copy_wait(env);
@@ -1202,6 +1439,7 @@ int dn_gae(const float* rewards, const float* values, const uint8_t* done, const
 
 static int state_xfer(dn_env* env, const dn_state_view* v, bool set, void* stream) {
     if (!env || !v) return fail(DN_EINVAL, "dn_get/set_state: null argument");
+    { const int rq = srv_quiesce(env); if (rq != DN_OK) return rq; }
     DeviceGuard guard(env->device);
     dn::StateView V;
     V.pos = v->pos; V.quat = v->quat; V.vel = v->vel; V.rpy_rates = v->rpy_rates; V.ang_v = v->ang_v;
@@ -1223,6 +1461,7 @@ int dn_set_state(dn_env* env, const dn_state_view* view, void* stream) { return 
 
 int dn_episode_stats(dn_env* env, dn_stats* host_out, int clear, void* stream) {
     if (!env || !host_out) return fail(DN_EINVAL, "dn_episode_stats: null argument");
+    { const int rq = srv_quiesce(env); if (rq != DN_OK) return rq; }
     DeviceGuard guard(env->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dn::Stats h;

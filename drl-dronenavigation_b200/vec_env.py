@@ -65,8 +65,9 @@ class GpuDroneVecEnv(_SB3VecEnv):
         self.collect_rollouts = bool(collect_rollouts)
         self._host_norm = bool(normalize_obs) and self.collect_rollouts
         self.host_path = env_kwargs.pop("host_path", "zero_copy")
-        if self.host_path not in ("zero_copy", "slab"):
+        if self.host_path not in ("zero_copy", "slab", "server"):
             raise ValueError(f"host_path={self.host_path!r}")
+        server_idle_us = int(env_kwargs.pop("server_idle_us", 2000))
         self.core = BatchedDroneEnv(num_envs, target_points, threshold=threshold, discount=discount,
                                     max_steps=max_steps, aviary_dim=aviary_dim,
                                     include_distance=include_distance, normalize_actions=normalize_actions,
@@ -82,7 +83,10 @@ class GpuDroneVecEnv(_SB3VecEnv):
         #   "zero_copy" (default): pinned, device-mapped buffers of this object; the fused kernel reads the actions and writes the
         #                results over PCIe itself and its last CTA writes the completion word the host polls (measured faster
         #                at every batch size up to 4096 envs: 24 vs 35 us per step);
-        #   "slab":      the handle's own pinned slab, one captured graph = H2D DMA, kernel, D2H DMA.
+        #   "slab":      the handle's own pinned slab, one captured graph = H2D DMA, kernel, D2H DMA;
+        #   "server":    the zero-copy buffers, stepped by the RESIDENT kernel (dn_host_server): no launch per step; the kernel
+        #                leaves after `server_idle_us` without a step and comes back with the next one.  step_async only stores
+        #                the actions; step_wait rings the doorbell and waits.
         if self.host_path == "slab":
             self._host_io, hb = self.core.host_buffers(with_episode_info=True)
         else:
@@ -103,6 +107,8 @@ class GpuDroneVecEnv(_SB3VecEnv):
             self.rollout_paths = [os.path.join(rollout_dir, f"rollout_{base + 1 + i}.txt") for i in range(N)]
             self._rms_mean, self._rms_var = np.zeros((N, D)), np.ones((N, D))         # normalize.RunningMeanStd per env
             self._rms_count = np.full(N, 1e-4)
+        if self.host_path == "server":
+            self.core.host_server(server_idle_us)
         torch.cuda.synchronize(self.core.device)
         self._t_start = time.time()
         self._pending = False
@@ -141,14 +147,18 @@ class GpuDroneVecEnv(_SB3VecEnv):
     def step_async(self, actions: np.ndarray) -> None:
         a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 4)
         self._h_actions[...] = a
-        self.core.step_host_async(self._host_io)
+        if self.host_path != "server":
+            self.core.step_host_async(self._host_io)
         self._pending = True
 
     def step_wait(self):
         if not self._pending:
             raise RuntimeError("step_wait() called without step_async()")
         self._pending = False
-        self.core.step_host_wait()
+        if self.host_path == "server":
+            self.core.step_host(self._host_io)
+        else:
+            self.core.step_host_wait()
         obs = self._h_obs.copy()
         rews = self._h_rew.copy()
         bits = self._h_done

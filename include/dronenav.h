@@ -244,6 +244,19 @@ int dn_host_buffers(dn_env* env, int with_episode_info, dn_step_io* out);
 int dn_step_host_async(dn_env* env, const dn_step_io* host_io);
 int dn_step_host_wait(dn_env* env);
 
+/* Resident step server for the zero-copy form of dn_step_host (pinned, device-mapped caller buffers).  A host step through a
+ * kernel launch costs ~13 us on a B200 before a byte has moved (launch, scheduling, completion hand-off).  With idle_us > 0 the
+ * step kernel (the dn_step_many variant) stays RESIDENT on the GPU instead: dn_step_host writes the step's actions pointer and a
+ * sequence number to a doorbell word in pinned memory and polls the completion word; no launch per step.  The kernel leaves by
+ * itself after `idle_us` microseconds without a command (so a device-wide synchronise elsewhere in the process waits at most
+ * that long) and the next dn_step_host launches it again; every other call on the handle stops it first.  All CTAs of the
+ * resident grid must fit on the device at once: DN_EINVAL above 4 CTAs (256 environments) per SM.  idle_us = 0 switches the
+ * server off (the default).  What SB3's SubprocVecEnv workers are to the reference -- processes that stay alive between
+ * steps and wait on a pipe (Sol/Model/PBDroneSimulator.py:171-200) -- this is to the GPU path.
+ * dn_host_server_stats: how many residencies (kernel launches) and steps the server has run. */
+int dn_host_server(dn_env* env, int idle_us);
+int dn_host_server_stats(dn_env* env, int64_t* residencies, int64_t* steps);
+
 /* The action map alone, elementwise over `n` action components (device pointers):
  * PBDroneEnv._preprocessAction(rescale_action(a)) (PBDroneEnv.py:872-895,949-971) or the RPM map
  * (BaseSingleAgentAviary.py:176-179), whichever the handle was created with.  Bit-identical to

@@ -295,6 +295,73 @@ def test_step_host_slab_graph_path_equals_device_step(N, with_info):
         e.close()
 
 
+@pytest.mark.parametrize("N,norm,idle_us", [(777, False, 2000), (4096, True, 2000), (12, True, 50), (1, False, 2000)])
+def test_step_host_resident_server_equals_device_step(N, norm, idle_us):
+    """dn_host_server: the RESIDENT step kernel (dn_step_many variant, one host doorbell per step) == dn_step launch by launch --
+    every output bit for bit, with rotating action buffers, across idle exits and re-launches of the resident kernel, and with
+    other calls on the handle (episode statistics, get_state, a plain device step) in between."""
+    import time
+    envs = [_make("circle", N, 8, normalize_obs=norm)[0] for _ in range(2)]
+    for e in envs:
+        e.reset()
+    D, T = 13, 40
+    acts = _actions("saturating", T, N, seed=9)
+    pin = lambda *s, dtype: torch.empty(*s, dtype=dtype).pin_memory()
+    h_act = pin(4, N, 4, dtype=torch.float32)
+    h = dict(o=pin(N, D, dtype=torch.float32), r=pin(N, dtype=torch.float32), d=pin(N, dtype=torch.uint8), t=pin(N, D, dtype=torch.float32),
+             f=pin(N, dtype=torch.int32), er=pin(N, dtype=torch.float32), el=pin(N, dtype=torch.int32))
+    ios = [envs[1]._make_io(h_act[k], h["o"], h["r"], h["d"], h["t"], h["f"], h["er"], h["el"]) for k in range(4)]
+    envs[1].host_server(idle_us)
+    n_done = 0
+    for t in range(T):
+        a_dev = torch.from_numpy(acts[t]).cuda()
+        o, r, d, f = envs[0].step(a_dev)
+        if t == 25:                                               # a plain device step in between stops the server first
+            o1, r1, d1, f1 = envs[1].step(a_dev)
+            torch.cuda.synchronize()
+            for x, y in ((o, o1), (r, r1), (d, d1), (f, f1)):
+                assert torch.equal(x, y)
+            continue
+        h_act[t % 4].copy_(torch.from_numpy(acts[t]))
+        envs[1].step_host(ios[t % 4])
+        for name, dev_t in (("o", o), ("r", r), ("d", d), ("f", f)):
+            np.testing.assert_array_equal(h[name].numpy(), dev_t.cpu().numpy(), err_msg=f"{name} t={t}")
+        done = d.cpu().numpy() != 0
+        n_done += int(done.sum())
+        np.testing.assert_array_equal(h["t"].numpy()[done], envs[0].terminal_obs.cpu().numpy()[done])
+        np.testing.assert_array_equal(h["el"].numpy()[done], envs[0].episode_length.cpu().numpy()[done])
+        np.testing.assert_array_equal(h["er"].numpy()[done], envs[0].episode_return.cpu().numpy()[done])
+        if t == 10:
+            time.sleep(0.02)                                      # longer than idle_us: the kernel has left, the next step re-launches it
+        if t == 18:                                               # statistics are flushed per step and readable at any time
+            assert envs[1].episode_stats(clear=False) == envs[0].episode_stats(clear=False)
+        if t == 30:
+            sa, sb = envs[0].get_state(), envs[1].get_state()
+            for k in sa:
+                assert torch.equal(sa[k], sb[k]), k
+    st = envs[1].host_server_stats()
+    assert st["steps"] == T - 1 and 3 <= st["residencies"] <= T - 1, st    # first launch, after the sleep, after each interleaved call
+    envs[1].host_server(0)
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert envs[1].episode_stats() == envs[0].episode_stats()
+    assert n_done > 0 or N <= 12
+    for e in envs:
+        e.close()
+
+
+def test_step_host_resident_server_limits():
+    from drl_dronenavigation_b200 import _lib as L
+    from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
+    from oracle.dyn_oracle import make_reference_env
+    ref = make_reference_env("circle")
+    env = BatchedDroneEnv(1 << 18, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS, circle=True)
+    with pytest.raises(L.DroneNavError, match="resident grid"):
+        env.host_server(1000)
+    env.close()
+
+
 def test_ragged_sizes_and_obs12():
     """N not a multiple of the CTA size (tail CTA takes the non-TMA store path), N = 1, 12-dim obs."""
     from drl_dronenavigation_b200.batched_env import BatchedDroneEnv
