@@ -44,7 +44,9 @@ constexpr uint32_t RING_BYTES = 131072;              // operand ring (>= 2 stage
 constexpr uint32_t EPI_BUF_BYTES = 4096;             // one chunk: 32 rows x 32 columns, hi plane (2 KB) | lo plane (2 KB)
 constexpr uint32_t EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;
 constexpr int MAX_COLSUM_COLS = 512;                 // widest DGRAD result whose column sums fit the shared-memory accumulator
-constexpr uint32_t COLSUM_BYTES = 4 * MAX_COLSUM_COLS * 4;
+constexpr int GROUP_FLOATS = 4 * MAX_COLSUM_COLS;      // shared-memory floats per problem of a launch (column sums [4][ld_out] / the bias vector)
+constexpr int MAX_GROUPS = 2;                         // problems of identical shape in one launch (the policy and the value net)
+constexpr uint32_t COLSUM_BYTES = MAX_GROUPS * GROUP_FLOATS * 4;
 constexpr uint32_t BAR_BYTES = 512;
 constexpr uint32_t SMEM_BYTES = 1024 /* alignment slack */ + RING_BYTES + EPI_BYTES + COLSUM_BYTES + BAR_BYTES;
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the even CTA of a pair
@@ -65,6 +67,13 @@ struct GemmArgs {
     long long slice_stride;         // elements between slices of `partial`
     float* colsum;                  // DGRAD, optional: [gridDim.x][ld_out] column sums of the FP32 result over this CTA's tiles
                                     // (= this CTA's share of the bias gradient of the layer below)
+    // Two problems of IDENTICAL shape in one launch (the policy net's and the value net's layer l): tiles [0, T) belong to the
+    // first problem (tensor maps 1..4 of the kernel, the pointers above), tiles [T, 2T) to the second (maps 5..8, the pointers
+    // below).  One wave quantisation instead of two: 256 tiles on 74 CTA pairs are 4 rounds, 512 tiles are 7.
+    int groups;                     // 1 or 2
+    const float* bias2;
+    float* partial2;
+    float* colsum2;
     int dbg;                        // DN_MLP_DBG (tools/micro/epilogue_probe.py only): 1 no activation math, 2 no staging / stores,
                                     // 4 no MMAs (epilogue cost alone), 8 no epilogue TMEM loads
 };
@@ -316,7 +325,8 @@ __device__ __forceinline__ void stage_split32(const float (&y)[32], uint8_t* buf
 template <int KIND, int BN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-          const __grid_constant__ CUtensorMap tmH, const GemmArgs g) {
+          const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+          const __grid_constant__ CUtensorMap tmC2, const __grid_constant__ CUtensorMap tmH2, const GemmArgs g) {
     static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256 && (CG == 1 || CG == 2) && (BN / CG) % 64 == 0, "tile shape");
     constexpr int BNL = BN / CG;                          // rows (K-major) / columns (MN-major) of B this CTA loads
     constexpr uint32_t A_BYTES = BM * BK * 2;             // one plane of the A tile: 16 KB
@@ -341,7 +351,8 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int planes = (g.passes == 3) ? 2 : 1;
     const uint32_t stage_bytes = planes * (A_BYTES + B_BYTES);
     const int stages = (RING_BYTES / stage_bytes) > MAX_STAGES ? MAX_STAGES : static_cast<int>(RING_BYTES / stage_bytes);
-    const int total_tiles = g.m_tiles * g.n_tiles * g.slices;
+    const int group_tiles = g.m_tiles * g.n_tiles * g.slices;     // tiles of one problem
+    const int total_tiles = group_tiles * g.groups;
 
     // Programmatic dependent launch (launch_one sets the attribute): the next kernel of the stream may be scheduled as soon as
     // this one's CTAs leave their SMs, and this kernel sets up (barriers, TMEM, descriptors) while its predecessor drains;
@@ -353,6 +364,12 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tma_prefetch_desc(&tmB);
         if constexpr (KIND != K_WGRAD) tma_prefetch_desc(&tmC);
         if constexpr (KIND == K_DGRAD) tma_prefetch_desc(&tmH);
+        if (g.groups > 1) {
+            tma_prefetch_desc(&tmA2);
+            tma_prefetch_desc(&tmB2);
+            if constexpr (KIND != K_WGRAD) tma_prefetch_desc(&tmC2);
+            if constexpr (KIND == K_DGRAD) tma_prefetch_desc(&tmH2);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -371,10 +388,12 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if constexpr (KIND == K_DGRAD) {
         if (g.colsum != nullptr)
-            for (int i = threadIdx.x; i < 4 * g.ld_out; i += NUM_THREADS) colsum_s[i] = 0.0f;
+            for (int gi = 0; gi < g.groups; ++gi)
+                for (int i = threadIdx.x; i < 4 * g.ld_out; i += NUM_THREADS) colsum_s[gi * GROUP_FLOATS + i] = 0.0f;
     }
     if constexpr (KIND == K_FWD) {                       // the layer's bias vector (<= 512 entries) next to the epilogue warps
-        for (int i = threadIdx.x; i < g.ld_out; i += NUM_THREADS) colsum_s[i] = __ldg(g.bias + i);
+        for (int gi = 0; gi < g.groups; ++gi)
+            for (int i = threadIdx.x; i < g.ld_out; i += NUM_THREADS) colsum_s[gi * GROUP_FLOATS + i] = __ldg((gi ? g.bias2 : g.bias) + i);
     }
     tc_fence_before();
     __syncthreads();
@@ -388,7 +407,11 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             int stage = 0;
             uint32_t phase = 0;
             for (int t = cid; t < total_tiles; t += ncl) {
-                const int nt = t % g.n_tiles, mt = (t / g.n_tiles) % g.m_tiles, sl = t / (g.n_tiles * g.m_tiles);
+                const bool g2 = t >= group_tiles;
+                const int tt = g2 ? t - group_tiles : t;
+                const CUtensorMap* mA = g2 ? &tmA2 : &tmA;
+                const CUtensorMap* mB = g2 ? &tmB2 : &tmB;
+                const int nt = tt % g.n_tiles, mt = (tt / g.n_tiles) % g.m_tiles, sl = tt / (g.n_tiles * g.m_tiles);
                 const int m0 = (mt * CG + rank) * BM;             // this CTA's accumulator rows
                 const int n0 = nt * BN + rank * BNL;              // this CTA's share of the B tile
                 const int kb0 = (KIND == K_WGRAD) ? static_cast<int>(static_cast<long long>(sl) * g.k_blocks / g.slices) : 0;
@@ -404,21 +427,21 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         uint8_t* da = sa + p * A_BYTES;
                         uint8_t* db = sb + p * B_BYTES;
                         if constexpr (KIND == K_FWD) {
-                            tma_load_2d<CG>(&tmA, &full_bar[stage], da, kb * BK, a_row + m0);                       // X rows, K slice
-                            tma_load_2d<CG>(&tmB, &full_bar[stage], db, kb * BK, b_row + n0);                       // W rows, K slice
+                            tma_load_2d<CG>(mA, &full_bar[stage], da, kb * BK, a_row + m0);                         // X rows, K slice
+                            tma_load_2d<CG>(mB, &full_bar[stage], db, kb * BK, b_row + n0);                         // W rows, K slice
                         } else if constexpr (KIND == K_DGRAD) {
-                            tma_load_2d<CG>(&tmA, &full_bar[stage], da, kb * BK, a_row + m0);                       // dY rows, N slice
+                            tma_load_2d<CG>(mA, &full_bar[stage], da, kb * BK, a_row + m0);                         // dY rows, N slice
 #pragma unroll
                             for (int j = 0; j < BNL / 64; ++j)                                                       // W rows = reduction
-                                tma_load_2d<CG>(&tmB, &full_bar[stage], db + j * MN_BOX_BYTES, n0 + j * 64, b_row + kb * BK);
+                                tma_load_2d<CG>(mB, &full_bar[stage], db + j * MN_BOX_BYTES, n0 + j * 64, b_row + kb * BK);
                         } else {
                             const int r0 = kb * BK;                                                                  // batch rows = reduction
 #pragma unroll
                             for (int j = 0; j < BM / 64; ++j)
-                                tma_load_2d<CG>(&tmA, &full_bar[stage], da + j * MN_BOX_BYTES, m0 + j * 64, a_row + r0);
+                                tma_load_2d<CG>(mA, &full_bar[stage], da + j * MN_BOX_BYTES, m0 + j * 64, a_row + r0);
 #pragma unroll
                             for (int j = 0; j < BNL / 64; ++j)
-                                tma_load_2d<CG>(&tmB, &full_bar[stage], db + j * MN_BOX_BYTES, n0 + j * 64, b_row + r0);
+                                tma_load_2d<CG>(mB, &full_bar[stage], db + j * MN_BOX_BYTES, n0 + j * 64, b_row + r0);
                         }
                     }
                     if (CG == 2 && rank != 0) mbar_arrive_leader(&full_bar[stage]);
@@ -438,7 +461,7 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 int n_kb = g.k_blocks;
                 if constexpr (KIND == K_WGRAD) {
-                    const int sl = t / (g.n_tiles * g.m_tiles);
+                    const int sl = (t >= group_tiles ? t - group_tiles : t) / (g.n_tiles * g.m_tiles);
                     n_kb = static_cast<int>(static_cast<long long>(sl + 1) * g.k_blocks / g.slices) - static_cast<int>(static_cast<long long>(sl) * g.k_blocks / g.slices);
                 }
                 for (int kb = 0; kb < n_kb; ++kb) {
@@ -480,18 +503,24 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         uint32_t acc_phase = 0;
         int item = 0;                                        // running chunk counter: buffer = item & 1
 
-        auto tile_rows = [&](int t) { return (((t / g.n_tiles) % g.m_tiles) * CG + rank) * BM + q * 32; };
-        auto tile_col = [&](int t, int ci) { return (t % g.n_tiles) * BN + half * (BN / 2) + ci * 32; };
+        // (t is the launch-wide tile index; tiles of the second problem start at group_tiles)
+        auto local = [&](int t) { return t >= group_tiles ? t - group_tiles : t; };
+        auto tile_rows = [&](int t) { return (((local(t) / g.n_tiles) % g.m_tiles) * CG + rank) * BM + q * 32; };
+        auto tile_col = [&](int t, int ci) { return (local(t) % g.n_tiles) * BN + half * (BN / 2) + ci * 32; };
         auto load_h = [&](int t, int ci, int b) {            // lane 0: H chunk (hi, lo) -> staging buffer b
+            const CUtensorMap* mH = t >= group_tiles ? &tmH2 : &tmH;
             mbar_expect_tx(&hb[b], write_lo ? 4096u : 2048u);
-            tma_load_2d<1>(&tmH, &hb[b], ebuf + b * EPI_BUF_BYTES, tile_col(t, ci), tile_rows(t));
-            if (write_lo) tma_load_2d<1>(&tmH, &hb[b], ebuf + b * EPI_BUF_BYTES + 2048, tile_col(t, ci), g.c_lo_row + tile_rows(t));
+            tma_load_2d<1>(mH, &hb[b], ebuf + b * EPI_BUF_BYTES, tile_col(t, ci), tile_rows(t));
+            if (write_lo) tma_load_2d<1>(mH, &hb[b], ebuf + b * EPI_BUF_BYTES + 2048, tile_col(t, ci), g.c_lo_row + tile_rows(t));
         };
         if constexpr (KIND == K_DGRAD) {
             if (lane == 0 && cid < total_tiles) load_h(cid, 0, 0);
         }
         for (int t = cid; t < total_tiles; t += ncl) {
-            const int sl = t / (g.n_tiles * g.m_tiles);
+            const bool g2 = t >= group_tiles;
+            const int sl = local(t) / (g.n_tiles * g.m_tiles);
+            const CUtensorMap* mC = g2 ? &tmC2 : &tmC;
+            float* const gsm = colsum_s + (g2 ? GROUP_FLOATS : 0);       // this problem's bias vector / column-sum accumulator
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * (BN / 2);
@@ -519,12 +548,12 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
                 if constexpr (KIND == K_WGRAD) {
-                    float4* dst = reinterpret_cast<float4*>(g.partial + sl * g.slice_stride + static_cast<long long>(row0 + lane) * g.ld_partial + col);
+                    float4* dst = reinterpret_cast<float4*>((g2 ? g.partial2 : g.partial) + sl * g.slice_stride + static_cast<long long>(row0 + lane) * g.ld_partial + col);
 #pragma unroll
                     for (int qd = 0; qd < 8; ++qd) dst[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
                 } else {
                     if constexpr (KIND == K_FWD) {
-                        const float4* sbias = reinterpret_cast<const float4*>(colsum_s + col);
+                        const float4* sbias = reinterpret_cast<const float4*>(gsm + col);
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
                             const float4 bb = sbias[j4];
@@ -579,8 +608,8 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         fence_proxy_async();                 // generic-proxy writes -> visible to the TMA (async proxy)
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&tmC, buf, col, row0);
-                            if (write_lo) tma_store_2d(&tmC, buf + 2048, col, g.c_lo_row + row0);
+                            tma_store_2d(mC, buf, col, row0);
+                            if (write_lo) tma_store_2d(mC, buf + 2048, col, g.c_lo_row + row0);
                             bulk_commit();
                         }
                     } else if (v[0] == 1.2345e-30f) {        // keeps the values alive
@@ -600,7 +629,7 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                     v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
                                 }
                             }
-                            colsum_s[q * g.ld_out + col + lane] += v[0];
+                            gsm[q * g.ld_out + col + lane] += v[0];
                         }
                     }
                 }
@@ -614,9 +643,12 @@ umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if constexpr (KIND == K_DGRAD) {
             if (g.colsum != nullptr) {
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");       // epilogue warps only
-                for (int c = threadIdx.x - EPI_WARP0 * 32; c < g.ld_out; c += EPI_WARPS * 32)
-                    g.colsum[static_cast<long long>(blockIdx.x) * g.ld_out + c] =
-                        ((colsum_s[c] + colsum_s[g.ld_out + c]) + colsum_s[2 * g.ld_out + c]) + colsum_s[3 * g.ld_out + c];
+                for (int gi = 0; gi < g.groups; ++gi) {
+                    const float* cs = colsum_s + gi * GROUP_FLOATS;
+                    float* dstc = gi ? g.colsum2 : g.colsum;
+                    for (int c = threadIdx.x - EPI_WARP0 * 32; c < g.ld_out; c += EPI_WARPS * 32)
+                        dstc[static_cast<long long>(blockIdx.x) * g.ld_out + c] = ((cs[c] + cs[g.ld_out + c]) + cs[2 * g.ld_out + c]) + cs[3 * g.ld_out + c];
+                }
             }
         }
     }

@@ -88,6 +88,7 @@ struct GemmPlan {       // one contraction, ready to launch
     int kind = 0, bn = 0, cg = 1, grid = 0;
     int tiles_n = 0;    // accumulator columns / bn
     CUtensorMap ma, mb, mc, mh;
+    CUtensorMap ma2, mb2, mc2, mh2;   // second problem of a grouped launch (args.groups == 2)
     GemmArgs args;
 };
 
@@ -131,7 +132,8 @@ int launch_one(const GemmPlan& p, cudaStream_t st) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 2 : 1;
-    PPO_CUDA(cudaLaunchKernelEx(&cfg, kern, p.ma, p.mb, p.mc, p.mh, p.args));
+    if (p.args.groups == 2) PPO_CUDA(cudaLaunchKernelEx(&cfg, kern, p.ma, p.mb, p.mc, p.mh, p.ma2, p.mb2, p.mc2, p.mh2, p.args));
+    else PPO_CUDA(cudaLaunchKernelEx(&cfg, kern, p.ma, p.mb, p.mc, p.mh, p.ma, p.mb, p.mc, p.mh, p.args));
     return DN_OK;
 }
 
@@ -166,7 +168,7 @@ int plan_fwd(GemmPlan* p, int passes, int M, int N, int K, const void* a, const 
     GemmArgs& g = p->args;
     memset(&g, 0, sizeof(g));
     g.m_tiles = rows_now / (BM * p->cg); g.n_tiles = N / p->bn; g.slices = 1; g.k_blocks = K / BK; g.passes = passes;
-    g.a_lo_row = M; g.b_lo_row = N; g.c_lo_row = M; g.act = act; g.bias = bias; g.ld_out = N;
+    g.a_lo_row = M; g.b_lo_row = N; g.c_lo_row = M; g.act = act; g.bias = bias; g.ld_out = N; g.groups = 1;
     g.dbg = env_int("DN_MLP_DBG");
     set_grid(p);
     return DN_OK;
@@ -184,7 +186,7 @@ int plan_dgrad(GemmPlan* p, int passes, int M, int N, int K, const void* a, cons
     GemmArgs& g = p->args;
     memset(&g, 0, sizeof(g));
     g.m_tiles = rows_now / (BM * p->cg); g.n_tiles = N / p->bn; g.slices = 1; g.k_blocks = K / BK; g.passes = passes;
-    g.a_lo_row = M; g.b_lo_row = K; g.c_lo_row = M; g.ld_out = N;
+    g.a_lo_row = M; g.b_lo_row = K; g.c_lo_row = M; g.ld_out = N; g.groups = 1;
     g.dbg = env_int("DN_MLP_DBG");
     set_grid(p);
     return DN_OK;
@@ -204,9 +206,25 @@ int plan_wgrad(GemmPlan* p, int passes, int Mo, int No, int rows, int slices, co
     memset(&g, 0, sizeof(g));
     g.m_tiles = Mo / (BM * p->cg); g.n_tiles = No / p->bn; g.slices = slices; g.k_blocks = rows_now / BK; g.passes = passes;
     g.a_lo_row = rows; g.b_lo_row = rows;
-    g.partial = partial; g.ld_partial = No; g.slice_stride = static_cast<long long>(Mo) * No;
+    g.partial = partial; g.ld_partial = No; g.slice_stride = static_cast<long long>(Mo) * No; g.groups = 1;
     set_grid(p);
     return DN_OK;
+}
+
+// One launch for two problems of identical shape (layer l of the policy and of the value net): `out` = a's problem + b's.
+// false if the two plans differ in anything but their pointers.
+bool merge_plans(GemmPlan* out, const GemmPlan& a, const GemmPlan& b) {
+    const GemmArgs &x = a.args, &y = b.args;
+    if (a.kind != b.kind || a.bn != b.bn || a.cg != b.cg || x.m_tiles != y.m_tiles || x.n_tiles != y.n_tiles || x.slices != y.slices ||
+        x.k_blocks != y.k_blocks || x.passes != y.passes || x.a_lo_row != y.a_lo_row || x.b_lo_row != y.b_lo_row || x.c_lo_row != y.c_lo_row ||
+        x.act != y.act || x.ld_out != y.ld_out || x.ld_partial != y.ld_partial || x.slice_stride != y.slice_stride ||
+        (x.colsum == nullptr) != (y.colsum == nullptr))
+        return false;
+    *out = a;
+    out->ma2 = b.ma; out->mb2 = b.mb; out->mc2 = b.mc; out->mh2 = b.mh;
+    out->args.groups = 2; out->args.bias2 = y.bias; out->args.partial2 = y.partial; out->args.colsum2 = y.colsum;
+    out->grid = grid_for(2 * x.m_tiles * x.n_tiles * x.slices, a.cg);
+    return true;
 }
 
 // ====================================================================================================================
@@ -248,6 +266,9 @@ struct dn_ppo {
     std::vector<Seg> segs_host;
     PlaneSeg* psegs_dev = nullptr; int* pseg_of_block_dev = nullptr; int plane_blocks = 0;
     int cur_rows = -1, table_rows = -1;
+    // the policy and the value net have the same hidden widths (PBDroneSimulator.py:251-258): layer l of both runs as ONE launch
+    bool grouped = false;
+    GemmPlan gfwd[MAX_LAYERS + 1], gdgrad[MAX_LAYERS + 1], gwgrad[MAX_LAYERS + 1];
     std::vector<void*> allocs;
 };
 
@@ -304,7 +325,7 @@ int setup_net(dn_ppo* h, Net& net, int L, const int32_t* hidden, const int64_t* 
 
 // Plans for `rows` rows: tensor maps over the full workspaces (lo plane max_rows rows after the hi plane), tile shapes and
 // counts for this row count (CTA pairs need multiples of 256 rows).
-int build_plans(dn_ppo* h, Net& net, int rows) {
+int build_plans(dn_ppo* h, Net& net, int rows, int groups) {
     int rc;
     for (int l = 1; l <= net.L; ++l) {
         const int N = net.n[l], K = net.n[l - 1];
@@ -316,7 +337,7 @@ int build_plans(dn_ppo* h, Net& net, int rows) {
         }
         int units = 0;
         const int wt = wgrad_tiles(N, K, h->sms, &units);
-        const int slices = std::min(wgrad_slices(rows, wt, units), net.slices_max[l]);
+        const int slices = std::min(wgrad_slices(rows, wt * groups, units), net.slices_max[l]);   // one work item per CTA (pair) per launch
         if ((rc = plan_wgrad(&net.wgrad[l], h->passes, N, K, h->max_rows, slices, net.dz[l], net.h[l - 1], net.wpart[l], rows))) return rc;
     }
     return DN_OK;
@@ -404,8 +425,23 @@ int build_plane_table(dn_ppo* h) {
 int ensure_rows(dn_ppo* h, int rows, bool train) {
     int rc;
     if (rows != h->cur_rows) {
-        if ((rc = build_plans(h, h->pi, rows)) || (rc = build_plans(h, h->vf, rows))) return rc;
-        h->cur_rows = rows;
+        bool same = h->pi.L == h->vf.L && getenv("DN_MLP_NO_GROUP") == nullptr;
+        for (int l = 1; same && l <= h->pi.L; ++l) same = h->pi.n[l] == h->vf.n[l];
+        if ((rc = build_plans(h, h->pi, rows, same ? 2 : 1)) || (rc = build_plans(h, h->vf, rows, same ? 2 : 1))) return rc;
+        for (int l = 1; same && l <= h->pi.L; ++l) {
+            same = merge_plans(&h->gfwd[l], h->pi.fwd[l], h->vf.fwd[l]) && merge_plans(&h->gwgrad[l], h->pi.wgrad[l], h->vf.wgrad[l]);
+            if (same && l > 1) {
+                same = merge_plans(&h->gdgrad[l], h->pi.dgrad[l], h->vf.dgrad[l]);
+                // the reduction table sums one column-sum row per CTA of the launch that wrote them
+                h->pi.dgrad[l].grid = h->vf.dgrad[l].grid = h->gdgrad[l].grid;
+            }
+        }
+        if (!same && h->pi.L == h->vf.L && getenv("DN_MLP_NO_GROUP") == nullptr) {
+            // shapes differ after all: plans with per-net slice counts
+            if ((rc = build_plans(h, h->pi, rows, 1)) || (rc = build_plans(h, h->vf, rows, 1))) return rc;
+        }
+        h->grouped = same;
+        h->cur_rows = rows;                        // (the reduction table depends on the row count alone and is keyed by it below)
     }
     if (train && rows != h->table_rows) {
         if ((rc = build_reduce_table(h, rows))) return rc;
@@ -461,6 +497,11 @@ int run_gather(dn_ppo* h, const float* obs, const dn_ppo_rollout* r, const long 
 
 int run_forward_chain(dn_ppo* h, cudaStream_t st) {
     int rc;
+    if (h->grouped) {
+        for (int l = 1; l <= h->pi.L; ++l)
+            if ((rc = launch_gemm(h->gfwd[l], st))) return rc;
+        return DN_OK;
+    }
     Net* nets[2] = {&h->pi, &h->vf};
     for (Net* net : nets)
         for (int l = 1; l <= net->L; ++l)
@@ -636,13 +677,20 @@ int dn_ppo_minibatch_grad(dn_ppo* h, const dn_ppo_rollout* r, const int64_t* idx
     a.partial = h->head_partial;
     if ((rc = run_head(h, a, head_blocks, st))) return rc;
     // backward through the hidden layers
-    Net* nets[2] = {&h->pi, &h->vf};
-    for (Net* net : nets)
-        for (int l = net->L; l >= 1; --l) {
-            // bias gradients ride along: layer L's in the head kernel, layer l-1's in the epilogue of this dgrad
-            if ((rc = launch_gemm(net->wgrad[l], st))) return rc;
-            if (l > 1 && (rc = launch_gemm(net->dgrad[l], st))) return rc;
+    // bias gradients ride along: layer L's in the head kernel, layer l-1's in the epilogue of the dgrad of layer l
+    if (h->grouped) {
+        for (int l = h->pi.L; l >= 1; --l) {
+            if ((rc = launch_gemm(h->gwgrad[l], st))) return rc;
+            if (l > 1 && (rc = launch_gemm(h->gdgrad[l], st))) return rc;
         }
+    } else {
+        Net* nets[2] = {&h->pi, &h->vf};
+        for (Net* net : nets)
+            for (int l = net->L; l >= 1; --l) {
+                if ((rc = launch_gemm(net->wgrad[l], st))) return rc;
+                if (l > 1 && (rc = launch_gemm(net->dgrad[l], st))) return rc;
+            }
+    }
     // every partial -> the flat bucket; statistics; early-stop vote
     ReduceArgs ra;
     memset(&ra, 0, sizeof(ra));
