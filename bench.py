@@ -578,7 +578,7 @@ def run_ppo(args, dev, world, rank, barrier, max_over_ranks):
            "minibatch": cfg.batch_size, "epochs_run": [o["epochs"] for o in outs], "minibatches_run": [o["minibatches"] for o in outs],
            "rollout_s": sum(o["rollout_s"] for o in outs), "update_s": sum(o["update_s"] for o in outs),
            "rollout_s_each": [round(o["rollout_s"], 5) for o in outs], "update_s_each": [round(o["update_s"], 5) for o in outs],
-           "env_share_of_rollout": None, "allreduce_calls": tr.learner.allreduce_calls, "allreduce_bytes": tr.learner.n_params * 4,
+           "env_share_of_rollout": None, "allreduce_calls": tr.learner.allreduce_calls, "allreduce_bytes": tr.learner.n_params * 4, "allreduce_impl": getattr(tr.learner, "allreduce_impl", "nccl" if world > 1 else "none"),
            "gpu_launches": int(env.launch_count - l0), "approx_kl": outs[-1]["approx_kl"],
            "normalize_obs": not args.no_norm_obs, "update_impl": outs[-1].get("impl", "torch/" + cfg.matmul_precision),
            "optimizer_steps": [o.get("optimizer_steps") for o in outs], "update_us_per_minibatch": 1e6 * sum(o["update_s"] for o in outs) / max(1, sum(o["minibatches"] for o in outs)),

@@ -135,6 +135,9 @@ SYMBOLS = {
     "dn_ppo_minibatch_grad": (C.c_int, [C.c_void_p, C.POINTER(dn_ppo_rollout), C.c_void_p, C.c_int32, C.c_void_p]),
     "dn_ppo_minibatch_apply": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dn_ppo_get_stats": (C.c_int, [C.c_void_p, C.POINTER(dn_ppo_stats), C.c_void_p]),
+    "dn_ppo_comm_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "dn_ppo_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dn_ppo_allreduce": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dn_ppo_poll": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dn_ppo_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dn_ppo_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),

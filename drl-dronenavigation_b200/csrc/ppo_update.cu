@@ -16,6 +16,7 @@
 #include "../../include/dronenav.h"
 #include "dn_umma.cuh"
 #include "ppo_kernels.cuh"
+#include "ppo_comm.cuh"
 
 int dn_internal_fail(int code, const std::string& msg);   // dronenav.cu: sets the thread-local dn_last_error message
 
@@ -267,6 +268,12 @@ struct dn_ppo {
     PlaneSeg* psegs_dev = nullptr; int* pseg_of_block_dev = nullptr; int plane_blocks = 0;
     int cur_rows = -1, table_rows = -1;
     // the policy and the value net have the same hidden widths (PBDroneSimulator.py:251-258): layer l of both runs as ONE launch
+    // gradient all-reduce over NVLink peer memory (ppo_comm.cuh); comm_base == nullptr: not set up
+    char* comm_base = nullptr;
+    size_t comm_bytes = 0;
+    dncomm::CommArgs comm;
+    bool comm_connected = false;
+    std::vector<void*> comm_opened;
     bool grouped = false;
     GemmPlan gfwd[MAX_LAYERS + 1], gdgrad[MAX_LAYERS + 1], gwgrad[MAX_LAYERS + 1];
     std::vector<void*> allocs;
@@ -627,6 +634,8 @@ int dn_ppo_create(const dn_ppo_config* cfg, int device, float* params, float* gr
 int dn_ppo_destroy(dn_ppo* h) {
     if (!h) return DN_OK;
     cudaSetDevice(h->device);
+    for (void* p : h->comm_opened) cudaIpcCloseMemHandle(p);
+    if (h->comm_base) cudaFree(h->comm_base);
     for (void* p : h->allocs) cudaFree(p);
     if (h->mirror) cudaFreeHost(h->mirror);
     if (h->segs_dev) cudaFree(h->segs_dev);
@@ -634,6 +643,68 @@ int dn_ppo_destroy(dn_ppo* h) {
     if (h->psegs_dev) cudaFree(h->psegs_dev);
     if (h->pseg_of_block_dev) cudaFree(h->pseg_of_block_dev);
     delete h;
+    return DN_OK;
+}
+
+// ---- gradient all-reduce over peer memory (ppo_comm.cuh) ----
+int dn_ppo_comm_create(dn_ppo* h, int32_t rank, int32_t world, unsigned char* handle_out) {
+    if (!h || !handle_out) return dn_internal_fail(DN_EINVAL, "dn_ppo_comm_create: null argument");
+    if (world < 2 || world > dncomm::MAX_RANKS || rank < 0 || rank >= world)
+        return dn_internal_fail(DN_EINVAL, "dn_ppo_comm_create: world must be 2..16 and 0 <= rank < world");
+    if (h->comm_base) return dn_internal_fail(DN_EINVAL, "dn_ppo_comm_create: already created");
+    static_assert(sizeof(cudaIpcMemHandle_t) == DN_PPO_COMM_HANDLE_BYTES, "IPC handle size");
+    cudaSetDevice(h->device);
+    const long long n = h->cfg.n_params + 1, q = 4ll * world;
+    const long long n_pad = (n + q - 1) / q * q;
+    h->comm_bytes = dncomm::FLAG_BYTES + 2 * static_cast<size_t>(n_pad) * sizeof(float) + 256;
+    PPO_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->comm_base), h->comm_bytes));
+    PPO_CUDA(cudaMemset(h->comm_base, 0, h->comm_bytes));
+    memset(&h->comm, 0, sizeof(h->comm));
+    h->comm.grads = h->grads; h->comm.n = n; h->comm.n_pad = n_pad; h->comm.rank = rank; h->comm.world = world;
+    // the epoch word and the CTA counter live behind the buffers (never touched by peers)
+    char* tail = h->comm_base + dncomm::FLAG_BYTES + 2 * static_cast<size_t>(n_pad) * sizeof(float);
+    h->comm.epoch = reinterpret_cast<uint32_t*>(tail);
+    h->comm.counter = reinterpret_cast<unsigned int*>(tail + 64);
+    h->comm.peer[rank] = h->comm_base;
+    cudaIpcMemHandle_t mh;
+    PPO_CUDA(cudaIpcGetMemHandle(&mh, h->comm_base));
+    memcpy(handle_out, &mh, sizeof(mh));
+    PPO_CUDA(cudaDeviceSynchronize());
+    return DN_OK;
+}
+
+int dn_ppo_comm_connect(dn_ppo* h, const unsigned char* handles) {
+    if (!h || !handles) return dn_internal_fail(DN_EINVAL, "dn_ppo_comm_connect: null argument");
+    if (!h->comm_base) return dn_internal_fail(DN_EINVAL, "dn_ppo_comm_connect: dn_ppo_comm_create first");
+    if (h->comm_connected) return DN_OK;
+    cudaSetDevice(h->device);
+    for (int p = 0; p < h->comm.world; ++p) {
+        if (p == h->comm.rank) continue;
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, handles + static_cast<size_t>(p) * DN_PPO_COMM_HANDLE_BYTES, sizeof(mh));
+        void* ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return dn_internal_fail(DN_ECUDA, std::string("dn_ppo_comm_connect: cudaIpcOpenMemHandle (peer-to-peer over NVLink / PCIe is required): ") +
+                                                  cudaGetErrorString(e));
+        }
+        h->comm_opened.push_back(ptr);
+        h->comm.peer[p] = static_cast<char*>(ptr);
+    }
+    h->comm_connected = true;
+    return DN_OK;
+}
+
+int dn_ppo_allreduce(dn_ppo* h, void* stream) {
+    if (!h) return dn_internal_fail(DN_EINVAL, "dn_ppo_allreduce: null handle");
+    if (!h->comm_connected) return dn_internal_fail(DN_EINVAL, "dn_ppo_allreduce: dn_ppo_comm_create + dn_ppo_comm_connect first");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dncomm::CommArgs& a = h->comm;
+    const int T = dncomm::AR_THREADS;
+    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((a.n_pad / 4 + T - 1) / T, h->sms)));   // all resident
+    dncomm::allreduce_kernel<<<blocks, T, 0, st>>>(a);
+    PPO_CUDA(cudaGetLastError());
     return DN_OK;
 }
 

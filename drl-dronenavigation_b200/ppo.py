@@ -303,6 +303,41 @@ class FusedUpdate:
         with torch.cuda.device(self.device):
             self.L.check(self.lib.dn_ppo_minibatch_apply(self.handle, self._stream()), "dn_ppo_minibatch_apply")
 
+    comm_ready = False
+
+    def comm_setup(self) -> bool:
+        """Gradient all-reduce over NVLink peer memory (dn_ppo_comm_create / _connect): every rank allocates its exchange region,
+        the 64-byte CUDA IPC handles are all-gathered through torch.distributed, every rank maps its peers' regions.  Collective:
+        all ranks call it at the same point.  Returns False -- on EVERY rank -- when the job spans several nodes, when
+        DN_PPO_ALLREDUCE=nccl, or when any rank could not map a peer (the caller then keeps ncclAllReduce)."""
+        import os
+        world, rank = dist.get_world_size(), dist.get_rank()
+        on_cuda = dist.get_backend() == "nccl"
+        dev = self.device if on_cuda else torch.device("cpu")
+        ok = (os.environ.get("DN_PPO_ALLREDUCE", "peer") != "nccl" and 2 <= world <= 16
+              and int(os.environ.get("LOCAL_WORLD_SIZE", world)) == world)
+        hb = (C.c_ubyte * 64)()
+        if ok:
+            with torch.cuda.device(self.device):
+                ok = self.lib.dn_ppo_comm_create(self.handle, rank, world, hb) == 0
+        mine = torch.tensor(list(hb) + [1 if ok else 0], dtype=torch.uint8, device=dev)
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        allh = torch.stack(allh).cpu()
+        ok = bool(allh[:, 64].min().item())
+        if ok:
+            buf = (C.c_ubyte * (64 * world))(*allh[:, :64].reshape(-1).tolist())
+            with torch.cuda.device(self.device):
+                ok = self.lib.dn_ppo_comm_connect(self.handle, buf) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self.comm_ready = bool(flag.item())
+        return self.comm_ready
+
+    def allreduce(self):
+        with torch.cuda.device(self.device):
+            self.L.check(self.lib.dn_ppo_allreduce(self.handle, self._stream()), "dn_ppo_allreduce")
+
     def poll(self):
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         self.lib.dn_ppo_poll(self.handle, C.byref(a), C.byref(b), C.byref(c))
@@ -424,6 +459,11 @@ class PPOLearner:
         n_mb = B // mb
         fu = self.ensure_fused(mb)
         world = _world()
+        # several ranks: the flat-bucket sum runs over NVLink peer memory inside the library (and inside the minibatch graph) when
+        # all ranks share a node, through ncclAllReduce between two graphs otherwise
+        peer = world > 1 and (fu.comm_ready or (not getattr(fu, "comm_tried", False) and fu.comm_setup()))
+        fu.comm_tried = True
+        self.allreduce_impl = "peer" if peer else ("nccl" if world > 1 else "none")
         ro = fu.L.dn_ppo_rollout()
         graphs = None
         if cfg.cuda_graph:
@@ -431,7 +471,7 @@ class PPOLearner:
             # single one when there is no all-reduce in between): removes the launch gaps between the short dependent kernels.
             # Graphs bake pointers in, so the rollout is staged in static tensors and the minibatch indices in a static buffer.
             fg = self._fused_graphs
-            key = (B, mb, obs.shape[1], actions.shape[1], world)
+            key = (B, mb, obs.shape[1], actions.shape[1], world, peer)
             if fg is None or fg["key"] != key or fg["fu"] is not fu:
                 fg = self._capture_fused(fu, key)
             for dst, src in zip(fg["static"], (obs, actions, old_logp, old_values, advantages, returns)):
@@ -456,15 +496,19 @@ class PPOLearner:
             for k in range(n_mb):
                 if graphs is not None:
                     graphs["idx"].copy_(perm[k * mb:(k + 1) * mb])
-                    graphs["grad"].replay()
+                    graphs["grad"].replay()              # one rank, or peer all-reduce: the whole step
                     if world > 1:
-                        dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM)
                         self.allreduce_calls += 1
-                        graphs["apply"].replay()
+                        if not peer:
+                            dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM)
+                            graphs["apply"].replay()
                 else:
                     fu.minibatch_grad(ro, perm[k * mb:(k + 1) * mb])
                     if world > 1:
-                        dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM)
+                        if peer:
+                            fu.allreduce()
+                        else:
+                            dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM)
                         self.allreduce_calls += 1
                     fu.minibatch_apply()
                 launched += 1
@@ -490,9 +534,10 @@ class PPOLearner:
     _fused_graphs = None
 
     def _capture_fused(self, fu: FusedUpdate, key):
-        """CUDA graphs of the fused minibatch step for rollouts of `key` = (B, mb, D, A, world).  With one rank the two halves are one
-        graph; with several the flat-bucket all-reduce sits between two graphs."""
-        B, mb, D, A, world = key
+        """CUDA graphs of the fused minibatch step for rollouts of `key` = (B, mb, D, A, world, peer).  One graph for the whole step
+        with one rank or with the peer-memory all-reduce (three kernels of the library between the halves); with ncclAllReduce the
+        collective sits between two graphs."""
+        B, mb, D, A, world, peer = key
         dev = self.device
         f = dict(dtype=torch.float32, device=dev)
         static = [torch.zeros(B, D, **f), torch.zeros(B, A, **f), torch.zeros(B, **f), torch.zeros(B, **f), torch.zeros(B, **f), torch.zeros(B, **f)]
@@ -506,6 +551,8 @@ class PPOLearner:
         with torch.cuda.stream(side):
             fu.begin_update()
             fu.minibatch_grad(ro, idx)
+            if world > 1 and peer:
+                fu.allreduce()                 # (every rank captures at the same point of the program: the peers answer)
             self._bucket[-1] = 1.0
             fu.minibatch_apply()
             fu.begin_update()
@@ -514,9 +561,11 @@ class PPOLearner:
         g_grad, g_apply = torch.cuda.CUDAGraph(), None
         with torch.cuda.graph(g_grad):
             fu.minibatch_grad(ro, idx)
-            if world == 1:
+            if world > 1 and peer:
+                fu.allreduce()
+            if world == 1 or peer:
                 fu.minibatch_apply()
-        if world > 1:
+        if world > 1 and not peer:
             g_apply = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_apply):
                 fu.minibatch_apply()

@@ -101,6 +101,21 @@ int dn_ppo_minibatch_grad(dn_ppo* h, const dn_ppo_rollout* r, const int64_t* idx
 /* Second half (sb3_ppo.py:283-294): if any rank voted to stop, this and every later call until dn_ppo_begin_update is a
  * no-op; otherwise grads / world_size -> clip_grad_norm_ -> Adam -> refreshed BF16 planes. */
 int dn_ppo_minibatch_apply(dn_ppo* h, void* stream);
+/* Data-parallel update (one process per GPU, every rank with its own handle and its own shard of the rollout): the sum over
+ * the ranks of the flat gradient bucket (n_params + 1 floats -- the last one carries the rank's KL early-stop vote), in place,
+ * between dn_ppo_minibatch_grad and dn_ppo_minibatch_apply (which divides by cfg.world_size).  The exchange runs over NVLink
+ * peer memory: dn_ppo_comm_create allocates this rank's exchange region and returns its CUDA IPC handle (64 bytes); the caller
+ * gathers the handles of all ranks with whatever it has (torch.distributed, MPI, a file) and passes them, rank-major, to
+ * dn_ppo_comm_connect.  dn_ppo_allreduce is then three short kernels (publish, reduce-scatter + push, collect) that wait for the
+ * peers through flags in the mapped regions: capturable in a CUDA graph, bit-identical results on every rank (every element is
+ * summed once, in rank order, by its owner).  Every rank must call it the same number of times; a wait that is not answered
+ * within seconds traps (CUDA error on the host) instead of hanging the GPU.  Single node only (CUDA IPC); the Python layer falls
+ * back to ncclAllReduce elsewhere.  What it replaces: nothing in the reference (its PPO is single-process, sb3_ppo.py:288-294). */
+#define DN_PPO_COMM_HANDLE_BYTES 64
+int dn_ppo_comm_create(dn_ppo* h, int32_t rank, int32_t world, unsigned char* handle_out);
+int dn_ppo_comm_connect(dn_ppo* h, const unsigned char* handles);
+int dn_ppo_allreduce(dn_ppo* h, void* stream);
+
 /* Statistics so far; synchronises `stream`. */
 int dn_ppo_get_stats(dn_ppo* h, dn_ppo_stats* out, void* stream);
 /* Non-blocking look at the early-stop state as of the last completed dn_ppo_minibatch_apply (pinned mirror). */

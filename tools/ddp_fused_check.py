@@ -53,8 +53,73 @@ calls = gathered(torch.tensor([float(L2.allreduce_calls), float(out2["launched_m
 assert all(torch.equal(calls[0], c) for c in calls), calls          # every rank issued the same number of collectives
 p2 = gathered(L2.flat_parameters())
 assert all(torch.equal(p2[0], p) for p in p2)
+# (3) the peer-memory all-reduce itself against ncclAllReduce on the same bucket
+fu = L.fused
+impl = L.allreduce_impl
+if impl == "peer":
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    for trial in range(5):
+        L._bucket.copy_(torch.randn(L._bucket.shape, device=dev, generator=g))
+        want = L._bucket.clone()
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+        fu.allreduce()
+        torch.cuda.synchronize()
+        got = gathered(L._bucket.clone())
+        assert all(torch.equal(got[0], x) for x in got), "peer all-reduce: ranks disagree"
+        if world == 2:
+            assert torch.equal(got[0], want), float((got[0] - want).abs().max())       # two addends: the sum does not depend on the order
+        else:
+            assert torch.allclose(got[0], want, rtol=1e-5, atol=1e-5), float((got[0] - want).abs().max())
+
+# (3b) the collective alone, back to back
+if impl == "peer":
+    def loop(fn, n=200):
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / n
+    L._bucket.zero_()
+    t_peer = loop(fu.allreduce)
+    t_nccl = loop(lambda: dist.all_reduce(L._bucket, op=dist.ReduceOp.SUM))
+    g_ar = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_ar):
+        for _ in range(10):
+            fu.allreduce()
+    t_peer_graph = loop(g_ar.replay, n=40) / 10
+    if rank == 0:
+        print(f"all-reduce of {L._bucket.numel()} floats alone, us per call: peer memory {t_peer:.1f} (launched), {t_peer_graph:.1f} (graph replay); ncclAllReduce {t_nccl:.1f}")
+
+# (4) time per optimiser step at the bench shape, peer memory vs ncclAllReduce (same data, same graphs otherwise)
+def timed(env_value):
+    os.environ["DN_PPO_ALLREDUCE"] = env_value
+    Lt = PPOLearner(13, 4, PPOConfig(batch_size=32768, n_epochs=2, target_kl=None, update_impl="fused"), device=dev)
+    rt = rollout(Lt, 1 << 19, seed=300 + rank)
+    gen = torch.Generator(device=dev).manual_seed(11)
+    Lt.update(*rt, generator=gen)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    o = Lt.update(*rt, generator=gen)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e3 / o["minibatches"]], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pf = gathered(Lt.flat_parameters())
+    assert all(torch.equal(pf[0], p) for p in pf)
+    return float(t.item()), Lt.allreduce_impl, pf[0]
+us_peer, impl_peer, p_peer = timed("peer")
+us_nccl, impl_nccl, p_nccl = timed("nccl")
+assert impl_nccl == "nccl"
+rel = float((p_peer - p_nccl).abs().max() / p_nccl.abs().max())
+assert rel < 1e-4, rel          # same update up to the order of the cross-rank sums
 if rank == 0:
-    print(f"ddp fused check ok: world {world}, update {out['minibatches']} minibatches / {L.allreduce_calls} all-reduces, "
+    print(f"ddp fused check ok: world {world}, all-reduce impl {impl}, update {out['minibatches']} minibatches / {L.allreduce_calls} all-reduces, "
           f"early stop after {out2['minibatches']} minibatches ({out2['optimizer_steps']} applied), launched {out2['launched_minibatches']}")
+    print(f"us per optimiser step (32768-sample minibatch, max over ranks): {impl_peer} {us_peer:.1f}, {impl_nccl} {us_nccl:.1f}; "
+          f"parameters after 32 steps differ by {rel:.1e} (order of the sums)")
 dist.barrier()
 dist.destroy_process_group()
