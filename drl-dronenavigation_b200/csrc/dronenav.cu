@@ -332,9 +332,9 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
             flush_stats(P, acc, tid);
             acc = BlockAcc{0.f, 0, 0, 0, 0};
             if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            __threadfence_system();
             __syncthreads();
             if (tid == 0) {
+                __threadfence_system();          // one fence per CTA: cumulative over the stores the barrier ordered before it
                 const unsigned int prev = atomicAdd(io.done_counter, 1u);
                 if (prev == gridDim.x - 1) {
                     *io.done_counter = 0u;
@@ -351,9 +351,9 @@ step_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io,
         // stores of the observation rows included) are made visible system-wide, the CTA counts itself done, and the last
         // CTA writes the step's sequence number to the pinned word the host is polling -- no stream query, no interrupt.
         if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        __threadfence_system();
         __syncthreads();
         if (tid == 0) {
+            __threadfence_system();              // one fence per CTA: cumulative over the stores the barrier ordered before it
             const unsigned int prev = atomicAdd(io.done_counter, 1u);
             if (prev == gridDim.x - 1) {
                 *io.done_counter = 0u;
