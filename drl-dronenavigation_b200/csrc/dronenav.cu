@@ -1209,8 +1209,7 @@ static int srv_step(dn_env* env) {
             if (rs != DN_OK) return rs;
         }
     }
-    env->srv_steps += 1;
-    env->launches += 0;
+    env->srv_steps += 1;          // (no launch: dn_launch_count counts the residencies)
     return DN_OK;
 }
 
