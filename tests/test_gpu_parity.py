@@ -385,7 +385,7 @@ def test_ragged_sizes_and_obs12():
 
 def test_vec_env_protocol_against_oracle_workers():
     """GpuDroneVecEnv (numpy, pinned host buffers) reproduces the SubprocVecEnv worker contract,
-    NormalizeObservation included (FP32 running statistics vs the reference's FP64: looser obs tolerance)."""
+    NormalizeObservation included (the normalised rows amplify FP32 state differences by 1 / sqrt(var): looser obs tolerance)."""
     from drl_dronenavigation_b200.vec_env import GpuDroneVecEnv
     from oracle.dyn_oracle import OracleWorker, make_reference_env
     N, T = 12, 200
@@ -419,6 +419,41 @@ def test_vec_env_protocol_against_oracle_workers():
     assert n_done > 10
     assert venv.env_is_wrapped(type("Monitor", (), {}))[0]
     venv.close()
+
+
+def test_vec_env_host_paths_agree():
+    """GpuDroneVecEnv with the three host paths (zero copy, slab + graph, resident server): the same SB3 protocol outputs bit for bit,
+    per-env NormalizeObservation and Monitor included."""
+    from drl_dronenavigation_b200.vec_env import GpuDroneVecEnv
+    from oracle.dyn_oracle import make_reference_env
+    N, T = 12, 120
+    ref = make_reference_env("circle")
+    venvs = {p: GpuDroneVecEnv(N, ref._target_points, aviary_dim=ref._aviary_dim, initial_xyzs=ref.INIT_XYZS, circle=True,
+                               include_distance=True, normalize_actions=True, normalize_obs=True, host_path=p)
+             for p in ("zero_copy", "slab", "server")}
+    obs0 = {p: v.reset() for p, v in venvs.items()}
+    acts = _actions("saturating", T, N, seed=21)
+    n_done = 0
+    for t in range(T):
+        outs = {p: v.step(acts[t]) for p, v in venvs.items()}
+        o, r, d, infos = outs["zero_copy"]
+        n_done += int(d.sum())
+        for p in ("slab", "server"):
+            o2, r2, d2, infos2 = outs[p]
+            np.testing.assert_array_equal(o, o2, err_msg=f"{p} t={t}")
+            np.testing.assert_array_equal(r, r2)
+            np.testing.assert_array_equal(d, d2)
+            for a, b in zip(infos, infos2):
+                assert a["found_targets"] == b["found_targets"] and ("episode" in a) == ("episode" in b)
+                if "episode" in a:
+                    assert a["episode"]["l"] == b["episode"]["l"] and a["episode"]["r"] == b["episode"]["r"]
+                    np.testing.assert_array_equal(a["terminal_observation"], b["terminal_observation"])
+    for p in ("slab", "server"):
+        np.testing.assert_array_equal(obs0["zero_copy"], obs0[p])
+    assert n_done > 5
+    assert venvs["server"].core.host_server_stats()["steps"] == T
+    for v in venvs.values():
+        v.close()
 
 
 FULL_SIZE = [
