@@ -25,7 +25,7 @@ namespace dncomm {
 constexpr int MAX_RANKS = 16;
 constexpr int FLAG_BYTES = 1024;                 // [2][MAX_RANKS] uint32, padded
 constexpr int AR_THREADS = 512;                  // per CTA: enough threads that the reduce phase is one or two NVLink round trips per thread
-constexpr uint32_t SPIN_CAP = 1u << 24;          // polls of local memory (~0.5 us each) before a wait gives up
+constexpr uint32_t SPIN_CAP = 1u << 27;          // polls of local memory (~0.5 us each, about a minute) before a wait gives up
 
 struct CommArgs {
     float* grads;                                // the learner's flat bucket (n floats incl. the vote)

@@ -464,6 +464,10 @@ class PPOLearner:
         peer = world > 1 and (fu.comm_ready or (not getattr(fu, "comm_tried", False) and fu.comm_setup()))
         fu.comm_tried = True
         self.allreduce_impl = "peer" if peer else ("nccl" if world > 1 else "none")
+        if peer:
+            # the exchange kernels wait for their peers on the device with a bounded spin: ranks enter the update together (one
+            # host barrier per update, not per minibatch; rank-0-only work between updates -- logging, checkpoints -- may take long)
+            dist.barrier()
         ro = fu.L.dn_ppo_rollout()
         graphs = None
         if cfg.cuda_graph:

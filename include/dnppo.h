@@ -109,7 +109,7 @@ int dn_ppo_minibatch_apply(dn_ppo* h, void* stream);
  * dn_ppo_comm_connect.  dn_ppo_allreduce is then three short kernels (publish, reduce-scatter + push, collect) that wait for the
  * peers through flags in the mapped regions: capturable in a CUDA graph, bit-identical results on every rank (every element is
  * summed once, in rank order, by its owner).  Every rank must call it the same number of times; a wait that is not answered
- * within seconds traps (CUDA error on the host) instead of hanging the GPU.  Single node only (CUDA IPC); the Python layer falls
+ * within about a minute traps (CUDA error on the host) instead of hanging the GPU.  Single node only (CUDA IPC); the Python layer falls
  * back to ncclAllReduce elsewhere.  What it replaces: nothing in the reference (its PPO is single-process, sb3_ppo.py:288-294). */
 #define DN_PPO_COMM_HANDLE_BYTES 64
 int dn_ppo_comm_create(dn_ppo* h, int32_t rank, int32_t world, unsigned char* handle_out);
