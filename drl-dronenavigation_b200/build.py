@@ -17,7 +17,7 @@ INC = os.path.join(PKG_DIR, "..", "include")
 # source -> headers it includes
 SOURCES = {
     "dronenav.cu": ["dn_params.h", "dn_device.cuh", "dn_host.h", os.path.join(INC, "dronenav.h")],
-    "ppo_update.cu": ["dn_umma.cuh", "ppo_kernels.cuh", os.path.join(INC, "dronenav.h"), os.path.join(INC, "dnppo.h")],
+    "ppo_update.cu": ["dn_umma.cuh", "ppo_kernels.cuh", "ppo_comm.cuh", os.path.join(INC, "dronenav.h"), os.path.join(INC, "dnppo.h")],
 }
 
 NVCC_FLAGS = [
