@@ -583,7 +583,30 @@ def run_ppo(args, dev, world, rank, barrier, max_over_ranks):
            "normalize_obs": not args.no_norm_obs, "update_impl": outs[-1].get("impl", "torch/" + cfg.matmul_precision),
            "optimizer_steps": [o.get("optimizer_steps") for o in outs], "update_us_per_minibatch": 1e6 * sum(o["update_s"] for o in outs) / max(1, sum(o["minibatches"] for o in outs)),
            "policy": "2 x MLP 13-512-512-256 (pi, vf), Tanh; update + rollout forward: hand-written sm_100a kernels (tcgen05 BF16 hi/lo planes, "
-                     "FP32 TMEM accumulation) unless update_impl says torch", "collective": "NCCL all-reduce of one flat FP32 gradient bucket per optimiser step" if world > 1 else "none (1 GPU)"}
+                     "FP32 TMEM accumulation) unless update_impl says torch"}
+    impl_ar = res["allreduce_impl"]
+    res["collective"] = ("none (1 GPU)" if world == 1 else
+                         "sum of one flat FP32 gradient bucket per optimiser step over NVLink peer memory (the library's own kernel, inside the minibatch graph)"
+                         if impl_ar == "peer" else "NCCL all-reduce of one flat FP32 gradient bucket per optimiser step")
+    # aggregate tensor-core roofline of the update: forward + dgrad + wgrad of both MLPs = (2 + 2 + 2) x sum(in x out) flop per sample and net,
+    # times the BF16 products issued per FP32 product (3 in the FP32-faithful mode), over the WHOLE update time (gather, heads, losses,
+    # reductions, clip and Adam included), against the measured dense BF16 rate
+    try:
+        arch = tuple(cfg.pi_arch)
+        dims = [(64, arch[0])] + [(arch[i], arch[i + 1]) for i in range(len(arch) - 1)]          # the 13-dim observation is padded to K = 64
+        passes = 3 if "bf16x3" in res["update_impl"] else 1
+        flop_per_sample = 2 * (4 * sum(i * o for i, o in dims) + 2 * sum(i * o for i, o in dims[1:])) * passes   # no dgrad below the first layer
+        n_samples = sum(o["minibatches"] for o in outs) * cfg.batch_size
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak_tf = float(json.load(f)["bf16_tflops"])
+        ach = flop_per_sample * n_samples / max(res["update_s"], 1e-9) / 1e12
+        if "fused" in res["update_impl"]:
+            res["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                               "kernel": "dnmma::umma_gemm<KIND, 256, 2> (all contractions of the update; per-kernel table: profiles/ppo_r02.md)",
+                               "flop_counting": f"{passes} BF16 product(s) per FP32 product; whole update time incl. gather, heads, reductions, clip, Adam",
+                               "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)"}
+    except Exception:  # noqa: BLE001
+        pass
     env.close()
     return res
 
