@@ -1096,7 +1096,11 @@ static int zero_copy_launch(dn_env* env) {
     }
     const bool signal = env->zc_flag_h != nullptr && getenv("DN_HOST_POLL_STREAM") == nullptr;
     env->zc_signalled = signal ? 1 : 0;
-    if (signal) { env->zc_seq += 1; if (env->zc_seq == 0u) env->zc_seq = 1u; env->zc_signal = 1; }
+    if (signal) {
+        env->zc_seq += 1; if (env->zc_seq == 0u) env->zc_seq = 1u; env->zc_signal = 1;
+        // the word is shared with the resident server (its own sequence numbers): never start a wait on a stale equal value
+        if (*reinterpret_cast<volatile unsigned int*>(env->zc_flag_h) == env->zc_seq) *reinterpret_cast<volatile unsigned int*>(env->zc_flag_h) = 0u;
+    }
     const int rc = launch_step(env, &env->host_mapped, 1, 1, env->host_stream);
     env->zc_signal = 0;
     return rc;
