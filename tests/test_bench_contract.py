@@ -49,3 +49,23 @@ def test_gpu_arm_line():
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
     assert "workload" in d["config"] and "l2" in d["config"] and "model" not in d["config"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_roofline_rows_find_the_committed_ncu_captures():
+    """bench.py's per-variant roofline rows quote the ncu DRAM bytes of the SAME configuration from profiles/ncu_summary_r*.json:
+    the lookup keys (envs, substeps, variant prefix) must match what tools/summarize_profiles*.py wrote."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.ncu_traffic(4096, 8) == 560640.0                      # headline kernel, 4096 envs
+    assert bench.ncu_traffic(4194304, 8) > 1.2e9 and bench.ncu_traffic(4194304, 1) > 1.1e9
+    for envs, sub, variant in ((12, 1, "norm_"), (4096, 8, "norm_"), (16384, 8, "phys3_"), (131072, 8, "full_rw3_"),
+                               (131072, 8, "full_rw8_"), (131072, 8, "full_rw9_")):
+        assert bench.ncu_traffic(envs, sub, variant) is not None, (envs, sub, variant)
+    assert bench.ncu_traffic(777, 8) is None and bench.ncu_traffic(4096, 8, "no_such_") is None
+    r = bench.roofline(4096, 4e-6, substeps=8)
+    assert r["bound"] == "hbm" and r["traffic"] == 560640.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert r["algorithmic_bytes_per_launch"] == 4096 * bench.BYTES_PER_ENV_STEP
