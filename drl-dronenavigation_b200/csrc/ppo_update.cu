@@ -115,8 +115,7 @@ int launch_one(const GemmPlan& p, cudaStream_t st) {
         PPO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM_BYTES)));
         attr_set = true;
     }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.grid);
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
